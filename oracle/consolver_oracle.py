@@ -1,0 +1,443 @@
+"""TEST INFRASTRUCTURE ONLY — CPU oracle for the ConsistencySolver sampling step.
+
+A CPU restatement (torch-CPU fp32 tensor ops, op-for-op in the reference's rounding order) of the
+hot path of G-U-N/consolver.  The reference is itself torch code, so torch-CPU is the faithful
+arithmetic; every function cites the reference file:line it follows (paths relative to the
+reference root).  This module is the CHECKER for the CUDA kernels:
+
+  * only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
+    legs may import it.  The product package `consolver_b200` never does and has no CPU fallback.
+  * PARITY PIN: the reference ships no tests / golden vectors for this path, so the
+    oracle is pinned against outputs of the unmodified reference itself, produced in the build
+    container by `oracle/make_golden.py` (through `oracle/ref_shim.py`) and committed as
+    `tests/golden/*.npz`.  `tests/test_oracle_golden.py` checks this module against every fixture.
+  * UNPINNED: the continuous/Gaussian policy (`ppo_type != "discrete"`): its source
+    (`factor_net_ppo_continous`) is absent from the reference, nothing exists to pin against, so it
+    is not restated here.
+
+Layout conventions: a "latent" is one sample's tensor (SD 4x64x64, FM 4096x64); history is a list of
+model outputs NEWEST FIRST; `coef[b, i]` multiplies history entry i (i=0 newest).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+F32 = torch.float32
+
+
+# --------------------------------------------------------------------------------------------
+# schedules
+# --------------------------------------------------------------------------------------------
+def sd_betas(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear",
+             trained_betas=None) -> torch.Tensor:
+    """scheduler_ppo.py:99-108 (+ betas_for_alpha_bar :25-45)."""
+    if trained_betas is not None:
+        return torch.tensor(trained_betas, dtype=F32)
+    if beta_schedule == "linear":
+        return torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=F32)
+    if beta_schedule == "scaled_linear":
+        return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=F32) ** 2
+    if beta_schedule == "squaredcos_cap_v2":
+        def abar(t):
+            return math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+        b = [min(1 - abar((i + 1) / num_train_timesteps) / abar(i / num_train_timesteps), 0.999)
+             for i in range(num_train_timesteps)]
+        return torch.tensor(b, dtype=F32)
+    raise NotImplementedError(f"{beta_schedule} schedule not implemented.")
+
+
+def sd_alphas_cumprod(betas: torch.Tensor) -> torch.Tensor:
+    """scheduler_ppo.py:110-111; fp32 cumprod."""
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def sd_timesteps(num_inference_steps: int, num_train_timesteps=1000, timestep_spacing="leading",
+                 steps_offset=0) -> np.ndarray:
+    """scheduler_ppo.py:142-163."""
+    n, T = num_inference_steps, num_train_timesteps
+    if n > T:
+        raise ValueError("num_inference_steps > num_train_timesteps")
+    if timestep_spacing == "linspace":
+        return np.linspace(0, T - 1, n).round()[::-1].copy().astype(np.int64)
+    if timestep_spacing == "leading":
+        ts = (np.arange(0, n) * (T // n)).round()[::-1].copy().astype(np.int64)
+        return ts + steps_offset
+    if timestep_spacing == "trailing":
+        return np.round(np.arange(T, 0, -(T / n))).astype(np.int64) - 1
+    raise ValueError(f"Unsupported timestep_spacing: {timestep_spacing}.")
+
+
+def sd_prev_timestep(t: int, num_inference_steps: int, num_train_timesteps=1000) -> int:
+    """scheduler_ppo.py:203 — NOT the next grid point: t - (T // n)."""
+    return int(t) - num_train_timesteps // num_inference_steps
+
+
+def ddim_scalars(alphas_cumprod: torch.Tensor, t: int, prev_t: int) -> Tuple[torch.Tensor, ...]:
+    """scheduler_ppo.py:309-312 and the `** 0.5` terms of :317,:323,:329-330, as fp32 0-d tensors:
+    (sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)); prev_t<0 uses alphas_cumprod[0] (:114,:310)."""
+    a_t = alphas_cumprod[int(t)]
+    a_p = alphas_cumprod[int(prev_t)] if prev_t >= 0 else alphas_cumprod[0]
+    b_t = 1 - a_t
+    b_p = 1 - a_p
+    return a_t ** 0.5, b_t ** 0.5, a_p ** 0.5, b_p ** 0.5
+
+
+def fm_sigmas(num_inference_steps=None, sigmas=None, mu=None, timesteps=None, *, num_train_timesteps=1000,
+              shift=1.0, use_dynamic_shifting=False, time_shift_type="exponential", shift_terminal=None,
+              invert_sigmas=False, use_karras_sigmas=False, use_exponential_sigmas=False,
+              sigma_min=None, sigma_max=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """edit_ppo/scheduler_fmppo.py:171-245 (+:142-151 for the ctor's default grid, :489-499, :516-530,
+    :546-550).  Returns (timesteps[n], sigmas[n+1]) fp32.  Beta sigmas (scipy) are not restated: no shipped
+    config uses them."""
+    if use_dynamic_shifting and mu is None:
+        raise ValueError("`mu` must be passed when `use_dynamic_shifting` is set to be `True`")
+    if sigmas is not None and timesteps is not None and len(sigmas) != len(timesteps):
+        raise ValueError("`sigmas` and `timesteps` should have the same length")
+    if num_inference_steps is not None:
+        if (sigmas is not None and len(sigmas) != num_inference_steps) or (
+                timesteps is not None and len(timesteps) != num_inference_steps):
+            raise ValueError("`sigmas`/`timesteps` length must equal num_inference_steps")
+    else:
+        num_inference_steps = len(sigmas) if sigmas is not None else len(timesteps)
+    ts_given = timesteps is not None
+    if ts_given:
+        timesteps = np.array(timesteps).astype(np.float32)
+    if sigmas is None:
+        if timesteps is None:
+            # ctor grid (:142-151): sigma_max/min come from the constructor's shifted 1000-point grid
+            t0 = np.linspace(1, num_train_timesteps, num_train_timesteps, dtype=np.float32)[::-1].copy()
+            s0 = torch.from_numpy(t0).to(F32) / num_train_timesteps
+            if not use_dynamic_shifting:
+                s0 = shift * s0 / (1 + (shift - 1) * s0)
+            smax = s0[0].item() if sigma_max is None else sigma_max
+            smin = s0[-1].item() if sigma_min is None else sigma_min
+            timesteps = np.linspace(smax * num_train_timesteps, smin * num_train_timesteps, num_inference_steps)
+        sig = timesteps / num_train_timesteps
+    else:
+        sig = np.array(sigmas).astype(np.float32)
+        num_inference_steps = len(sig)
+    if use_dynamic_shifting:
+        if time_shift_type == "exponential":
+            sig = math.exp(mu) / (math.exp(mu) + (1 / sig - 1) ** 1.0)
+        else:
+            sig = mu / (mu + (1 / sig - 1) ** 1.0)
+    else:
+        sig = shift * sig / (1 + (shift - 1) * sig)
+    if shift_terminal:
+        omz = 1 - sig
+        sig = 1 - omz / (omz[-1] / (1 - shift_terminal))
+    if use_karras_sigmas:
+        rho, ramp = 7.0, np.linspace(0, 1, num_inference_steps)
+        lo, hi = sig[-1].item() ** (1 / rho), sig[0].item() ** (1 / rho)
+        sig = (hi + ramp * (lo - hi)) ** rho
+    elif use_exponential_sigmas:
+        sig = np.exp(np.linspace(math.log(sig[0].item()), math.log(sig[-1].item()), num_inference_steps))
+    sig_t = torch.from_numpy(np.asarray(sig)).to(dtype=F32)
+    ts_t = torch.from_numpy(timesteps).to(dtype=F32) if ts_given else sig_t * num_train_timesteps
+    if invert_sigmas:
+        sig_t = 1.0 - sig_t
+        ts_t = sig_t * num_train_timesteps
+        sig_t = torch.cat([sig_t, torch.ones(1)])
+    else:
+        sig_t = torch.cat([sig_t, torch.zeros(1)])
+    return ts_t, sig_t
+
+
+# --------------------------------------------------------------------------------------------
+# policy (FactorNetPPO)
+# --------------------------------------------------------------------------------------------
+def action_dims(variant: str, order_dim: int, scaler_dim: int, mu_dim: int = 0) -> int:
+    """factor_net_ppo.py:66 (sd) / edit_ppo/factor_net_ppo.py:67 (fm)."""
+    return order_dim + scaler_dim - 1 + (mu_dim if variant == "fm" else 0)
+
+
+def action_value_table(variant: str, num_actions: int, order_dim: int, scaler_dim: int, mu_dim: int = 0) -> torch.Tensor:
+    """Bin values [A, K]: factor_net_ppo.py:87-102 (sd) / edit_ppo/factor_net_ppo.py:92-110 (fm)."""
+    K = num_actions
+    A = action_dims(variant, order_dim, scaler_dim, mu_dim)
+    rows = []
+    for i in range(A):
+        if i == 0:
+            rows.append(torch.linspace(0, 2 if variant == "sd" else 1, K))
+        elif i == 1 and (variant == "sd" or i < order_dim - 1):
+            rows.append(torch.linspace(-2, 0, K))
+        elif i < order_dim - 1:
+            rows.append(torch.linspace(-1, 1, K))
+        elif variant == "sd" or i < order_dim + scaler_dim - 1:
+            rows.append(torch.linspace(-0.05, 0.05, K))
+        else:
+            rows.append(torch.cat((torch.tensor([0.0]), torch.linspace(0.5, 0.99, K - 1))))
+    return torch.stack(rows)
+
+
+def cosine_features(epsilon: torch.Tensor, order_dim: int) -> torch.Tensor:
+    """factor_net_ppo.py:108-130 — cos-sim of history slot 0 vs slots 1..order_dim-1 (use_conv=True only)."""
+    B = epsilon.shape[0]
+    flat = epsilon.reshape(B, order_dim, -1)
+    first = flat[:, 0, :]
+    return torch.cat([torch.nn.functional.cosine_similarity(flat[:, i, :], first, dim=-1).unsqueeze(-1)
+                      for i in range(1, order_dim)], dim=-1)
+
+
+def policy_probs(sd: Dict[str, torch.Tensor], x: torch.Tensor, variant: str,
+                 epsilon: Optional[torch.Tensor] = None, order_dim: int = 4) -> torch.Tensor:
+    """forward_: factor_net_ppo.py:137-157 (sd: x/999, softmax) / edit_ppo/factor_net_ppo.py:149-169
+    (fm: identity normalise, softmax(logits/0.01)).  x: [R, 2] in the model dtype; returns [R, A, K] fp32.
+    `epsilon` (stacked history [R, order_dim, ...]) switches on the use_conv feature path."""
+    av = sd["action_values"]
+    A, K = av.shape
+    xn = x.float() / 999.0 if variant == "sd" else x.float()
+    if epsilon is not None:
+        xn = torch.cat([xn, cosine_features(epsilon, order_dim)], dim=-1)
+    h = torch.relu(torch.nn.functional.linear(xn, sd["mlp.0.weight"].float(), sd["mlp.0.bias"].float()))
+    h = torch.relu(torch.nn.functional.linear(h, sd["mlp.2.weight"].float(), sd["mlp.2.bias"].float()))
+    logits = torch.nn.functional.linear(h, sd["mlp.4.weight"].float(), sd["mlp.4.bias"].float()).view(-1, A, K)
+    if variant == "fm":
+        logits = logits / 0.01
+    return torch.softmax(logits, dim=-1)
+
+
+def sample_indices(probs: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """factor_net_ppo.py:161 — torch.multinomial(p.view(-1,K), 1) is argmax(p / q), q ~ Exp(1) drawn as
+    `empty_like(p).exponential_(1)` from the default generator (ATen multinomial n_sample==1 fast path).
+    probs [B, A, K], q [B*A, K] -> idx [B, A] int64."""
+    B, A, K = probs.shape
+    return torch.argmax(probs.reshape(-1, K) / q, dim=-1).view(B, A)
+
+
+def draw_q(B: int, A: int, K: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """The RNG contract of the path: one exponential_ draw of shape [B*A, K] fp32 per step."""
+    return torch.empty(B * A, K, dtype=F32).exponential_(1, generator=generator)
+
+
+def gather_actions(sd: Dict[str, torch.Tensor], probs: torch.Tensor, idx: torch.Tensor):
+    """factor_net_ppo.py:164-168: (bin values, probabilities of the sampled bins), both [B, A]."""
+    B = idx.shape[0]
+    av = sd["action_values"].unsqueeze(0).expand(B, -1, -1)
+    return (torch.gather(av, 2, idx.unsqueeze(-1)).squeeze(-1),
+            probs.gather(2, idx.unsqueeze(-1)).squeeze(-1))
+
+
+def action_indices_from_values(sd, actions: torch.Tensor) -> torch.Tensor:
+    """factor_net_ppo.py:174-178 — nearest-bin recovery on the PPO-update side."""
+    av = sd["action_values"]
+    idx = torch.zeros_like(actions, dtype=torch.long)
+    for d in range(av.shape[0]):
+        idx[:, d] = (actions[:, d].unsqueeze(-1) - av[d]).abs().argmin(dim=-1)
+    return idx
+
+
+def action_probs_entropy(sd, x: torch.Tensor, actions: torch.Tensor, variant: str):
+    """get_action_probs: factor_net_ppo.py:170-184 -> (selected probs [R,A], normalised entropy [R,A])."""
+    probs = policy_probs(sd, x, variant)
+    idx = action_indices_from_values(sd, actions)
+    # reference divides by torch.log(tensor(K, dtype)) (fp32); do the same to stay bit-identical
+    ent = torch.distributions.Categorical(probs=probs).entropy() / torch.log(
+        torch.as_tensor(probs.shape[2], dtype=probs.dtype))
+    return probs.gather(2, idx.unsqueeze(-1)).squeeze(-1), ent
+
+
+def step_masks(B: int, A: int, n_hist: int, order_dim: int) -> torch.Tensor:
+    """scheduler_ppo.py:248-249."""
+    m = torch.ones(B, A, dtype=F32)
+    m[:, n_hist - 1:order_dim - 1] = 0
+    return m
+
+
+def coefficients(actions: torch.Tensor, n_hist: int, order_dim: int, scaler_dim: int):
+    """scheduler_ppo.py:253-259 + set_default_coefficients :165-175 (same in edit_ppo/scheduler_fmppo.py
+    :249-268).  Returns (coef list of n_hist tensors [B] newest first — for n_hist==1 the reference
+    bypasses the coefficient and uses the estimate itself (:263-265) so coef is None —, scale list)."""
+    a = [actions[:, i] for i in range(order_dim - 1)]
+    s = [actions[:, i] for i in range(order_dim - 1, order_dim + scaler_dim - 1)]
+    a.append(a[-1] if a else None)  # placeholder (:166)
+    a[0] = a[0] + 1
+    if n_hist > 1:
+        a[n_hist - 1] = 1 - torch.sum(torch.stack(a[:n_hist - 1]), dim=0)
+    s = [v + 1 for v in s]
+    return (a[:n_hist] if n_hist > 1 else None), s
+
+
+# --------------------------------------------------------------------------------------------
+# per-element update (what the fused CUDA step kernel computes)
+# --------------------------------------------------------------------------------------------
+def cfg_combine(uncond: torch.Tensor, cond: torch.Tensor, guidance: float) -> torch.Tensor:
+    """denoise_ppo.py:97-100: u + g*(c - u)."""
+    return uncond + guidance * (cond - uncond)
+
+
+def _bc(v: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    return v.view(-1, *([1] * (like.dim() - 1)))
+
+
+def combine_history(hist: Sequence[torch.Tensor], coef, scale, sample: torch.Tensor):
+    """scheduler_ppo.py:263-280: eff = sum_i c_i * e_i (python sum, left to right from 0), then the
+    optional (1+s0) / (1+s1) scalings.  Returns (eff, sample')."""
+    if coef is None:
+        eff = hist[0]
+    else:
+        eff = sum(_bc(c, e) * e for c, e in zip(coef, hist))
+    if len(scale) >= 1:
+        eff = eff * _bc(scale[0], eff)
+    if len(scale) == 2:
+        sample = sample * _bc(scale[1], sample)
+    elif len(scale) > 2:
+        raise NotImplementedError
+    return eff, sample
+
+
+def ddim_update(sample, eff, scalars, prediction_type="epsilon"):
+    """scheduler_ppo.py:306-332 (_get_prev_sample), eta=0, no clipping."""
+    sa_t, sb_t, sa_p, sb_p = scalars
+    if prediction_type == "v_prediction":
+        eff = sa_t * eff + sb_t * sample
+    elif prediction_type != "epsilon":
+        raise ValueError(f"Unsupported prediction_type: {prediction_type}")
+    x0 = (sample - sb_t * eff) / sa_t
+    return sa_p * x0 + sb_p * eff
+
+
+def fm_update(sample, eff, dt, out_dtype):
+    """edit_ppo/scheduler_fmppo.py:354,:429,:436: fp32 sample + dt*eff, cast to the model dtype."""
+    return (sample + dt * eff).to(out_dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# stateful runners with the reference's step() contract (used by tests and the CPU baseline)
+# --------------------------------------------------------------------------------------------
+class OracleSDScheduler:
+    """PPOScheduler restated (scheduler_ppo.py:81-332).  `step()` returns the reference's 5-tuple.
+    `forced_idx` (optional [B, A] int64) replaces the sampled indices (for latent parity with injected
+    actions); `q` (optional) replaces the default-generator draw."""
+
+    def __init__(self, state_dict, *, num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02,
+                 beta_schedule="linear", trained_betas=None, prediction_type="epsilon",
+                 timestep_spacing="leading", steps_offset=0, order_dim=4, scaler_dim=2, use_conv=False):
+        self.sd = {k: torch.as_tensor(v) for k, v in state_dict.items()}
+        self.T, self.order_dim, self.scaler_dim = num_train_timesteps, order_dim, scaler_dim
+        self.prediction_type, self.spacing, self.offset = prediction_type, timestep_spacing, steps_offset
+        self.use_conv = use_conv
+        self.alphas_cumprod = sd_alphas_cumprod(
+            sd_betas(num_train_timesteps, beta_start, beta_end, beta_schedule, trained_betas))
+        self.n = None
+        self.hist: List[torch.Tensor] = []
+
+    def set_timesteps(self, n: int):
+        self.timesteps = torch.from_numpy(sd_timesteps(n, self.T, self.spacing, self.offset))
+        self.n = n
+        self.hist = []
+
+    def step(self, model_output, timestep, sample, q=None, forced_idx=None):
+        if self.n is None:
+            raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
+        t = int(timestep)
+        prev_t = sd_prev_timestep(t, self.n, self.T)
+        B = model_output.shape[0]
+        x = torch.tensor([[t, prev_t]], dtype=model_output.dtype).repeat(B, 1)
+        self.hist = ([model_output] + self.hist)[: self.order_dim]      # newest first
+        n_hist = len(self.hist)
+        eps_stack = torch.stack(self.hist, dim=1)     # :222-232, built (and paid for) on every step
+        if n_hist < self.order_dim:
+            pad = torch.zeros(B, self.order_dim - n_hist, *model_output.shape[1:], dtype=model_output.dtype)
+            eps_stack = torch.cat([eps_stack, pad], dim=1)
+        probs = policy_probs(self.sd, x, "sd", eps_stack if self.use_conv else None, self.order_dim)
+        A, K = probs.shape[1:]
+        if forced_idx is None:
+            if q is None:
+                q = draw_q(B, A, K)
+            idx = sample_indices(probs, q)
+        else:
+            idx = forced_idx
+        actions, act_probs = gather_actions(self.sd, probs, idx)
+        masks = step_masks(B, A, n_hist, self.order_dim)
+        coef, scale = coefficients(actions, n_hist, self.order_dim, self.scaler_dim)
+        eff, smp = combine_history(self.hist, coef, scale, sample)
+        prev = ddim_update(smp, eff, ddim_scalars(self.alphas_cumprod, t, prev_t), self.prediction_type)
+        self.last_idx, self.last_probs_full = idx, probs
+        return prev, actions, act_probs, {"x": x, "epsilon": eps_stack}, masks
+
+
+class OracleFMScheduler:
+    """FMPPOScheduler restated (edit_ppo/scheduler_fmppo.py:108-455), per_token_timesteps excluded."""
+
+    def __init__(self, state_dict, *, num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False,
+                 time_shift_type="exponential", shift_terminal=None, invert_sigmas=False,
+                 use_karras_sigmas=False, use_exponential_sigmas=False, order_dim=4, scaler_dim=2, mu_dim=1,
+                 use_conv=False):
+        self.sd = {k: torch.as_tensor(v) for k, v in state_dict.items()}
+        self.kw = dict(num_train_timesteps=num_train_timesteps, shift=shift,
+                       use_dynamic_shifting=use_dynamic_shifting, time_shift_type=time_shift_type,
+                       shift_terminal=shift_terminal, invert_sigmas=invert_sigmas,
+                       use_karras_sigmas=use_karras_sigmas, use_exponential_sigmas=use_exponential_sigmas)
+        self.order_dim, self.scaler_dim, self.mu_dim, self.use_conv = order_dim, scaler_dim, mu_dim, use_conv
+        self.n = None
+        self.hist: List[torch.Tensor] = []
+
+    def set_timesteps(self, num_inference_steps=None, sigmas=None, mu=None, timesteps=None):
+        self.timesteps, self.sigmas = fm_sigmas(num_inference_steps, sigmas, mu, timesteps, **self.kw)
+        self.n = len(self.timesteps)
+        self.step_index = None
+        self.begin_index = None
+        self.hist = []
+
+    def set_begin_index(self, i=0):
+        self.begin_index = i
+
+    def step(self, model_output, timestep, sample, q=None, forced_idx=None):
+        if self.n is None:
+            raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
+        if isinstance(timestep, int) or (torch.is_tensor(timestep) and not timestep.is_floating_point()):
+            raise ValueError("Passing integer indices as timesteps to `step()` is not supported.")
+        if self.step_index is None:
+            if self.begin_index is None:
+                hits = (self.timesteps == timestep).nonzero()
+                self.step_index = hits[1 if len(hits) > 1 else 0].item()
+            else:
+                self.step_index = self.begin_index
+        sample = sample.to(F32)
+        self.hist = ([model_output] + self.hist)[: self.order_dim]
+        n_hist = len(self.hist)
+        cur, nxt = self.sigmas[self.step_index], self.sigmas[self.step_index + 1]
+        dt = nxt - cur
+        B = model_output.shape[0]
+        x = torch.tensor([[cur, nxt]], dtype=model_output.dtype).repeat(B, 1)
+        eps_stack = torch.stack(self.hist, dim=1)
+        if n_hist < self.order_dim:
+            pad = torch.zeros(B, self.order_dim - n_hist, *model_output.shape[1:], dtype=model_output.dtype)
+            eps_stack = torch.cat([eps_stack, pad], dim=1)
+        probs = policy_probs(self.sd, x, "fm", eps_stack if self.use_conv else None, self.order_dim)
+        A, K = probs.shape[1:]
+        if forced_idx is None:
+            if q is None:
+                q = draw_q(B, A, K)
+            idx = sample_indices(probs, q)
+        else:
+            idx = forced_idx
+        actions, act_probs = gather_actions(self.sd, probs, idx)
+        masks = step_masks(B, A, n_hist, self.order_dim)
+        coef, scale = coefficients(actions, n_hist, self.order_dim, self.scaler_dim)  # mu params unused (:409,:440)
+        eff, smp = combine_history(self.hist, coef, scale, sample)
+        prev = fm_update(smp, eff, dt, model_output.dtype)
+        self.step_index += 1
+        self.last_idx, self.last_probs_full = idx, probs
+        return prev, actions, act_probs, {"x": x, "epsilon": eps_stack}, masks
+
+
+def run_sd_preview(sched: OracleSDScheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: float,
+                   qs: Optional[Sequence[torch.Tensor]] = None, forced_idx=None):
+    """The caller loop of denoise_ppo.py:62-113 with the denoiser replaced by given CFG pairs
+    ([2B, ...] each, unconditional half first, :66/:97).  Returns (final latents, per-step records)."""
+    x = x_T
+    rec = []
+    for i, t in enumerate(sched.timesteps):
+        u, c = pairs[i].chunk(2)
+        eps = cfg_combine(u, c, guidance)
+        out = sched.step(eps, t, x, q=None if qs is None else qs[i],
+                         forced_idx=None if forced_idx is None else forced_idx[i])
+        x = out[0]
+        rec.append(out)
+    return x, rec

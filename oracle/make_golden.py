@@ -1,0 +1,231 @@
+"""TEST INFRASTRUCTURE ONLY — writes tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (the only place /root/reference exists):
+
+    python oracle/make_golden.py            # regenerates every fixture
+
+Each fixture holds the inputs and the reference's own outputs for one scheduler configuration:
+weights (`sd.*`), initial latent, per-step model outputs, the Exp(1) draw `q` that
+`torch.multinomial` consumed (recovered by re-seeding the default generator with the same seed;
+the script asserts argmax(p/q) reproduces the reference's indices), sampled actions / probs / masks,
+the full softmax table and the next latent.  bf16 tensors are stored as their uint16 bit patterns
+(`__bf16__` lists the keys).  The tests never read /root/reference; they read these files.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+SD_PROD = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, num_train_timesteps=1000,
+               steps_offset=1, timestep_spacing="trailing", order_dim=4, scaler_dim=0, use_conv=False)
+FM_PROD = dict(shift=3.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15, base_image_seq_len=256,
+               max_image_seq_len=4096, order_dim=2, scaler_dim=0, mu_dim=0)
+
+
+def _np(t: torch.Tensor, bf16_keys, key):
+    t = t.detach().cpu()
+    if t.dtype == torch.bfloat16:
+        bf16_keys.append(key)
+        return t.contiguous().view(torch.int16).numpy().view(np.uint16)
+    return t.numpy()
+
+
+def _seed_policy(fn, seed, last_std):
+    """Random-init stand-in for the unreachable published checkpoint: default nn.Linear init for
+    layers 0/2 under `seed`, last layer N(0, last_std^2) weight, small bias (the reference zero-inits
+    the SD last layer -> uniform policy, which would leave the sampling path untested)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in fn.named_parameters():
+            if name.startswith("mlp.4"):
+                p.copy_(torch.randn(p.shape, generator=g) * (last_std if name.endswith("weight") else 0.1))
+            else:
+                bound = 1.0 / (p.shape[-1] if p.dim() > 1 else fn.mlp[int(name.split(".")[1])].in_features) ** 0.5
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
+
+
+def _hook_probs(fn, store):
+    orig = fn.forward_
+
+    def wrapped(x_dict):
+        p = orig(x_dict)
+        store.append(p.detach().clone())
+        return p
+
+    fn.forward_ = wrapped
+
+
+def gen_sd(name, *, B, shape, n, guidance, seed, last_std=0.5, dtype=torch.float32, **cfg_over):
+    ref = ref_shim.load_reference()
+    cfg = dict(SD_PROD, **cfg_over)
+    fkw = dict(embedding_dim=64, hidden_dim=cfg.pop("hidden_dim", 256), num_actions=cfg.pop("num_actions", 11))
+    with ref_shim.quiet():
+        s = ref.PPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
+    _seed_policy(s.factor_net, seed, last_std)
+    full = []
+    _hook_probs(s.factor_net, full)
+    s.set_timesteps(n)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, *shape, generator=g).to(dtype)
+    bf, d = [], {}
+    d["x_T"] = _np(x, bf, "x_T")
+    for k, v in s.factor_net.state_dict().items():
+        d[f"sd.{k}"] = v.numpy()
+    d["timesteps"] = s.timesteps.numpy()
+    A, K = s.factor_net.action_dims, s.factor_net.num_actions
+    for i, t in enumerate(s.timesteps):
+        pair = torch.randn(2 * B, *shape, generator=g).to(dtype)
+        u, c = pair.chunk(2)
+        eps = u + guidance * (c - u)                      # denoise_ppo.py:97-100
+        torch.manual_seed(seed * 1000 + i)
+        with ref_shim.quiet():
+            x, actions, probs, conds, masks = s.step(eps, t, x, return_dict=False)
+        torch.manual_seed(seed * 1000 + i)
+        q = torch.empty(B * A, K).exponential_(1)
+        idx = torch.argmax(full[i].view(-1, K) / q, dim=-1).view(B, A)
+        assert torch.equal(s.factor_net.action_values[torch.arange(A), idx], actions), "q recovery failed"
+        d[f"pair_{i}"] = _np(pair, bf, f"pair_{i}")
+        d[f"eps_{i}"] = _np(eps, bf, f"eps_{i}")
+        d[f"q_{i}"] = q.numpy()
+        d[f"idx_{i}"] = idx.numpy()
+        d[f"actions_{i}"] = actions.detach().numpy()
+        d[f"probs_{i}"] = probs.detach().numpy()
+        d[f"probs_full_{i}"] = full[i].numpy()
+        d[f"masks_{i}"] = masks.numpy()
+        d[f"condx_{i}"] = _np(conds["x"], bf, f"condx_{i}")
+        d[f"prev_{i}"] = _np(x, bf, f"prev_{i}")
+        assert conds["epsilon"].shape == (B, cfg["order_dim"], *shape)
+        assert torch.equal(conds["epsilon"][:, 0], eps)
+    meta = dict(kind="sd", B=B, shape=list(shape), n=n, guidance=guidance, seed=seed, config=cfg,
+                factor_net_kwargs=fkw, dtype=str(dtype).split(".")[-1], torch=torch.__version__)
+    d["__meta__"] = np.array(json.dumps(meta))
+    d["__bf16__"] = np.array(json.dumps(bf))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, "A=%d K=%d" % (A, K))
+
+
+def gen_fm(name, *, B, shape, n, seed, dtype, last_std=0.02, use_begin_index=True, **cfg_over):
+    ref = ref_shim.load_reference()
+    cfg = dict(FM_PROD, **cfg_over)
+    fkw = dict(hidden_dim=cfg.pop("hidden_dim", 256), num_actions=cfg.pop("num_actions", 11))
+    with ref_shim.quiet():
+        s = ref.FMPPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
+    _seed_policy(s.factor_net, seed, last_std)
+    full = []
+    _hook_probs(s.factor_net, full)
+    s.set_timesteps(n, sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+    if use_begin_index:
+        s.set_begin_index(0)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, *shape, generator=g).to(dtype)
+    bf, d = [], {}
+    d["x_T"] = _np(x, bf, "x_T")
+    for k, v in s.factor_net.state_dict().items():
+        d[f"sd.{k}"] = v.numpy()
+    d["timesteps"] = s.timesteps.numpy()
+    d["sigmas"] = s.sigmas.numpy()
+    A, K = s.factor_net.action_dims, s.factor_net.num_actions
+    for i, t in enumerate(s.timesteps):
+        v = torch.randn(B, *shape, generator=g).to(dtype)
+        torch.manual_seed(seed * 1000 + i)
+        with ref_shim.quiet():
+            x, actions, probs, conds, masks = s.step(v, t, x, return_dict=False)
+        torch.manual_seed(seed * 1000 + i)
+        q = torch.empty(B * A, K).exponential_(1)
+        idx = torch.argmax(full[i].view(-1, K) / q, dim=-1).view(B, A)
+        assert torch.equal(s.factor_net.action_values[torch.arange(A), idx], actions), "q recovery failed"
+        d[f"v_{i}"] = _np(v, bf, f"v_{i}")
+        d[f"q_{i}"] = q.numpy()
+        d[f"idx_{i}"] = idx.numpy()
+        d[f"actions_{i}"] = actions.detach().numpy()
+        d[f"probs_{i}"] = probs.detach().numpy()
+        d[f"probs_full_{i}"] = full[i].numpy()
+        d[f"masks_{i}"] = masks.numpy()
+        d[f"condx_{i}"] = _np(conds["x"], bf, f"condx_{i}")
+        d[f"prev_{i}"] = _np(x, bf, f"prev_{i}")
+    meta = dict(kind="fm", B=B, shape=list(shape), n=n, seed=seed, config=cfg, factor_net_kwargs=fkw,
+                dtype=str(dtype).split(".")[-1], mu=1.15, use_begin_index=use_begin_index,
+                torch=torch.__version__)
+    d["__meta__"] = np.array(json.dumps(meta))
+    d["__bf16__"] = np.array(json.dumps(bf))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, "A=%d K=%d" % (A, K))
+
+
+def gen_update_side(name, variant, seed, **kw):
+    """FactorNetPPO.get_action_probs (factor_net_ppo.py:170-184): the PPO-update-side evaluation."""
+    ref = ref_shim.load_reference()
+    with ref_shim.quiet():
+        fn = (ref.FactorNetPPO_SD if variant == "sd" else ref.FactorNetPPO_FM)(**kw)
+    _seed_policy(fn, seed, 0.5 if variant == "sd" else 0.02)
+    g = torch.Generator().manual_seed(seed)
+    R = 14
+    if variant == "sd":
+        t = torch.randint(0, 1000, (R, 1), generator=g).float()
+        x = torch.cat([t, t - 66], dim=1)
+    else:
+        x = torch.rand(R, 2, generator=g)
+    with ref_shim.quiet():
+        torch.manual_seed(seed)
+        actions, _ = fn.sample_action({"x": x})
+        probs, ent = fn(dict(x=x), actions)
+    d = {f"sd.{k}": v.numpy() for k, v in fn.state_dict().items()}
+    d.update(x=x.numpy(), actions=actions.numpy(), probs=probs.detach().numpy(), entropy=ent.detach().numpy())
+    d["__meta__"] = np.array(json.dumps(dict(kind="update", variant=variant, kwargs=kw, torch=torch.__version__)))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    small = (4, 8, 8)
+    # --- SD / PPOScheduler: production config at several step counts (warm-up depths, n=7 quirk) -------
+    for n in (2, 5, 7, 8, 12):
+        gen_sd(f"sd_eps_s0_n{n}_B3", B=3, shape=small, n=n, guidance=3.0, seed=10 + n,
+               hidden_dim=256 if n == 8 else 64)
+    gen_sd("sd_eps_s0_n8_B1_full", B=1, shape=(4, 64, 64), n=8, guidance=3.0, seed=3)       # BASELINE config 0
+    gen_sd("sd_eps_s0_n8_B64", hidden_dim=64, B=64, shape=(4, 4, 4), n=8, guidance=3.0, seed=4)
+    # --- scaler dims, v-prediction, other spacings / schedules / orders -------------------------------
+    gen_sd("sd_eps_s1_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=21, scaler_dim=1)
+    gen_sd("sd_eps_s2_n8_B3", B=3, shape=small, n=8, guidance=3.0, seed=22, scaler_dim=2)
+    gen_sd("sd_v_s0_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=23, prediction_type="v_prediction")
+    gen_sd("sd_v_s2_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=7.5, seed=24, prediction_type="v_prediction",
+           scaler_dim=2)
+    gen_sd("sd_eps_leading_linear_o3_n6_B2", hidden_dim=64, B=2, shape=small, n=6, guidance=1.5, seed=25,
+           timestep_spacing="leading", beta_schedule="linear", beta_start=1e-4, beta_end=0.02, order_dim=3,
+           scaler_dim=1)
+    gen_sd("sd_eps_linspace_cos_o2_n9_B2", hidden_dim=64, B=2, shape=small, n=9, guidance=3.0, seed=26,
+           timestep_spacing="linspace", beta_schedule="squaredcos_cap_v2", order_dim=2, scaler_dim=0)
+    gen_sd("sd_eps_k161_o4_s2_n4_B2", hidden_dim=64, B=2, shape=small, n=4, guidance=3.0, seed=27, scaler_dim=2,
+           num_actions=161, last_std=0.2)                                                     # ctor defaults
+    gen_sd("sd_eps_s0_n8_B2_ragged", hidden_dim=64, B=2, shape=(3, 5, 7), n=8, guidance=3.0, seed=28)        # N_s % 4 != 0
+    # --- FM / FMPPOScheduler --------------------------------------------------------------------------
+    tok = (16, 8)
+    gen_fm("fm_o2_s0_m0_bf16_n8_B3", B=3, shape=tok, n=8, seed=31, dtype=torch.bfloat16)     # FLUX prod
+    gen_fm("fm_o2_s0_m0_f32_n8_B3", hidden_dim=64, B=3, shape=tok, n=8, seed=32, dtype=torch.float32)
+    gen_fm("fm_o4_s2_m1_bf16_n8_B3", B=3, shape=tok, n=8, seed=33, dtype=torch.bfloat16, order_dim=4,
+           scaler_dim=2, mu_dim=1)                                                            # ctor defaults
+    gen_fm("fm_o4_s0_m0_f32_n5_B2", hidden_dim=64, B=2, shape=tok, n=5, seed=34, dtype=torch.float32, order_dim=4)
+    gen_fm("fm_o4_s1_m0_bf16_n6_B2", hidden_dim=64, B=2, shape=tok, n=6, seed=35, dtype=torch.bfloat16, order_dim=4,
+           scaler_dim=1)
+    gen_fm("fm_o2_s0_m0_bf16_n4_B2_search", hidden_dim=64, B=2, shape=tok, n=4, seed=36, dtype=torch.bfloat16,
+           use_begin_index=False)
+    gen_fm("fm_o2_s0_m0_bf16_n3_B1_full", B=1, shape=(4096, 64), n=3, seed=37, dtype=torch.bfloat16)
+    # --- PPO-update side ------------------------------------------------------------------------------
+    gen_update_side("update_sd_o4_s0", "sd", 41, hidden_dim=256, num_actions=11, order_dim=4, scaler_dim=0)
+    gen_update_side("update_fm_o2_s0_m0", "fm", 42, hidden_dim=256, num_actions=11, order_dim=2, scaler_dim=0,
+                    mu_dim=0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Pins the CPU oracle (oracle/consolver_oracle.py) against the reference's own outputs (tests/golden)."""
+import pytest
+import torch
+
+import consolver_oracle as orc
+from golden_io import Golden, names
+
+SD = names("sd_")
+FM = names("fm_")
+
+
+def _sd_sched(g):
+    return orc.OracleSDScheduler(g.state_dict, **g.meta["config"])
+
+
+@pytest.mark.parametrize("name", SD)
+def test_sd_oracle_matches_reference(name):
+    g = Golden(name)
+    m = g.meta
+    s = _sd_sched(g)
+    s.set_timesteps(m["n"])
+    assert torch.equal(s.timesteps, g["timesteps"])
+    x = g["x_T"]
+    for i, t in enumerate(s.timesteps):
+        u, c = g[f"pair_{i}"].chunk(2)
+        eps = orc.cfg_combine(u, c, m["guidance"])
+        assert torch.equal(eps, g[f"eps_{i}"])
+        x, actions, probs, conds, masks = s.step(eps, t, x, q=g[f"q_{i}"])
+        assert torch.equal(s.last_idx, g[f"idx_{i}"]), f"step {i} indices"
+        assert torch.equal(actions, g[f"actions_{i}"])
+        assert torch.equal(masks, g[f"masks_{i}"])
+        assert torch.equal(conds["x"], g[f"condx_{i}"])
+        torch.testing.assert_close(s.last_probs_full, g[f"probs_full_{i}"], rtol=0, atol=1e-7)
+        torch.testing.assert_close(probs, g[f"probs_{i}"], rtol=0, atol=1e-7)
+        assert torch.equal(x, g[f"prev_{i}"]), f"step {i} latent not bit-exact"
+
+
+@pytest.mark.parametrize("name", FM)
+def test_fm_oracle_matches_reference(name):
+    g = Golden(name)
+    m = g.meta
+    cfg = dict(m["config"])
+    for k in ("base_shift", "max_shift", "base_image_seq_len", "max_image_seq_len"):
+        cfg.pop(k, None)
+    s = orc.OracleFMScheduler(g.state_dict, **cfg)
+    import numpy as np
+    s.set_timesteps(m["n"], sigmas=np.linspace(1.0, 1 / m["n"], m["n"]), mu=m["mu"])
+    if m["use_begin_index"]:
+        s.set_begin_index(0)
+    assert torch.equal(s.timesteps, g["timesteps"])
+    assert torch.equal(s.sigmas, g["sigmas"])
+    x = g["x_T"]
+    for i, t in enumerate(s.timesteps):
+        x, actions, probs, conds, masks = s.step(g[f"v_{i}"], t, x, q=g[f"q_{i}"])
+        assert torch.equal(s.last_idx, g[f"idx_{i}"]), f"step {i} indices"
+        assert torch.equal(actions, g[f"actions_{i}"])
+        assert torch.equal(masks, g[f"masks_{i}"])
+        assert torch.equal(conds["x"], g[f"condx_{i}"])
+        torch.testing.assert_close(s.last_probs_full, g[f"probs_full_{i}"], rtol=1e-6, atol=1e-7)
+        assert x.dtype == g[f"prev_{i}"].dtype
+        assert torch.equal(x, g[f"prev_{i}"]), f"step {i} latent not bit-exact"
+
+
+@pytest.mark.parametrize("name", names("update_"))
+def test_update_side_oracle(name):
+    g = Golden(name)
+    p, e = orc.action_probs_entropy(g.state_dict, g["x"], g["actions"], g.meta["variant"])
+    torch.testing.assert_close(p, g["probs"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(e, g["entropy"], rtol=1e-5, atol=1e-6)
+
+
+def test_action_value_tables_match_reference_buffers():
+    for name in SD + FM:
+        g = Golden(name)
+        c, f = g.meta["config"], g.meta["factor_net_kwargs"]
+        tab = orc.action_value_table(g.meta["kind"], f["num_actions"], c["order_dim"], c["scaler_dim"],
+                                     c.get("mu_dim", 0))
+        assert torch.equal(tab, g.state_dict["action_values"]), name
