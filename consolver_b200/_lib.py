@@ -1,0 +1,95 @@
+"""ctypes binding of libconsolver.so (the C ABI declared in include/consolver.h).
+
+There is NO CPU / PyTorch fallback: if the library cannot be built or loaded, importing the kernels raises.
+The .so is built in-tree by `consolver_b200.build.build_library()` (nvcc, sm_100a)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libconsolver.so")
+
+F32, F16, BF16 = 0, 1, 2
+FLAG_VPRED, FLAG_EFF_SCALE, FLAG_X_SCALE, FLAG_PDL = 1, 2, 4, 8
+MAX_ORDER, MAX_HIDDEN, MAX_LOGITS, MAX_IN = 8, 1024, 4096, 16
+
+_p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> (restype, argtypes): must list every symbol declared in include/consolver.h
+SIGNATURES = {
+    "consolver_abi_version": (_i, []),
+    "consolver_error_string": (C.c_char_p, [_i]),
+    "consolver_policy_f32": (_i, [_p] * 7 + [_f] * 4 + [_p, _i] + [_p, _p] + [_i] * 7 + [_p] * 7 + [_p]),
+    "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
+    "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _f, _i, _i, _i64, _p]),
+    "consolver_sd_policy_and_step": (_i, [_p] * 7 + [_f] * 4 + [_p, _p] + [_i] * 4 + [_p] * 7 +
+                                     [_i, _p, _p, _f, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
+    "consolver_set_step_launch": (_i, [_i, _i]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class ConsolverError(RuntimeError):
+    pass
+
+
+def load(autobuild: bool = True):
+    """Load (building first if the .so is missing or stale and nvcc is present).  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if autobuild and os.environ.get("CONSOLVER_NO_AUTOBUILD") != "1":
+            try:
+                from .build import build_library
+
+                build_library()
+            except Exception as e:  # noqa: BLE001
+                if not os.path.exists(LIB_PATH):
+                    raise ConsolverError(
+                        f"libconsolver.so is missing and could not be built ({e}). consolver_b200 has no "
+                        "CPU/PyTorch fallback: run `python -m consolver_b200.build` with nvcc available.") from e
+        if not os.path.exists(LIB_PATH):
+            raise ConsolverError(f"{LIB_PATH} not found; run `python -m consolver_b200.build`")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise ConsolverError(f"libconsolver.so does not export {name}; rebuild it") from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.consolver_abi_version() != 1:
+            raise ConsolverError("libconsolver.so ABI version mismatch; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().consolver_error_string(rc).decode()
+        raise ConsolverError(f"{what}: {msg} (code {rc})")
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+
+    try:
+        return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[torch_dtype]
+    except KeyError:
+        raise TypeError(f"consolver_b200: unsupported latent dtype {torch_dtype}") from None
+
+
+def ptr_array(ptrs):
+    """host array of device pointers for the `hist` arguments"""
+    n = max(len(ptrs), 1)
+    arr = (C.c_void_p * n)()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr

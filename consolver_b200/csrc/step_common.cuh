@@ -1,0 +1,108 @@
+// step_common.cuh — shared pieces of the fused solver-step kernels (SD and FM).
+//
+// Streaming design (HBM-bound, ~1.5 flop/byte): every latent-sized operand is read exactly once with
+// 128-bit non-coherent loads that bypass L1 allocation, all loads of a thread are issued before the first
+// use (memory-level parallelism = UNROLL x number of streams), math is fp32 with explicitly rounded
+// intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn are never contracted into FMAs, so the fp32 path is
+// bit-identical to the reference's op-by-op torch arithmetic), results are written once with 128-bit stores.
+// A CTA never straddles two samples, so the per-sample coefficients are CTA-uniform broadcast loads.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/consolver.h"
+
+namespace consolver {
+
+constexpr int kMaxOlder = CONSOLVER_MAX_ORDER - 1;
+
+struct StepParams {
+  const void* e0;
+  const void* cond;      // non-null: CFG pair, e0 is the unconditional half
+  void* slot_out;        // nullable
+  const void* hist[kMaxOlder];
+  const void* x;
+  void* x_out;
+  const float* coef;
+  int coef_stride;
+  int order_dim;
+  int n_hist;
+  int flags;
+  float guidance;
+  float k0, k1, k2, k3;  // SD: sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev), sqrt(1-abar_prev); FM: k0 = dt
+  long long n_per_sample;   // elements
+  long long nvec_per_sample;  // thread-vectors per sample (n_per_sample / ELEMS)
+  int chunks_per_sample;
+  int B;
+};
+
+// ---- element traits -------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int kPerVec = 4;
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+  static constexpr bool k16 = false;
+};
+template <> struct Elem<__half> {
+  static constexpr int kPerVec = 8;
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+  static constexpr bool k16 = true;
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kPerVec = 8;
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  static constexpr bool k16 = true;
+};
+
+// ---- 128-bit streaming accessors ------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st16(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// A thread-vector of E elements of type T held as raw 16-byte words (E*sizeof(T) is 16 or 32 bytes).
+template <typename T, int E> struct Raw {
+  static constexpr int kWords = (E * (int)sizeof(T)) / 16;
+  uint4 w[kWords];
+  __device__ __forceinline__ void load(const T* p) {
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) w[i] = ld_stream16(reinterpret_cast<const char*>(p) + 16 * i);
+  }
+  __device__ __forceinline__ void store(T* p) const {
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) st16(reinterpret_cast<char*>(p) + 16 * i, w[i]);
+  }
+  __device__ __forceinline__ float get(int i) const { return Elem<T>::to_f(reinterpret_cast<const T*>(w)[i]); }
+  __device__ __forceinline__ void set(int i, float v) { reinterpret_cast<T*>(w)[i] = Elem<T>::from_f(v); }
+};
+// scalar fallback (E == 1): ragged sizes / unaligned pointers
+template <typename T> struct Raw<T, 1> {
+  T v;
+  __device__ __forceinline__ void load(const T* p) { v = __ldg(p); }
+  __device__ __forceinline__ void store(T* p) const { *p = v; }
+  __device__ __forceinline__ float get(int) const { return Elem<T>::to_f(v); }
+  __device__ __forceinline__ void set(int, float f) { v = Elem<T>::from_f(f); }
+};
+
+// process-global launch tuning (consolver_set_step_launch)
+struct StepLaunchCfg {
+  int threads;
+  int unroll;
+};
+StepLaunchCfg step_launch_cfg();
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace consolver

@@ -1,0 +1,31 @@
+// step_fm.cu — C-ABI entry point of the fused flow-matching (Euler-form) solver step.  See include/consolver.h.
+#include "step_kernel.cuh"
+
+using namespace consolver;
+
+extern "C" int consolver_step_fm(int dtype, int x_dtype, const void* e0, void* slot_out,
+                                 const void* const* hist, int n_hist, const void* x, void* x_out,
+                                 const float* coef, int coef_stride, int order_dim, float dt, int flags,
+                                 int B, int64_t n_per_sample, consolver_stream_t stream) {
+  StepParams p;
+  int rc = fill_common(p, e0, nullptr, slot_out, hist, n_hist, x, x_out, coef, coef_stride, order_dim,
+                       flags & ~CONSOLVER_FLAG_VPRED, B, (long long)n_per_sample);
+  if (rc) return rc;
+  p.k0 = dt;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool al = all_aligned(p);
+  if (x_dtype != dtype && x_dtype != CONSOLVER_F32) return CONSOLVER_ERR_DTYPE;
+  switch (dtype) {
+    case CONSOLVER_F32:
+      return launch_step<float, float, kModeFM>(p, al && n_per_sample % 4 == 0, s);
+    case CONSOLVER_F16:
+      if (x_dtype == CONSOLVER_F32) return launch_step<__half, float, kModeFM>(p, al && n_per_sample % 8 == 0, s);
+      return launch_step<__half, __half, kModeFM>(p, al && n_per_sample % 8 == 0, s);
+    case CONSOLVER_BF16:
+      if (x_dtype == CONSOLVER_F32)
+        return launch_step<__nv_bfloat16, float, kModeFM>(p, al && n_per_sample % 8 == 0, s);
+      return launch_step<__nv_bfloat16, __nv_bfloat16, kModeFM>(p, al && n_per_sample % 8 == 0, s);
+    default:
+      return CONSOLVER_ERR_DTYPE;
+  }
+}

@@ -1,0 +1,193 @@
+// step_kernel.cuh — the fused solver-step kernel template (SD DDIM-form and FM Euler-form) and its launcher.
+//
+// One launch reads, per sample, the newest model output (or the CFG pair), the n_hist-1 older history
+// slots and the current latent ONCE and writes the next latent (and, optionally, the CFG-combined model
+// output into its history-ring slot) ONCE:   bytes/sample = (n_hist + 4) * N * sizeof(T)   with a CFG pair.
+// Reference arithmetic being fused: denoise_ppo.py:96-100, scheduler_ppo.py:263-280 and :306-332,
+// edit_ppo/scheduler_fmppo.py:354,:413-436.
+#pragma once
+#include "step_common.cuh"
+
+namespace consolver {
+
+enum : int { kModeSD = 0, kModeFM = 1 };
+
+// NH  > 0 : history depth known at compile time (1..4), loads fully unrolled
+// NH == 0 : runtime depth (5..8), guarded loads
+template <typename T, typename TX, int NH, int MODE, int E, int U>
+__global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
+  constexpr int kOlder = NH ? NH - 1 : kMaxOlder;
+  const int b = blockIdx.x / p.chunks_per_sample;
+  const int chunk = blockIdx.x - b * p.chunks_per_sample;
+  const long long base = (long long)b * p.n_per_sample;
+  const long long v0 = (long long)chunk * ((long long)blockDim.x * U) + threadIdx.x;
+  const int nh = NH ? NH : p.n_hist;
+  const bool pair = p.cond != nullptr;
+
+  Raw<T, E> r_e0[U], r_c[U];
+  Raw<T, E> r_h[U][kOlder > 0 ? kOlder : 1];
+  Raw<TX, E> r_x[U];
+  long long off[U];
+  bool live[U];
+
+  // ---- issue every load before the first use ------------------------------------------------------------
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long v = v0 + (long long)u * blockDim.x;
+    live[u] = v < p.nvec_per_sample;
+    off[u] = base + v * E;
+    if (live[u]) {
+      r_e0[u].load(static_cast<const T*>(p.e0) + off[u]);
+      if (pair) r_c[u].load(static_cast<const T*>(p.cond) + off[u]);
+      r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
+#pragma unroll
+      for (int j = 0; j < kOlder; ++j)
+        if (NH || j < nh - 1) r_h[u][j].load(static_cast<const T*>(p.hist[j]) + off[u]);
+    }
+  }
+
+  // ---- per-sample coefficients (CTA-uniform).  Under PDL the preceding policy kernel may still be running:
+  //      the bulk loads above do not depend on it, only these few floats do. ------------------------------------
+  if (p.flags & CONSOLVER_FLAG_PDL) grid_dependency_wait();
+  const float* cf = p.coef + (long long)b * p.coef_stride;
+  float c[kOlder + 1];
+#pragma unroll
+  for (int j = 0; j < kOlder + 1; ++j) c[j] = (j < nh && nh > 1) ? __ldg(cf + j) : 0.f;
+  const bool eff_scale = p.flags & CONSOLVER_FLAG_EFF_SCALE;
+  const bool x_scale = p.flags & CONSOLVER_FLAG_X_SCALE;
+  const float cs0 = eff_scale ? __ldg(cf + p.order_dim) : 1.f;
+  const float cs1 = x_scale ? __ldg(cf + p.order_dim + 1) : 1.f;
+  const bool vpred = p.flags & CONSOLVER_FLAG_VPRED;
+  const float g = p.guidance;
+
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!live[u]) continue;
+    Raw<T, E> r_slot, r_out;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      // CFG: u + g*(c - u)                                            denoise_ppo.py:100
+      float eps = r_e0[u].get(i);
+      if (pair) {
+        eps = __fadd_rn(eps, __fmul_rn(g, __fsub_rn(r_c[u].get(i), eps)));
+        if (Elem<T>::k16) eps = Elem<T>::to_f(Elem<T>::from_f(eps));  // the value the ring keeps
+        r_slot.set(i, eps);
+      }
+      // eff = ((0 + c0*e0) + c1*e1) + ...                              scheduler_ppo.py:263-272
+      float eff;
+      if (nh == 1) {
+        eff = eps;
+      } else {
+        eff = __fadd_rn(0.f, __fmul_rn(c[0], eps));
+#pragma unroll
+        for (int j = 0; j < kOlder; ++j)
+          if (NH || j < nh - 1) eff = __fadd_rn(eff, __fmul_rn(c[j + 1], r_h[u][j].get(i)));
+      }
+      if (eff_scale) eff = __fmul_rn(eff, cs0);                       // :274-277
+      float xs = r_x[u].get(i);
+      if (x_scale) xs = __fmul_rn(xs, cs1);                           // :278
+      float out;
+      if (MODE == kModeSD) {
+        if (vpred) eff = __fadd_rn(__fmul_rn(p.k0, eff), __fmul_rn(p.k1, xs));          // :316-317
+        const float x0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.k1, eff)), p.k0);          // :323
+        out = __fadd_rn(__fmul_rn(p.k2, x0), __fmul_rn(p.k3, eff));                     // :329-330
+      } else {
+        float prod = __fmul_rn(p.k0, eff);                            // edit_ppo/scheduler_fmppo.py:429
+        // 0-d fp32 `dt` times a 16-bit tensor is rounded to that dtype (first step, no scalers)
+        if (Elem<T>::k16 && nh == 1 && !eff_scale) prod = Elem<T>::to_f(Elem<T>::from_f(prod));
+        out = __fadd_rn(xs, prod);
+      }
+      r_out.set(i, out);
+    }
+    r_out.store(static_cast<T*>(p.x_out) + off[u]);
+    if (pair && p.slot_out) r_slot.store(static_cast<T*>(p.slot_out) + off[u]);
+  }
+  // plain (non-pair) step with a ring slot requested: copy e0 through
+  if (!pair && p.slot_out) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (live[u]) r_e0[u].store(static_cast<T*>(p.slot_out) + off[u]);
+  }
+}
+
+template <typename T, typename TX, int NH, int MODE, int E, int U>
+static int launch_one(StepParams& p, int threads, cudaStream_t stream) {
+  const long long per_cta = (long long)threads * U;
+  p.chunks_per_sample = (int)((p.nvec_per_sample + per_cta - 1) / per_cta);
+  const long long grid = (long long)p.chunks_per_sample * p.B;
+  if (grid <= 0 || grid > 0x7fffffffLL) return CONSOLVER_ERR_SIZE;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (p.flags & CONSOLVER_FLAG_PDL) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, step_kernel<T, TX, NH, MODE, E, U>, (const StepParams)p);
+  return (int)e;
+}
+
+template <typename T, typename TX, int NH, int MODE>
+static int launch_nh(StepParams& p, bool vec_ok, cudaStream_t stream) {
+  StepLaunchCfg lc = step_launch_cfg();
+  int threads = lc.threads > 0 ? lc.threads : 256;
+  if (!vec_ok) {
+    p.nvec_per_sample = p.n_per_sample;
+    return launch_one<T, TX, NH, MODE, 1, 1>(p, threads, stream);
+  }
+  constexpr int E = Elem<T>::kPerVec;
+  p.nvec_per_sample = p.n_per_sample / E;
+  int unroll = lc.unroll;
+  if (unroll <= 0) {
+    // default: 2 vectors/thread once the grid is at least ~8 CTAs per SM, else 1 (small batches need CTAs)
+    const long long ctas_u2 = ((p.nvec_per_sample + 2LL * threads - 1) / (2LL * threads)) * p.B;
+    unroll = ctas_u2 >= 148LL * 8 ? 2 : 1;
+  }
+  if (unroll >= 2) return launch_one<T, TX, NH, MODE, E, 2>(p, threads, stream);
+  return launch_one<T, TX, NH, MODE, E, 1>(p, threads, stream);
+}
+
+template <typename T, typename TX, int MODE>
+static int launch_step(StepParams& p, bool vec_ok, cudaStream_t stream) {
+  switch (p.n_hist) {
+    case 1: return launch_nh<T, TX, 1, MODE>(p, vec_ok, stream);
+    case 2: return launch_nh<T, TX, 2, MODE>(p, vec_ok, stream);
+    case 3: return launch_nh<T, TX, 3, MODE>(p, vec_ok, stream);
+    case 4: return launch_nh<T, TX, 4, MODE>(p, vec_ok, stream);
+    default: return launch_nh<T, TX, 0, MODE>(p, vec_ok, stream);
+  }
+}
+
+// argument validation shared by both entry points; fills p.hist
+inline int fill_common(StepParams& p, const void* e0, const void* cond, void* slot_out, const void* const* hist,
+                       int n_hist, const void* x, void* x_out, const float* coef, int coef_stride, int order_dim,
+                       int flags, int B, long long n_per_sample) {
+  if (!e0 || !x || !x_out || !coef) return CONSOLVER_ERR_NULL;
+  if (order_dim < 2 || order_dim > CONSOLVER_MAX_ORDER || n_hist < 1 || n_hist > order_dim) return CONSOLVER_ERR_SIZE;
+  if (coef_stride < order_dim + 2 || B <= 0 || n_per_sample <= 0) return CONSOLVER_ERR_SIZE;
+  if (n_hist > 1 && !hist) return CONSOLVER_ERR_NULL;
+  p = StepParams{};
+  p.e0 = e0; p.cond = cond; p.slot_out = slot_out; p.x = x; p.x_out = x_out;
+  for (int j = 0; j < n_hist - 1; ++j) {
+    if (!hist[j]) return CONSOLVER_ERR_NULL;
+    p.hist[j] = hist[j];
+  }
+  p.coef = coef; p.coef_stride = coef_stride; p.order_dim = order_dim; p.n_hist = n_hist; p.flags = flags;
+  p.n_per_sample = n_per_sample; p.B = B;
+  return 0;
+}
+
+inline bool all_aligned(const StepParams& p) {
+  bool ok = aligned16(p.e0) && aligned16(p.x) && aligned16(p.x_out);
+  if (p.cond) ok = ok && aligned16(p.cond);
+  if (p.slot_out) ok = ok && aligned16(p.slot_out);
+  for (int j = 0; j < p.n_hist - 1; ++j) ok = ok && aligned16(p.hist[j]);
+  return ok;
+}
+
+}  // namespace consolver

@@ -1,0 +1,187 @@
+"""FactorNetPPO — the coefficient policy of ConsistencySolver, as an nn.Module whose state_dict is
+interchangeable with the reference's (`action_values`, `mlp.{0,2,4}.{weight,bias}`; factor_net_ppo.py:57-102 for
+the SD variant, edit_ppo/factor_net_ppo.py:57-110 for the flow-matching variant).
+
+Sampling (`sample_action`) runs the hand-written policy kernel (csrc/policy.cu) through the C ABI: the MLP +
+softmax is evaluated once per step (the input row is identical for every sample, scheduler_ppo.py:207-210),
+then every sample draws its bins as argmax(p/q) with q ~ Exp(1) taken from torch's default CUDA generator in
+exactly the shape torch.multinomial would consume (factor_net_ppo.py:161), so seeds reproduce the reference's
+actions.  The PPO-update side (`get_action_probs`) needs autograd and stays on torch ops.
+There is no CPU path: tensors must live on a CUDA device."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _action_values(variant: str, K: int, order_dim: int, scaler_dim: int, mu_dim: int) -> torch.Tensor:
+    first = torch.linspace(0, 2 if variant == "sd" else 1, K)
+    second = torch.linspace(-2, 0, K)
+    middle = torch.linspace(-1, 1, K)
+    scaler = torch.linspace(-0.05, 0.05, K)
+    A = order_dim + scaler_dim - 1 + (mu_dim if variant == "fm" else 0)
+    rows = []
+    for i in range(A):
+        if i == 0:
+            rows.append(first)
+        elif i == 1 and (variant == "sd" or i < order_dim - 1):
+            rows.append(second)
+        elif i < order_dim - 1:
+            rows.append(middle)
+        elif variant == "sd" or i < order_dim + scaler_dim - 1:
+            rows.append(scaler)
+        else:
+            rows.append(torch.cat((torch.tensor([0.0]), torch.linspace(0.5, 0.99, K - 1))))
+    return torch.stack(rows)
+
+
+class FactorNetPPO(nn.Module):
+    """SD variant (factor_net_ppo.py:57-184).  Constructor kwargs as in the reference; `embedding_dim`,
+    `input_channels`, `conv_out_channels` are accepted and ignored there too (:58-60 vs :70-81)."""
+
+    variant = "sd"
+    x_div = 999.0      # normalize_input: x.float() / 999.0   (factor_net_ppo.py:104-106)
+    temperature = 1.0  # softmax(logits)                     (factor_net_ppo.py:156)
+
+    def __init__(self, embedding_dim=1024, hidden_dim=256, num_actions=161, order_dim=4, scaler_dim=2,
+                 use_conv=False, input_channels=4, conv_out_channels=8, mu_dim=0):
+        super().__init__()
+        if order_dim < 2 or order_dim > _lib.MAX_ORDER:
+            raise ValueError(f"order_dim must be in [2, {_lib.MAX_ORDER}]")
+        self.num_actions = num_actions
+        self.order_dim = order_dim
+        self.scaler_dim = scaler_dim
+        self.mu_dim = mu_dim if self.variant == "fm" else 0
+        self.action_dims = order_dim + scaler_dim + self.mu_dim - 1
+        self.use_conv = use_conv
+        self.hidden_dim = hidden_dim
+        in_dim = 2 + ((order_dim - 1) if use_conv else 0)
+        self.mlp = nn.Sequential(
+            nn.Linear(in_dim, hidden_dim), nn.ReLU(),
+            nn.Linear(hidden_dim, hidden_dim), nn.ReLU(),
+            nn.Linear(hidden_dim, num_actions * self.action_dims),
+        )
+        if self.variant == "sd":  # uniform policy at start (factor_net_ppo.py:82-83); the FM variant keeps
+            nn.init.zeros_(self.mlp[-1].bias)  # the default init (edit_ppo/factor_net_ppo.py:87-88)
+            nn.init.zeros_(self.mlp[-1].weight)
+        self.register_buffer("action_values",
+                             _action_values(self.variant, num_actions, order_dim, scaler_dim, self.mu_dim))
+        if hidden_dim > _lib.MAX_HIDDEN or num_actions * self.action_dims > _lib.MAX_LOGITS:
+            raise ValueError("policy too large for the kernel limits in include/consolver.h")
+        self._w32_cache = None
+
+    # ---- fp32 weight pointers for the kernel (the reference may cast the module to fp16, gen_ppo.py:193-195;
+    #      the kernel always computes in fp32) -----------------------------------------------------------------
+    def kernel_weights(self):
+        ps = [self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight, self.mlp[2].bias,
+              self.mlp[4].weight, self.mlp[4].bias, self.action_values]
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        c = self._w32_cache
+        if c is None or c[0] != key:
+            if not ps[0].is_cuda:
+                raise RuntimeError("consolver_b200 has no CPU path: move factor_net to a CUDA device")
+            ws = [p.detach() if (p.dtype == torch.float32 and p.is_contiguous())
+                  else p.detach().float().contiguous() for p in ps]
+            self._w32_cache = c = (key, ws, [w.data_ptr() for w in ws])
+        return c[2]
+
+    def normalize_input(self, x):
+        return x.float() / 999.0 if self.variant == "sd" else x.float()
+
+    def forward(self, x_dict, actions=None):
+        if actions is None:
+            return self.sample_action(x_dict)
+        return self.get_action_probs(x_dict, actions)
+
+    # ---- sampling side: CUDA kernel --------------------------------------------------------------------------
+    def sample_action(self, x_dict: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(actions [B,A], probs [B,A]) as factor_net_ppo.py:159-168.  `x_dict['x']` is [B,2] with identical
+        rows (the scheduler's contract); use_conv additionally reads x_dict['epsilon']."""
+        x = x_dict["x"]
+        if not x.is_cuda:
+            raise RuntimeError("consolver_b200 has no CPU path: x_dict['x'] must be a CUDA tensor")
+        if self.use_conv:
+            raise NotImplementedError("use_conv=True sampling goes through the scheduler (cosine features)")
+        B = x.shape[0]
+        row = x[0].float().tolist()  # host read; the schedulers call policy_launch directly and never sync
+        out = self.policy_launch(row[0], row[1], B, n_hist=self.order_dim, stream=None)
+        return out["actions"], out["probs"]
+
+    def policy_launch(self, x0: float, x1: float, B: int, n_hist: int, *, q: Optional[torch.Tensor] = None,
+                      idx_in: Optional[torch.Tensor] = None, out: Optional[dict] = None, stream=None,
+                      feat: Optional[torch.Tensor] = None):
+        """Launch the policy kernel.  `q` None => drawn here from the default CUDA generator with the shape
+        torch.multinomial consumes ([B*A, K] fp32)."""
+        lib = _lib.load()
+        w = self.kernel_weights()
+        dev = self.action_values.device
+        A, K = self.action_dims, self.num_actions
+        if q is None and idx_in is None:
+            q = torch.empty((B * A, K), device=dev, dtype=torch.float32).exponential_(1)
+        if out is None:
+            out = alloc_policy_outputs(B, A, K, self.order_dim, dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.consolver_policy_f32(
+            *w, x0, x1, self.x_div, self.temperature,
+            feat.data_ptr() if feat is not None else None, feat.shape[1] if feat is not None else 0,
+            q.data_ptr() if q is not None else None, idx_in.data_ptr() if idx_in is not None else None,
+            B, self.hidden_dim, A, K, self.order_dim, self.scaler_dim, n_hist,
+            out["probs_table"].data_ptr(), out["idx"].data_ptr(), out["actions"].data_ptr(),
+            out["probs"].data_ptr(), out["logp"].data_ptr(), out["masks"].data_ptr(), out["coef"].data_ptr(),
+            stream)
+        _lib.check(rc, "consolver_policy_f32")
+        return out
+
+    # ---- PPO-update side: torch autograd (factor_net_ppo.py:137-157, :170-184) ----------------------------------
+    def forward_(self, x_dict):
+        x = self.normalize_input(x_dict["x"])
+        if self.use_conv:
+            from .features import cosine_features
+
+            x = torch.cat([x, cosine_features(x_dict["epsilon"], self.order_dim)], dim=-1)
+        logits = self.mlp(x).view(-1, self.action_dims, self.num_actions)
+        if self.variant == "fm":
+            logits = logits / 0.01
+        return torch.softmax(logits, dim=-1)
+
+    def get_action_probs(self, x_dict, actions):
+        probs = self.forward_(x_dict)
+        actions = actions.to(probs.device)
+        idx = (actions.unsqueeze(-1) - self.action_values.unsqueeze(0)).abs().argmin(dim=-1)
+        ent = torch.distributions.Categorical(probs=probs).entropy() / math.log(self.num_actions)
+        return probs.gather(2, idx.unsqueeze(-1)).squeeze(-1), ent
+
+
+class FactorNetPPOFM(FactorNetPPO):
+    """Flow-matching variant (edit_ppo/factor_net_ppo.py:57-196): identity input normalisation (:112-114),
+    softmax temperature 0.01 (:168), first bin row linspace(0,1) (:92), optional (unused) mu dims (:96,:109)."""
+
+    variant = "fm"
+    x_div = 1.0
+    temperature = 0.01
+
+    def __init__(self, embedding_dim=1024, hidden_dim=256, num_actions=161, order_dim=4, scaler_dim=2, mu_dim=1,
+                 use_conv=False, input_channels=4, conv_out_channels=8):
+        super().__init__(embedding_dim, hidden_dim, num_actions, order_dim, scaler_dim, use_conv,
+                         input_channels, conv_out_channels, mu_dim=mu_dim)
+
+
+def alloc_policy_outputs(B, A, K, order_dim, device, lead=()):
+    """Buffers the policy kernel writes; `lead` prepends dims (the schedulers allocate [n_steps, ...] once per
+    trajectory so the per-step results ARE the trajectory record — no unsqueeze/cat at the end)."""
+    f = dict(device=device, dtype=torch.float32)
+    return dict(
+        probs_table=torch.empty(*lead, A, K, **f),
+        idx=torch.empty(*lead, B, A, device=device, dtype=torch.int64),
+        actions=torch.empty(*lead, B, A, **f),
+        probs=torch.empty(*lead, B, A, **f),
+        logp=torch.empty(*lead, B, A, **f),
+        masks=torch.empty(*lead, B, A, **f),
+        coef=torch.empty(*lead, B, order_dim + 2, **f),
+    )

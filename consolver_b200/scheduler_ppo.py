@@ -1,0 +1,334 @@
+"""PPOScheduler — drop-in for the reference's `scheduler_ppo.PPOScheduler` (scheduler_ppo.py:48-361): same
+constructor kwargs, `set_timesteps()` / `step()` signatures and 5-tuple return, same `factor_net` state_dict —
+with the per-step work done by two hand-written sm_100a kernels behind the C ABI (include/consolver.h):
+
+  policy kernel  MLP once per step + softmax + per-sample categorical draw + coefficient/mask assembly
+  step kernel    CFG combine + linear-multistep combine over the in-place history ring + DDIM update,
+                 one pass over HBM
+
+What changes relative to the reference, none of it numerical:
+  * no host synchronisation inside `step()`: per-timestep scalars are tabulated on the host at construction,
+    the timestep value comes from the host copy of the grid (see `sync_free`), nothing is printed;
+  * the history is a ring of references / scheduler-owned slots, never stacked; `conds['epsilon']` is
+    materialised lazily (config_utils.LazyConds);
+  * `step_cfg()` (new, optional) takes the raw [2B,...] CFG pair and the guidance scale so the caller's
+    `u + g*(c-u)` (denoise_ppo.py:96-100) is fused into the same pass;
+  * per-step `actions / probs / masks` are views into per-trajectory buffers (`trajectory()` returns the
+    [B, n-1, A] record denoise_ppo.py:105-118 builds with unsqueeze+cat).
+There is no CPU path: inputs must be CUDA tensors and libconsolver.so must load.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config_utils import KARRAS_COMPATIBLES, BaseOutput, ConfigMixin, LazyConds, SchedulerMixin, register_to_config
+from .factor_net import FactorNetPPO, alloc_policy_outputs
+
+
+@dataclasses.dataclass
+class PPOSchedulerOutput(BaseOutput):
+    """`return_dict=True` result.  (The reference builds a diffusers SchedulerOutput with five fields,
+    scheduler_ppo.py:299, which raises with stock diffusers; this carries the same five fields.)"""
+    prev_sample: torch.Tensor = None
+    actions: Optional[torch.Tensor] = None
+    probs: Optional[torch.Tensor] = None
+    conds: Optional[Dict] = None
+    masks: Optional[torch.Tensor] = None
+
+
+def _cosine_alpha_bar_betas(n: int, max_beta: float = 0.999) -> torch.Tensor:
+    bar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2  # noqa: E731
+    return torch.tensor([min(1 - bar((i + 1) / n) / bar(i / n), max_beta) for i in range(n)], dtype=torch.float32)
+
+
+class _Trajectory:
+    """Per-(set_timesteps, batch shape) device state: policy outputs for every step, the Exp(1) buffer, the
+    history ring.  Allocated once; `step()` itself allocates only the returned latent."""
+
+    def __init__(self, sched: "PPOScheduler", B, shape, dtype, device):
+        fn = sched.factor_net_module
+        self.key = (B, tuple(shape), dtype, device)
+        self.n = max(int(sched.num_inference_steps), 1)
+        A, K, od = fn.action_dims, fn.num_actions, sched.config.order_dim
+        self.out = alloc_policy_outputs(B, A, K, od, device, lead=(self.n,))
+        self.q = torch.empty((B * A, K), device=device, dtype=torch.float32)
+        self.ring = None  # [order_dim, B, *shape], allocated on the first step_cfg()
+        self.ring_shape = (od, B, *shape)
+        self.dtype, self.device = dtype, device
+        # conds['x'] rows for the whole grid: one H2D copy per trajectory instead of one per step
+        ts = sched._timesteps_host
+        rows = [[float(t), float(t - sched._stride)] for t in ts]
+        self.condx = torch.tensor(rows, dtype=dtype).to(device, non_blocking=True)
+        self.condx_host = torch.tensor(rows, dtype=dtype).float().numpy()
+        self.count = 0
+
+    def slot(self, i):
+        if self.ring is None:
+            self.ring = torch.empty(self.ring_shape, device=self.device, dtype=self.dtype)
+        return self.ring[i % self.ring_shape[0]]
+
+
+class PPOScheduler(SchedulerMixin, ConfigMixin):
+    """Learned linear-multistep DDIM-form solver (ConsistencySolver) for eps / v-prediction models."""
+
+    _compatibles = KARRAS_COMPATIBLES
+    order = 1
+
+    @register_to_config
+    def __init__(
+        self,
+        num_train_timesteps: int = 1000,
+        beta_start: float = 0.0001,
+        beta_end: float = 0.02,
+        beta_schedule: str = "linear",
+        trained_betas: Optional[Union[np.ndarray, List[float]]] = None,
+        prediction_type: str = "epsilon",
+        timestep_spacing: str = "leading",
+        steps_offset: int = 0,
+        order_dim: int = 4,
+        scaler_dim: int = 2,
+        use_conv=False,
+        ppo_type="discrete",
+        factor_net_kwargs: Optional[Dict] = None,
+    ):
+        # noise schedule (scheduler_ppo.py:99-114), fp32 on the host like the reference
+        if trained_betas is not None:
+            self.betas = torch.tensor(trained_betas, dtype=torch.float32)
+        elif beta_schedule == "linear":
+            self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            self.betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps,
+                                        dtype=torch.float32) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = _cosine_alpha_bar_betas(num_train_timesteps)
+        else:
+            raise NotImplementedError(f"{beta_schedule} schedule not implemented.")
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        # sqrt tables the kernel scalars are read from: the same fp32 ops as scheduler_ppo.py:309-330
+        # (`** 0.5` of abar_t and of 1 - abar_t), evaluated for every t once instead of per step
+        self._sqrt_abar = (self.alphas_cumprod ** 0.5).numpy()
+        self._sqrt_1m_abar = ((1 - self.alphas_cumprod) ** 0.5).numpy()
+
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self._timesteps_host = np.arange(0, num_train_timesteps)[::-1].copy()
+        self.timesteps = torch.from_numpy(self._timesteps_host)
+
+        if order_dim < 2 or order_dim > _lib.MAX_ORDER:
+            raise ValueError(f"order_dim must be in [2, {_lib.MAX_ORDER}]")
+        if scaler_dim not in (0, 1, 2):
+            raise NotImplementedError("more than two scale parameters are not supported")  # scheduler_ppo.py:279
+        if prediction_type not in ("epsilon", "v_prediction"):
+            raise ValueError(f"Unsupported prediction_type: {prediction_type}")
+        kw = dict(factor_net_kwargs) if factor_net_kwargs is not None else {}
+        kw.update(order_dim=order_dim, scaler_dim=scaler_dim, use_conv=use_conv)
+        kw.setdefault("embedding_dim", 32)
+        kw.setdefault("hidden_dim", 256)
+        if ppo_type != "discrete":
+            # scheduler_ppo.py:139 instantiates FactorNetPPOContinous, whose source is not part of the reference
+            raise NotImplementedError("ppo_type != 'discrete': the continuous policy does not exist in the reference")
+        kw.setdefault("num_actions", 161)
+        self.factor_net = FactorNetPPO(**kw)
+
+        self._hist: List[torch.Tensor] = []   # model outputs, NEWEST FIRST (references or ring slots)
+        self._traj: Optional[_Trajectory] = None
+        self._step_count = 0
+        self._stride = 0
+        #: True (default): a CUDA `timestep` tensor is NOT read back; the value is taken from the host copy of
+        #: the grid at the current step count (pipelines step in grid order).  False: `.item()` it (one sync).
+        self.sync_free = True
+        #: link the policy and step kernels with programmatic dependent launch
+        self.use_pdl = True
+        #: replay instead of sampling: {'idx': seq of [B,A] int64 per step} forces the bins (PPO replay, parity
+        #: tests with injected actions); {'q': seq of [B*A,K] fp32 per step} supplies the Exp(1) draw.
+        self.replay: Optional[Dict] = None
+
+    # ------------------------------------------------------------------------------------------------------
+    @property
+    def factor_net_module(self) -> FactorNetPPO:
+        fn = self.factor_net
+        return fn.module if hasattr(fn, "module") else fn   # DDP-wrapped during training (scheduler_ppo.py:239)
+
+    @property
+    def ets(self) -> List[torch.Tensor]:
+        """History oldest-first, the reference's attribute name (scheduler_ppo.py:123)."""
+        return self._hist[::-1]
+
+    def set_timesteps(self, num_inference_steps: int, device: Union[str, torch.device] = None):
+        """scheduler_ppo.py:142-163."""
+        T = self.config.num_train_timesteps
+        if num_inference_steps > T:
+            raise ValueError(f"`num_inference_steps` ({num_inference_steps}) cannot be larger than "
+                             f"`num_train_timesteps` ({T}).")
+        n = self.num_inference_steps = num_inference_steps
+        sp = self.config.timestep_spacing
+        if sp == "linspace":
+            ts = np.linspace(0, T - 1, n).round()[::-1].copy().astype(np.int64)
+        elif sp == "leading":
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        elif sp == "trailing":
+            ts = np.round(np.arange(T, 0, -(T / n))).astype(np.int64) - 1
+        else:
+            raise ValueError(f"Unsupported timestep_spacing: {sp}.")
+        self._timesteps_host = ts
+        self._stride = T // n                       # prev_t = t - T//n (scheduler_ppo.py:203)
+        self.timesteps = torch.from_numpy(ts).to(device)
+        self._hist = []
+        self._traj = None
+        self._step_count = 0
+
+    def scale_model_input(self, sample: torch.Tensor, timestep: Optional[int] = None) -> torch.Tensor:
+        return sample
+
+    # ------------------------------------------------------------------------------------------------------
+    def _host_timestep(self, timestep) -> int:
+        if isinstance(timestep, torch.Tensor):
+            if timestep.is_cuda:
+                if self.sync_free:
+                    return int(self._timesteps_host[self._step_count % len(self._timesteps_host)])
+                return int(timestep.item())
+            return int(timestep)
+        return int(timestep)
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True):
+        """Same contract as scheduler_ppo.py:178-299.  `return_dict=False` ->
+        (prev_sample, actions [B,A], probs [B,A], conds {'x','epsilon'}, masks [B,A])."""
+        return self._step(model_output, None, 0.0, timestep, sample, return_dict, None)
+
+    def step_cfg(self, noise_pred: torch.Tensor, timestep, sample: torch.Tensor, guidance_scale: float,
+                 return_dict: bool = False, out: Optional[torch.Tensor] = None):
+        """Fused variant: `noise_pred` is the denoiser output for torch.cat([latents]*2) — unconditional half
+        first (denoise_ppo.py:66,:97) — and `u + g*(c-u)` is formed inside the step kernel, which also writes
+        it into this step's slot of the scheduler-owned history ring."""
+        B = sample.shape[0]
+        if noise_pred.shape[0] != 2 * B:
+            raise ValueError("step_cfg expects the [2B, ...] classifier-free-guidance pair")
+        if not noise_pred.is_contiguous():
+            noise_pred = noise_pred.contiguous()
+        return self._step(noise_pred[:B], noise_pred[B:], float(guidance_scale), timestep, sample, return_dict, out)
+
+    def _step(self, e0, cond, guidance, timestep, sample, return_dict, out):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
+        if not (e0.is_cuda and sample.is_cuda):
+            raise RuntimeError("consolver_b200 has no CPU path: model_output and sample must be CUDA tensors")
+        if sample.dtype != e0.dtype:
+            raise TypeError(f"sample ({sample.dtype}) and model_output ({e0.dtype}) must share a dtype")
+        cfg = self.config
+        fn = self.factor_net_module
+        if fn.use_conv:
+            raise NotImplementedError("use_conv=True is not wired into the fused path yet")
+        od = cfg.order_dim
+        t = self._host_timestep(timestep)
+        prev_t = t - self._stride
+        B = sample.shape[0]
+        N = sample.numel() // B
+        e0 = e0 if e0.is_contiguous() else e0.contiguous()
+        sample = sample if sample.is_contiguous() else sample.contiguous()
+        tr = self._traj
+        if tr is None or tr.key != (B, tuple(sample.shape[1:]), e0.dtype, e0.device):
+            tr = self._traj = _Trajectory(self, B, sample.shape[1:], e0.dtype, e0.device)
+        i = tr.count % tr.n
+        older = self._hist[: od - 1]
+        n_hist = len(older) + 1
+
+        # policy input row (t, prev_t) rounded through the model dtype (scheduler_ppo.py:207)
+        if t == self._timesteps_host[i]:
+            x0, x1 = float(tr.condx_host[i, 0]), float(tr.condx_host[i, 1])
+            conds_x = tr.condx[i:i + 1].expand(B, 2)
+        else:
+            row = torch.tensor([[t, prev_t]], dtype=e0.dtype)
+            x0, x1 = (float(v) for v in row.float()[0])
+            conds_x = row.to(e0.device).expand(B, 2)
+
+        sa_t, sb_t = float(self._sqrt_abar[t]), float(self._sqrt_1m_abar[t])
+        pi = prev_t if prev_t >= 0 else 0            # final step uses alphas_cumprod[0] (scheduler_ppo.py:114,:310)
+        sa_p, sb_p = float(self._sqrt_abar[pi]), float(self._sqrt_1m_abar[pi])
+
+        o = tr.out
+        q_ptr, idx_ptr = tr.q.data_ptr(), None
+        if self.replay is None:
+            tr.q.exponential_(1)                     # the draw torch.multinomial makes (factor_net_ppo.py:161)
+        elif self.replay.get("idx") is not None:
+            forced = self.replay["idx"][tr.count].to(device=e0.device, dtype=torch.int64).contiguous()
+            q_ptr, idx_ptr = None, forced.data_ptr()
+        else:
+            tr.q.copy_(self.replay["q"][tr.count].reshape(tr.q.shape))
+        x_out = out if out is not None else torch.empty_like(sample)
+        slot = tr.slot(tr.count) if cond is not None else None
+        flags = (_lib.FLAG_VPRED if cfg.prediction_type == "v_prediction" else 0) | \
+                (_lib.FLAG_PDL if self.use_pdl else 0)
+        hist_ptrs = _lib.ptr_array([h.data_ptr() for h in older])
+        w = fn.kernel_weights()
+        lib = _lib.load()
+        rc = lib.consolver_sd_policy_and_step(
+            *w, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr,
+            fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
+            o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
+            o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(),
+            _lib.dtype_code(e0.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, guidance,
+            slot.data_ptr() if slot is not None else None, hist_ptrs, n_hist, sample.data_ptr(), x_out.data_ptr(),
+            od, sa_t, sb_t, sa_p, sb_p, flags, B, N, torch.cuda.current_stream(e0.device).cuda_stream)
+        _lib.check(rc, "consolver_sd_policy_and_step")
+
+        newest = slot if cond is not None else e0     # plain step keeps the caller's tensor by reference, as
+        self._hist = [newest] + older                 # the reference does (scheduler_ppo.py:214-218)
+        tr.count += 1
+        self._step_count += 1
+
+        hist_now = list(self._hist)
+        shape = tuple(sample.shape[1:])
+
+        def _stack():
+            s = torch.stack(hist_now, dim=1)
+            if len(hist_now) < od:
+                s = torch.cat([s, s.new_zeros(B, od - len(hist_now), *shape)], dim=1)
+            return s
+
+        actions, probs, masks = o["actions"][i], o["probs"][i], o["masks"][i]
+        conds = LazyConds(conds_x, _stack)
+        if not return_dict:
+            return (x_out, actions, probs, conds, masks)
+        return PPOSchedulerOutput(prev_sample=x_out, actions=actions, probs=probs, conds=conds, masks=masks)
+
+    # ------------------------------------------------------------------------------------------------------
+    def trajectory(self, skip_first: bool = True):
+        """The rollout record denoise_ppo.py:105-118 assembles with unsqueeze+cat, as views of the
+        per-trajectory buffers: dict(x [B,n',2], probs/actions/masks/idx [B,n',A]) for steps 1..count-1."""
+        tr = self._traj
+        if tr is None:
+            raise ValueError("no trajectory recorded; call step() first")
+        lo, hi = (1 if skip_first else 0), min(tr.count, tr.n)
+        B = tr.key[0]
+        pick = lambda k: tr.out[k][lo:hi].transpose(0, 1)  # noqa: E731
+        return dict(x=tr.condx[lo:hi].unsqueeze(0).expand(B, hi - lo, 2), probs=pick("probs"),
+                    actions=pick("actions"), masks=pick("masks"), idx=pick("idx"), logp=pick("logp"))
+
+    def last_policy(self):
+        """Full softmax table [A,K], sampled indices [B,A] and coefficient records [B,order_dim+2] of the most
+        recent step (views)."""
+        tr = self._traj
+        i = (tr.count - 1) % tr.n
+        return dict(probs_table=tr.out["probs_table"][i], idx=tr.out["idx"][i], coef=tr.out["coef"][i],
+                    logp=tr.out["logp"][i])
+
+    def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        """DDPM forward noising (scheduler_ppo.py:336-358); not on the hot path, plain torch."""
+        ac = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
+        timesteps = timesteps.to(original_samples.device)
+        a = (ac[timesteps] ** 0.5).flatten()
+        b = ((1 - ac[timesteps]) ** 0.5).flatten()
+        while a.dim() < original_samples.dim():
+            a, b = a.unsqueeze(-1), b.unsqueeze(-1)
+        return a * original_samples + b * noise
+
+    def __len__(self):
+        return self.config.num_train_timesteps

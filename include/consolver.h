@@ -1,0 +1,169 @@
+/*
+ * consolver.h — C ABI of libconsolver.so: the B200 (sm_100a) implementation of the ConsistencySolver
+ * sampling step (G-U-N/consolver `PPOScheduler.step` / `FMPPOScheduler.step` + `FactorNetPPO.sample_action`
+ * + the caller's CFG combine).
+ *
+ * Boundary rules (every entry point):
+ *   - plain pointers + sizes + a CUDA stream handle; no torch / C++ types;
+ *   - all data pointers are DEVICE pointers unless the comment says "host";
+ *   - the library never allocates, never synchronises and never throws; the caller owns all memory;
+ *   - returns 0 on success, a negative CONSOLVER_ERR_* for a rejected argument, or a positive
+ *     cudaError_t if the launch failed.
+ *
+ * The reference has no native interface for this path (it is pure PyTorch), so each entry point cites the
+ * reference Python lines it replaces (paths relative to the reference root).
+ */
+#ifndef CONSOLVER_H_
+#define CONSOLVER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CONSOLVER_ABI_VERSION 1
+
+/* element type of latents / model outputs */
+#define CONSOLVER_F32  0
+#define CONSOLVER_F16  1
+#define CONSOLVER_BF16 2
+
+#define CONSOLVER_MAX_ORDER   8     /* order_dim  <= 8  (reference default 4, FLUX config 2)          */
+#define CONSOLVER_MAX_HIDDEN  1024  /* hidden_dim <= 1024 (reference default 256)                     */
+#define CONSOLVER_MAX_LOGITS  4096  /* action_dims * num_actions <= 4096 (reference default 5*161)    */
+#define CONSOLVER_MAX_IN      16    /* MLP input width (2, or 2+order_dim-1 with use_conv)            */
+
+/* per-sample coefficient record written by consolver_policy_f32 and read by the step kernels:
+ *   coef[b*stride + i]            i < order_dim : multiplier of history entry i (0 = newest)
+ *   coef[b*stride + order_dim]    (1 + s0) multiplier of the combined model output (1 if scaler_dim == 0)
+ *   coef[b*stride + order_dim+1]  (1 + s1) multiplier of the sample               (1 if scaler_dim <  2)
+ * stride = order_dim + 2. */
+#define CONSOLVER_COEF_STRIDE(order_dim) ((order_dim) + 2)
+
+/* flags of the step entry points */
+#define CONSOLVER_FLAG_VPRED        1   /* prediction_type == "v_prediction" (scheduler_ppo.py:316-317)            */
+#define CONSOLVER_FLAG_EFF_SCALE    2   /* scaler_dim >= 1: eff *= coef[order_dim]     (scheduler_ppo.py:274-277)  */
+#define CONSOLVER_FLAG_X_SCALE      4   /* scaler_dim == 2: sample *= coef[order_dim+1] (scheduler_ppo.py:278)     */
+#define CONSOLVER_FLAG_PDL          8   /* launch with programmatic dependent launch: the bulk loads are issued
+                                           before waiting on the preceding (policy) kernel's coefficients        */
+
+#define CONSOLVER_ERR_NULL        (-1)
+#define CONSOLVER_ERR_SIZE        (-2)
+#define CONSOLVER_ERR_UNSUPPORTED (-3)
+#define CONSOLVER_ERR_DTYPE       (-4)
+
+typedef void* consolver_stream_t; /* a cudaStream_t */
+
+#if defined(__GNUC__)
+#define CONSOLVER_API __attribute__((visibility("default")))
+#else
+#define CONSOLVER_API
+#endif
+
+CONSOLVER_API int consolver_abi_version(void);
+/* human-readable text for any return value of this library (static storage). */
+CONSOLVER_API const char* consolver_error_string(int err);
+
+/*
+ * Policy step: FactorNetPPO.forward_ + sample_action (factor_net_ppo.py:137-168; FM variant
+ * edit_ppo/factor_net_ppo.py:149-180) and the scheduler's mask / coefficient assembly
+ * (scheduler_ppo.py:248-259 + set_default_coefficients :165-175; edit_ppo/scheduler_fmppo.py:403-410).
+ *
+ * The MLP input is the same for every sample of the batch (scheduler_ppo.py:207-210), so the MLP + softmax is
+ * evaluated ONCE per launch (per CTA) on x = (x0, x1) / x_div; then every sample b draws its A indices as
+ * argmax_k probs[a,k] / q[b,a,k] — exactly what torch.multinomial(probs.view(-1,K), 1) computes with
+ * q = empty_like(probs).exponential_(1) (factor_net_ppo.py:161) — lowest index on ties.
+ *
+ *   w1 [H,in_dim] b1 [H] w2 [H,H] b2 [H] w3 [A*K,H] b3 [A*K]   row-major fp32 (nn.Linear layout: mlp.{0,2,4})
+ *   action_values [A,K]      the `action_values` buffer of the state_dict (bin values)
+ *   x0,x1                    (t, prev_t) for SD / (sigma, sigma_next) for FM, already rounded through the model
+ *                            dtype as the reference's torch.tensor(..., dtype=model_output.dtype) does
+ *   x_div                    999.0 for SD (normalize_input), 1.0 for FM
+ *   temp                     softmax temperature divisor: 1.0 for SD, 0.01 for FM (logits / 0.01)
+ *   feat [B,n_feat] or NULL  extra per-sample MLP inputs (use_conv cosine features); in_dim = 2 + n_feat.
+ *                            When non-NULL the MLP is evaluated per sample.
+ *   q [B*A,K] or NULL        the Exp(1) draw; NULL => use idx_in
+ *   idx_in [B,A] or NULL     forced bin indices (replay / PPO update); exactly one of q, idx_in is given
+ *   n_hist                   number of model outputs in the history INCLUDING the current one (1..order_dim)
+ * outputs (any may be NULL except coef):
+ *   probs_table [A,K]        full softmax table of the shared row (undefined when feat != NULL)
+ *   idx [B,A] int64          sampled bin indices
+ *   actions [B,A]            bin values (the reference's `actions`)
+ *   act_probs [B,A]          probabilities of the sampled bins (the reference's `probs`)
+ *   act_logp [B,A]           log(act_probs + 1e-9) (train_ppo.py:410-411)
+ *   masks [B,A]              1 everywhere except columns n_hist-1 .. order_dim-2 (scheduler_ppo.py:248-249)
+ *   coef [B,order_dim+2]     see CONSOLVER_COEF_STRIDE
+ */
+CONSOLVER_API int consolver_policy_f32(const float* w1, const float* b1, const float* w2, const float* b2,
+                         const float* w3, const float* b3, const float* action_values,
+                         float x0, float x1, float x_div, float temp,
+                         const float* feat, int n_feat,
+                         const float* q, const int64_t* idx_in,
+                         int B, int H, int A, int K, int order_dim, int scaler_dim, int n_hist,
+                         float* probs_table, int64_t* idx, float* actions, float* act_probs, float* act_logp,
+                         float* masks, float* coef, consolver_stream_t stream);
+
+/*
+ * Fused SD solver step: CFG combine (denoise_ppo.py:96-100) + linear-multistep combine over the history
+ * (scheduler_ppo.py:263-280) + DDIM update (scheduler_ppo.py:306-332), one pass over HBM.
+ *
+ *   dtype            CONSOLVER_F32 / F16 / BF16: element type of every latent-sized buffer (math is fp32; for
+ *                    F32 the result is bit-identical to the reference's op-by-op fp32 arithmetic)
+ *   e0               newest model output [B,N]; if `cond` != NULL it is the UNCONDITIONAL half and
+ *                    eps = e0 + guidance*(cond - e0) is formed in the kernel
+ *   slot_out         NULL, or [B,N]: receives eps (the in-place history-ring slot of this step)
+ *   hist (host)      array of n_hist-1 device pointers to the older model outputs, newest first
+ *   x, x_out         current / next latent [B,N]
+ *   coef             [B,coef_stride] from consolver_policy_f32; n_hist == 1 bypasses the coefficient
+ *                    (scheduler_ppo.py:263-265)
+ *   sa_t,sb_t,sa_p,sb_p   sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev), sqrt(1-abar_prev) (fp32 values)
+ *   n_per_sample     N = C*H*W elements of one sample
+ */
+CONSOLVER_API int consolver_step_sd(int dtype, const void* e0, const void* cond, float guidance, void* slot_out,
+                      const void* const* hist, int n_hist, const void* x, void* x_out,
+                      const float* coef, int coef_stride, int order_dim,
+                      float sa_t, float sb_t, float sa_p, float sb_p, int flags,
+                      int B, int64_t n_per_sample, consolver_stream_t stream);
+
+/*
+ * Fused flow-matching solver step (edit_ppo/scheduler_fmppo.py:354,:413-436): fp32 upcast of the sample,
+ * multistep combine, x' = x*(1+s1) + dt*eff*(1+s0), cast to the model dtype.
+ *   dtype     element type of model outputs, history and x_out
+ *   x_dtype   element type of the incoming sample (dtype or CONSOLVER_F32)
+ *   dt        sigma_next - sigma (fp32 value)
+ * With n_hist == 1, scaler_dim == 0 and a 16-bit dtype the reference's `dt * model_output` product is rounded
+ * to the model dtype before the fp32 add (0-d fp32 tensor times bf16 tensor); the kernel reproduces that.
+ */
+CONSOLVER_API int consolver_step_fm(int dtype, int x_dtype, const void* e0, void* slot_out,
+                      const void* const* hist, int n_hist, const void* x, void* x_out,
+                      const float* coef, int coef_stride, int order_dim, float dt, int flags,
+                      int B, int64_t n_per_sample, consolver_stream_t stream);
+
+/*
+ * One call per scheduler step for the fused-CFG SD path: consolver_policy_f32 followed by consolver_step_sd on
+ * the same stream (saves one host crossing; the two kernels are linked by programmatic dependent launch when
+ * CONSOLVER_FLAG_PDL is set).  Arguments as in the two functions above.
+ */
+CONSOLVER_API int consolver_sd_policy_and_step(const float* w1, const float* b1, const float* w2, const float* b2,
+                                 const float* w3, const float* b3, const float* action_values,
+                                 float x0, float x1, float x_div, float temp,
+                                 const float* q, const int64_t* idx_in,
+                                 int H, int A, int K, int scaler_dim,
+                                 float* probs_table, int64_t* idx, float* actions, float* act_probs,
+                                 float* act_logp, float* masks, float* coef,
+                                 int dtype, const void* e0, const void* cond, float guidance, void* slot_out,
+                                 const void* const* hist, int n_hist, const void* x, void* x_out,
+                                 int order_dim, float sa_t, float sb_t, float sa_p, float sb_p, int flags,
+                                 int B, int64_t n_per_sample, consolver_stream_t stream);
+
+/* Tuning knobs for benchmarking (process-global; not part of the numerical contract).
+ *   threads: CTA size of the step kernels (32..512, multiple of 32; 0 = default)
+ *   unroll : 16-byte vectors per thread per stream (1, 2 or 4; 0 = default)                          */
+CONSOLVER_API int consolver_set_step_launch(int threads, int unroll);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONSOLVER_H_ */

@@ -1,0 +1,63 @@
+"""Thin torch<->C-ABI helpers for the tests: every call goes through libconsolver.so exactly as a foreign
+host (cgo/JNI/ctypes) would — raw device pointers, sizes, a stream handle."""
+import torch
+
+from consolver_b200 import _lib
+
+
+def sd_to_dev(sd, device="cuda"):
+    return {k: v.to(device=device, dtype=torch.float32).contiguous() for k, v in sd.items()}
+
+
+def weights(sd):
+    return [sd[k].data_ptr() for k in ("mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "mlp.4.weight",
+                                      "mlp.4.bias", "action_values")]
+
+
+def policy(sd, x0, x1, x_div, temp, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None, feat=None):
+    lib = _lib.load()
+    A, K = sd["action_values"].shape
+    H = sd["mlp.0.weight"].shape[0]
+    dev = sd["action_values"].device
+    f = dict(device=dev, dtype=torch.float32)
+    out = dict(probs_table=torch.full((A, K), -1.0, **f), idx=torch.full((B, A), -1, device=dev, dtype=torch.int64),
+               actions=torch.zeros(B, A, **f), probs=torch.zeros(B, A, **f), logp=torch.zeros(B, A, **f),
+               masks=torch.zeros(B, A, **f), coef=torch.zeros(B, order_dim + 2, **f))
+    rc = lib.consolver_policy_f32(
+        *weights(sd), float(x0), float(x1), float(x_div), float(temp),
+        feat.data_ptr() if feat is not None else None, feat.shape[1] if feat is not None else 0,
+        q.data_ptr() if q is not None else None, idx_in.data_ptr() if idx_in is not None else None,
+        B, H, A, K, order_dim, scaler_dim, n_hist,
+        out["probs_table"].data_ptr(), out["idx"].data_ptr(), out["actions"].data_ptr(), out["probs"].data_ptr(),
+        out["logp"].data_ptr(), out["masks"].data_ptr(), out["coef"].data_ptr(),
+        torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "consolver_policy_f32")
+    return out
+
+
+def step_sd(e0, cond, guidance, hist, x, coef, order_dim, scalars, flags=0, slot=False):
+    lib = _lib.load()
+    B = x.shape[0]
+    N = x.numel() // B
+    x_out = torch.empty_like(x)
+    slot_t = torch.empty_like(x) if slot else None
+    rc = lib.consolver_step_sd(
+        _lib.dtype_code(x.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, float(guidance),
+        slot_t.data_ptr() if slot else None, _lib.ptr_array([h.data_ptr() for h in hist]), len(hist) + 1,
+        x.data_ptr(), x_out.data_ptr(), coef.data_ptr(), coef.shape[1], order_dim,
+        *[float(s) for s in scalars], flags, B, N, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "consolver_step_sd")
+    return x_out, slot_t
+
+
+def step_fm(e0, hist, x, coef, order_dim, dt, flags=0):
+    lib = _lib.load()
+    B = x.shape[0]
+    N = x.numel() // B
+    x_out = torch.empty(x.shape, device=x.device, dtype=e0.dtype)
+    rc = lib.consolver_step_fm(
+        _lib.dtype_code(e0.dtype), _lib.dtype_code(x.dtype), e0.data_ptr(), None,
+        _lib.ptr_array([h.data_ptr() for h in hist]), len(hist) + 1, x.data_ptr(), x_out.data_ptr(),
+        coef.data_ptr(), coef.shape[1], order_dim, float(dt), flags, B, N, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "consolver_step_fm")
+    return x_out

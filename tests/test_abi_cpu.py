@@ -1,0 +1,79 @@
+"""CPU-side checks of the C ABI: the library builds/loads, exports every symbol include/consolver.h declares,
+the ctypes signatures cover them, and argument validation answers with error codes before touching CUDA."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from consolver_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "consolver.h")).read()
+    return sorted(set(re.findall(r"CONSOLVER_API\s+[\w\s\*]+?\b(consolver_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared()
+    for n in ("consolver_policy_f32", "consolver_step_sd", "consolver_step_fm", "consolver_sd_policy_and_step",
+              "consolver_abi_version", "consolver_error_string"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\sT\s+(consolver_\w+)", out))
+    for n in _declared():
+        assert n in exported, f"{n} declared in consolver.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+        assert hasattr(lib, n)
+    assert lib.consolver_abi_version() == 1
+
+
+def test_header_compiles_as_plain_c():
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "consolver.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_library_is_built_for_sm_100a():
+    r = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in r.stdout
+
+
+def test_argument_validation_returns_error_codes_without_a_gpu():
+    lib = _lib.load()
+    # null weights
+    rc = lib.consolver_policy_f32(*([None] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, None, None, 1, 256, 3, 11, 4, 0, 1,
+                                  *([None] * 7), None)
+    assert rc == -1
+    rc = lib.consolver_step_sd(0, None, None, 0.0, None, None, 1, None, None, None, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1,
+                               16, None)
+    assert rc == -1
+    one = 16  # any non-null fake address: validation must fail on sizes before any dereference / launch
+    rc = lib.consolver_step_sd(0, one, None, 0.0, None, None, 5, one, one, one, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1, 16, None)
+    assert rc == -2  # n_hist > order_dim
+    rc = lib.consolver_step_sd(0, one, None, 0.0, None, None, 1, one, one, one, 6, 9, 1.0, 0.0, 1.0, 0.0, 0, 1, 16, None)
+    assert rc == -2  # order_dim > CONSOLVER_MAX_ORDER
+    rc = lib.consolver_step_sd(7, one, None, 0.0, None, None, 1, one, one, one, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1, 16, None)
+    assert rc == -4  # dtype
+    rc = lib.consolver_step_fm(2, 1, one, None, None, 1, one, one, one, 6, 4, -0.1, 0, 1, 16, None)
+    assert rc == -4  # x_dtype must be dtype or f32
+    rc = lib.consolver_policy_f32(*([one] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, one, one, 1, 256, 3, 11, 4, 0, 1,
+                                  *([one] * 7), None)
+    assert rc == -1  # both q and idx_in
+    rc = lib.consolver_policy_f32(*([one] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, one, None, 1, 2048, 3, 11, 4, 0, 1,
+                                  *([one] * 7), None)
+    assert rc == -2  # hidden too large
+    assert lib.consolver_set_step_launch(100, 1) == -2
+    assert lib.consolver_set_step_launch(0, 0) == 0
+    for code in (0, -1, -2, -3, -4, 700):
+        assert lib.consolver_error_string(code)
+    with pytest.raises(_lib.ConsolverError):
+        _lib.check(-2, "x")

@@ -1,0 +1,195 @@
+"""GPU parity, kernel level: every entry point of the C ABI against the CPU oracle on seeded inputs, plus the
+edge cases (ragged / unaligned sizes, every history depth up to CONSOLVER_MAX_ORDER, all scaler / prediction
+flags, 16-bit I/O, forced indices, multi-CTA policy grids)."""
+import itertools
+
+import pytest
+import torch
+
+import abi_helpers as ah
+import consolver_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_sd(variant, H, K, order_dim, scaler_dim, mu_dim, seed, last_std):
+    g = torch.Generator().manual_seed(seed)
+    A = orc.action_dims(variant, order_dim, scaler_dim, mu_dim)
+    r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1)  # noqa: E731
+    return {
+        "mlp.0.weight": r(H, 2) / 2 ** 0.5, "mlp.0.bias": r(H) / 2 ** 0.5,
+        "mlp.2.weight": r(H, H) / H ** 0.5, "mlp.2.bias": r(H) / H ** 0.5,
+        "mlp.4.weight": torch.randn(A * K, H, generator=g) * last_std, "mlp.4.bias": torch.randn(A * K, generator=g) * 0.1,
+        "action_values": orc.action_value_table(variant, K, order_dim, scaler_dim, mu_dim),
+    }
+
+
+POLICY_CASES = [
+    # variant, H, K, order_dim, scaler_dim, mu_dim, B
+    ("sd", 256, 11, 4, 0, 0, 64), ("sd", 256, 11, 4, 2, 0, 3), ("sd", 256, 161, 4, 2, 0, 5),
+    ("sd", 64, 11, 2, 0, 0, 1), ("sd", 100, 7, 3, 1, 0, 9), ("sd", 30, 5, 8, 2, 0, 4), ("sd", 1024, 11, 4, 0, 0, 2),
+    ("fm", 256, 11, 2, 0, 0, 10), ("fm", 256, 11, 4, 2, 1, 7), ("sd", 256, 11, 4, 0, 0, 4096), ("sd", 256, 11, 4, 0, 0, 1500),
+]
+
+
+@pytest.mark.parametrize("variant,H,K,od,sdim,mu,B", POLICY_CASES)
+def test_policy_kernel_vs_oracle(variant, H, K, od, sdim, mu, B):
+    sd = make_sd(variant, H, K, od, sdim, mu, seed=H + K + B, last_std=0.5 if variant == "sd" else 0.02)
+    dsd = ah.sd_to_dev(sd)
+    A = sd["action_values"].shape[0]
+    x = torch.tensor([[874.0, 749.0]]) if variant == "sd" else torch.tensor([[0.9567, 0.9045]])
+    g = torch.Generator().manual_seed(B)
+    for n_hist in sorted({1, 2, od}):
+        q = torch.empty(B * A, K).exponential_(1, generator=g)
+        out = ah.policy(dsd, x[0, 0], x[0, 1], 999.0 if variant == "sd" else 1.0, 1.0 if variant == "sd" else 0.01,
+                        B, od, sdim, n_hist, q=q.cuda())
+        probs = orc.policy_probs(sd, x, variant)                       # [1, A, K]
+        rtol = 0 if variant == "sd" else 2e-4
+        torch.testing.assert_close(out["probs_table"].cpu(), probs[0], rtol=rtol, atol=1e-6 if variant == "sd" else 1e-7)
+        # the draw itself is checked against the kernel's own table (bit-exact argmax of p/q) ...
+        tab = out["probs_table"].cpu().unsqueeze(0).expand(B, A, K)
+        idx = orc.sample_indices(tab, q)
+        assert torch.equal(out["idx"].cpu(), idx)
+        # ... and against the oracle's table wherever the two tables do not disagree on a near-tie
+        idx_o = orc.sample_indices(probs.expand(B, A, K), q)
+        assert (out["idx"].cpu() != idx_o).float().mean() <= 1e-3
+        actions, act_probs = orc.gather_actions(sd, tab, idx)
+        assert torch.equal(out["actions"].cpu(), actions)
+        assert torch.equal(out["probs"].cpu(), act_probs)
+        torch.testing.assert_close(out["logp"].cpu(), torch.log(act_probs + 1e-9), rtol=0, atol=1e-6)
+        assert torch.equal(out["masks"].cpu(), orc.step_masks(B, A, n_hist, od))
+        coef, scale = orc.coefficients(actions, n_hist, od, sdim)
+        c = out["coef"].cpu()
+        if coef is not None:
+            for j, cj in enumerate(coef):
+                assert torch.equal(c[:, j], cj), f"coef {j} n_hist {n_hist}"
+        for j in range(sdim):
+            assert torch.equal(c[:, od + j], scale[j])
+        for j in range(sdim, 2):
+            assert torch.all(c[:, od + j] == 1)
+
+
+def test_policy_forced_indices():
+    sd = make_sd("sd", 256, 11, 4, 2, 0, seed=5, last_std=0.5)
+    dsd = ah.sd_to_dev(sd)
+    B, A, K = 33, 5, 11
+    idx = torch.randint(0, K, (B, A))
+    out = ah.policy(dsd, 499.0, 374.0, 999.0, 1.0, B, 4, 2, 4, idx_in=idx.cuda())
+    assert torch.equal(out["idx"].cpu(), idx)
+    tab = out["probs_table"].cpu().unsqueeze(0).expand(B, A, K)
+    actions, act_probs = orc.gather_actions(sd, tab, idx)
+    assert torch.equal(out["actions"].cpu(), actions) and torch.equal(out["probs"].cpu(), act_probs)
+
+
+def _rand_coef(B, od, g, sdim):
+    c = torch.randn(B, od + 2, generator=g)
+    c[:, od:] = 1 + 0.05 * torch.randn(B, 2, generator=g)
+    return c
+
+
+def _oracle_sd(e0, cond, guidance, hist, x, c, od, scalars, vpred, sdim):
+    eps = orc.cfg_combine(e0, cond, guidance) if cond is not None else e0
+    n_hist = len(hist) + 1
+    coef = None if n_hist == 1 else [c[:, j] for j in range(n_hist)]
+    scale = [c[:, od + j] for j in range(sdim)]
+    eff, xs = orc.combine_history([eps] + hist, coef, scale, x)
+    sc = [torch.tensor(v, dtype=torch.float32) for v in scalars]
+    return orc.ddim_update(xs, eff, sc, "v_prediction" if vpred else "epsilon"), eps
+
+
+SHAPES = [(3, (4, 8, 8)), (2, (3, 5, 7)), (1, (4, 64, 64)), (5, (1, 1, 1)), (2, (1030,))]
+
+
+@pytest.mark.parametrize("B,shape", SHAPES)
+@pytest.mark.parametrize("n_hist", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("pair,vpred,sdim", [(True, False, 0), (False, False, 0), (True, True, 2), (False, True, 1),
+                                             (True, False, 2)])
+def test_step_sd_f32_bit_exact(B, shape, n_hist, pair, vpred, sdim):
+    od = max(n_hist, 4)
+    g = torch.Generator().manual_seed(n_hist * 100 + B)
+    rn = lambda: torch.randn(B, *shape, generator=g)  # noqa: E731
+    e0, cond, x = rn(), (rn() if pair else None), rn()
+    hist = [rn() for _ in range(n_hist - 1)]
+    c = _rand_coef(B, od, g, sdim)
+    scalars = (0.8378, 0.5460, 0.9151, 0.4033)
+    flags = (1 if vpred else 0) | (2 if sdim >= 1 else 0) | (4 if sdim >= 2 else 0)
+    ref, eps = _oracle_sd(e0, cond, 3.0, hist, x, c, od, scalars, vpred, sdim)
+    out, slot = ah.step_sd(e0.cuda(), cond.cuda() if pair else None, 3.0, [h.cuda() for h in hist], x.cuda(),
+                           c.cuda(), od, scalars, flags, slot=True)
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(slot.cpu(), eps)
+
+
+def test_step_sd_unaligned_pointers_use_scalar_path():
+    B, N, od = 3, 257, 4
+    g = torch.Generator().manual_seed(0)
+    big = lambda: torch.randn(B * N + 1, generator=g).cuda()[1:].view(B, N)  # 4-byte aligned only  # noqa: E731
+    e0, cond, x, h1 = big(), big(), big(), big()
+    c = _rand_coef(B, od, g, 0)
+    scalars = (0.3, 0.95, 0.5, 0.86)
+    ref, _ = _oracle_sd(e0.cpu(), cond.cpu(), 2.0, [h1.cpu()], x.cpu(), c, od, scalars, False, 0)
+    out, _ = ah.step_sd(e0, cond, 2.0, [h1], x, c.cuda(), od, scalars, 0)
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n_hist", [1, 4])
+def test_step_sd_16bit_io(dtype, n_hist):
+    """16-bit I/O: fp32 math on the upcast inputs, one rounding at the end (the reference's fp16 pipeline rounds
+    after every op; bit parity with that arithmetic is not a goal — SURVEY §7)."""
+    B, shape, od = 3, (4, 16, 16), 4
+    g = torch.Generator().manual_seed(7)
+    rn = lambda: torch.randn(B, *shape, generator=g).to(dtype)  # noqa: E731
+    e0, cond, x = rn(), rn(), rn()
+    hist = [rn() for _ in range(n_hist - 1)]
+    c = _rand_coef(B, od, g, 0)
+    scalars = (0.8378, 0.5460, 0.9151, 0.4033)
+    eps = orc.cfg_combine(e0.float(), cond.float(), 3.0).to(dtype)
+    ref, _ = _oracle_sd(eps.float(), None, 0.0, [h.float() for h in hist], x.float(), c, od, scalars, False, 0)
+    out, slot = ah.step_sd(e0.cuda(), cond.cuda(), 3.0, [h.cuda() for h in hist], x.cuda(), c.cuda(), od, scalars, 0,
+                           slot=True)
+    assert torch.equal(slot.cpu(), eps)
+    assert torch.equal(out.cpu(), ref.to(dtype))
+
+
+@pytest.mark.parametrize("dtype,x_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                           (torch.bfloat16, torch.float32), (torch.float16, torch.float16)])
+@pytest.mark.parametrize("n_hist,sdim", [(1, 0), (1, 2), (2, 0), (4, 1), (6, 2)])
+@pytest.mark.parametrize("B,shape", [(2, (16, 8)), (3, (5, 3)), (1, (4096, 64))])
+def test_step_fm_bit_exact(dtype, x_dtype, n_hist, sdim, B, shape):
+    od = max(n_hist, 2)
+    g = torch.Generator().manual_seed(n_hist + B)
+    v = torch.randn(B, *shape, generator=g).to(dtype)
+    x = torch.randn(B, *shape, generator=g).to(x_dtype)
+    hist = [torch.randn(B, *shape, generator=g).to(dtype) for _ in range(n_hist - 1)]
+    c = _rand_coef(B, od, g, sdim)
+    dt = torch.tensor(0.8403, dtype=torch.float32) - torch.tensor(0.9045, dtype=torch.float32)
+    coef = None if n_hist == 1 else [c[:, j] for j in range(n_hist)]
+    scale = [c[:, od + j] for j in range(sdim)]
+    eff, xs = orc.combine_history([v] + hist, coef, scale, x.to(torch.float32))
+    ref = orc.fm_update(xs, eff, dt, dtype)
+    flags = (2 if sdim >= 1 else 0) | (4 if sdim >= 2 else 0)
+    out = ah.step_fm(v.cuda(), [h.cuda() for h in hist], x.cuda(), c.cuda(), od, float(dt), flags)
+    assert out.dtype == dtype
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_launch_config_knobs_do_not_change_results():
+    from consolver_b200 import _lib
+    lib = _lib.load()
+    B, shape, od = 4, (4, 64, 64), 4
+    g = torch.Generator().manual_seed(3)
+    rn = lambda: torch.randn(B, *shape, generator=g).cuda()  # noqa: E731
+    e0, cond, x, h = rn(), rn(), rn(), [rn(), rn(), rn()]
+    c = _rand_coef(B, od, g, 0).cuda()
+    scalars = (0.8378, 0.5460, 0.9151, 0.4033)
+    base, _ = ah.step_sd(e0, cond, 3.0, h, x, c, od, scalars, 0)
+    try:
+        for threads, unroll in itertools.product((64, 128, 512), (1, 2)):
+            assert lib.consolver_set_step_launch(threads, unroll) == 0
+            out, _ = ah.step_sd(e0, cond, 3.0, h, x, c, od, scalars, 0)
+            assert torch.equal(out, base)
+        out, _ = ah.step_sd(e0, cond, 3.0, h, x, c, od, scalars, 8)   # PDL launch attribute
+        assert torch.equal(out, base)
+    finally:
+        lib.consolver_set_step_launch(0, 0)

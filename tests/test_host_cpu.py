@@ -1,0 +1,158 @@
+"""Host-side logic of the drop-in schedulers (no GPU): constructor/config surface, schedules against the golden
+vectors, state_dict interchange, error behaviour, lazy conds."""
+import numpy as np
+import pytest
+import torch
+
+import consolver_b200 as cb
+from consolver_b200.config_utils import LazyConds
+from golden_io import Golden, names
+
+PROD = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, num_train_timesteps=1000,
+            steps_offset=1, timestep_spacing="trailing", order_dim=4, scaler_dim=0, use_conv=False,
+            factor_net_kwargs=dict(embedding_dim=64, hidden_dim=256, num_actions=11))
+
+
+@pytest.mark.parametrize("name", names("sd_"))
+def test_sd_schedule_and_state_dict_match_reference(name):
+    g = Golden(name)
+    m = g.meta
+    s = cb.PPOScheduler(factor_net_kwargs=dict(m["factor_net_kwargs"]), **m["config"])
+    ref_sd = g.state_dict
+    own = s.factor_net.state_dict()
+    assert list(own.keys()) == list(ref_sd.keys())
+    assert all(own[k].shape == ref_sd[k].shape for k in own)
+    assert torch.equal(own["action_values"], ref_sd["action_values"])      # incl. the -1.49e-08 bin
+    s.factor_net.load_state_dict(ref_sd)
+    s.set_timesteps(m["n"])
+    assert torch.equal(s.timesteps, g["timesteps"])
+    assert len(s) == 1000 and s.init_noise_sigma == 1.0 and s.order == 1
+    x = torch.randn(2, 3)
+    assert s.scale_model_input(x, 5) is x
+
+
+@pytest.mark.parametrize("name", names("fm_"))
+def test_fm_schedule_and_state_dict_match_reference(name):
+    g = Golden(name)
+    m = g.meta
+    s = cb.FMPPOScheduler(factor_net_kwargs=dict(m["factor_net_kwargs"]), **m["config"])
+    assert list(s.factor_net.state_dict().keys()) == list(g.state_dict.keys())
+    assert torch.equal(s.factor_net.action_values, g.state_dict["action_values"])
+    s.factor_net.load_state_dict(g.state_dict)
+    s.set_timesteps(m["n"], sigmas=np.linspace(1.0, 1 / m["n"], m["n"]), mu=m["mu"])
+    assert torch.equal(s.timesteps, g["timesteps"]) and torch.equal(s.sigmas, g["sigmas"])
+    assert s.step_index is None and s.begin_index is None
+    s.set_begin_index(0)
+    assert s.begin_index == 0
+
+
+def test_sd_config_surface_and_defaults():
+    s = cb.PPOScheduler(**PROD)
+    assert s.config.order_dim == 4 and s.config["scaler_dim"] == 0 and s.config.get("prediction_type") == "epsilon"
+    assert s.config.ppo_type == "discrete" and s.config.trained_betas is None
+    d = cb.PPOScheduler()      # reference defaults (scheduler_ppo.py:82-97, :132-136)
+    fn = d.factor_net
+    assert (fn.hidden_dim, fn.num_actions, fn.action_dims) == (256, 161, 5)
+    assert fn.mlp[0].in_features == 2 and fn.mlp[4].out_features == 5 * 161
+    assert torch.count_nonzero(fn.mlp[4].weight) == 0 and torch.count_nonzero(fn.mlp[4].bias) == 0
+    assert sum(p.numel() for p in s.factor_net.parameters()) == 75041     # production policy
+    f = cb.FMPPOScheduler()
+    assert f.factor_net.action_dims == 4 + 2 + 1 - 1 and f.config.mu_dim == 1
+    assert torch.count_nonzero(f.factor_net.mlp[4].weight) > 0            # FM variant keeps default init
+
+
+def test_sd_timestep_grids():
+    s = cb.PPOScheduler(**PROD)
+    s.set_timesteps(8)
+    assert s.timesteps.tolist() == [999, 874, 749, 624, 499, 374, 249, 124]
+    s.set_timesteps(7)
+    assert s._stride == 142 and s.timesteps[1].item() == 856           # prev_t = t - 1000//n quirk
+    lead = cb.PPOScheduler(timestep_spacing="leading", steps_offset=1)
+    lead.set_timesteps(4)
+    assert lead.timesteps.tolist() == [751, 501, 251, 1]
+    lin = cb.PPOScheduler(timestep_spacing="linspace")
+    lin.set_timesteps(3)
+    assert lin.timesteps.tolist() == [999, 500, 0]
+
+
+def test_error_behaviour_matches_reference():
+    s = cb.PPOScheduler(**PROD)
+    x = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(ValueError, match="set_timesteps"):
+        s.step(x, 999, x)
+    with pytest.raises(ValueError):
+        s.set_timesteps(1001)
+    with pytest.raises(ValueError, match="timestep_spacing"):
+        cb.PPOScheduler(timestep_spacing="bogus").set_timesteps(4)
+    with pytest.raises(NotImplementedError):
+        cb.PPOScheduler(beta_schedule="bogus")
+    with pytest.raises(ValueError):
+        cb.PPOScheduler(prediction_type="sample")
+    with pytest.raises(NotImplementedError):
+        cb.PPOScheduler(ppo_type="continuous")
+    s.set_timesteps(4)
+    with pytest.raises(RuntimeError, match="no CPU path"):     # the product never falls back to the CPU
+        s.step(x, 999, x)
+    f = cb.FMPPOScheduler(use_dynamic_shifting=True)
+    with pytest.raises(ValueError, match="mu"):
+        f.set_timesteps(4)
+    f = cb.FMPPOScheduler(order_dim=2, scaler_dim=0, mu_dim=0)
+    v = torch.zeros(1, 4, 4)
+    with pytest.raises(ValueError, match="set_timesteps"):
+        f.step(v, 1.0, v)
+    f.set_timesteps(4)
+    with pytest.raises(ValueError, match="integer"):
+        f.step(v, 3, v)
+    with pytest.raises(ValueError, match="integer"):
+        f.step(v, torch.tensor(3), v)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        f.step(v, f.timesteps[0], v)
+    with pytest.raises(ValueError):
+        cb.FMPPOScheduler(use_karras_sigmas=True, use_exponential_sigmas=True)
+    with pytest.raises(ValueError):
+        cb.FMPPOScheduler(time_shift_type="cubic")
+    with pytest.raises(ValueError, match="same length"):
+        f.set_timesteps(3, sigmas=[1.0, 0.5])
+
+
+def test_fm_sigma_variants_run():
+    for kw in (dict(use_karras_sigmas=True), dict(use_exponential_sigmas=True), dict(shift=3.0),
+               dict(shift_terminal=0.02), dict(invert_sigmas=True), dict(time_shift_type="linear", use_dynamic_shifting=True)):
+        f = cb.FMPPOScheduler(order_dim=2, scaler_dim=0, mu_dim=0, **kw)
+        f.set_timesteps(6, mu=0.8 if kw.get("use_dynamic_shifting") else None)
+        assert f.sigmas.shape == (7,) and f.timesteps.shape == (6,)
+        assert f.index_for_timestep(f.timesteps[2]) == 2
+    f = cb.FMPPOScheduler(shift=3.0, order_dim=2, scaler_dim=0, mu_dim=0)
+    f.set_timesteps(8)
+    f.set_begin_index(3)
+    lat, noise = torch.ones(2, 4), torch.zeros(2, 4)
+    out = f.scale_noise(lat, f.timesteps[:2], noise)
+    torch.testing.assert_close(out, (1 - f.sigmas[3]) * lat)
+
+
+def test_add_noise_matches_closed_form():
+    s = cb.PPOScheduler(**PROD)
+    x0, n = torch.randn(3, 4, 2, 2), torch.randn(3, 4, 2, 2)
+    t = torch.tensor([0, 500, 999])
+    out = s.add_noise(x0, n, t)
+    a = s.alphas_cumprod[t].view(3, 1, 1, 1)
+    torch.testing.assert_close(out, a.sqrt() * x0 + (1 - a).sqrt() * n)
+
+
+def test_lazy_conds_materialises_on_access_only():
+    calls = []
+    c = LazyConds(torch.zeros(2, 2), lambda: calls.append(1) or torch.ones(2, 4, 3))
+    assert c["x"].shape == (2, 2) and not calls
+    assert "epsilon" in c and not calls
+    assert c["epsilon"].shape == (2, 4, 3) and calls == [1]
+    assert c.get("epsilon") is c["epsilon"] and calls == [1]
+    assert sorted(c.keys()) == ["epsilon", "x"]
+
+
+def test_fp16_cast_of_the_policy_keeps_a_loadable_state_dict():
+    """gen_ppo.py:188-195 loads model.ckpt then casts the module (and its buffer) to fp16."""
+    s = cb.PPOScheduler(**PROD)
+    sd = {k: v.clone() for k, v in s.factor_net.state_dict().items()}
+    s.factor_net.load_state_dict(sd)
+    s.factor_net.to(dtype=torch.float16)
+    assert s.factor_net.action_values.dtype == torch.float16

@@ -1,0 +1,91 @@
+"""Solver-step microbench (BASELINE config 2): fused SD step kernel over a batch sweep, through the C ABI,
+CUDA-event timed, rotating buffer sets so the working set exceeds L2.  Prints one JSON object per point."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from consolver_b200 import _lib  # noqa: E402
+
+L2_BYTES = 126 * 2 ** 20
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def bench_sd(B, n_hist=4, pair=True, N=4 * 64 * 64, dtype=torch.float32, iters=200, flags=0, min_bytes=3 * L2_BYTES,
+             order_dim=4):
+    lib = _lib.load()
+    es = torch.empty((), dtype=dtype).element_size()
+    tensors = (n_hist - 1) + 2 + (2 if pair else 1) + (1 if pair else 0)   # reads + writes (x', slot)
+    bytes_per_launch = tensors * B * N * es
+    nsets = max(2, min(64, -(-min_bytes // bytes_per_launch)))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    mk = lambda: torch.randn(B, N, device="cuda", generator=g).to(dtype)  # noqa: E731
+    sets = []
+    for _ in range(nsets):
+        sets.append(dict(e0=mk(), cond=mk() if pair else None, x=mk(), hist=[mk() for _ in range(n_hist - 1)],
+                         out=torch.empty(B, N, device="cuda", dtype=dtype),
+                         slot=torch.empty(B, N, device="cuda", dtype=dtype) if pair else None))
+    coef = torch.randn(B, order_dim + 2, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    code = _lib.dtype_code(dtype)
+
+    def launch(s):
+        rc = lib.consolver_step_sd(code, s["e0"].data_ptr(), s["cond"].data_ptr() if pair else None, 3.0,
+                                   s["slot"].data_ptr() if pair else None,
+                                   _lib.ptr_array([h.data_ptr() for h in s["hist"]]), n_hist, s["x"].data_ptr(),
+                                   s["out"].data_ptr(), coef.data_ptr(), order_dim + 2, order_dim,
+                                   0.8378, 0.5460, 0.9151, 0.4033, flags, B, N, stream)
+        assert rc == 0, rc
+
+    for i in range(max(3, nsets)):
+        launch(sets[i % nsets])
+    torch.cuda.synchronize()
+    best = None
+    times = []
+    for rep in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            launch(sets[i % nsets])
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b) / iters * 1e3)  # us per launch
+    times.sort()
+    us = times[len(times) // 2]
+    return dict(B=B, n_hist=n_hist, pair=pair, dtype=str(dtype).split(".")[-1], us_median=round(us, 3),
+                us_best=round(times[0], 3), bytes=bytes_per_launch, gbs=round(bytes_per_launch / us / 1e3, 1),
+                gbs_best=round(bytes_per_launch / times[0] / 1e3, 1), nsets=nsets)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batches", default="1,4,16,64,256,1024,4096")
+    ap.add_argument("--threads", default="0")
+    ap.add_argument("--unroll", default="0")
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--pdl", type=int, default=0)
+    a = ap.parse_args()
+    peak, src = load_peak()
+    lib = _lib.load()
+    for th in [int(v) for v in a.threads.split(",")]:
+        for un in [int(v) for v in a.unroll.split(",")]:
+            assert lib.consolver_set_step_launch(th, un) == 0
+            for B in [int(v) for v in a.batches.split(",")]:
+                r = bench_sd(B, iters=a.iters, flags=8 if a.pdl else 0)
+                r.update(threads=th, unroll=un, frac=round(r["gbs"] / peak, 3), peak=peak, peak_src=src)
+                print(json.dumps(r), flush=True)
+    lib.consolver_set_step_launch(0, 0)
+
+
+if __name__ == "__main__":
+    main()
