@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ConsistencySolver sampling hot path on B200.
+
+Workload (BASELINE.json configs[1], solver path): SD1.5-shape latents 4x64x64 fp32, 8-step trailing schedule,
+CFG=3, order_dim=4, scaler_dim=0, production policy (2->256->256->33), batch 64 per GPU.  The denoiser is NOT
+the product: its outputs are resident synthetic CFG pairs (the "random eps stand-in for the U-Net" of configs[0]);
+`with_denoiser` reports the same loop with a random-init SD1.5-architecture U-Net in the middle when requested.
+
+A "step" = one 8-step preview of one batch of 64 latents: 8 x (Exp(1) draw + policy kernel + fused step kernel).
+  value      previews/s, inputs resident in HBM, rotating pool of batches larger than L2, CUDA-event timed,
+             max over ranks (weak scaling: every rank runs its own shard of prompts/seeds, no collective)
+  e2e        previews/s through the public scheduler API with HOST buffers: every step uploads the initial
+             latents and the 8 CFG pairs from pinned memory and reads the final latents + rollout record back
+  roofline   the fused step kernel (dominant kernel) at this workload's launch shape, timed live with CUDA events
+             on its launch stream; `roofline_sweep` repeats it for larger batches (BASELINE config 2)
+  cpu_baseline / --impl reference   the CPU oracle port of the reference scheduler on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SD_CFG = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, num_train_timesteps=1000,
+              steps_offset=1, timestep_spacing="trailing", order_dim=4, scaler_dim=0, use_conv=False)
+FN_KW = dict(embedding_dim=64, hidden_dim=256, num_actions=11)
+SHAPE = (4, 64, 64)
+N_STEPS = 8
+GUIDANCE = 3.0
+L2_BYTES = 126 * 2 ** 20
+HIST_DEPTHS = [1, 2, 3, 4, 4, 4, 4, 4]                     # n_hist per step of an 8-step preview
+TENSORS_PER_PREVIEW = sum(n + 4 for n in HIST_DEPTHS)       # 58 latent-sized transfers / sample
+
+
+def policy_state_dict(seed=0):
+    """Random-init stand-in for the published checkpoint: default nn.Linear init for layers 0/2,
+    N(0, 0.05^2) last-layer weight, zero bias, all under one seed."""
+    g = torch.Generator().manual_seed(seed)
+    H, AK = FN_KW["hidden_dim"], 3 * FN_KW["num_actions"]
+    u = lambda *s, fan: (torch.rand(*s, generator=g) * 2 - 1) / fan ** 0.5  # noqa: E731
+    from consolver_b200.factor_net import _action_values
+
+    return {"action_values": _action_values("sd", FN_KW["num_actions"], 4, 0, 0),
+            "mlp.0.weight": u(H, 2, fan=2), "mlp.0.bias": u(H, fan=2),
+            "mlp.2.weight": u(H, H, fan=H), "mlp.2.bias": u(H, fan=H),
+            "mlp.4.weight": torch.randn(AK, H, generator=g) * 0.05, "mlp.4.bias": torch.zeros(AK)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) — runs during the timed region
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self._stop, self.ok = [], set(), threading.Event(), False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.max = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def make_scheduler(device, sd):
+    import consolver_b200 as cb
+
+    s = cb.PPOScheduler(factor_net_kwargs=dict(FN_KW), **SD_CFG)
+    s.factor_net.load_state_dict(sd)
+    s.factor_net.to(device)
+    return s
+
+
+def synth_batch(B, seed, device, pin=False):
+    """Synthetic inputs of one preview batch: x_T ~ N(0,1) and one N(0,1) CFG pair per step."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, *SHAPE, generator=g)
+    pairs = torch.randn(N_STEPS, 2 * B, *SHAPE, generator=g)
+    if device is None:
+        return (x.pin_memory(), pairs.pin_memory()) if pin else (x, pairs)
+    return x.to(device), pairs.to(device)
+
+
+def time_step_kernel(B, n_hist, device, iters=64, pool_bytes=3 * L2_BYTES):
+    """Average device time of ONE fused-step launch (CFG pair, n_hist deep) over `iters` launches on rotating
+    buffer sets larger than L2, captured in a CUDA graph so host launch gaps do not enter; CUDA events on the
+    launch stream."""
+    from consolver_b200 import _lib
+
+    lib = _lib.load()
+    N = SHAPE[0] * SHAPE[1] * SHAPE[2]
+    per_launch = (n_hist + 4) * B * N * 4
+    nsets = int(max(2, min(64, -(-pool_bytes // per_launch))))
+    mk = lambda: torch.randn(B, N, device=device)  # noqa: E731
+    sets = [dict(u=mk(), c=mk(), x=mk(), h=[mk() for _ in range(n_hist - 1)], o=torch.empty(B, N, device=device),
+                 s=torch.empty(B, N, device=device)) for _ in range(nsets)]
+    coef = torch.randn(B, 6, device=device)
+
+    def launch(st, stream):
+        rc = lib.consolver_step_sd(0, st["u"].data_ptr(), st["c"].data_ptr(), GUIDANCE, st["s"].data_ptr(),
+                                   _lib.ptr_array([t.data_ptr() for t in st["h"]]), n_hist, st["x"].data_ptr(),
+                                   st["o"].data_ptr(), coef.data_ptr(), 6, 4, 0.8378, 0.5460, 0.9151, 0.4033, 0,
+                                   B, N, stream)
+        assert rc == 0, rc
+
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for i in range(max(3, nsets)):
+            launch(sets[i % nsets], side.cuda_stream)
+    torch.cuda.current_stream(device).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        st = torch.cuda.current_stream(device).cuda_stream
+        for i in range(iters):
+            launch(sets[i % nsets], st)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(device)
+    ts = []
+    for _ in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize(device)
+        ts.append(a.elapsed_time(b) * 1e3 / iters)
+    ts.sort()
+    return ts[len(ts) // 2], per_launch, nsets
+
+
+def run_ours(args, rank, world, device):
+    import consolver_b200  # noqa: F401  (fails loudly if libconsolver.so cannot be built/loaded)
+    from consolver_b200.denoise import GraphedPreview, preview_from_pairs
+
+    B = args.batch
+    sd = policy_state_dict(0)
+    bytes_per_batch = (1 + 2 * N_STEPS) * B * SHAPE[0] * SHAPE[1] * SHAPE[2] * 4
+    pool_n = int(max(2, -(-2 * L2_BYTES // bytes_per_batch)))
+    pool = []
+    for j in range(pool_n):
+        s = make_scheduler(device, sd)
+        x, pairs = synth_batch(B, 1234 + rank * 1000 + j, device)          # shard = distinct seeds per rank
+        gp = GraphedPreview(s, x, list(pairs.unbind(0)), GUIDANCE, N_STEPS) if not args.eager else None
+        pool.append((s, x, pairs, gp))
+    torch.manual_seed(1000 + rank)
+
+    def one_step(k):
+        s, x, pairs, gp = pool[k % pool_n]
+        if gp is not None:
+            return gp.replay()
+        s.set_timesteps(N_STEPS, device=device)
+        return preview_from_pairs(s, x, pairs.unbind(0), GUIDANCE)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    for k in range(args.warmup):
+        one_step(k)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(torch.cuda.current_device()) as clk:
+        a.record()
+        for k in range(args.steps):
+            one_step(args.warmup + k)
+        b.record()
+        barrier()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    value = world * args.steps * B / (ms / 1e3)
+
+    if args.no_extras:
+        return {"metric": "sd15_8step_solver_previews_per_s", "value": round(value, 1), "unit": "previews/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4)}
+    # ---- e2e: host buffers -> scheduler API -> host, copies inside the timed region ---------------------------
+    s_e2e = make_scheduler(device, sd)
+    hx, hpairs = synth_batch(B, 99 + rank, None, pin=True)
+    dx = torch.empty_like(hx, device=device)
+    dpairs = [torch.empty_like(hpairs[0], device=device) for _ in range(2)]
+    hout = torch.empty_like(hx).pin_memory()
+    hrec = torch.empty(N_STEPS, B, 3).pin_memory()
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+
+    def e2e_step():
+        s_e2e.set_timesteps(N_STEPS, device=device)
+        evs = []
+        x = None
+        free = [None, None]
+        for i in range(N_STEPS):
+            with torch.cuda.stream(copy_stream):
+                if i == 0:
+                    dx.copy_(hx, non_blocking=True)
+                if free[i % 2] is not None:
+                    copy_stream.wait_event(free[i % 2])              # buffer consumed by step i-2
+                dpairs[i % 2].copy_(hpairs[i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            main.wait_event(ev)
+            x = s_e2e.step_cfg(dpairs[i % 2], s_e2e.timesteps[i], dx if i == 0 else x, GUIDANCE)[0]
+            done = torch.cuda.Event()
+            done.record(main)
+            free[i % 2] = done
+        hout.copy_(x, non_blocking=True)
+        hrec.copy_(s_e2e._traj.out["probs"], non_blocking=True)
+        main.synchronize()
+        return hout
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_val = world * e2e_steps * B / e2e_s
+    h2d = (hx.numel() + hpairs.numel()) * 4
+    d2h = (hout.numel() + hrec.numel()) * 4
+
+    out = {
+        "metric": "sd15_8step_solver_previews_per_s", "value": round(value, 1), "unit": "previews/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] solver path: SD1.5 latents 4x64x64 fp32, 8-step trailing, CFG=3, "
+                               "order_dim=4, scaler_dim=0, policy 2-256-256-33, batch 64/GPU, denoiser = resident "
+                               "synthetic CFG pairs", "batch_per_gpu": B, "solver_steps": N_STEPS,
+                   "l2_policy": f"inputs larger than L2: rotating pool of {pool_n} resident batches "
+                                f"({pool_n * bytes_per_batch >> 20} MiB)",
+                   "launch": "eager" if args.eager else "cuda_graph(8-step loop)", "sharding": f"dp{world} by prompt/seed, no collective"},
+        "e2e": {"value": round(e2e_val, 1), "unit": "previews/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": args.steps * (1 + N_STEPS * 2),   # per preview: 1 table + 8 x (sample + step) kernels
+        "clocks": clk.summary(),
+    }
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak, src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks \
+            else (6650.0, "fallback (B200_PROFILING.md)")
+        us, nbytes, nsets = time_step_kernel(B, 4, device)
+        out["roofline"] = {"bound": "hbm", "kernel": "step_kernel<f32,NH=4,CFG pair>", "batch": B,
+                           "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
+                           "frac": round(nbytes / us / 1e3 / peak, 4), "traffic": None, "us_per_launch": round(us, 3),
+                           "algorithmic_bytes": nbytes, "peak_source": src}
+        sweep = []
+        for Bs in (256, 1024, 4096):
+            us, nbytes, nsets = time_step_kernel(Bs, 4, device, iters=32)
+            sweep.append({"batch": Bs, "us_per_launch": round(us, 3), "achieved": round(nbytes / us / 1e3, 1),
+                          "frac": round(nbytes / us / 1e3 / peak, 4)})
+        out["roofline_sweep"] = sweep
+        out["cpu_baseline"] = cpu_baseline(B, budget_s=args.cpu_budget)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference) — the only place bench.py touches oracle/
+# ------------------------------------------------------------------------------------------------------------
+def _oracle_preview_fn(B):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import consolver_oracle as orc
+
+    sd = policy_state_dict(0)
+    sched = orc.OracleSDScheduler(sd, **{k: v for k, v in SD_CFG.items()})
+    x, pairs = synth_batch(B, 1234, None)
+
+    def run():
+        sched.set_timesteps(N_STEPS)
+        return orc.run_sd_preview(sched, x, list(pairs.unbind(0)), GUIDANCE)[0]
+
+    return run
+
+
+def cpu_baseline(B, budget_s=10.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    run = _oracle_preview_fn(B)
+    run()
+    t0 = time.perf_counter()
+    n = 0
+    best = float("inf")
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 2000):
+        t1 = time.perf_counter()
+        run()
+        best = min(best, time.perf_counter() - t1)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": round(n * B / dt, 1), "unit": "previews/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} full 8-step previews of batch {B} (same workload unit, ~{dt:.1f} s of CPU work), torch-CPU "
+                      f"oracle port of the reference scheduler incl. CFG combine, no debug prints",
+            "best_ms_per_step": round(best * 1e3, 2), "algorithmic_gbs": round(
+                TENSORS_PER_PREVIEW * B * 65536 / best / 1e9, 2)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = args.batch
+    run = _oracle_preview_fn(B)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    v = round(args.steps * B / dt, 1)
+    return {"impl": "reference", "metric": "sd15_8step_solver_previews_per_s", "value": v, "unit": "previews/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] solver path on the host CPU (oracle port of the reference "
+                                   "PPOScheduler, torch-CPU ops): SD1.5 latents 4x64x64 fp32, 8-step, CFG=3, batch 64",
+                       "batch_per_gpu": B, "solver_steps": N_STEPS},
+            "cpu_baseline": {"value": v, "unit": "previews/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} full 8-step previews of batch {B}"},
+            "e2e": {"value": v, "unit": "previews/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--eager", action="store_true", help="python-eager launches instead of the CUDA graph")
+    ap.add_argument("--cpu-budget", type=float, default=10.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / roofline / cpu_baseline (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50        # bounded sample: ~50 ms per step on a host CPU
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    out = run_ours(args, rank, world, device)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

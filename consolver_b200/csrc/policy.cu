@@ -1,14 +1,20 @@
-// policy.cu — the coefficient policy of the ConsistencySolver step as ONE kernel launch:
-//   MLP (in -> H -> H -> A*K, ReLU) + softmax per action dim + per-sample categorical draw
-//   argmax_k p[a,k]/q[b,a,k] + bin-value / probability gather + mask and multistep-coefficient assembly.
-// Reference: factor_net_ppo.py:137-168 (FM: edit_ppo/factor_net_ppo.py:149-180), scheduler_ppo.py:248-259,
-// :165-175.  The reference evaluates the MLP on B identical rows (scheduler_ppo.py:207-210); here every CTA
-// evaluates it once (75k MACs, weights stream from L2 with 128-bit loads, activations live in shared memory)
-// and then serves its slice of the batch.  This is matrix-VECTOR work: every weight is used once per CTA, so
-// it runs on the CUDA cores with warp-shuffle reductions — tensor cores / smem staging of the weights would
-// add a pass with no reuse.  Dot products accumulate in fp64 and round once, which puts the logits within
-// half an ulp of the exact value (any fp32 summation order the reference's BLAS may use is an ulp-level
-// perturbation of that).
+// policy.cu — the coefficient policy of the ConsistencySolver step.
+//
+//   table kernel   MLP (in -> H -> H -> A*K, ReLU) + softmax per action dim for R input rows, one CTA per row
+//   sample kernel  per-sample categorical draw argmax_k p[a,k]/q[b,a,k] + bin-value / probability gather + mask
+//                  and multistep-coefficient assembly, from a given probability table
+//   fused kernel   both in one launch (every CTA evaluates the MLP once, then serves its slice of the batch)
+//
+// Reference: factor_net_ppo.py:137-168 (FM: edit_ppo/factor_net_ppo.py:149-180), scheduler_ppo.py:248-259,:165-175.
+// The reference evaluates the MLP on B identical rows per step (scheduler_ppo.py:207-210).  The row depends only
+// on the timestep grid, so the schedulers evaluate all n rows of a trajectory in ONE table launch and each step
+// then runs only the sample kernel.
+//
+// The MLP is matrix-VECTOR work (75k MACs, every weight used once per row): it runs on the CUDA cores, one warp
+// per output row with 8 rows of 128-bit weight loads in flight per warp, L2 prefetch of the whole weight set at
+// kernel start, activations in shared memory, fp32 FMAs inside a lane and an fp64 butterfly across lanes.
+// Tensor cores / shared-memory staging of the weights would add a pass with no reuse.
+// The Exp(1) slab of a CTA is contiguous; it is prefetched into shared memory with cp.async while the MLP runs.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -19,12 +25,16 @@
 namespace consolver {
 
 constexpr int kPolicyThreads = 512;
+constexpr int kMaxSamplesPerCta = 512;
+constexpr int kQSlabBytes = 96 * 1024;
 
 struct PolicyParams {
   const float *w1, *b1, *w2, *b2, *w3, *b3, *action_values;
   float x0, x1, x_div, temp;
+  const float* x_rows;      // table kernel: [R,2] rows (overrides x0,x1)
   const float* feat;
   int n_feat;
+  const float* probs_in;    // sample kernel: [A,K] table
   const float* q;
   const long long* idx_in;
   int B, H, A, K, order_dim, scaler_dim, n_hist;
@@ -32,6 +42,7 @@ struct PolicyParams {
   long long* idx;
   float *actions, *act_probs, *act_logp, *masks, *coef;
   int samples_per_cta;
+  int stage_q;              // 1: the CTA's q slab fits the shared-memory budget
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -44,18 +55,33 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// y[r] = act(b[r] + W[r,:] . x) for r in [0,R): one warp per row, ROWS rows in flight per warp.
+// pull `bytes` starting at p into L2, one 128-byte line per thread per round
+__device__ __forceinline__ void prefetch_range_l2(const void* p, size_t bytes) {
+  const char* c = static_cast<const char*>(p);
+  for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128) prefetch_l2(c + o);
+}
+
+// y[r] = act(b[r] + W[r,:] . x) for r in [0,R): one warp per row, ROWS rows of loads in flight per warp.
 template <bool RELU>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias,
                                             const float* x_s, float* y_s, int R, int C) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const bool vec = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15u) == 0);
-  constexpr int ROWS = 4;
+  constexpr int ROWS = 8;
   for (int r0 = warp * ROWS; r0 < R; r0 += nwarp * ROWS) {
-    double acc[ROWS];
+    float acc[ROWS];
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) acc[i] = 0.0;
+    for (int i = 0; i < ROWS; ++i) acc[i] = 0.f;
     if (vec) {
       const int C4 = C >> 2;
       for (int c = lane; c < C4; c += 32) {
@@ -67,22 +93,22 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
         const float4 xv = reinterpret_cast<const float4*>(x_s)[c];
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
-          acc[i] = fma((double)w[i].x, (double)xv.x, acc[i]);
-          acc[i] = fma((double)w[i].y, (double)xv.y, acc[i]);
-          acc[i] = fma((double)w[i].z, (double)xv.z, acc[i]);
-          acc[i] = fma((double)w[i].w, (double)xv.w, acc[i]);
+          acc[i] = fmaf(w[i].x, xv.x, acc[i]);
+          acc[i] = fmaf(w[i].y, xv.y, acc[i]);
+          acc[i] = fmaf(w[i].z, xv.z, acc[i]);
+          acc[i] = fmaf(w[i].w, xv.w, acc[i]);
         }
       }
     } else {
       for (int c = lane; c < C; c += 32) {
 #pragma unroll
         for (int i = 0; i < ROWS; ++i)
-          if (r0 + i < R) acc[i] = fma((double)__ldg(W + (size_t)(r0 + i) * C + c), (double)x_s[c], acc[i]);
+          if (r0 + i < R) acc[i] = fmaf(__ldg(W + (size_t)(r0 + i) * C + c), x_s[c], acc[i]);
       }
     }
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
-      const double s = warp_sum(acc[i]);
+      const double s = warp_sum((double)acc[i]);
       if (lane == 0 && r0 + i < R) {
         float v = (float)(s + (double)__ldg(bias + r0 + i));
         y_s[r0 + i] = RELU ? fmaxf(v, 0.f) : v;
@@ -129,116 +155,241 @@ __device__ __forceinline__ void mlp_softmax(const PolicyParams& p, int in_dim, c
   __syncthreads();
 }
 
-// draw / gather / coefficient assembly for sample b, probabilities in p_s
-__device__ __forceinline__ void serve_sample(const PolicyParams& p, int b, const float* p_s) {
+// Start the asynchronous copy of this CTA's contiguous Exp(1) slab q[b_begin*A*K ...] into shared memory.
+__device__ __forceinline__ void stage_q_begin(const PolicyParams& p, int b_begin, int nb, float* q_s) {
+  if (!p.q || !p.stage_q) return;
+  const size_t n = (size_t)nb * p.A * p.K;
+  const float* src = p.q + (size_t)b_begin * p.A * p.K;
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    const size_t n4 = n >> 2;
+    for (size_t i = threadIdx.x; i < n4; i += blockDim.x) cp_async16(q_s + 4 * i, src + 4 * i);
+    for (size_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) cp_async4(q_s + i, src + i);
+  } else {
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) cp_async4(q_s + i, src + i);
+  }
+  cp_async_commit();
+}
+
+// draw / gather for every (sample, action-dim) pair of the CTA, then coefficient assembly per sample.
+// p_s: probability table [A,K] in shared memory; q_s: staged Exp(1) slab (or unused); act_s: [nb*A] scratch.
+__device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin, int nb, const float* p_s,
+                                             const float* q_s, float* act_s) {
   const int A = p.A, K = p.K, od = p.order_dim;
-  float act[CONSOLVER_MAX_ORDER + 4];  // first order_dim+1 action values are all the coefficients need
-  for (int a = 0; a < A; ++a) {
+  if (p.q && p.stage_q) cp_async_wait_all();
+  __syncthreads();
+  for (int pr = threadIdx.x; pr < nb * A; pr += blockDim.x) {
+    const int a = pr % A;
+    const size_t o = (size_t)b_begin * A + pr;
     int best = 0;
     if (p.q) {
-      const float* qr = p.q + ((size_t)b * A + a) * K;
+      const float* pa = p_s + a * K;
       float bv = -INFINITY;
-      for (int k = 0; k < K; ++k) {
-        const float r = __fdiv_rn(p_s[a * K + k], __ldg(qr + k));   // p / q, argmax, first index on ties
-        if (k == 0 || r > bv) { bv = r; best = k; }
+      if (p.stage_q) {
+        const float* qr = q_s + (size_t)pr * K;
+        for (int k = 0; k < K; ++k) {
+          const float r = __fdiv_rn(pa[k], qr[k]);                 // p / q, argmax, first index on ties
+          if (k == 0 || r > bv) { bv = r; best = k; }
+        }
+      } else {
+        const float* qr = p.q + o * K;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+          const float r = __fdiv_rn(pa[k], __ldg(qr + k));
+          if (k == 0 || r > bv) { bv = r; best = k; }
+        }
       }
     } else {
-      best = (int)p.idx_in[(size_t)b * A + a];
+      best = (int)p.idx_in[o];
       best = best < 0 ? 0 : (best >= K ? K - 1 : best);
     }
     const float av = __ldg(p.action_values + a * K + best);
-    const float pr = p_s[a * K + best];
-    const size_t o = (size_t)b * A + a;
+    const float prb = p_s[a * K + best];
+    act_s[pr] = av;
     if (p.idx) p.idx[o] = best;
     if (p.actions) p.actions[o] = av;
-    if (p.act_probs) p.act_probs[o] = pr;
-    if (p.act_logp) p.act_logp[o] = logf(__fadd_rn(pr, 1e-9f));
+    if (p.act_probs) p.act_probs[o] = prb;
+    if (p.act_logp) p.act_logp[o] = logf(__fadd_rn(prb, 1e-9f));
     if (p.masks) p.masks[o] = (a >= p.n_hist - 1 && a < od - 1) ? 0.f : 1.f;   // scheduler_ppo.py:248-249
-    if (a < od + 1) act[a] = av;
   }
+  __syncthreads();
   // set_default_coefficients (scheduler_ppo.py:165-175): c0 = a0 + 1, c_{n-1} = 1 - sum(c_0..c_{n-2})
-  float* c = p.coef + (size_t)b * (od + 2);
   const int n = p.n_hist;
-  float c0 = __fadd_rn(act[0], 1.f);
-  float run = c0;
-  for (int i = 0; i < od; ++i) {
-    float v = 0.f;
-    if (n == 1) {
-      v = (i == 0) ? 1.f : 0.f;                 // the step kernel bypasses the coefficient when n_hist == 1
-    } else if (i == 0) {
-      v = c0;
-    } else if (i < n - 1) {
-      v = act[i];
-      run = __fadd_rn(run, v);
-    } else if (i == n - 1) {
-      v = __fsub_rn(1.f, run);
+  for (int bl = threadIdx.x; bl < nb; bl += blockDim.x) {
+    const float* act = act_s + (size_t)bl * A;
+    float* c = p.coef + (size_t)(b_begin + bl) * (od + 2);
+    const float c0 = __fadd_rn(act[0], 1.f);
+    float run = c0;
+    for (int i = 0; i < od; ++i) {
+      float v = 0.f;
+      if (n == 1) {
+        v = (i == 0) ? 1.f : 0.f;               // the step kernel bypasses the coefficient when n_hist == 1
+      } else if (i == 0) {
+        v = c0;
+      } else if (i < n - 1) {
+        v = act[i];
+        run = __fadd_rn(run, v);
+      } else if (i == n - 1) {
+        v = __fsub_rn(1.f, run);
+      }
+      c[i] = v;
     }
-    c[i] = v;
+    c[od] = p.scaler_dim >= 1 ? __fadd_rn(act[od - 1], 1.f) : 1.f;
+    c[od + 1] = p.scaler_dim >= 2 ? __fadd_rn(act[od], 1.f) : 1.f;
   }
-  c[od] = p.scaler_dim >= 1 ? __fadd_rn(act[od - 1], 1.f) : 1.f;
-  c[od + 1] = p.scaler_dim >= 2 ? __fadd_rn(act[od], 1.f) : 1.f;
 }
 
+struct Smem {
+  float *x, *h1, *h2, *lg, *p, *act, *q;
+};
+__host__ __device__ __forceinline__ size_t r4(size_t n) { return (n + 3) & ~(size_t)3; }  // 16-byte granules
+__device__ __forceinline__ Smem carve(float* base, int H, int AK, int spc, int A) {
+  Smem s;
+  s.x = base;
+  s.h1 = s.x + CONSOLVER_MAX_IN;
+  s.h2 = s.h1 + r4(H);
+  s.lg = s.h2 + r4(H);
+  s.p = s.lg + r4(AK);
+  s.act = s.p + r4(AK);
+  s.q = s.act + r4((size_t)spc * A);
+  return s;
+}
+static size_t smem_floats(int H, int AK, int spc, int A, size_t q_floats) {
+  return CONSOLVER_MAX_IN + 2 * r4(H) + 2 * r4(AK) + r4((size_t)spc * A) + q_floats;
+}
+
+// ---- fused: MLP + sampling --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPolicyThreads) policy_kernel(const PolicyParams p) {
-  // let a dependent (PDL) step kernel start its bulk loads right away
-  grid_launch_dependents();
-  extern __shared__ float smem[];
-  const int H = p.H, AK = p.A * p.K;
-  float* x_s = smem;                       // [CONSOLVER_MAX_IN]
-  float* h1_s = x_s + CONSOLVER_MAX_IN;    // [H]
-  float* h2_s = h1_s + H;                  // [H]
-  float* lg_s = h2_s + H;                  // [AK]
-  float* p_s = lg_s + AK;                  // [AK]
+  grid_launch_dependents();   // a dependent (PDL) step kernel may start its bulk loads right away
+  extern __shared__ __align__(16) float smem[];
+  const int AK = p.A * p.K;
+  const Smem s = carve(smem, p.H, AK, p.samples_per_cta, p.A);
   const int in_dim = 2 + p.n_feat;
   const int b_begin = blockIdx.x * p.samples_per_cta;
-  const int b_end = min(p.B, b_begin + p.samples_per_cta);
+  const int nb = min(p.B - b_begin, p.samples_per_cta);
+
+  prefetch_range_l2(p.w2, (size_t)p.H * p.H * sizeof(float));
+  prefetch_range_l2(p.w3, (size_t)AK * p.H * sizeof(float));
+  stage_q_begin(p, b_begin, nb, s.q);
 
   if (p.feat == nullptr) {
     if (threadIdx.x == 0) {
-      x_s[0] = __fdiv_rn(p.x0, p.x_div);   // normalize_input: x.float() / 999.0 (identity for FM)
-      x_s[1] = __fdiv_rn(p.x1, p.x_div);
+      s.x[0] = __fdiv_rn(p.x0, p.x_div);   // normalize_input: x.float() / 999.0 (identity for FM)
+      s.x[1] = __fdiv_rn(p.x1, p.x_div);
     }
     __syncthreads();
-    mlp_softmax(p, in_dim, x_s, h1_s, h2_s, lg_s, p_s);
+    mlp_softmax(p, in_dim, s.x, s.h1, s.h2, s.lg, s.p);
     if (blockIdx.x == 0 && p.probs_table)
-      for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[i] = p_s[i];
-    for (int b = b_begin + threadIdx.x; b < b_end; b += blockDim.x) serve_sample(p, b, p_s);
+      for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[i] = s.p[i];
+    sample_phase(p, b_begin, nb, s.p, s.q, s.act);
   } else {
-    // use_conv: per-sample features -> per-sample MLP (one sample at a time per CTA)
-    for (int b = b_begin; b < b_end; ++b) {
+    // use_conv: per-sample features -> per-sample MLP (samples_per_cta is small here)
+    for (int bl = 0; bl < nb; ++bl) {
+      const int b = b_begin + bl;
       if (threadIdx.x == 0) {
-        x_s[0] = __fdiv_rn(p.x0, p.x_div);
-        x_s[1] = __fdiv_rn(p.x1, p.x_div);
+        s.x[0] = __fdiv_rn(p.x0, p.x_div);
+        s.x[1] = __fdiv_rn(p.x1, p.x_div);
       }
-      if (threadIdx.x < p.n_feat) x_s[2 + threadIdx.x] = __ldg(p.feat + (size_t)b * p.n_feat + threadIdx.x);
+      if (threadIdx.x < p.n_feat) s.x[2 + threadIdx.x] = __ldg(p.feat + (size_t)b * p.n_feat + threadIdx.x);
       __syncthreads();
-      mlp_softmax(p, in_dim, x_s, h1_s, h2_s, lg_s, p_s);
-      if (threadIdx.x == 0) serve_sample(p, b, p_s);
+      mlp_softmax(p, in_dim, s.x, s.h1, s.h2, s.lg, s.p);
+      PolicyParams one = p;
+      one.stage_q = 0;
+      sample_phase(one, b, 1, s.p, s.q, s.act);
       __syncthreads();
     }
   }
 }
 
-static int launch_policy(const PolicyParams& pp, cudaStream_t stream) {
-  PolicyParams p = pp;
-  if (!p.w1 || !p.b1 || !p.w2 || !p.b2 || !p.w3 || !p.b3 || !p.action_values || !p.coef) return CONSOLVER_ERR_NULL;
-  if ((p.q == nullptr) == (p.idx_in == nullptr)) return CONSOLVER_ERR_NULL;  // exactly one of them
-  if (p.B <= 0 || p.H <= 0 || p.H > CONSOLVER_MAX_HIDDEN || p.A <= 0 || p.K <= 0 ||
-      (long long)p.A * p.K > CONSOLVER_MAX_LOGITS)
-    return CONSOLVER_ERR_SIZE;
+// ---- table only: one CTA per input row -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPolicyThreads) policy_table_kernel(const PolicyParams p) {
+  grid_launch_dependents();
+  extern __shared__ __align__(16) float smem[];
+  const int AK = p.A * p.K;
+  const Smem s = carve(smem, p.H, AK, 0, p.A);
+  prefetch_range_l2(p.w2, (size_t)p.H * p.H * sizeof(float));
+  prefetch_range_l2(p.w3, (size_t)AK * p.H * sizeof(float));
+  if (threadIdx.x < 2) s.x[threadIdx.x] = __fdiv_rn(__ldg(p.x_rows + 2 * blockIdx.x + threadIdx.x), p.x_div);
+  __syncthreads();
+  mlp_softmax(p, 2, s.x, s.h1, s.h2, s.lg, s.p);
+  for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[(size_t)blockIdx.x * AK + i] = s.p[i];
+}
+
+// ---- sampling only, from a given table -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPolicyThreads) policy_sample_kernel(const PolicyParams p) {
+  grid_launch_dependents();
+  extern __shared__ __align__(16) float smem[];
+  const int AK = p.A * p.K;
+  const Smem s = carve(smem, 0, AK, p.samples_per_cta, p.A);
+  const int b_begin = blockIdx.x * p.samples_per_cta;
+  const int nb = min(p.B - b_begin, p.samples_per_cta);
+  stage_q_begin(p, b_begin, nb, s.q);
+  for (int i = threadIdx.x; i < AK; i += blockDim.x) s.p[i] = __ldg(p.probs_in + i);
+  if (blockIdx.x == 0 && p.probs_table && p.probs_table != p.probs_in)
+    for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[i] = __ldg(p.probs_in + i);
+  sample_phase(p, b_begin, nb, s.p, s.q, s.act);
+}
+
+enum : int { kLaunchFused = 0, kLaunchTable = 1, kLaunchSample = 2 };
+
+static int check_dims(const PolicyParams& p) {
+  if (p.B <= 0 || p.A <= 0 || p.K <= 0 || (long long)p.A * p.K > CONSOLVER_MAX_LOGITS) return CONSOLVER_ERR_SIZE;
   if (p.order_dim < 2 || p.order_dim > CONSOLVER_MAX_ORDER || p.scaler_dim < 0 || p.scaler_dim > 2 ||
       p.n_hist < 1 || p.n_hist > p.order_dim || p.A < p.order_dim + p.scaler_dim - 1)
     return CONSOLVER_ERR_SIZE;
+  return 0;
+}
+
+static int launch_policy(const PolicyParams& pp, int mode, int rows, cudaStream_t stream) {
+  PolicyParams p = pp;
+  const bool need_mlp = mode != kLaunchSample;
+  if (need_mlp) {
+    if (!p.w1 || !p.b1 || !p.w2 || !p.b2 || !p.w3 || !p.b3) return CONSOLVER_ERR_NULL;
+    if (p.H <= 0 || p.H > CONSOLVER_MAX_HIDDEN) return CONSOLVER_ERR_SIZE;
+    if (!(p.temp > 0.f) || !(p.x_div != 0.f)) return CONSOLVER_ERR_SIZE;
+  }
+  if (mode == kLaunchTable) {
+    if (!p.x_rows || !p.probs_table) return CONSOLVER_ERR_NULL;
+    if (rows <= 0 || p.A <= 0 || p.K <= 0 || (long long)p.A * p.K > CONSOLVER_MAX_LOGITS) return CONSOLVER_ERR_SIZE;
+    const size_t smem = smem_floats(p.H, p.A * p.K, 0, p.A, 0) * sizeof(float);
+    policy_table_kernel<<<rows, kPolicyThreads, smem, stream>>>(p);
+    return (int)cudaGetLastError();
+  }
+  if (!p.action_values || !p.coef) return CONSOLVER_ERR_NULL;
+  if (mode == kLaunchSample && !p.probs_in) return CONSOLVER_ERR_NULL;
+  if ((p.q == nullptr) == (p.idx_in == nullptr)) return CONSOLVER_ERR_NULL;  // exactly one of them
+  int rc = check_dims(p);
+  if (rc) return rc;
   if (p.n_feat < 0 || 2 + p.n_feat > CONSOLVER_MAX_IN || (p.n_feat > 0 && !p.feat)) return CONSOLVER_ERR_SIZE;
   if (p.n_feat == 0) p.feat = nullptr;
-  if (!(p.temp > 0.f) || !(p.x_div != 0.f)) return CONSOLVER_ERR_SIZE;
-  // shared row: 512 samples per CTA (every CTA re-derives the 33-float table from L2-resident weights);
-  // per-sample MLP: spread the batch over the SMs
-  p.samples_per_cta = p.feat ? (p.B + 147) / 148 : kPolicyThreads;
-  if (p.samples_per_cta < 1) p.samples_per_cta = 1;
-  const int grid = (p.B + p.samples_per_cta - 1) / p.samples_per_cta;
-  const size_t smem = (size_t)(CONSOLVER_MAX_IN + 2 * p.H + 2 * p.A * p.K) * sizeof(float);
-  policy_kernel<<<grid, kPolicyThreads, smem, stream>>>(p);
+
+  const int AK = p.A * p.K;
+  int spc;
+  if (p.feat) {
+    spc = (p.B + 147) / 148;                       // per-sample MLP: spread the batch over the SMs
+  } else {
+    spc = kQSlabBytes / (AK * (int)sizeof(float));
+    // sampling-only launches carry no per-CTA MLP cost: use more, smaller CTAs
+    if (mode == kLaunchSample) spc = min(spc, max(64, (p.B + 147) / 148));
+    spc = max(1, min(spc, kMaxSamplesPerCta));
+    spc = min(spc, p.B);
+    if (spc >= 4) spc &= ~3;                       // keeps every CTA's q slab 16-byte aligned
+  }
+  p.samples_per_cta = spc;
+  p.stage_q = (p.q != nullptr && !p.feat && (size_t)spc * AK * sizeof(float) <= (size_t)kQSlabBytes) ? 1 : 0;
+  const size_t q_floats = p.stage_q ? (size_t)spc * AK : 0;
+  const int grid = (p.B + spc - 1) / spc;
+  const int H = mode == kLaunchSample ? 0 : p.H;
+  const size_t smem = smem_floats(H, AK, spc, p.A, q_floats) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(policy_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  if (mode == kLaunchSample)
+    policy_sample_kernel<<<grid, kPolicyThreads, smem, stream>>>(p);
+  else
+    policy_kernel<<<grid, kPolicyThreads, smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -274,11 +425,36 @@ extern "C" int consolver_policy_f32(const float* w1, const float* b1, const floa
   p.B = B; p.H = H; p.A = A; p.K = K; p.order_dim = order_dim; p.scaler_dim = scaler_dim; p.n_hist = n_hist;
   p.probs_table = probs_table; p.idx = reinterpret_cast<long long*>(idx); p.actions = actions;
   p.act_probs = act_probs; p.act_logp = act_logp; p.masks = masks; p.coef = coef;
-  return launch_policy(p, static_cast<cudaStream_t>(stream));
+  return launch_policy(p, kLaunchFused, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int consolver_policy_table_f32(const float* w1, const float* b1, const float* w2, const float* b2,
+                                          const float* w3, const float* b3, const float* x_rows, int rows,
+                                          float x_div, float temp, int H, int A, int K, float* probs_tables,
+                                          consolver_stream_t stream) {
+  PolicyParams p = {};
+  p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
+  p.x_rows = x_rows; p.x_div = x_div; p.temp = temp; p.H = H; p.A = A; p.K = K; p.probs_table = probs_tables;
+  return launch_policy(p, kLaunchTable, rows, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int consolver_policy_sample_f32(const float* probs_in, const float* action_values, const float* q,
+                                           const int64_t* idx_in, int B, int A, int K, int order_dim,
+                                           int scaler_dim, int n_hist, int64_t* idx, float* actions,
+                                           float* act_probs, float* act_logp, float* masks, float* coef,
+                                           consolver_stream_t stream) {
+  PolicyParams p = {};
+  p.probs_in = probs_in; p.action_values = action_values; p.q = q;
+  p.idx_in = reinterpret_cast<const long long*>(idx_in);
+  p.B = B; p.A = A; p.K = K; p.order_dim = order_dim; p.scaler_dim = scaler_dim; p.n_hist = n_hist;
+  p.idx = reinterpret_cast<long long*>(idx); p.actions = actions; p.act_probs = act_probs; p.act_logp = act_logp;
+  p.masks = masks; p.coef = coef;
+  return launch_policy(p, kLaunchSample, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, const float* w2, const float* b2,
                                             const float* w3, const float* b3, const float* action_values,
+                                            const float* probs_in,
                                             float x0, float x1, float x_div, float temp,
                                             const float* q, const int64_t* idx_in,
                                             int H, int A, int K, int scaler_dim,
@@ -289,9 +465,15 @@ extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, co
                                             void* x_out, int order_dim, float sa_t, float sb_t, float sa_p,
                                             float sb_p, int flags, int B, int64_t n_per_sample,
                                             consolver_stream_t stream) {
-  int rc = consolver_policy_f32(w1, b1, w2, b2, w3, b3, action_values, x0, x1, x_div, temp, nullptr, 0, q, idx_in,
-                                B, H, A, K, order_dim, scaler_dim, n_hist, probs_table, idx, actions, act_probs,
-                                act_logp, masks, coef, stream);
+  int rc;
+  if (probs_in) {
+    rc = consolver_policy_sample_f32(probs_in, action_values, q, idx_in, B, A, K, order_dim, scaler_dim, n_hist,
+                                     idx, actions, act_probs, act_logp, masks, coef, stream);
+  } else {
+    rc = consolver_policy_f32(w1, b1, w2, b2, w3, b3, action_values, x0, x1, x_div, temp, nullptr, 0, q, idx_in,
+                              B, H, A, K, order_dim, scaler_dim, n_hist, probs_table, idx, actions, act_probs,
+                              act_logp, masks, coef, stream);
+  }
   if (rc) return rc;
   int f = flags;
   if (scaler_dim >= 1) f |= CONSOLVER_FLAG_EFF_SCALE;

@@ -92,9 +92,16 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
         const float x0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.k1, eff)), p.k0);          // :323
         out = __fadd_rn(__fmul_rn(p.k2, x0), __fmul_rn(p.k3, eff));                     // :329-330
       } else {
-        float prod = __fmul_rn(p.k0, eff);                            // edit_ppo/scheduler_fmppo.py:429
-        // 0-d fp32 `dt` times a 16-bit tensor is rounded to that dtype (first step, no scalers)
-        if (Elem<T>::k16 && nh == 1 && !eff_scale) prod = Elem<T>::to_f(Elem<T>::from_f(prod));
+        // edit_ppo/scheduler_fmppo.py:429.  First step without scalers: `dt * model_output` is a 0-d fp32
+        // tensor times a 16-bit tensor, which torch evaluates in the 16-bit dtype — dt is rounded to it, the
+        // product is formed in fp32 and rounded to it — before the fp32 add with the upcast sample.
+        float prod;
+        if (Elem<T>::k16 && nh == 1 && !eff_scale) {
+          const float dt16 = Elem<T>::to_f(Elem<T>::from_f(p.k0));
+          prod = Elem<T>::to_f(Elem<T>::from_f(__fmul_rn(dt16, eff)));
+        } else {
+          prod = __fmul_rn(p.k0, eff);
+        }
         out = __fadd_rn(xs, prod);
       }
       r_out.set(i, out);

@@ -1,0 +1,98 @@
+"""Caller side of the hot path: the denoise loop that drives the scheduler (reference: denoise_ppo.py:6-120 for
+SD1.5; edit_ppo/denoise_diffusion.py:101-157 for FLUX).  The denoiser itself (U-Net / DiT) is any callable and is
+NOT the product; what this module changes relative to the reference loop:
+
+  * CFG is fused into the scheduler step (`step_cfg`), so the three elementwise kernels of
+    denoise_ppo.py:97-100 disappear;
+  * the rollout record (conds / probs / actions / masks for steps i > 0, denoise_ppo.py:105-118) is a set of
+    views into the scheduler's per-trajectory buffers — no per-step unsqueeze, no final cat, and the
+    `conds['epsilon']` stack (hundreds of MiB, dead unless use_conv) is never built;
+  * `GraphedPreview` captures the whole n-step solver loop (with a graph-safe RNG draw) in one CUDA graph.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Sequence, Tuple
+
+import torch
+
+from .scheduler_ppo import PPOScheduler
+
+
+def denoise_loop(scheduler: PPOScheduler, denoiser: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor],
+                 noise: torch.Tensor, cfg: float = 3.0, num_inference_steps: int = 50,
+                 record: bool = True) -> Tuple[torch.Tensor, Optional[Dict[str, torch.Tensor]]]:
+    """SD-style sampling loop with classifier-free guidance (denoise_ppo.py:52-120).
+
+    `denoiser(latent_model_input [2B,...], t, i)` returns the noise prediction for the CFG-doubled batch
+    (unconditional half first) — or for the plain batch when cfg <= 1.  Returns (latents, record) where record
+    has the reference's layout: x [B,n-1,2], probs / actions / masks [B,n-1,A]."""
+    latents = noise.clone()
+    scheduler.set_timesteps(num_inference_steps, device=noise.device)
+    do_cfg = cfg > 1.0
+    for i, t in enumerate(scheduler.timesteps):
+        model_in = torch.cat([latents] * 2) if do_cfg else latents
+        model_in = scheduler.scale_model_input(model_in, t)
+        pred = denoiser(model_in, t, i)
+        if do_cfg:
+            latents = scheduler.step_cfg(pred, t, latents, cfg)[0]
+        else:
+            latents = scheduler.step(pred, t, latents, return_dict=False)[0]
+    return latents, (scheduler.trajectory() if record and num_inference_steps > 1 else None)
+
+
+def preview_from_pairs(scheduler: PPOScheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: float,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Solver-only preview: the denoiser is replaced by given per-step CFG pairs ([2B,...] each) — BASELINE
+    config 0/2's 'random eps stand-in for the U-Net'.  `set_timesteps` must have been called."""
+    x = x_T
+    n = len(pairs)
+    for i in range(n):
+        x = scheduler.step_cfg(pairs[i], scheduler.timesteps[i], x, guidance, out=out if i == n - 1 else None)[0]
+    return x
+
+
+class GraphedPreview:
+    """One CUDA graph for a whole n-step solver-only preview over fixed device buffers.
+
+    The graph holds, per step: the Exp(1) draw (torch's graph-safe Philox: every replay advances the default
+    generator exactly as eager execution would), the policy kernel and the fused step kernel — 3 launches per
+    step, no host work at replay.  Inputs are read from the buffers given at capture time (refill them, or build
+    one GraphedPreview per resident batch)."""
+
+    def __init__(self, scheduler: PPOScheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: float,
+                 num_inference_steps: int):
+        self.scheduler = scheduler
+        self.x_T, self.pairs, self.guidance, self.n = x_T, list(pairs), guidance, num_inference_steps
+        self.out = torch.empty_like(x_T)
+        dev = x_T.device
+        scheduler.set_timesteps(num_inference_steps, device=dev)
+        # warm-up on a side stream (allocates the trajectory buffers and the ring outside the capture)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        self._rewind()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
+        self._rewind()
+
+    def _rewind(self):
+        sch = self.scheduler
+        sch._hist = []
+        sch._step_count = 0
+        if sch._traj is not None:
+            sch._traj.count = 0
+            sch._traj.table_pass = -1      # the capture (and every replay) re-evaluates the probability tables
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out
+
+    def record(self):
+        """rollout record of the last replay (views; valid until the next replay)"""
+        tr = self.scheduler._traj
+        tr.count = self.n
+        rec = self.scheduler.trajectory()
+        return rec

@@ -138,6 +138,18 @@ class FactorNetPPO(nn.Module):
         _lib.check(rc, "consolver_policy_f32")
         return out
 
+    def policy_tables(self, x_rows: torch.Tensor, out: torch.Tensor, stream=None):
+        """Probability tables for many input rows in one launch: x_rows [R,2] fp32 (device) -> out [R,A,K]."""
+        lib = _lib.load()
+        w = self.kernel_weights()
+        if stream is None:
+            stream = torch.cuda.current_stream(x_rows.device).cuda_stream
+        rc = lib.consolver_policy_table_f32(*w[:6], x_rows.data_ptr(), x_rows.shape[0], self.x_div, self.temperature,
+                                            self.hidden_dim, self.action_dims, self.num_actions, out.data_ptr(),
+                                            stream)
+        _lib.check(rc, "consolver_policy_table_f32")
+        return out
+
     # ---- PPO-update side: torch autograd (factor_net_ppo.py:137-157, :170-184) ----------------------------------
     def forward_(self, x_dict):
         x = self.normalize_input(x_dict["x"])

@@ -40,8 +40,10 @@ class _FMTrajectory:
         rows = [[float(s[i]), float(s[i + 1])] for i in range(len(s) - 1)]
         host = torch.tensor(rows, dtype=dtype)          # (sigma, sigma_next) rounded through the model dtype (:383)
         self.condx = host.to(device, non_blocking=True)
+        self.condx_f32 = host.float().to(device, non_blocking=True)
         self.condx_host = host.float().numpy()
         self.count = 0
+        self.table_pass = -1
 
 
 class FMPPOScheduler(SchedulerMixin, ConfigMixin):
@@ -303,13 +305,16 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         x_out = torch.empty(sample.shape, device=e0.device, dtype=e0.dtype)
         lib = _lib.load()
         stream = torch.cuda.current_stream(e0.device).cuda_stream
-        rc = lib.consolver_policy_f32(
-            *fn.kernel_weights(), x0, x1, fn.x_div, fn.temperature, None, 0, q_ptr, idx_ptr,
-            B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
-            o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
-            o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(),
-            stream)
-        _lib.check(rc, "consolver_policy_f32")
+        # all n (sigma, sigma_next) rows of the schedule go through the MLP in one launch per pass
+        if tr.table_pass != tr.count // tr.n:
+            fn.policy_tables(tr.condx_f32, o["probs_table"], stream)
+            tr.table_pass = tr.count // tr.n
+        w = fn.kernel_weights()
+        rc = lib.consolver_policy_sample_f32(
+            o["probs_table"][si].data_ptr(), w[6], q_ptr, idx_ptr, B, fn.action_dims, fn.num_actions, od,
+            cfg.scaler_dim, n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
+            o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
+        _lib.check(rc, "consolver_policy_sample_f32")
         flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0) \
             | (_lib.FLAG_PDL if self.use_pdl else 0)
         rc = lib.consolver_step_fm(
@@ -351,8 +356,8 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
     def last_policy(self):
         tr = self._traj
         i = (tr.count - 1) % tr.n
-        return dict(probs_table=tr.out["probs_table"][i], idx=tr.out["idx"][i], coef=tr.out["coef"][i],
-                    logp=tr.out["logp"][i])
+        return dict(probs_table=tr.out["probs_table"][(self._step_index - 1) % tr.n], idx=tr.out["idx"][i],
+                    coef=tr.out["coef"][i], logp=tr.out["logp"][i])
 
     def scale_noise(self, sample: torch.Tensor, timestep, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward process of flow matching (edit_ppo/scheduler_fmppo.py:457-484); not on the hot path."""

@@ -64,9 +64,12 @@ class _Trajectory:
         # conds['x'] rows for the whole grid: one H2D copy per trajectory instead of one per step
         ts = sched._timesteps_host
         rows = [[float(t), float(t - sched._stride)] for t in ts]
-        self.condx = torch.tensor(rows, dtype=dtype).to(device, non_blocking=True)
-        self.condx_host = torch.tensor(rows, dtype=dtype).float().numpy()
+        host = torch.tensor(rows, dtype=dtype)
+        self.condx = host.to(device, non_blocking=True)
+        self.condx_f32 = host.float().to(device, non_blocking=True)   # policy-table kernel input [n,2]
+        self.condx_host = host.float().numpy()
         self.count = 0
+        self.table_pass = -1   # trajectory pass (count // n) whose probability tables are in out['probs_table']
 
     def slot(self, i):
         if self.ring is None:
@@ -254,6 +257,13 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         sa_p, sb_p = float(self._sqrt_abar[pi]), float(self._sqrt_1m_abar[pi])
 
         o = tr.out
+        # The policy input row depends only on the timestep grid: evaluate the MLP + softmax for ALL n rows in one
+        # launch at the first step of a pass; every step then only samples from its row of the table.
+        on_grid = t == self._timesteps_host[i]
+        if on_grid and tr.table_pass != tr.count // tr.n:
+            fn.policy_tables(tr.condx_f32, o["probs_table"])
+            tr.table_pass = tr.count // tr.n
+        probs_in = o["probs_table"][i].data_ptr() if on_grid else None
         q_ptr, idx_ptr = tr.q.data_ptr(), None
         if self.replay is None:
             tr.q.exponential_(1)                     # the draw torch.multinomial makes (factor_net_ppo.py:161)
@@ -270,7 +280,7 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         w = fn.kernel_weights()
         lib = _lib.load()
         rc = lib.consolver_sd_policy_and_step(
-            *w, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr,
+            *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr,
             fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
             o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
             o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(),

@@ -142,12 +142,36 @@ CONSOLVER_API int consolver_step_fm(int dtype, int x_dtype, const void* e0, void
                       int B, int64_t n_per_sample, consolver_stream_t stream);
 
 /*
- * One call per scheduler step for the fused-CFG SD path: consolver_policy_f32 followed by consolver_step_sd on
- * the same stream (saves one host crossing; the two kernels are linked by programmatic dependent launch when
- * CONSOLVER_FLAG_PDL is set).  Arguments as in the two functions above.
+ * Probability tables only: MLP + softmax (factor_net_ppo.py:137-157) for `rows` input rows in one launch (one CTA
+ * per row).  The schedulers call it once per trajectory with the (t, prev_t) / (sigma, sigma_next) rows of the
+ * whole timestep grid — the policy input does not depend on the sample — and then run only
+ * consolver_policy_sample_f32 per step.
+ *   x_rows [rows,2] fp32 (device)      probs_tables [rows,A,K] (device, out)
+ */
+CONSOLVER_API int consolver_policy_table_f32(const float* w1, const float* b1, const float* w2, const float* b2,
+                                             const float* w3, const float* b3, const float* x_rows, int rows,
+                                             float x_div, float temp, int H, int A, int K, float* probs_tables,
+                                             consolver_stream_t stream);
+
+/*
+ * Sampling only, from a given probability table probs_in [A,K]: the draw, gathers, masks and coefficient assembly
+ * of consolver_policy_f32 (factor_net_ppo.py:159-168; scheduler_ppo.py:248-259,:165-175).  Same outputs.
+ */
+CONSOLVER_API int consolver_policy_sample_f32(const float* probs_in, const float* action_values, const float* q,
+                                              const int64_t* idx_in, int B, int A, int K, int order_dim,
+                                              int scaler_dim, int n_hist, int64_t* idx, float* actions,
+                                              float* act_probs, float* act_logp, float* masks, float* coef,
+                                              consolver_stream_t stream);
+
+/*
+ * One call per scheduler step for the SD path: the policy (consolver_policy_sample_f32 when probs_in != NULL,
+ * else consolver_policy_f32 with the weights) followed by consolver_step_sd on the same stream.  Saves one host
+ * crossing; with CONSOLVER_FLAG_PDL the step kernel is a programmatic dependent launch whose bulk loads overlap
+ * the policy kernel.  Arguments as in the functions above.
  */
 CONSOLVER_API int consolver_sd_policy_and_step(const float* w1, const float* b1, const float* w2, const float* b2,
                                  const float* w3, const float* b3, const float* action_values,
+                                 const float* probs_in,
                                  float x0, float x1, float x_div, float temp,
                                  const float* q, const int64_t* idx_in,
                                  int H, int A, int K, int scaler_dim,

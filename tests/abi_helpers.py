@@ -61,3 +61,32 @@ def step_fm(e0, hist, x, coef, order_dim, dt, flags=0):
         coef.data_ptr(), coef.shape[1], order_dim, float(dt), flags, B, N, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "consolver_step_fm")
     return x_out
+
+
+def policy_table(sd, x_rows, x_div, temp):
+    lib = _lib.load()
+    A, K = sd["action_values"].shape
+    H = sd["mlp.0.weight"].shape[0]
+    x_rows = x_rows.to(device=sd["action_values"].device, dtype=torch.float32).contiguous()
+    out = torch.full((x_rows.shape[0], A, K), -1.0, device=x_rows.device)
+    rc = lib.consolver_policy_table_f32(*weights(sd)[:6], x_rows.data_ptr(), x_rows.shape[0], float(x_div), float(temp),
+                                        H, A, K, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "consolver_policy_table_f32")
+    return out
+
+
+def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None):
+    lib = _lib.load()
+    A, K = sd["action_values"].shape
+    dev = table.device
+    f = dict(device=dev, dtype=torch.float32)
+    out = dict(idx=torch.full((B, A), -1, device=dev, dtype=torch.int64), actions=torch.zeros(B, A, **f),
+               probs=torch.zeros(B, A, **f), logp=torch.zeros(B, A, **f), masks=torch.zeros(B, A, **f),
+               coef=torch.zeros(B, order_dim + 2, **f))
+    rc = lib.consolver_policy_sample_f32(
+        table.data_ptr(), sd["action_values"].data_ptr(), q.data_ptr() if q is not None else None,
+        idx_in.data_ptr() if idx_in is not None else None, B, A, K, order_dim, scaler_dim, n_hist,
+        out["idx"].data_ptr(), out["actions"].data_ptr(), out["probs"].data_ptr(), out["logp"].data_ptr(),
+        out["masks"].data_ptr(), out["coef"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "consolver_policy_sample_f32")
+    return out

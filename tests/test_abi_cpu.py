@@ -18,7 +18,7 @@ def _declared():
 
 def test_header_declares_the_expected_entry_points():
     names = _declared()
-    for n in ("consolver_policy_f32", "consolver_step_sd", "consolver_step_fm", "consolver_sd_policy_and_step",
+    for n in ("consolver_policy_f32", "consolver_policy_table_f32", "consolver_policy_sample_f32", "consolver_step_sd", "consolver_step_fm", "consolver_sd_policy_and_step",
               "consolver_abi_version", "consolver_error_string"):
         assert n in names
 

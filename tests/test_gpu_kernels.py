@@ -193,3 +193,41 @@ def test_launch_config_knobs_do_not_change_results():
         assert torch.equal(out, base)
     finally:
         lib.consolver_set_step_launch(0, 0)
+
+
+@pytest.mark.parametrize("variant,H,K,od,sdim,mu,B", POLICY_CASES)
+def test_table_and_sample_kernels_match_the_fused_policy_kernel(variant, H, K, od, sdim, mu, B):
+    """The per-trajectory table launch + per-step sample launch must give exactly what the fused launch gives."""
+    sd = make_sd(variant, H, K, od, sdim, mu, seed=H + K + B, last_std=0.5 if variant == "sd" else 0.02)
+    dsd = ah.sd_to_dev(sd)
+    A = sd["action_values"].shape[0]
+    rows = torch.tensor([[999.0, 874.0], [874.0, 749.0], [124.0, -1.0]]) if variant == "sd" else \
+        torch.tensor([[1.0, 0.9567], [0.9567, 0.9045], [0.3109, 0.0]])
+    x_div, temp = (999.0, 1.0) if variant == "sd" else (1.0, 0.01)
+    tables = ah.policy_table(dsd, rows, x_div, temp)
+    ref = orc.policy_probs(sd, rows, variant)
+    torch.testing.assert_close(tables.cpu(), ref, rtol=0 if variant == "sd" else 2e-4,
+                               atol=1e-6 if variant == "sd" else 1e-7)
+    g = torch.Generator().manual_seed(B + 1)
+    q = torch.empty(B * A, K).exponential_(1, generator=g).cuda()
+    for r, n_hist in ((1, od), (2, 1)):
+        fused = ah.policy(dsd, rows[r, 0], rows[r, 1], x_div, temp, B, od, sdim, n_hist, q=q)
+        assert torch.equal(fused["probs_table"], tables[r])
+        split = ah.policy_sample(dsd, tables[r], B, od, sdim, n_hist, q=q)
+        for k in ("idx", "actions", "probs", "logp", "masks", "coef"):
+            assert torch.equal(split[k], fused[k]), k
+    forced = torch.randint(0, K, (B, A)).cuda()
+    a = ah.policy_sample(dsd, tables[0], B, od, sdim, 2, idx_in=forced)
+    assert torch.equal(a["idx"], forced)
+
+
+def test_policy_q_slab_unaligned_base():
+    """q handed over at a 4-byte-aligned (not 16) address: the cp.async staging falls back to 4-byte copies."""
+    sd = make_sd("sd", 64, 11, 4, 0, 0, seed=1, last_std=0.5)
+    dsd = ah.sd_to_dev(sd)
+    B, A, K = 37, 3, 11
+    qbig = torch.empty(B * A * K + 1).exponential_(1).cuda()
+    q = qbig[1:].view(B * A, K)
+    out = ah.policy(dsd, 624.0, 499.0, 999.0, 1.0, B, 4, 0, 4, q=q)
+    tab = out["probs_table"].cpu().unsqueeze(0).expand(B, A, K)
+    assert torch.equal(out["idx"].cpu(), orc.sample_indices(tab, q.cpu()))

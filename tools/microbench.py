@@ -21,8 +21,35 @@ def load_peak():
     return 6650.0, "fallback"
 
 
+def bench_copy(nbytes_total, iters=50):
+    """torch b.copy_(a) moving the same total bytes (half read, half written): the 'copy at this size' yardstick"""
+    n = nbytes_total // 2 // 4
+    nsets = max(2, min(64, -(-3 * L2_BYTES // nbytes_total)))
+    bufs = [(torch.randn(n, device="cuda"), torch.empty(n, device="cuda")) for _ in range(nsets)]
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for a, b in bufs:
+            b.copy_(a)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            a, b = bufs[i % nsets]
+            b.copy_(a)
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / iters * 1e3)
+    ts.sort()
+    return round(ts[2], 3), round(2 * n * 4 / ts[2] / 1e3, 1)
+
+
 def bench_sd(B, n_hist=4, pair=True, N=4 * 64 * 64, dtype=torch.float32, iters=200, flags=0, min_bytes=3 * L2_BYTES,
-             order_dim=4):
+             order_dim=4, graph=False):
     lib = _lib.load()
     es = torch.empty((), dtype=dtype).element_size()
     tensors = (n_hist - 1) + 2 + (2 if pair else 1) + (1 if pair else 0)   # reads + writes (x', slot)
@@ -40,6 +67,7 @@ def bench_sd(B, n_hist=4, pair=True, N=4 * 64 * 64, dtype=torch.float32, iters=2
     code = _lib.dtype_code(dtype)
 
     def launch(s):
+        nonlocal stream
         rc = lib.consolver_step_sd(code, s["e0"].data_ptr(), s["cond"].data_ptr() if pair else None, 3.0,
                                    s["slot"].data_ptr() if pair else None,
                                    _lib.ptr_array([h.data_ptr() for h in s["hist"]]), n_hist, s["x"].data_ptr(),
@@ -47,16 +75,33 @@ def bench_sd(B, n_hist=4, pair=True, N=4 * 64 * 64, dtype=torch.float32, iters=2
                                    0.8378, 0.5460, 0.9151, 0.4033, flags, B, N, stream)
         assert rc == 0, rc
 
-    for i in range(max(3, nsets)):
-        launch(sets[i % nsets])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        stream = side.cuda_stream
+        for i in range(max(3, nsets)):
+            launch(sets[i % nsets])
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    best = None
+    stream = torch.cuda.current_stream().cuda_stream
+    cg = None
+    if graph:
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            stream = torch.cuda.current_stream().cuda_stream
+            for i in range(iters):
+                launch(sets[i % nsets])
+        cg.replay()
+        torch.cuda.synchronize()
     times = []
     for rep in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(iters):
-            launch(sets[i % nsets])
+        if cg is not None:
+            cg.replay()
+        else:
+            for i in range(iters):
+                launch(sets[i % nsets])
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b) / iters * 1e3)  # us per launch
@@ -74,6 +119,8 @@ def main():
     ap.add_argument("--unroll", default="0")
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--pdl", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--copy", type=int, default=1)
     a = ap.parse_args()
     peak, src = load_peak()
     lib = _lib.load()
@@ -81,8 +128,10 @@ def main():
         for un in [int(v) for v in a.unroll.split(",")]:
             assert lib.consolver_set_step_launch(th, un) == 0
             for B in [int(v) for v in a.batches.split(",")]:
-                r = bench_sd(B, iters=a.iters, flags=8 if a.pdl else 0)
-                r.update(threads=th, unroll=un, frac=round(r["gbs"] / peak, 3), peak=peak, peak_src=src)
+                r = bench_sd(B, iters=a.iters, flags=8 if a.pdl else 0, graph=bool(a.graph))
+                if a.copy:
+                    r["copy_us"], r["copy_gbs"] = bench_copy(r["bytes"])
+                r.update(graph=a.graph, threads=th, unroll=un, frac=round(r["gbs"] / peak, 3), peak=peak, peak_src=src)
                 print(json.dumps(r), flush=True)
     lib.consolver_set_step_launch(0, 0)
 
