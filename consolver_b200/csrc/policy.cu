@@ -173,8 +173,11 @@ __device__ __forceinline__ void stage_q_begin(const PolicyParams& p, int b_begin
 // draw / gather for every (sample, action-dim) pair of the CTA, then coefficient assembly per sample.
 // p_s: probability table [A,K] in shared memory; q_s: staged Exp(1) slab (or unused); act_s: [nb*A] scratch.
 __device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin, int nb, const float* p_s,
-                                             const float* q_s, float* act_s) {
+                                             const float* q_s, float* act_s, float* av_s) {
   const int A = p.A, K = p.K, od = p.order_dim;
+  // bin values into shared memory (av_s aliases the logits scratch, dead after the softmax): the gather below
+  // then has no dependent global load
+  for (int i = threadIdx.x; i < A * K; i += blockDim.x) av_s[i] = __ldg(p.action_values + i);
   if (p.q && p.stage_q) cp_async_wait_all();
   __syncthreads();
   for (int pr = threadIdx.x; pr < nb * A; pr += blockDim.x) {
@@ -202,7 +205,7 @@ __device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin,
       best = (int)p.idx_in[o];
       best = best < 0 ? 0 : (best >= K ? K - 1 : best);
     }
-    const float av = __ldg(p.action_values + a * K + best);
+    const float av = av_s[a * K + best];
     const float prb = p_s[a * K + best];
     act_s[pr] = av;
     if (p.idx) p.idx[o] = best;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kPolicyThreads) policy_kernel(const PolicyPara
     mlp_softmax(p, in_dim, s.x, s.h1, s.h2, s.lg, s.p);
     if (blockIdx.x == 0 && p.probs_table)
       for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[i] = s.p[i];
-    sample_phase(p, b_begin, nb, s.p, s.q, s.act);
+    sample_phase(p, b_begin, nb, s.p, s.q, s.act, s.lg);
   } else {
     // use_conv: per-sample features -> per-sample MLP (samples_per_cta is small here)
     for (int bl = 0; bl < nb; ++bl) {
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(kPolicyThreads) policy_kernel(const PolicyPara
       mlp_softmax(p, in_dim, s.x, s.h1, s.h2, s.lg, s.p);
       PolicyParams one = p;
       one.stage_q = 0;
-      sample_phase(one, b, 1, s.p, s.q, s.act);
+      sample_phase(one, b, 1, s.p, s.q, s.act, s.lg);
       __syncthreads();
     }
   }
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(kPolicyThreads) policy_sample_kernel(const Pol
   for (int i = threadIdx.x; i < AK; i += blockDim.x) s.p[i] = __ldg(p.probs_in + i);
   if (blockIdx.x == 0 && p.probs_table && p.probs_table != p.probs_in)
     for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[i] = __ldg(p.probs_in + i);
-  sample_phase(p, b_begin, nb, s.p, s.q, s.act);
+  sample_phase(p, b_begin, nb, s.p, s.q, s.act, s.lg);
 }
 
 enum : int { kLaunchFused = 0, kLaunchTable = 1, kLaunchSample = 2 };
