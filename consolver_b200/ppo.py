@@ -1,0 +1,170 @@
+"""PPO update side of ConsistencySolver: the clipped-ratio policy loss on a rollout record and the
+data-parallel gradient exchange.  Reference: train_ppo.py:376-437 (advantages, loss), factor_net_ppo.py:170-184
+(`get_action_probs`), accelerate/DDP gradient all-reduce (train_ppo.py:257,:430; edit_ppo/train_ppo.py:177,:382).
+
+What is different from the reference, none of it numerical:
+  * the MLP is evaluated on the n-1 DISTINCT condition rows of a rollout, not on B*(n-1) replicated rows
+    (`conds['x']` is `[[t, prev_t]].repeat(B, 1)`, scheduler_ppo.py:207-210); the per-sample probabilities are gathers
+    from those tables, so forward values are identical and the gradient is the same sum;
+  * bins are taken from the recorded indices (the reference re-derives them with an argmin over |a - values|,
+    factor_net_ppo.py:174-178, which round-trips exactly — SURVEY §8a T1);
+  * gradients live in ONE flat fp32 buffer (75 041 floats for the production policy); the exchange is a single
+    all-reduce(AVG) on it over NCCL/NVLink — latency-bound, no bucketing — instead of DDP's hook machinery;
+  * the random step count of a rollout comes from a shared seeded RNG instead of a broadcast
+    (edit_ppo/train_ppo.py:275-283).
+This module is training-side torch code (autograd); it is not the sampling hot path and runs on any device."""
+from __future__ import annotations
+
+import math
+import random
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# flat parameter / gradient storage
+# ---------------------------------------------------------------------------------------------------------------
+class FlatParams:
+    """Re-homes the parameters (and their .grad) of a module into two contiguous fp32 buffers, so the optimizer
+    sees ordinary parameters while collectives and checksums touch one tensor."""
+
+    def __init__(self, module: torch.nn.Module):
+        ps = [p for p in module.parameters() if p.requires_grad]
+        if not ps:
+            raise ValueError("module has no trainable parameters")
+        dev, dt = ps[0].device, ps[0].dtype
+        n = sum(p.numel() for p in ps)
+        self.flat = torch.empty(n, device=dev, dtype=dt)
+        self.grad = torch.zeros(n, device=dev, dtype=dt)
+        o = 0
+        for p in ps:
+            k = p.numel()
+            self.flat[o:o + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[o:o + k].view_as(p)
+            p.grad = self.grad[o:o + k].view_as(p)
+            o += k
+        self.params = ps
+        self.numel = n
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, (o, k) in zip(self.params, self._spans()):
+            if p.grad is None or p.grad.data_ptr() != self.grad[o:o + k].data_ptr():
+                p.grad = self.grad[o:o + k].view_as(p)      # an optimizer's zero_grad(set_to_none=True) detached it
+
+    def _spans(self):
+        o = 0
+        for p in self.params:
+            yield o, p.numel()
+            o += p.numel()
+
+    def checksum(self) -> float:
+        """the reference's DDP self-check: a per-rank parameter sum (train_ppo.py:452-455)"""
+        return float(self.flat.double().sum())
+
+
+def broadcast_parameters(flat: FlatParams, src: int = 0):
+    """C2 of SURVEY §2.2: one broadcast of the weights from rank 0 at start."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat.flat, src=src)
+
+
+def allreduce_gradients(flat: FlatParams):
+    """C1 of SURVEY §2.2: average the flat gradient buffer over ranks — one latency-bound collective."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat.grad, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+        flat.grad.div_(dist.get_world_size())
+
+
+def shared_step_count(step: int, seed: int, lo: int = 2, hi: int = 15) -> int:
+    """Number of inference steps of rollout `step`, identical on every rank without a collective
+    (train_ppo.py:345 draws random.choice(range(2,16)) under identical seeds; the FLUX driver broadcasts it)."""
+    return random.Random(seed * 1_000_003 + step).choice(list(range(lo, hi + 1)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# advantages and loss
+# ---------------------------------------------------------------------------------------------------------------
+def advantages_from_rewards(rewards: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+    """train_ppo.py:376-390: standardise within the rank's batch, x10, repeat per step, zero the unused dims.
+    rewards [B,1], masks [B,n',A] -> advantages [B,n',A]."""
+    adv = (rewards - rewards.mean()) / (rewards.std() + 1e-8) * 10
+    return adv.view(-1, 1, 1) * masks
+
+
+def ppo_loss(factor_net, x_rows: torch.Tensor, idx: torch.Tensor, old_probs: torch.Tensor,
+             advantages: torch.Tensor, clip_range: float = 0.2, entropy_coef: float = 0.0
+             ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """Clipped PPO loss of train_ppo.py:406-427 on one rollout record.
+
+      x_rows     [n',2]     the distinct condition rows (t, prev_t) of steps 1..n-1 (`trajectory()['x'][0]`)
+      idx        [B,n',A]   sampled bin indices            old_probs [B,n',A]  their probabilities at rollout time
+      advantages [B,n',A]   from advantages_from_rewards
+    """
+    fn = factor_net.module if hasattr(factor_net, "module") else factor_net
+    tables = fn.forward_({"x": x_rows})                                       # [n',A,K], autograd
+    n1, A, K = tables.shape
+    B = idx.shape[0]
+    cur = tables.unsqueeze(0).expand(B, n1, A, K).gather(3, idx.unsqueeze(-1)).squeeze(-1)   # [B,n',A]
+    logp = (cur + 1e-9).log().sum(dim=2, keepdim=True)                         # joint over action dims
+    old_logp = (old_probs + 1e-9).log().sum(dim=2, keepdim=True)
+    ratio = (logp - old_logp).exp()
+    clipped = torch.clamp(ratio, 1 - clip_range, 1 + clip_range)
+    policy_loss = -torch.min(advantages * ratio, advantages * clipped).mean()
+    # Categorical(probs).entropy() / log K (factor_net_ppo.py:180-181); its mean over the B*n'*A replicated
+    # entries equals the mean over the distinct rows
+    ent = torch.distributions.Categorical(probs=tables).entropy() / torch.log(
+        torch.as_tensor(K, dtype=tables.dtype, device=tables.device))
+    entropy_loss = -entropy_coef * ent.mean()
+    loss = policy_loss + entropy_loss
+    return loss, dict(policy_loss=policy_loss.detach(), entropy=ent.mean().detach(), ratio_mean=ratio.mean().detach())
+
+
+def ppo_update(factor_net, flat: FlatParams, optimizer, record: Dict[str, torch.Tensor], rewards: torch.Tensor,
+               ppo_epochs: int = 1, clip_range: float = 0.2, entropy_coef: float = 0.0,
+               max_grad_norm: Optional[float] = 1.0) -> Dict[str, float]:
+    """ppo_epochs x (loss, backward, flat all-reduce, clip, optimizer step) — train_ppo.py:406-437.
+    `record` is `scheduler.trajectory()` (views); it is detached/cloned here because the next rollout reuses the
+    buffers."""
+    x_rows = record["x"][0].detach().float().clone()
+    idx = record["idx"].detach().clone()
+    old_probs = record["probs"].detach().clone()
+    adv = advantages_from_rewards(rewards.detach(), record["masks"].detach()).clone()
+    stats = {}
+    for _ in range(ppo_epochs):
+        flat.zero_grad()
+        loss, info = ppo_loss(factor_net, x_rows, idx, old_probs, adv, clip_range, entropy_coef)
+        loss.backward()
+        allreduce_gradients(flat)
+        if max_grad_norm is not None:
+            norm = flat.grad.norm()
+            flat.grad.mul_(torch.clamp(max_grad_norm / (norm + 1e-6), max=1.0))    # clip_grad_norm_ on the flat buffer
+            stats["grad_norm"] = float(norm)
+        optimizer.step()
+        stats.update(loss=float(loss.detach()), **{k: float(v) for k, v in info.items()})
+    return stats
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rollout (SD): B replicas of ONE (noise, target) pair differing only by the sampled actions
+# ---------------------------------------------------------------------------------------------------------------
+def rollout_sd(scheduler, denoiser, noise_one: torch.Tensor, batch: int, cfg: float, num_inference_steps: int):
+    """data_processing.py:65-80 (`repeat_random_sample`) + denoise_ppo.py:62-118: replicate one noise sample B times,
+    run the CFG sampling loop, return (final latents [B,...], record views)."""
+    from .denoise import denoise_loop
+
+    noise = noise_one.unsqueeze(0).expand(batch, *noise_one.shape).contiguous()
+    with torch.no_grad():
+        return denoise_loop(scheduler, denoiser, noise, cfg=cfg, num_inference_steps=num_inference_steps)
+
+
+def latent_mse_reward(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Synthetic stand-in for the reference's image-space rewards (edit_ppo/reward_model.py needs pretrained
+    weights): negative latent MSE to the teacher latent, shape [B,1] like calculate_reward's outputs."""
+    return -((pred.float() - target.float()) ** 2).flatten(1).mean(dim=1, keepdim=True)

@@ -1,0 +1,83 @@
+"""GPU: PPO rollout through the CUDA scheduler + torch-autograd update (SURVEY §8f N1 / BASELINE config 5)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PROD = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, num_train_timesteps=1000,
+            steps_offset=1, timestep_spacing="trailing", order_dim=4, scaler_dim=0, use_conv=False,
+            factor_net_kwargs=dict(embedding_dim=64, hidden_dim=256, num_actions=11))
+
+
+def _denoiser(seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    w = torch.randn(4, 4, device="cuda", generator=g) * 0.3
+
+    def f(x, t, i):                                  # a cheap stand-in with the U-Net's signature/shape
+        return torch.einsum("oc,bchw->bohw", w, x) + 0.1 * torch.randn(x.shape, device="cuda", generator=g)
+    return f
+
+
+def test_rollout_record_is_consistent_with_the_autograd_policy_and_update_runs():
+    import consolver_b200 as cb
+    from consolver_b200 import ppo
+
+    torch.manual_seed(0)
+    s = cb.PPOScheduler(**PROD)
+    with torch.no_grad():
+        s.factor_net.mlp[4].weight.normal_(0, 0.05)
+    s.factor_net.cuda()
+    flat = ppo.FlatParams(s.factor_net)
+    opt = torch.optim.AdamW(s.factor_net.parameters(), lr=1e-3)
+    B, n = 16, 6
+    noise = torch.randn(4, 16, 16, device="cuda")
+    target = torch.randn(4, 16, 16, device="cuda")
+    lat, rec = ppo.rollout_sd(s, _denoiser(1), noise, B, cfg=3.0, num_inference_steps=n)
+    assert lat.shape == (B, 4, 16, 16) and rec["idx"].shape == (B, n - 1, 3)
+    assert rec["x"].shape == (B, n - 1, 2) and rec["masks"][:, 0].tolist() == [[1.0, 0.0, 0.0]] * B
+    # rows differ across samples only through the sampled actions
+    assert len({tuple(r) for r in rec["idx"][:, -1].tolist()}) > 1
+    # the probabilities recorded by the CUDA policy kernel are the autograd module's probabilities at those bins
+    tables = s.factor_net.forward_({"x": rec["x"][0].float()})
+    cur = tables.unsqueeze(0).expand(B, n - 1, 3, 11).gather(3, rec["idx"].unsqueeze(-1)).squeeze(-1)
+    torch.testing.assert_close(cur, rec["probs"], rtol=0, atol=1e-6)
+    torch.testing.assert_close(rec["logp"], torch.log(rec["probs"] + 1e-9), rtol=0, atol=1e-6)
+    rewards = ppo.latent_mse_reward(lat, target.unsqueeze(0).expand_as(lat))
+    assert rewards.shape == (B, 1)
+    before = flat.checksum()
+    stats = ppo.ppo_update(s.factor_net, flat, opt, rec, rewards, ppo_epochs=2, clip_range=0.2, entropy_coef=0.01)
+    assert abs(stats["ratio_mean"] - 1.0) < 0.2 and stats["loss"] == stats["loss"]
+    assert flat.checksum() != before
+    # the next rollout sees the updated weights (tables are re-evaluated per trajectory)
+    lat2, rec2 = ppo.rollout_sd(s, _denoiser(1), noise, B, cfg=3.0, num_inference_steps=n)
+    t2 = s.factor_net.forward_({"x": rec2["x"][0].float()})
+    cur2 = t2.unsqueeze(0).expand(B, n - 1, 3, 11).gather(3, rec2["idx"].unsqueeze(-1)).squeeze(-1)
+    torch.testing.assert_close(cur2, rec2["probs"], rtol=0, atol=1e-6)
+
+
+def test_graphed_preview_matches_eager_and_advances_the_generator():
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedPreview, preview_from_pairs
+
+    s = cb.PPOScheduler(**PROD)
+    with torch.no_grad():
+        s.factor_net.mlp[4].weight.normal_(0, 0.05)
+    s.factor_net.cuda()
+    B, n = 8, 8
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, 4, 64, 64, device="cuda", generator=g)
+    pairs = [torch.randn(2 * B, 4, 64, 64, device="cuda", generator=g) for _ in range(n)]
+    gp = GraphedPreview(s, x, pairs, 3.0, n)
+    torch.manual_seed(77)
+    out_g = gp.replay().clone()
+    idx_g = gp.record()["idx"].clone()
+    out_g2 = gp.replay().clone()                      # the generator advanced: different actions
+    e = cb.PPOScheduler(**PROD)
+    e.factor_net.load_state_dict(s.factor_net.state_dict())
+    e.factor_net.cuda()
+    e.set_timesteps(n, device="cuda")
+    torch.manual_seed(77)
+    out_e = preview_from_pairs(e, x, pairs, 3.0)
+    assert torch.equal(e.trajectory()["idx"], idx_g)
+    assert torch.equal(out_e, out_g)
+    assert not torch.equal(out_g, out_g2)
