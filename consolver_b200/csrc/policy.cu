@@ -295,6 +295,9 @@ __global__ void __launch_bounds__(kPolicyThreads) policy_kernel(const PolicyPara
       if (threadIdx.x < p.n_feat) s.x[2 + threadIdx.x] = __ldg(p.feat + (size_t)b * p.n_feat + threadIdx.x);
       __syncthreads();
       mlp_softmax(p, in_dim, s.x, s.h1, s.h2, s.lg, s.p);
+      if (p.probs_table)   // per-sample tables [B,A,K]
+        for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[(size_t)b * AK + i] = s.p[i];
+      __syncthreads();     // sample_phase overwrites the logits scratch aliased by the bin-value stage
       PolicyParams one = p;
       one.stage_q = 0;
       sample_phase(one, b, 1, s.p, s.q, s.act, s.lg);

@@ -271,8 +271,6 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
             self._init_step_index(timestep)
         cfg = self.config
         fn = self.factor_net_module
-        if fn.use_conv:
-            raise NotImplementedError("use_conv=True is not wired into the fused path yet")
         od = cfg.order_dim
         e0 = model_output if model_output.is_contiguous() else model_output.contiguous()
         sample = sample if sample.is_contiguous() else sample.contiguous()
@@ -305,16 +303,33 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         x_out = torch.empty(sample.shape, device=e0.device, dtype=e0.dtype)
         lib = _lib.load()
         stream = torch.cuda.current_stream(e0.device).cuda_stream
-        # all n (sigma, sigma_next) rows of the schedule go through the MLP in one launch per pass
-        if tr.table_pass != tr.count // tr.n:
-            fn.policy_tables(tr.condx_f32, o["probs_table"], stream)
-            tr.table_pass = tr.count // tr.n
         w = fn.kernel_weights()
-        rc = lib.consolver_policy_sample_f32(
-            o["probs_table"][si].data_ptr(), w[6], q_ptr, idx_ptr, B, fn.action_dims, fn.num_actions, od,
-            cfg.scaler_dim, n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
-            o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
-        _lib.check(rc, "consolver_policy_sample_f32")
+        if not fn.use_conv:
+            # all n (sigma, sigma_next) rows of the schedule go through the MLP in one launch per pass
+            if tr.table_pass != tr.count // tr.n:
+                fn.policy_tables(tr.condx_f32, o["probs_table"], stream)
+                tr.table_pass = tr.count // tr.n
+            rc = lib.consolver_policy_sample_f32(
+                o["probs_table"][si].data_ptr(), w[6], q_ptr, idx_ptr, B, fn.action_dims, fn.num_actions, od,
+                cfg.scaler_dim, n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
+                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
+            _lib.check(rc, "consolver_policy_sample_f32")
+        else:
+            # use_conv=True: cosine features of the history (pass 1), per-sample MLP, then the fused step (pass 2)
+            from .features import cosine_features_cuda, workspace_bytes
+
+            if getattr(tr, "_conv", None) is None:
+                tr._conv = (torch.empty(B, od - 1, device=e0.device, dtype=torch.float32),
+                            torch.empty(workspace_bytes(B, od) // 8 + 1, device=e0.device, dtype=torch.float64),
+                            torch.empty(tr.n, B, fn.action_dims, fn.num_actions, device=e0.device))
+            feat, ws, full = tr._conv
+            cosine_features_cuda(e0, None, 0.0, older, od, feat, ws, stream)
+            rc = lib.consolver_policy_f32(
+                *w, x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
+                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
+                full[i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
+                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
+            _lib.check(rc, "consolver_policy_f32")
         flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0) \
             | (_lib.FLAG_PDL if self.use_pdl else 0)
         rc = lib.consolver_step_fm(
@@ -356,8 +371,9 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
     def last_policy(self):
         tr = self._traj
         i = (tr.count - 1) % tr.n
-        return dict(probs_table=tr.out["probs_table"][(self._step_index - 1) % tr.n], idx=tr.out["idx"][i],
-                    coef=tr.out["coef"][i], logp=tr.out["logp"][i])
+        table = tr._conv[2][i] if getattr(tr, "_conv", None) is not None else \
+            tr.out["probs_table"][(self._step_index - 1) % tr.n]
+        return dict(probs_table=table, idx=tr.out["idx"][i], coef=tr.out["coef"][i], logp=tr.out["logp"][i])
 
     def scale_noise(self, sample: torch.Tensor, timestep, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward process of flow matching (edit_ppo/scheduler_fmppo.py:457-484); not on the hot path."""

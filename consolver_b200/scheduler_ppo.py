@@ -71,6 +71,18 @@ class _Trajectory:
         self.count = 0
         self.table_pass = -1   # trajectory pass (count // n) whose probability tables are in out['probs_table']
 
+    def conv_buffers(self, fn):
+        """use_conv=True scratch: features [B,od-1], reduction workspace, per-sample tables [n,B,A,K]"""
+        if getattr(self, "_conv", None) is None:
+            from .features import workspace_bytes
+
+            B, od = self.key[0], self.ring_shape[0]
+            self._conv = (torch.empty(B, od - 1, device=self.device, dtype=torch.float32),
+                          torch.empty(workspace_bytes(B, od) // 8 + 1, device=self.device, dtype=torch.float64),
+                          torch.empty(self.n, B, fn.action_dims, fn.num_actions, device=self.device,
+                                      dtype=torch.float32))
+        return self._conv
+
     def slot(self, i):
         if self.ring is None:
             self.ring = torch.empty(self.ring_shape, device=self.device, dtype=self.dtype)
@@ -227,8 +239,6 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
             raise TypeError(f"sample ({sample.dtype}) and model_output ({e0.dtype}) must share a dtype")
         cfg = self.config
         fn = self.factor_net_module
-        if fn.use_conv:
-            raise NotImplementedError("use_conv=True is not wired into the fused path yet")
         od = cfg.order_dim
         t = self._host_timestep(timestep)
         prev_t = t - self._stride
@@ -257,13 +267,6 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         sa_p, sb_p = float(self._sqrt_abar[pi]), float(self._sqrt_1m_abar[pi])
 
         o = tr.out
-        # The policy input row depends only on the timestep grid: evaluate the MLP + softmax for ALL n rows in one
-        # launch at the first step of a pass; every step then only samples from its row of the table.
-        on_grid = t == self._timesteps_host[i]
-        if on_grid and tr.table_pass != tr.count // tr.n:
-            fn.policy_tables(tr.condx_f32, o["probs_table"])
-            tr.table_pass = tr.count // tr.n
-        probs_in = o["probs_table"][i].data_ptr() if on_grid else None
         q_ptr, idx_ptr = tr.q.data_ptr(), None
         if self.replay is None:
             tr.q.exponential_(1)                     # the draw torch.multinomial makes (factor_net_ppo.py:161)
@@ -279,15 +282,44 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         hist_ptrs = _lib.ptr_array([h.data_ptr() for h in older])
         w = fn.kernel_weights()
         lib = _lib.load()
-        rc = lib.consolver_sd_policy_and_step(
-            *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr,
-            fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
-            o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
-            o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(),
-            _lib.dtype_code(e0.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, guidance,
-            slot.data_ptr() if slot is not None else None, hist_ptrs, n_hist, sample.data_ptr(), x_out.data_ptr(),
-            od, sa_t, sb_t, sa_p, sb_p, flags, B, N, torch.cuda.current_stream(e0.device).cuda_stream)
-        _lib.check(rc, "consolver_sd_policy_and_step")
+        stream = torch.cuda.current_stream(e0.device).cuda_stream
+        step_args = (_lib.dtype_code(e0.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, guidance,
+                     slot.data_ptr() if slot is not None else None, hist_ptrs, n_hist, sample.data_ptr(),
+                     x_out.data_ptr())
+        if not fn.use_conv:
+            # The policy input row depends only on the timestep grid: evaluate the MLP + softmax for ALL n rows in
+            # one launch at the first step of a pass; every step then only samples from its row of the table.
+            on_grid = t == self._timesteps_host[i]
+            if on_grid and tr.table_pass != tr.count // tr.n:
+                fn.policy_tables(tr.condx_f32, o["probs_table"])
+                tr.table_pass = tr.count // tr.n
+            probs_in = o["probs_table"][i].data_ptr() if on_grid else None
+            rc = lib.consolver_sd_policy_and_step(
+                *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr,
+                fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
+                o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
+                o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(),
+                o["coef"][i].data_ptr(), *step_args, od, sa_t, sb_t, sa_p, sb_p, flags, B, N, stream)
+            _lib.check(rc, "consolver_sd_policy_and_step")
+        else:
+            # use_conv=True (factor_net_ppo.py:146-149): two passes.  Pass 1 reduces the cosine features of the
+            # history against the newest output (formed from the CFG pair on the fly); the policy MLP then runs per
+            # sample on [t, t_prev, cos_1..]; pass 2 is the ordinary fused step.
+            from .features import cosine_features_cuda
+
+            feat, ws, full = tr.conv_buffers(fn)
+            cosine_features_cuda(e0, cond, guidance, older, od, feat, ws, stream)
+            rc = lib.consolver_policy_f32(
+                *w, x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
+                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
+                full[i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
+                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
+            _lib.check(rc, "consolver_policy_f32")
+            sflags = flags | (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | \
+                (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
+            rc = lib.consolver_step_sd(*step_args, o["coef"][i].data_ptr(), od + 2, od, sa_t, sb_t, sa_p, sb_p,
+                                       sflags, B, N, stream)
+            _lib.check(rc, "consolver_step_sd")
 
         newest = slot if cond is not None else e0     # plain step keeps the caller's tensor by reference, as
         self._hist = [newest] + older                 # the reference does (scheduler_ppo.py:214-218)
@@ -327,8 +359,8 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         recent step (views)."""
         tr = self._traj
         i = (tr.count - 1) % tr.n
-        return dict(probs_table=tr.out["probs_table"][i], idx=tr.out["idx"][i], coef=tr.out["coef"][i],
-                    logp=tr.out["logp"][i])
+        table = tr._conv[2][i] if getattr(tr, "_conv", None) is not None else tr.out["probs_table"][i]
+        return dict(probs_table=table, idx=tr.out["idx"][i], coef=tr.out["coef"][i], logp=tr.out["logp"][i])
 
     def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         """DDPM forward noising (scheduler_ppo.py:336-358); not on the hot path, plain torch."""

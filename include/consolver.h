@@ -88,7 +88,7 @@ CONSOLVER_API const char* consolver_error_string(int err);
  *   idx_in [B,A] or NULL     forced bin indices (replay / PPO update); exactly one of q, idx_in is given
  *   n_hist                   number of model outputs in the history INCLUDING the current one (1..order_dim)
  * outputs (any may be NULL except coef):
- *   probs_table [A,K]        full softmax table of the shared row (undefined when feat != NULL)
+ *   probs_table [A,K]        full softmax table of the shared row ([B,A,K], one table per sample, when feat != NULL)
  *   idx [B,A] int64          sampled bin indices
  *   actions [B,A]            bin values (the reference's `actions`)
  *   act_probs [B,A]          probabilities of the sampled bins (the reference's `probs`)
@@ -181,6 +181,19 @@ CONSOLVER_API int consolver_sd_policy_and_step(const float* w1, const float* b1,
                                  const void* const* hist, int n_hist, const void* x, void* x_out,
                                  int order_dim, float sa_t, float sb_t, float sa_p, float sb_p, int flags,
                                  int B, int64_t n_per_sample, consolver_stream_t stream);
+
+/*
+ * use_conv=True first pass: per-sample cosine similarity between the newest model output and each older history
+ * slot (factor_net_ppo.py:108-130; zero for slots not yet filled), written as feat [B, order_dim-1] for the
+ * `feat` argument of consolver_policy_f32.  e0/cond/guidance/hist/n_hist as in consolver_step_sd (with `cond` the
+ * newest output is formed as e0 + guidance*(cond - e0) on the fly).  `workspace` is caller-owned scratch of
+ * consolver_cosine_features_workspace(B, order_dim) bytes (8-byte aligned); it is zeroed on the stream here.
+ */
+CONSOLVER_API size_t consolver_cosine_features_workspace(int B, int order_dim);
+CONSOLVER_API int consolver_cosine_features(int dtype, const void* e0, const void* cond, float guidance,
+                                            const void* const* hist, int n_hist, int order_dim, int B,
+                                            int64_t n_per_sample, void* workspace, float* feat,
+                                            consolver_stream_t stream);
 
 /* Tuning knobs for benchmarking (process-global; not part of the numerical contract).
  *   threads: CTA size of the step kernels (32..512, multiple of 32; 0 = default)

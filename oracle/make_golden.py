@@ -209,6 +209,9 @@ def main():
     gen_sd("sd_eps_k161_o4_s2_n4_B2", hidden_dim=64, B=2, shape=small, n=4, guidance=3.0, seed=27, scaler_dim=2,
            num_actions=161, last_std=0.2)                                                     # ctor defaults
     gen_sd("sd_eps_s0_n8_B2_ragged", hidden_dim=64, B=2, shape=(3, 5, 7), n=8, guidance=3.0, seed=28)        # N_s % 4 != 0
+    gen_sd("sd_eps_conv_s0_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=29, use_conv=True)
+    gen_sd("sd_v_conv_s2_o3_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=2.0, seed=30, use_conv=True,
+           order_dim=3, scaler_dim=2, prediction_type="v_prediction")
     # --- FM / FMPPOScheduler --------------------------------------------------------------------------
     tok = (16, 8)
     gen_fm("fm_o2_s0_m0_bf16_n8_B3", B=3, shape=tok, n=8, seed=31, dtype=torch.bfloat16)     # FLUX prod
@@ -220,6 +223,8 @@ def main():
            scaler_dim=1)
     gen_fm("fm_o2_s0_m0_bf16_n4_B2_search", hidden_dim=64, B=2, shape=tok, n=4, seed=36, dtype=torch.bfloat16,
            use_begin_index=False)
+    gen_fm("fm_conv_o4_s0_m0_bf16_n6_B2", hidden_dim=64, B=2, shape=tok, n=6, seed=38, dtype=torch.bfloat16, order_dim=4,
+           use_conv=True)
     gen_fm("fm_o2_s0_m0_bf16_n3_B1_full", B=1, shape=(4096, 64), n=3, seed=37, dtype=torch.bfloat16)
     # --- PPO-update side ------------------------------------------------------------------------------
     gen_update_side("update_sd_o4_s0", "sd", 41, hidden_dim=256, num_actions=11, order_dim=4, scaler_dim=0)

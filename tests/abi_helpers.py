@@ -20,7 +20,7 @@ def policy(sd, x0, x1, x_div, temp, B, order_dim, scaler_dim, n_hist, q=None, id
     H = sd["mlp.0.weight"].shape[0]
     dev = sd["action_values"].device
     f = dict(device=dev, dtype=torch.float32)
-    out = dict(probs_table=torch.full((A, K), -1.0, **f), idx=torch.full((B, A), -1, device=dev, dtype=torch.int64),
+    out = dict(probs_table=torch.full((B, A, K) if feat is not None else (A, K), -1.0, **f), idx=torch.full((B, A), -1, device=dev, dtype=torch.int64),
                actions=torch.zeros(B, A, **f), probs=torch.zeros(B, A, **f), logp=torch.zeros(B, A, **f),
                masks=torch.zeros(B, A, **f), coef=torch.zeros(B, order_dim + 2, **f))
     rc = lib.consolver_policy_f32(
@@ -90,3 +90,18 @@ def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=No
         out["masks"].data_ptr(), out["coef"].data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "consolver_policy_sample_f32")
     return out
+
+
+def cosine_features(e0, cond, guidance, hist, order_dim):
+    lib = _lib.load()
+    B = e0.shape[0]
+    N = e0.numel() // B
+    nbytes = lib.consolver_cosine_features_workspace(B, order_dim)
+    ws = torch.empty(nbytes // 8 + 1, device=e0.device, dtype=torch.float64)
+    feat = torch.full((B, order_dim - 1), -7.0, device=e0.device)
+    rc = lib.consolver_cosine_features(_lib.dtype_code(e0.dtype), e0.data_ptr(),
+                                       cond.data_ptr() if cond is not None else None, float(guidance),
+                                       _lib.ptr_array([h.data_ptr() for h in hist]), len(hist) + 1, order_dim, B, N,
+                                       ws.data_ptr(), feat.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "consolver_cosine_features")
+    return feat

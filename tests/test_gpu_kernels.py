@@ -231,3 +231,41 @@ def test_policy_q_slab_unaligned_base():
     out = ah.policy(dsd, 624.0, 499.0, 999.0, 1.0, B, 4, 0, 4, q=q)
     tab = out["probs_table"].cpu().unsqueeze(0).expand(B, A, K)
     assert torch.equal(out["idx"].cpu(), orc.sample_indices(tab, q.cpu()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,shape", [(3, (4, 8, 8)), (2, (3, 5, 7)), (64, (4, 64, 64)), (1, (1,))])
+@pytest.mark.parametrize("n_hist,od,pair", [(1, 4, False), (2, 4, True), (4, 4, True), (3, 3, False), (6, 8, True)])
+def test_cosine_features_vs_oracle(dtype, B, shape, n_hist, od, pair):
+    g = torch.Generator().manual_seed(B + n_hist)
+    rn = lambda: torch.randn(B, *shape, generator=g).to(dtype)  # noqa: E731
+    e0, cond = rn(), (rn() if pair else None)
+    hist = [rn() * (j + 1) for j in range(n_hist - 1)]
+    eps = orc.cfg_combine(e0.float(), cond.float(), 2.5).to(dtype) if pair else e0
+    stack = torch.stack([eps] + hist + [torch.zeros_like(eps)] * (od - n_hist), dim=1).float()
+    ref = orc.cosine_features(stack, od)
+    got = ah.cosine_features(e0.cuda(), cond.cuda() if pair else None, 2.5, [h.cuda() for h in hist], od)
+    torch.testing.assert_close(got.cpu(), ref, rtol=0, atol=2e-6)
+    assert torch.all(got[:, n_hist - 1:] == 0)
+
+
+def test_policy_per_sample_features_vs_oracle():
+    """use_conv: MLP input [t, t_prev, cos_1..cos_{od-1}] per sample -> per-sample tables."""
+    od, K, H, B = 4, 11, 64, 9
+    g = torch.Generator().manual_seed(0)
+    sd = make_sd("sd", H, K, od, 0, 0, seed=3, last_std=0.5)
+    sd["mlp.0.weight"] = (torch.rand(H, 2 + od - 1, generator=g) * 2 - 1) / 5 ** 0.5
+    dsd = ah.sd_to_dev(sd)
+    feat = torch.rand(B, od - 1, generator=g) * 2 - 1
+    q = torch.empty(B * 3, K).exponential_(1, generator=g)
+    out = ah.policy(dsd, 749.0, 624.0, 999.0, 1.0, B, od, 0, 4, q=q.cuda(), feat=feat.cuda().contiguous())
+    xn = torch.cat([(torch.tensor([[749.0, 624.0]]) / 999.0).expand(B, 2), feat], dim=1)
+    F = torch.nn.functional
+    h = torch.relu(F.linear(xn, sd["mlp.0.weight"], sd["mlp.0.bias"]))
+    h = torch.relu(F.linear(h, sd["mlp.2.weight"], sd["mlp.2.bias"]))
+    ref = torch.softmax(F.linear(h, sd["mlp.4.weight"], sd["mlp.4.bias"]).view(B, 3, K), dim=-1)
+    torch.testing.assert_close(out["probs_table"].cpu(), ref, rtol=0, atol=1e-6)
+    idx = orc.sample_indices(out["probs_table"].cpu(), q)
+    assert torch.equal(out["idx"].cpu(), idx)
+    actions, act_probs = orc.gather_actions(sd, out["probs_table"].cpu(), idx)
+    assert torch.equal(out["actions"].cpu(), actions) and torch.equal(out["probs"].cpu(), act_probs)

@@ -54,13 +54,19 @@ def test_c_oracle_sd_trajectory_matches_reference(lib, name):
         assert torch.equal(eps, g[f"eps_{i}"])
         hist = ([eps] + hist)[:od]
         n_hist = len(hist)
-        table = g[f"probs_full_{i}"][0].contiguous()     # the reference's own softmax table
         q = g[f"q_{i}"].contiguous()
         idx = torch.empty(B, A, dtype=torch.int64)
         actions, probs, masks = torch.empty(B, A), torch.empty(B, A), torch.empty(B, A)
         coef = torch.empty(B, od + 2)
-        lib.oracle_policy_sample(_p(table), _p(av), _p(q), B, A, K, od, sdim, n_hist, _p(idx), _p(actions), _p(probs),
-                                 _p(masks), _p(coef))
+        if not cfg.get("use_conv"):
+            table = g[f"probs_full_{i}"][0].contiguous()     # the reference's own softmax table (rows identical)
+            lib.oracle_policy_sample(_p(table), _p(av), _p(q), B, A, K, od, sdim, n_hist, _p(idx), _p(actions),
+                                     _p(probs), _p(masks), _p(coef))
+        else:                                                # use_conv: one table per sample
+            for b in range(B):
+                table = g[f"probs_full_{i}"][b].contiguous()
+                lib.oracle_policy_sample(_p(table), _p(av), _p(q[b * A:(b + 1) * A]), 1, A, K, od, sdim, n_hist,
+                                         _p(idx[b]), _p(actions[b]), _p(probs[b]), _p(masks[b]), _p(coef[b]))
         assert torch.equal(idx, g[f"idx_{i}"])
         assert torch.equal(actions, g[f"actions_{i}"]) and torch.equal(probs, g[f"probs_{i}"])
         assert torch.equal(masks, g[f"masks_{i}"])
