@@ -145,7 +145,7 @@ def time_step_kernel(B, n_hist, device, iters=64, pool_bytes=3 * L2_BYTES):
     def launch(st, stream):
         rc = lib.consolver_step_sd(0, st["u"].data_ptr(), st["c"].data_ptr(), GUIDANCE, st["s"].data_ptr(),
                                    _lib.ptr_array([t.data_ptr() for t in st["h"]]), n_hist, st["x"].data_ptr(),
-                                   st["o"].data_ptr(), coef.data_ptr(), 6, 4, 0.8378, 0.5460, 0.9151, 0.4033, 0,
+                                   st["o"].data_ptr(), None, 0, coef.data_ptr(), 6, 4, 0.8378, 0.5460, 0.9151, 0.4033, 0,
                                    B, N, stream)
         assert rc == 0, rc
 
@@ -173,6 +173,100 @@ def time_step_kernel(B, n_hist, device, iters=64, pool_bytes=3 * L2_BYTES):
         ts.append(a.elapsed_time(b) * 1e3 / iters)
     ts.sort()
     return ts[len(ts) // 2], per_launch, nsets
+
+
+def time_fm_kernel(B, device, n_hist=2, iters=32, pool_bytes=3 * L2_BYTES):
+    """FM (FLUX-Kontext shape, BASELINE configs[3]) fused step: packed latents [B,4096,64] bf16, order_dim=2 steady
+    state — reads v, x and one older slot, writes x' = 4 tensors of 512 KiB per sample."""
+    from consolver_b200 import _lib
+
+    lib = _lib.load()
+    N = 4096 * 64
+    per_launch = (n_hist + 2) * B * N * 2
+    nsets = int(max(2, min(64, -(-pool_bytes // per_launch))))
+    mk = lambda: torch.randn(B, N, device=device).bfloat16()  # noqa: E731
+    sets = [dict(v=mk(), x=mk(), h=[mk() for _ in range(n_hist - 1)],
+                 o=torch.empty(B, N, device=device, dtype=torch.bfloat16)) for _ in range(nsets)]
+    coef = torch.randn(B, 4, device=device)
+
+    def launch(st, stream):
+        rc = lib.consolver_step_fm(2, 2, st["v"].data_ptr(), None, _lib.ptr_array([t.data_ptr() for t in st["h"]]),
+                                   n_hist, st["x"].data_ptr(), st["o"].data_ptr(), None, 0, coef.data_ptr(), 4, 2,
+                                   -0.0433, 0,
+                                   B, N, stream)
+        assert rc == 0, rc
+
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for i in range(max(3, nsets)):
+            launch(sets[i % nsets], side.cuda_stream)
+    torch.cuda.current_stream(device).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        st = torch.cuda.current_stream(device).cuda_stream
+        for i in range(iters):
+            launch(sets[i % nsets], st)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(device)
+    ts = []
+    for _ in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize(device)
+        ts.append(a.elapsed_time(b) * 1e3 / iters)
+    ts.sort()
+    return ts[len(ts) // 2], per_launch
+
+
+def with_denoiser(B, device, sd, previews=3):
+    """The same 8-step CFG loop with a random-init SD1.5-architecture U-Net (bf16, channels_last, SDPA) producing the
+    model outputs — timed, not the product.  Reports previews/s and the solver's share of the loop."""
+    from consolver_b200.denoise import denoise_loop
+    from consolver_b200.standins import SD15UNet
+
+    torch.manual_seed(0)
+    unet = SD15UNet().to(device=device, dtype=torch.bfloat16).to(memory_format=torch.channels_last).eval()
+    ctx = torch.randn(2 * B, 77, 768, device=device, dtype=torch.bfloat16)
+    sched = make_scheduler(device, sd)
+    solver_events = []
+    orig = sched.step_cfg
+
+    def timed_step(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(*a, **k)
+        e1.record()
+        solver_events.append((e0, e1))
+        return r
+
+    sched.step_cfg = timed_step
+
+    @torch.no_grad()
+    def den(x, t, i):
+        return unet(x.to(dtype=torch.bfloat16, memory_format=torch.channels_last), t, ctx).float()
+
+    noise = torch.randn(B, *SHAPE, device=device)
+    denoise_loop(sched, den, noise, cfg=GUIDANCE, num_inference_steps=N_STEPS)          # warm-up (cuDNN autotune)
+    torch.cuda.synchronize(device)
+    solver_events.clear()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(previews):
+        denoise_loop(sched, den, noise, cfg=GUIDANCE, num_inference_steps=N_STEPS)
+    b.record()
+    torch.cuda.synchronize(device)
+    ms = a.elapsed_time(b) / previews
+    solver_ms = sum(x.elapsed_time(y) for x, y in solver_events) / previews
+    del unet
+    torch.cuda.empty_cache()
+    return {"value": round(B / (ms / 1e3), 2), "unit": "previews/s", "denoiser": "random-init SD1.5-architecture U-Net "
+            "(859.5 M params), bf16 channels_last, 2B rows per call (CFG), stock PyTorch — timed, not the product",
+            "ms_per_preview_batch": round(ms, 2), "solver_ms_per_preview_batch": round(solver_ms, 4),
+            "solver_share": round(solver_ms / ms, 6), "previews_timed": previews, "batch_per_gpu": B}
 
 
 def run_ours(args, rank, world, device):
@@ -322,7 +416,26 @@ def run_ours(args, rank, world, device):
             sweep.append({"batch": Bs, "us_per_launch": round(us, 3), "achieved": round(nbytes / us / 1e3, 1),
                           "frac": round(nbytes / us / 1e3 / peak, 4)})
         out["roofline_sweep"] = sweep
+        fm = []
+        for Bs in (1, 8, 64, 512):
+            us, nbytes = time_fm_kernel(Bs, device)
+            fm.append({"batch": Bs, "us_per_launch": round(us, 3), "achieved": round(nbytes / us / 1e3, 1),
+                       "frac": round(nbytes / us / 1e3 / peak, 4)})
+        out["roofline_fm_flux_bf16"] = {"kernel": "step_kernel<bf16,NH=2,FM>", "shape": "[B,4096,64] bf16 (FLUX-Kontext "
+                                        "packed 1024^2 latents), order_dim=2", "bytes_per_sample": 4 * 4096 * 64 * 2,
+                                        "points": fm}
         out["cpu_baseline"] = cpu_baseline(B, budget_s=args.cpu_budget)
+    if not args.no_denoiser:
+        try:
+            wd = with_denoiser(B, device, sd)
+            if world > 1:
+                t = torch.tensor([wd["ms_per_preview_batch"]], device=device)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                wd["ms_per_preview_batch"] = round(t.item(), 2)
+                wd["value"] = round(world * B / (t.item() / 1e3), 2)
+            out["with_denoiser"] = wd
+        except Exception as e:  # noqa: BLE001  (the stand-in is optional; the solver numbers above stand on their own)
+            out["with_denoiser"] = {"error": repr(e)[:200]}
     return out
 
 
@@ -397,6 +510,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--eager", action="store_true", help="python-eager launches instead of the CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
+    ap.add_argument("--no-denoiser", action="store_true", help="skip the with_denoiser (U-Net stand-in) measurement")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / roofline / cpu_baseline (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -22,12 +22,12 @@ SIGNATURES = {
     "consolver_abi_version": (_i, []),
     "consolver_error_string": (C.c_char_p, [_i]),
     "consolver_policy_f32": (_i, [_p] * 7 + [_f] * 4 + [_p, _i] + [_p, _p] + [_i] * 7 + [_p] * 7 + [_p]),
-    "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
-    "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _f, _i, _i, _i64, _p]),
+    "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
+    "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
     "consolver_policy_table_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i, _p, _p]),
     "consolver_policy_sample_f32": (_i, [_p] * 4 + [_i] * 6 + [_p] * 6 + [_p]),
     "consolver_sd_policy_and_step": (_i, [_p] * 8 + [_f] * 4 + [_p, _p] + [_i] * 4 + [_p] * 7 +
-                                     [_i, _p, _p, _f, _p, _p, _i, _p, _p, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
+                                     [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_set_step_launch": (_i, [_i, _i]),
     "consolver_cosine_features_workspace": (C.c_size_t, [_i, _i]),
     "consolver_cosine_features": (_i, [_i, _p, _p, _f, _p, _i, _i, _i, _i64, _p, _p, _p]),

@@ -468,7 +468,8 @@ extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, co
                                             float* act_logp, float* masks, float* coef,
                                             int dtype, const void* e0, const void* cond, float guidance,
                                             void* slot_out, const void* const* hist, int n_hist, const void* x,
-                                            void* x_out, int order_dim, float sa_t, float sb_t, float sa_p,
+                                            void* x_out, void* x_out2, int64_t out2_stride, int order_dim,
+                                            float sa_t, float sb_t, float sa_p,
                                             float sb_p, int flags, int B, int64_t n_per_sample,
                                             consolver_stream_t stream) {
   int rc;
@@ -484,7 +485,7 @@ extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, co
   int f = flags;
   if (scaler_dim >= 1) f |= CONSOLVER_FLAG_EFF_SCALE;
   if (scaler_dim >= 2) f |= CONSOLVER_FLAG_X_SCALE;
-  return consolver_step_sd(dtype, e0, cond, guidance, slot_out, hist, n_hist, x, x_out, coef,
+  return consolver_step_sd(dtype, e0, cond, guidance, slot_out, hist, n_hist, x, x_out, x_out2, out2_stride, coef,
                            CONSOLVER_COEF_STRIDE(order_dim), order_dim, sa_t, sb_t, sa_p, sb_p, f, B, n_per_sample,
                            stream);
 }

@@ -25,6 +25,8 @@ struct StepParams {
   const void* hist[kMaxOlder];
   const void* x;
   void* x_out;
+  void* x_out2;           // nullable: second copy of x' (e.g. the other half of the next CFG-doubled denoiser input)
+  long long out2_stride;  // elements between consecutive samples in x_out2
   const float* coef;
   int coef_stride;
   int order_dim;

@@ -5,11 +5,12 @@ using namespace consolver;
 
 extern "C" int consolver_step_fm(int dtype, int x_dtype, const void* e0, void* slot_out,
                                  const void* const* hist, int n_hist, const void* x, void* x_out,
+                                 void* x_out2, int64_t out2_stride,
                                  const float* coef, int coef_stride, int order_dim, float dt, int flags,
                                  int B, int64_t n_per_sample, consolver_stream_t stream) {
   StepParams p;
-  int rc = fill_common(p, e0, nullptr, slot_out, hist, n_hist, x, x_out, coef, coef_stride, order_dim,
-                       flags & ~CONSOLVER_FLAG_VPRED, B, (long long)n_per_sample);
+  int rc = fill_common(p, e0, nullptr, slot_out, hist, n_hist, x, x_out, x_out2, (long long)out2_stride, coef,
+                       coef_stride, order_dim, flags & ~CONSOLVER_FLAG_VPRED, B, (long long)n_per_sample);
   if (rc) return rc;
   p.k0 = dt;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

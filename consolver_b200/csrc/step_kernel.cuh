@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
       r_out.set(i, out);
     }
     r_out.store(static_cast<T*>(p.x_out) + off[u]);
+    if (p.x_out2) r_out.store(static_cast<T*>(p.x_out2) + (long long)b * p.out2_stride + (off[u] - base));
     if (pair && p.slot_out) r_slot.store(static_cast<T*>(p.slot_out) + off[u]);
   }
   // plain (non-pair) step with a ring slot requested: copy e0 through
@@ -172,14 +173,16 @@ static int launch_step(StepParams& p, bool vec_ok, cudaStream_t stream) {
 
 // argument validation shared by both entry points; fills p.hist
 inline int fill_common(StepParams& p, const void* e0, const void* cond, void* slot_out, const void* const* hist,
-                       int n_hist, const void* x, void* x_out, const float* coef, int coef_stride, int order_dim,
-                       int flags, int B, long long n_per_sample) {
+                       int n_hist, const void* x, void* x_out, void* x_out2, long long out2_stride,
+                       const float* coef, int coef_stride, int order_dim, int flags, int B, long long n_per_sample) {
   if (!e0 || !x || !x_out || !coef) return CONSOLVER_ERR_NULL;
   if (order_dim < 2 || order_dim > CONSOLVER_MAX_ORDER || n_hist < 1 || n_hist > order_dim) return CONSOLVER_ERR_SIZE;
   if (coef_stride < order_dim + 2 || B <= 0 || n_per_sample <= 0) return CONSOLVER_ERR_SIZE;
   if (n_hist > 1 && !hist) return CONSOLVER_ERR_NULL;
   p = StepParams{};
   p.e0 = e0; p.cond = cond; p.slot_out = slot_out; p.x = x; p.x_out = x_out;
+  p.x_out2 = x_out2; p.out2_stride = out2_stride > 0 ? out2_stride : n_per_sample;
+  if (x_out2 && p.out2_stride < n_per_sample) return CONSOLVER_ERR_SIZE;
   for (int j = 0; j < n_hist - 1; ++j) {
     if (!hist[j]) return CONSOLVER_ERR_NULL;
     p.hist[j] = hist[j];
@@ -193,6 +196,7 @@ inline bool all_aligned(const StepParams& p) {
   bool ok = aligned16(p.e0) && aligned16(p.x) && aligned16(p.x_out);
   if (p.cond) ok = ok && aligned16(p.cond);
   if (p.slot_out) ok = ok && aligned16(p.slot_out);
+  if (p.x_out2) ok = ok && aligned16(p.x_out2) && (p.out2_stride % 8 == 0);
   for (int j = 0; j < p.n_hist - 1; ++j) ok = ok && aligned16(p.hist[j]);
   return ok;
 }

@@ -18,12 +18,13 @@ extern "C" int consolver_set_step_launch(int threads, int unroll) {
 
 extern "C" int consolver_step_sd(int dtype, const void* e0, const void* cond, float guidance, void* slot_out,
                                  const void* const* hist, int n_hist, const void* x, void* x_out,
+                                 void* x_out2, int64_t out2_stride,
                                  const float* coef, int coef_stride, int order_dim,
                                  float sa_t, float sb_t, float sa_p, float sb_p, int flags,
                                  int B, int64_t n_per_sample, consolver_stream_t stream) {
   StepParams p;
-  int rc = fill_common(p, e0, cond, slot_out, hist, n_hist, x, x_out, coef, coef_stride, order_dim, flags, B,
-                       (long long)n_per_sample);
+  int rc = fill_common(p, e0, cond, slot_out, hist, n_hist, x, x_out, x_out2, (long long)out2_stride, coef,
+                       coef_stride, order_dim, flags, B, (long long)n_per_sample);
   if (rc) return rc;
   p.guidance = guidance;
   p.k0 = sa_t; p.k1 = sb_t; p.k2 = sa_p; p.k3 = sb_p;

@@ -26,17 +26,25 @@ def denoise_loop(scheduler: PPOScheduler, denoiser: Callable[[torch.Tensor, torc
     `denoiser(latent_model_input [2B,...], t, i)` returns the noise prediction for the CFG-doubled batch
     (unconditional half first) — or for the plain batch when cfg <= 1.  Returns (latents, record) where record
     has the reference's layout: x [B,n-1,2], probs / actions / masks [B,n-1,A]."""
-    latents = noise.clone()
     scheduler.set_timesteps(num_inference_steps, device=noise.device)
     do_cfg = cfg > 1.0
-    for i, t in enumerate(scheduler.timesteps):
-        model_in = torch.cat([latents] * 2) if do_cfg else latents
-        model_in = scheduler.scale_model_input(model_in, t)
-        pred = denoiser(model_in, t, i)
-        if do_cfg:
-            latents = scheduler.step_cfg(pred, t, latents, cfg)[0]
-        else:
+    B = noise.shape[0]
+    if not do_cfg:
+        latents = noise.clone()
+        for i, t in enumerate(scheduler.timesteps):
+            pred = denoiser(scheduler.scale_model_input(latents, t), t, i)
             latents = scheduler.step(pred, t, latents, return_dict=False)[0]
+        return latents, (scheduler.trajectory() if record and num_inference_steps > 1 else None)
+    # CFG: two ping-pong [2B,...] denoiser inputs.  The step kernel writes x' into BOTH halves of the next input
+    # (out / out2), so torch.cat([latents] * 2) (denoise_ppo.py:66: read N, write 2N per step) never runs.
+    bufs = [noise.new_empty((2 * B, *noise.shape[1:])) for _ in range(2)]
+    bufs[0][:B].copy_(noise)
+    bufs[0][B:].copy_(noise)
+    for i, t in enumerate(scheduler.timesteps):
+        cur, nxt = bufs[i % 2], bufs[(i + 1) % 2]
+        pred = denoiser(scheduler.scale_model_input(cur, t), t, i)
+        scheduler.step_cfg(pred, t, cur[:B], cfg, out=nxt[:B], out2=nxt[B:])
+    latents = bufs[len(scheduler.timesteps) % 2][:B]
     return latents, (scheduler.trajectory() if record and num_inference_steps > 1 else None)
 
 

@@ -254,9 +254,12 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, s_churn: float = 0.0,
              s_tmin: float = 0.0, s_tmax: float = float("inf"), s_noise: float = 1.0,
              generator: Optional[torch.Generator] = None, per_token_timesteps: Optional[torch.Tensor] = None,
-             return_dict: bool = True):
+             return_dict: bool = True, out2: Optional[torch.Tensor] = None):
         """Same contract as edit_ppo/scheduler_fmppo.py:306-455 (s_churn/s_tmin/s_tmax/s_noise/generator are
-        accepted and unused there as well)."""
+        accepted and unused there as well).  `out2` (new, optional): a second destination for the next latent with
+        contiguous samples and any sample stride, e.g. `latent_model_input[:, :L]` of the next transformer call,
+        which removes the caller's torch.cat([latents, image_latents], dim=1) copy of the latents
+        (edit_ppo/denoise_diffusion.py:102)."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
         if isinstance(timestep, int) or (isinstance(timestep, torch.Tensor) and
@@ -335,6 +338,7 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         rc = lib.consolver_step_fm(
             _lib.dtype_code(e0.dtype), _lib.dtype_code(sample.dtype), e0.data_ptr(), None,
             _lib.ptr_array([h.data_ptr() for h in older]), n_hist, sample.data_ptr(), x_out.data_ptr(),
+            out2.data_ptr() if out2 is not None else None, out2.stride(0) if out2 is not None else 0,
             o["coef"][i].data_ptr(), od + 2, od, dt, flags, B, N, stream)
         _lib.check(rc, "consolver_step_fm")
 

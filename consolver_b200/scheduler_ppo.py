@@ -219,18 +219,25 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         return self._step(model_output, None, 0.0, timestep, sample, return_dict, None)
 
     def step_cfg(self, noise_pred: torch.Tensor, timestep, sample: torch.Tensor, guidance_scale: float,
-                 return_dict: bool = False, out: Optional[torch.Tensor] = None):
+                 return_dict: bool = False, out: Optional[torch.Tensor] = None,
+                 out2: Optional[torch.Tensor] = None):
         """Fused variant: `noise_pred` is the denoiser output for torch.cat([latents]*2) — unconditional half
         first (denoise_ppo.py:66,:97) — and `u + g*(c-u)` is formed inside the step kernel, which also writes
-        it into this step's slot of the scheduler-owned history ring."""
+        it into this step's slot of the scheduler-owned history ring.  `out` / `out2`: optional destinations for the
+        next latent — e.g. the two halves of the next CFG-doubled denoiser input, which removes the caller's
+        torch.cat([latents] * 2) (denoise_ppo.py:66)."""
         B = sample.shape[0]
         if noise_pred.shape[0] != 2 * B:
             raise ValueError("step_cfg expects the [2B, ...] classifier-free-guidance pair")
         if not noise_pred.is_contiguous():
             noise_pred = noise_pred.contiguous()
-        return self._step(noise_pred[:B], noise_pred[B:], float(guidance_scale), timestep, sample, return_dict, out)
+        if out2 is not None and (out2.shape != sample.shape or out2.dtype != sample.dtype or
+                                 not out2[0].is_contiguous()):
+            raise ValueError("out2 must have the sample's shape/dtype with contiguous samples")
+        return self._step(noise_pred[:B], noise_pred[B:], float(guidance_scale), timestep, sample, return_dict, out,
+                          out2)
 
-    def _step(self, e0, cond, guidance, timestep, sample, return_dict, out):
+    def _step(self, e0, cond, guidance, timestep, sample, return_dict, out, out2=None):
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
         if not (e0.is_cuda and sample.is_cuda):
@@ -285,7 +292,8 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         stream = torch.cuda.current_stream(e0.device).cuda_stream
         step_args = (_lib.dtype_code(e0.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, guidance,
                      slot.data_ptr() if slot is not None else None, hist_ptrs, n_hist, sample.data_ptr(),
-                     x_out.data_ptr())
+                     x_out.data_ptr(), out2.data_ptr() if out2 is not None else None,
+                     out2.stride(0) if out2 is not None else 0)
         if not fn.use_conv:
             # The policy input row depends only on the timestep grid: evaluate the MLP + softmax for ALL n rows in
             # one launch at the first step of a pass; every step then only samples from its row of the table.

@@ -116,6 +116,10 @@ CONSOLVER_API int consolver_policy_f32(const float* w1, const float* b1, const f
  *   slot_out         NULL, or [B,N]: receives eps (the in-place history-ring slot of this step)
  *   hist (host)      array of n_hist-1 device pointers to the older model outputs, newest first
  *   x, x_out         current / next latent [B,N]
+ *   x_out2           NULL, or a second destination for the next latent with `out2_stride` elements between
+ *                    samples (0 = N): lets the caller have x' land directly in the other half of the next
+ *                    CFG-doubled denoiser input (denoise_ppo.py:66) or inside a wider packed sequence
+ *                    (edit_ppo/denoise_diffusion.py:102) instead of running torch.cat
  *   coef             [B,coef_stride] from consolver_policy_f32; n_hist == 1 bypasses the coefficient
  *                    (scheduler_ppo.py:263-265)
  *   sa_t,sb_t,sa_p,sb_p   sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev), sqrt(1-abar_prev) (fp32 values)
@@ -123,6 +127,7 @@ CONSOLVER_API int consolver_policy_f32(const float* w1, const float* b1, const f
  */
 CONSOLVER_API int consolver_step_sd(int dtype, const void* e0, const void* cond, float guidance, void* slot_out,
                       const void* const* hist, int n_hist, const void* x, void* x_out,
+                      void* x_out2, int64_t out2_stride,
                       const float* coef, int coef_stride, int order_dim,
                       float sa_t, float sb_t, float sa_p, float sb_p, int flags,
                       int B, int64_t n_per_sample, consolver_stream_t stream);
@@ -138,6 +143,7 @@ CONSOLVER_API int consolver_step_sd(int dtype, const void* e0, const void* cond,
  */
 CONSOLVER_API int consolver_step_fm(int dtype, int x_dtype, const void* e0, void* slot_out,
                       const void* const* hist, int n_hist, const void* x, void* x_out,
+                      void* x_out2, int64_t out2_stride,
                       const float* coef, int coef_stride, int order_dim, float dt, int flags,
                       int B, int64_t n_per_sample, consolver_stream_t stream);
 
@@ -179,6 +185,7 @@ CONSOLVER_API int consolver_sd_policy_and_step(const float* w1, const float* b1,
                                  float* act_logp, float* masks, float* coef,
                                  int dtype, const void* e0, const void* cond, float guidance, void* slot_out,
                                  const void* const* hist, int n_hist, const void* x, void* x_out,
+                                 void* x_out2, int64_t out2_stride,
                                  int order_dim, float sa_t, float sb_t, float sa_p, float sb_p, int flags,
                                  int B, int64_t n_per_sample, consolver_stream_t stream);
 

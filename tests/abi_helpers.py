@@ -35,7 +35,7 @@ def policy(sd, x0, x1, x_div, temp, B, order_dim, scaler_dim, n_hist, q=None, id
     return out
 
 
-def step_sd(e0, cond, guidance, hist, x, coef, order_dim, scalars, flags=0, slot=False):
+def step_sd(e0, cond, guidance, hist, x, coef, order_dim, scalars, flags=0, slot=False, out2=None):
     lib = _lib.load()
     B = x.shape[0]
     N = x.numel() // B
@@ -44,13 +44,14 @@ def step_sd(e0, cond, guidance, hist, x, coef, order_dim, scalars, flags=0, slot
     rc = lib.consolver_step_sd(
         _lib.dtype_code(x.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, float(guidance),
         slot_t.data_ptr() if slot else None, _lib.ptr_array([h.data_ptr() for h in hist]), len(hist) + 1,
-        x.data_ptr(), x_out.data_ptr(), coef.data_ptr(), coef.shape[1], order_dim,
+        x.data_ptr(), x_out.data_ptr(), out2.data_ptr() if out2 is not None else None,
+        out2.stride(0) if out2 is not None else 0, coef.data_ptr(), coef.shape[1], order_dim,
         *[float(s) for s in scalars], flags, B, N, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "consolver_step_sd")
     return x_out, slot_t
 
 
-def step_fm(e0, hist, x, coef, order_dim, dt, flags=0):
+def step_fm(e0, hist, x, coef, order_dim, dt, flags=0, out2=None):
     lib = _lib.load()
     B = x.shape[0]
     N = x.numel() // B
@@ -58,6 +59,7 @@ def step_fm(e0, hist, x, coef, order_dim, dt, flags=0):
     rc = lib.consolver_step_fm(
         _lib.dtype_code(e0.dtype), _lib.dtype_code(x.dtype), e0.data_ptr(), None,
         _lib.ptr_array([h.data_ptr() for h in hist]), len(hist) + 1, x.data_ptr(), x_out.data_ptr(),
+        out2.data_ptr() if out2 is not None else None, out2.stride(0) if out2 is not None else 0,
         coef.data_ptr(), coef.shape[1], order_dim, float(dt), flags, B, N, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "consolver_step_fm")
     return x_out

@@ -53,17 +53,20 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     rc = lib.consolver_policy_f32(*([None] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, None, None, 1, 256, 3, 11, 4, 0, 1,
                                   *([None] * 7), None)
     assert rc == -1
-    rc = lib.consolver_step_sd(0, None, None, 0.0, None, None, 1, None, None, None, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1,
-                               16, None)
+    rc = lib.consolver_step_sd(0, None, None, 0.0, None, None, 1, None, None, None, 0, None, 6, 4, 1.0, 0.0, 1.0, 0.0,
+                               0, 1, 16, None)
     assert rc == -1
     one = 16  # any non-null fake address: validation must fail on sizes before any dereference / launch
-    rc = lib.consolver_step_sd(0, one, None, 0.0, None, None, 5, one, one, one, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1, 16, None)
+    rc = lib.consolver_step_sd(0, one, None, 0.0, None, None, 5, one, one, None, 0, one, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1,
+                               16, None)
     assert rc == -2  # n_hist > order_dim
-    rc = lib.consolver_step_sd(0, one, None, 0.0, None, None, 1, one, one, one, 6, 9, 1.0, 0.0, 1.0, 0.0, 0, 1, 16, None)
+    rc = lib.consolver_step_sd(0, one, None, 0.0, None, None, 1, one, one, None, 0, one, 6, 9, 1.0, 0.0, 1.0, 0.0, 0, 1,
+                               16, None)
     assert rc == -2  # order_dim > CONSOLVER_MAX_ORDER
-    rc = lib.consolver_step_sd(7, one, None, 0.0, None, None, 1, one, one, one, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1, 16, None)
+    rc = lib.consolver_step_sd(7, one, None, 0.0, None, None, 1, one, one, None, 0, one, 6, 4, 1.0, 0.0, 1.0, 0.0, 0, 1,
+                               16, None)
     assert rc == -4  # dtype
-    rc = lib.consolver_step_fm(2, 1, one, None, None, 1, one, one, one, 6, 4, -0.1, 0, 1, 16, None)
+    rc = lib.consolver_step_fm(2, 1, one, None, None, 1, one, one, None, 0, one, 6, 4, -0.1, 0, 1, 16, None)
     assert rc == -4  # x_dtype must be dtype or f32
     rc = lib.consolver_policy_f32(*([one] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, one, one, 1, 256, 3, 11, 4, 0, 1,
                                   *([one] * 7), None)

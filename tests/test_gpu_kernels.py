@@ -269,3 +269,51 @@ def test_policy_per_sample_features_vs_oracle():
     assert torch.equal(out["idx"].cpu(), idx)
     actions, act_probs = orc.gather_actions(sd, out["probs_table"].cpu(), idx)
     assert torch.equal(out["actions"].cpu(), actions) and torch.equal(out["probs"].cpu(), act_probs)
+
+
+def test_second_destination_out2():
+    """x' also lands in a second buffer (other half of the next CFG-doubled input / a wider packed sequence)."""
+    B, shape, od = 3, (4, 16, 16), 4
+    g = torch.Generator().manual_seed(11)
+    rn = lambda: torch.randn(B, *shape, generator=g).cuda()  # noqa: E731
+    e0, cond, x, h = rn(), rn(), rn(), [rn()]
+    c = _rand_coef(B, od, g, 0).cuda()
+    scalars = (0.8378, 0.5460, 0.9151, 0.4033)
+    nxt = torch.zeros(2 * B, *shape, device="cuda")
+    out, _ = ah.step_sd(e0, cond, 3.0, h, x, c, od, scalars, 0, out2=nxt[B:])
+    assert torch.equal(nxt[B:], out) and torch.count_nonzero(nxt[:B]) == 0
+    # FM: strided destination inside a [B, 2L, D] packed sequence
+    v, xf = torch.randn(B, 64, 8, device="cuda").bfloat16(), torch.randn(B, 64, 8, device="cuda").bfloat16()
+    wide = torch.zeros(B, 128, 8, device="cuda", dtype=torch.bfloat16)
+    cf = _rand_coef(B, 2, g, 0).cuda()
+    o = ah.step_fm(v, [], xf, cf, 2, -0.05, 0, out2=wide[:, :64])
+    assert torch.equal(wide[:, :64], o) and torch.count_nonzero(wide[:, 64:]) == 0
+
+
+def test_denoise_loop_without_cat_matches_manual_loop():
+    import consolver_b200 as cb
+    from consolver_b200.denoise import denoise_loop
+
+    kw = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, steps_offset=1,
+              timestep_spacing="trailing", order_dim=4, scaler_dim=0,
+              factor_net_kwargs=dict(hidden_dim=64, num_actions=11))
+    torch.manual_seed(0)
+    a, b = cb.PPOScheduler(**kw), cb.PPOScheduler(**kw)
+    with torch.no_grad():
+        a.factor_net.mlp[4].weight.normal_(0, 0.3)
+    b.factor_net.load_state_dict(a.factor_net.state_dict())
+    a.factor_net.cuda(), b.factor_net.cuda()
+    w = torch.randn(4, 4, device="cuda") * 0.3
+    den = lambda xin, t, i: torch.einsum("oc,bchw->bohw", w * (1 + 0.1 * i), xin)  # noqa: E731
+    noise = torch.randn(5, 4, 16, 16, device="cuda")
+    torch.manual_seed(5)
+    lat, rec = denoise_loop(a, den, noise, cfg=3.0, num_inference_steps=6)
+    torch.manual_seed(5)
+    b.set_timesteps(6, device="cuda")
+    x = noise.clone()
+    for i, t in enumerate(b.timesteps):
+        pred = den(torch.cat([x] * 2), t, i)
+        u, c = pred.chunk(2)
+        x = b.step(u + 3.0 * (c - u), t, x, return_dict=False)[0]     # the reference's caller-side sequence
+    assert torch.equal(lat, x)
+    assert torch.equal(rec["idx"], b.trajectory()["idx"])

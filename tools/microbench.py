@@ -71,7 +71,7 @@ def bench_sd(B, n_hist=4, pair=True, N=4 * 64 * 64, dtype=torch.float32, iters=2
         rc = lib.consolver_step_sd(code, s["e0"].data_ptr(), s["cond"].data_ptr() if pair else None, 3.0,
                                    s["slot"].data_ptr() if pair else None,
                                    _lib.ptr_array([h.data_ptr() for h in s["hist"]]), n_hist, s["x"].data_ptr(),
-                                   s["out"].data_ptr(), coef.data_ptr(), order_dim + 2, order_dim,
+                                   s["out"].data_ptr(), None, 0, coef.data_ptr(), order_dim + 2, order_dim,
                                    0.8378, 0.5460, 0.9151, 0.4033, flags, B, N, stream)
         assert rc == 0, rc
 
