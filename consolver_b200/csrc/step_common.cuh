@@ -69,7 +69,9 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   return r;
 }
 __device__ __forceinline__ void st16(void* p, const uint4& v) {
-  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  // streaming (evict-first) stores: measured +4.3 % over default-policy stores on B200 for this 6-read / 2-write
+  // mix (profiles/step_variants_r01.txt): 7246 vs 6948 GB/s at B=4096
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -120,6 +120,7 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         self.sync_free = True
         self.use_pdl = True
         self.replay: Optional[Dict] = None    # see PPOScheduler.replay
+        self.fixed_coefficients = None        # see PPOScheduler.fixed_coefficients
 
     # ---- small properties / helpers of the reference surface ---------------------------------------------------
     @property
@@ -288,7 +289,8 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         if si + 1 >= len(self._sigmas_host):
             raise IndexError("FMPPOScheduler.step called past the end of the sigma schedule")
         i = tr.count % tr.n
-        older = self._hist[: od - 1]
+        depth = od if self.fixed_coefficients is None else min(od, getattr(self, "fixed_depth", od) or od)
+        older = self._hist[: depth - 1]
         n_hist = len(older) + 1
         dt = float(np.float32(self._sigmas_host[si + 1]) - np.float32(self._sigmas_host[si]))   # :373-376
         x0, x1 = float(tr.condx_host[si, 0]), float(tr.condx_host[si, 1])
@@ -296,7 +298,9 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
 
         o = tr.out
         q_ptr, idx_ptr = tr.q.data_ptr(), None
-        if self.replay is None:
+        if self.fixed_coefficients is not None:
+            pass                                        # baseline solvers draw nothing
+        elif self.replay is None:
             tr.q.exponential_(1)                        # the draw torch.multinomial makes
         elif self.replay.get("idx") is not None:
             forced = self.replay["idx"][tr.count].to(device=e0.device, dtype=torch.int64).contiguous()
@@ -306,8 +310,16 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         x_out = torch.empty(sample.shape, device=e0.device, dtype=e0.dtype)
         lib = _lib.load()
         stream = torch.cuda.current_stream(e0.device).cuda_stream
-        w = fn.kernel_weights()
-        if not fn.use_conv:
+        w = fn.kernel_weights() if self.fixed_coefficients is None else None
+        coef_ptr = o["coef"][i].data_ptr()
+        if self.fixed_coefficients is not None:
+            cache = tr.__dict__.setdefault("_fixed", {})
+            if n_hist not in cache:
+                c = [float(v) for v in self.fixed_coefficients(n_hist)]
+                row = torch.tensor(c + [0.0] * (od - n_hist) + [1.0, 1.0], dtype=torch.float32)
+                cache[n_hist] = row.to(e0.device).expand(B, od + 2).contiguous()
+            coef_ptr = cache[n_hist].data_ptr()
+        elif not fn.use_conv:
             # all n (sigma, sigma_next) rows of the schedule go through the MLP in one launch per pass
             if tr.table_pass != tr.count // tr.n:
                 fn.policy_tables(tr.condx_f32, o["probs_table"], stream)
@@ -339,7 +351,7 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
             _lib.dtype_code(e0.dtype), _lib.dtype_code(sample.dtype), e0.data_ptr(), None,
             _lib.ptr_array([h.data_ptr() for h in older]), n_hist, sample.data_ptr(), x_out.data_ptr(),
             out2.data_ptr() if out2 is not None else None, out2.stride(0) if out2 is not None else 0,
-            o["coef"][i].data_ptr(), od + 2, od, dt, flags, B, N, stream)
+            coef_ptr, od + 2, od, dt, flags, B, N, stream)
         _lib.check(rc, "consolver_step_fm")
 
         self._hist = [e0] + older
@@ -357,6 +369,8 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
             return s
 
         actions, probs, masks = o["actions"][i], o["probs"][i], o["masks"][i]
+        if self.fixed_coefficients is not None:
+            actions = probs = masks = None
         conds = LazyConds(conds_x, _stack)
         if not return_dict:
             return (x_out, actions, probs, conds, masks)

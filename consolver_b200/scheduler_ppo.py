@@ -165,6 +165,9 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         #: replay instead of sampling: {'idx': seq of [B,A] int64 per step} forces the bins (PPO replay, parity
         #: tests with injected actions); {'q': seq of [B*A,K] fp32 per step} supplies the Exp(1) draw.
         self.replay: Optional[Dict] = None
+        #: None, or a callable n_hist -> sequence of n_hist multipliers (newest first, summing to 1): the policy is
+        #: bypassed and the fused step runs with these fixed coefficients (see consolver_b200.baselines)
+        self.fixed_coefficients = None
 
     # ------------------------------------------------------------------------------------------------------
     @property
@@ -257,7 +260,8 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         if tr is None or tr.key != (B, tuple(sample.shape[1:]), e0.dtype, e0.device):
             tr = self._traj = _Trajectory(self, B, sample.shape[1:], e0.dtype, e0.device)
         i = tr.count % tr.n
-        older = self._hist[: od - 1]
+        depth = od if self.fixed_coefficients is None else min(od, getattr(self, "fixed_depth", od) or od)
+        older = self._hist[: depth - 1]
         n_hist = len(older) + 1
 
         # policy input row (t, prev_t) rounded through the model dtype (scheduler_ppo.py:207)
@@ -275,7 +279,9 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
 
         o = tr.out
         q_ptr, idx_ptr = tr.q.data_ptr(), None
-        if self.replay is None:
+        if self.fixed_coefficients is not None:
+            pass                                     # baseline solvers draw nothing
+        elif self.replay is None:
             tr.q.exponential_(1)                     # the draw torch.multinomial makes (factor_net_ppo.py:161)
         elif self.replay.get("idx") is not None:
             forced = self.replay["idx"][tr.count].to(device=e0.device, dtype=torch.int64).contiguous()
@@ -287,14 +293,21 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         flags = (_lib.FLAG_VPRED if cfg.prediction_type == "v_prediction" else 0) | \
                 (_lib.FLAG_PDL if self.use_pdl else 0)
         hist_ptrs = _lib.ptr_array([h.data_ptr() for h in older])
-        w = fn.kernel_weights()
+        w = fn.kernel_weights() if self.fixed_coefficients is None else None
         lib = _lib.load()
         stream = torch.cuda.current_stream(e0.device).cuda_stream
         step_args = (_lib.dtype_code(e0.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, guidance,
                      slot.data_ptr() if slot is not None else None, hist_ptrs, n_hist, sample.data_ptr(),
                      x_out.data_ptr(), out2.data_ptr() if out2 is not None else None,
                      out2.stride(0) if out2 is not None else 0)
-        if not fn.use_conv:
+        if self.fixed_coefficients is not None:
+            # baseline solvers: same fused kernel, coefficients from a fixed table instead of the
+            # policy — DDIM is depth 1, Adams-Bashforth / iPNDM style multistep are depths 2..4
+            coef_t = self._fixed_coef_rows(tr, n_hist, B, od)
+            rc = lib.consolver_step_sd(*step_args, coef_t.data_ptr(), od + 2, od, sa_t, sb_t, sa_p, sb_p,
+                                       flags & ~_lib.FLAG_PDL, B, N, stream)
+            _lib.check(rc, "consolver_step_sd")
+        elif not fn.use_conv:
             # The policy input row depends only on the timestep grid: evaluate the MLP + softmax for ALL n rows in
             # one launch at the first step of a pass; every step then only samples from its row of the table.
             on_grid = t == self._timesteps_host[i]
@@ -344,10 +357,22 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
             return s
 
         actions, probs, masks = o["actions"][i], o["probs"][i], o["masks"][i]
+        if self.fixed_coefficients is not None:
+            actions = probs = masks = None
         conds = LazyConds(conds_x, _stack)
         if not return_dict:
             return (x_out, actions, probs, conds, masks)
         return PPOSchedulerOutput(prev_sample=x_out, actions=actions, probs=probs, conds=conds, masks=masks)
+
+    def _fixed_coef_rows(self, tr, n_hist, B, od):
+        cache = tr.__dict__.setdefault("_fixed", {})
+        if n_hist not in cache:
+            c = [float(v) for v in self.fixed_coefficients(n_hist)]
+            if len(c) != n_hist:
+                raise ValueError("fixed_coefficients(n_hist) must return n_hist values")
+            row = torch.tensor(c + [0.0] * (od - n_hist) + [1.0, 1.0], dtype=torch.float32)
+            cache[n_hist] = row.to(tr.device).expand(B, od + 2).contiguous()
+        return cache[n_hist]
 
     # ------------------------------------------------------------------------------------------------------
     def trajectory(self, skip_first: bool = True):

@@ -112,6 +112,49 @@ def bench_sd(B, n_hist=4, pair=True, N=4 * 64 * 64, dtype=torch.float32, iters=2
                 gbs_best=round(bytes_per_launch / times[0] / 1e3, 1), nsets=nsets)
 
 
+def torch_reference_step(pair, x, hist, coef, guidance, sc):
+    """The reference's op sequence for one steady-state step, as stock torch ops on the GPU: CFG combine
+    (denoise_ppo.py:97-100), the dead stack copy (scheduler_ppo.py:222), the python-sum combine (:272) and
+    _get_prev_sample (:306-332).  17 full-size elementwise kernels + one stack — the bar the fused kernel replaces."""
+    u, c = pair.chunk(2)
+    eps = u + guidance * (c - u)
+    ets = [eps] + hist
+    torch.stack(ets, dim=1)
+    eff = sum(cj.view(-1, 1) * e for cj, e in zip(coef.unbind(1), ets))
+    sa_t, sb_t, sa_p, sb_p = sc
+    x0 = (x - sb_t * eff) / sa_t
+    return sa_p * x0 + sb_p * eff, eps
+
+
+def bench_torch_reference(B, mode="eager", N=4 * 64 * 64, iters=30, min_bytes=3 * L2_BYTES):
+    per = 8 * B * N * 4
+    nsets = max(2, min(16, -(-min_bytes // per)))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    mk = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    sets = [dict(pair=mk(2 * B, N), x=mk(B, N), hist=[mk(B, N) for _ in range(3)]) for _ in range(nsets)]
+    coef = mk(B, 4)
+    sc = [torch.tensor(v) for v in (0.8378, 0.5460, 0.9151, 0.4033)]     # 0-d CPU scalars, as in the reference
+    fn = torch_reference_step
+    if mode == "compile":
+        fn = torch.compile(torch_reference_step, dynamic=False)
+    for i in range(3):
+        fn(sets[i % nsets]["pair"], sets[i % nsets]["x"], sets[i % nsets]["hist"], coef, 3.0, sc)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            s = sets[i % nsets]
+            fn(s["pair"], s["x"], s["hist"], coef, 3.0, sc)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / iters * 1e3)
+    ts.sort()
+    return dict(B=B, impl=f"torch-{mode} reference op sequence on the GPU", us_median=round(ts[2], 2),
+                gbs_algorithmic=round(per / ts[2] / 1e3, 1))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", default="1,4,16,64,256,1024,4096")
@@ -121,6 +164,7 @@ def main():
     ap.add_argument("--pdl", type=int, default=0)
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--copy", type=int, default=1)
+    ap.add_argument("--torch-ref", default="", help="comma list of eager,compile: also time the reference op sequence")
     a = ap.parse_args()
     peak, src = load_peak()
     lib = _lib.load()
@@ -134,6 +178,14 @@ def main():
                 r.update(graph=a.graph, threads=th, unroll=un, frac=round(r["gbs"] / peak, 3), peak=peak, peak_src=src)
                 print(json.dumps(r), flush=True)
     lib.consolver_set_step_launch(0, 0)
+    for mode in [m for m in a.torch_ref.split(",") if m]:
+        for B in [int(v) for v in a.batches.split(",")]:
+            try:
+                r = bench_torch_reference(B, mode)
+                r.update(frac=round(r["gbs_algorithmic"] / peak, 3))
+                print(json.dumps(r), flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(json.dumps({"B": B, "impl": f"torch-{mode}", "error": repr(e)[:200]}), flush=True)
 
 
 if __name__ == "__main__":
