@@ -25,13 +25,27 @@ SIGNATURES = {
     "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
     "consolver_policy_table_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i, _p, _p]),
-    "consolver_policy_sample_f32": (_i, [_p] * 4 + [_i] * 6 + [_p] * 6 + [_p]),
-    "consolver_sd_policy_and_step": (_i, [_p] * 8 + [_f] * 4 + [_p, _p] + [_i] * 4 + [_p] * 7 +
+    "consolver_policy_sample_f32": (_i, [_p] * 4 + [_p, _p] + [_i] * 6 + [_p] * 6 + [_p]),
+    "consolver_rng_state_advance": (_i, [_p, C.c_uint64, _p]),
+    "consolver_torch_philox_plan": (_i, [_i64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "consolver_sd_policy_and_step": (_i, [_p] * 8 + [_f] * 4 + [_p, _p, _p] + [_i] * 4 + [_p] * 7 +
                                      [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_set_step_launch": (_i, [_i, _i]),
     "consolver_cosine_features_workspace": (C.c_size_t, [_i, _i]),
     "consolver_cosine_features": (_i, [_i, _p, _p, _f, _p, _i, _i, _i, _i64, _p, _p, _p]),
 }
+
+class Rng(C.Structure):
+    """consolver_rng_t"""
+    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("state", C.c_void_p), ("nthreads", C.c_uint32)]
+
+
+def philox_plan(numel: int):
+    """(nthreads, generator offset increment) of torch's exponential_ launch for `numel` elements"""
+    nt, inc = C.c_uint32(0), C.c_uint64(0)
+    check(load().consolver_torch_philox_plan(numel, C.byref(nt), C.byref(inc)), "consolver_torch_philox_plan")
+    return nt.value, inc.value
+
 
 _lib = None
 _lock = threading.Lock()

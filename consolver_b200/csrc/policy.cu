@@ -16,6 +16,7 @@
 // Tensor cores / shared-memory staging of the weights would add a pass with no reuse.
 // The Exp(1) slab of a CTA is contiguous; it is prefetched into shared memory with cp.async while the MLP runs.
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -43,7 +44,34 @@ struct PolicyParams {
   float *actions, *act_probs, *act_logp, *masks, *coef;
   int samples_per_cta;
   int stage_q;              // 1: the CTA's q slab fits the shared-memory budget
+  // in-kernel Exp(1) draw reproducing torch's CUDA `exponential_` stream (rng_mode != 0; q and idx_in are NULL)
+  int rng_mode;
+  unsigned long long rng_seed, rng_offset;
+  const unsigned long long* rng_state;   // nullable device [2] = {seed, offset}: overrides rng_seed, ADDS to rng_offset
+  unsigned int rng_nthreads;              // grid*block of the torch launch being reproduced
+  float* q_out;                           // nullable [B*A,K]: the draw, for checking
 };
+
+// The value torch.empty(numel).exponential_(1) writes at linear index `li` for generator state (seed, offset).
+// ATen's distribution_elementwise_grid_stride_kernel (unroll 4): thread `idx` of `nthreads` initialises
+// Philox4x32-10 with curand_init(seed, idx, offset) and its j-th curand_uniform4 feeds elements
+// idx + nthreads*(4*j + ii), ii = 0..3; the uniform u in (0,1] becomes -log(u), with log(u) replaced by -eps/2 when
+// u >= 1 - eps/2 (ATen transformation::exponential).  Philox counter = {offset/4 + j (64 bit), idx (64 bit)}.
+__device__ __forceinline__ float torch_exponential_at(unsigned long long seed, unsigned long long offset,
+                                                      unsigned int nthreads, unsigned long long li) {
+  const unsigned long long idx = li % nthreads;
+  const unsigned long long r = li / nthreads;
+  const unsigned long long lo = (offset >> 2) + (r >> 2);
+  const uint4 ctr = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)idx, (unsigned)(idx >> 32));
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  const uint4 o = curand_Philox4x32_10(ctr, key);
+  const unsigned ii = (unsigned)(r & 3);
+  const unsigned x = ii == 0 ? o.x : ii == 1 ? o.y : ii == 2 ? o.z : o.w;
+  const float u = _curand_uniform(x);
+  const float eps = 1.1920928955078125e-07f;
+  const float lg = (u >= 1.0f - eps / 2) ? -eps / 2 : __logf(u);   // at::log is __logf on the device (ATen/NumericUtils.h)
+  return -lg;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -157,8 +185,20 @@ __device__ __forceinline__ void mlp_softmax(const PolicyParams& p, int in_dim, c
 
 // Start the asynchronous copy of this CTA's contiguous Exp(1) slab q[b_begin*A*K ...] into shared memory.
 __device__ __forceinline__ void stage_q_begin(const PolicyParams& p, int b_begin, int nb, float* q_s) {
-  if (!p.q || !p.stage_q) return;
+  if (!p.stage_q) return;
   const size_t n = (size_t)nb * p.A * p.K;
+  if (p.rng_mode) {
+    // generate the slab instead of copying it: one Philox block per element, spread over the whole CTA
+    const unsigned long long seed = p.rng_state ? p.rng_state[0] : p.rng_seed;
+    const unsigned long long off = p.rng_offset + (p.rng_state ? p.rng_state[1] : 0ull);
+    const unsigned long long first = (unsigned long long)b_begin * p.A * p.K;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const float qv = torch_exponential_at(seed, off, p.rng_nthreads, first + i);
+      q_s[i] = qv;
+      if (p.q_out) p.q_out[first + i] = qv;
+    }
+    return;
+  }
   const float* src = p.q + (size_t)b_begin * p.A * p.K;
   if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
     const size_t n4 = n >> 2;
@@ -184,22 +224,33 @@ __device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin,
     const int a = pr % A;
     const size_t o = (size_t)b_begin * A + pr;
     int best = 0;
-    if (p.q) {
+    if (p.stage_q) {                                               // slab staged (copied or generated) in smem
+      const float* pa = p_s + a * K;
+      const float* qr = q_s + (size_t)pr * K;
+      float bv = -INFINITY;
+      for (int k = 0; k < K; ++k) {
+        const float r = __fdiv_rn(pa[k], qr[k]);                   // p / q, argmax, first index on ties
+        if (k == 0 || r > bv) { bv = r; best = k; }
+      }
+    } else if (p.rng_mode) {
+      const float* pa = p_s + a * K;
+      const unsigned long long seed = p.rng_state ? p.rng_state[0] : p.rng_seed;
+      const unsigned long long off = p.rng_offset + (p.rng_state ? p.rng_state[1] : 0ull);
+      float bv = -INFINITY;
+      for (int k = 0; k < K; ++k) {
+        const float qv = torch_exponential_at(seed, off, p.rng_nthreads, (unsigned long long)o * K + k);
+        if (p.q_out) p.q_out[o * K + k] = qv;
+        const float r = __fdiv_rn(pa[k], qv);
+        if (k == 0 || r > bv) { bv = r; best = k; }
+      }
+    } else if (p.q) {
       const float* pa = p_s + a * K;
       float bv = -INFINITY;
-      if (p.stage_q) {
-        const float* qr = q_s + (size_t)pr * K;
-        for (int k = 0; k < K; ++k) {
-          const float r = __fdiv_rn(pa[k], qr[k]);                 // p / q, argmax, first index on ties
-          if (k == 0 || r > bv) { bv = r; best = k; }
-        }
-      } else {
-        const float* qr = p.q + o * K;
+      const float* qr = p.q + o * K;
 #pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-          const float r = __fdiv_rn(pa[k], __ldg(qr + k));
-          if (k == 0 || r > bv) { bv = r; best = k; }
-        }
+      for (int k = 0; k < K; ++k) {
+        const float r = __fdiv_rn(pa[k], __ldg(qr + k));
+        if (k == 0 || r > bv) { bv = r; best = k; }
       }
     } else {
       best = (int)p.idx_in[o];
@@ -362,7 +413,8 @@ static int launch_policy(const PolicyParams& pp, int mode, int rows, cudaStream_
   }
   if (!p.action_values || !p.coef) return CONSOLVER_ERR_NULL;
   if (mode == kLaunchSample && !p.probs_in) return CONSOLVER_ERR_NULL;
-  if ((p.q == nullptr) == (p.idx_in == nullptr)) return CONSOLVER_ERR_NULL;  // exactly one of them
+  if ((p.q != nullptr) + (p.idx_in != nullptr) + (p.rng_mode != 0) != 1) return CONSOLVER_ERR_NULL;  // exactly one
+  if (p.rng_mode && p.rng_nthreads == 0) return CONSOLVER_ERR_SIZE;
   int rc = check_dims(p);
   if (rc) return rc;
   if (p.n_feat < 0 || 2 + p.n_feat > CONSOLVER_MAX_IN || (p.n_feat > 0 && !p.feat)) return CONSOLVER_ERR_SIZE;
@@ -375,13 +427,14 @@ static int launch_policy(const PolicyParams& pp, int mode, int rows, cudaStream_
   } else {
     spc = kQSlabBytes / (AK * (int)sizeof(float));
     // sampling-only launches carry no per-CTA MLP cost: use more, smaller CTAs
-    if (mode == kLaunchSample) spc = min(spc, max(64, (p.B + 147) / 148));
+    if (mode == kLaunchSample) spc = min(spc, max(p.rng_mode ? 16 : 64, (p.B + 147) / 148));
     spc = max(1, min(spc, kMaxSamplesPerCta));
     spc = min(spc, p.B);
     if (spc >= 4) spc &= ~3;                       // keeps every CTA's q slab 16-byte aligned
   }
   p.samples_per_cta = spc;
-  p.stage_q = (p.q != nullptr && !p.feat && (size_t)spc * AK * sizeof(float) <= (size_t)kQSlabBytes) ? 1 : 0;
+  p.stage_q = ((p.q != nullptr || p.rng_mode) && !p.feat &&
+               (size_t)spc * AK * sizeof(float) <= (size_t)kQSlabBytes) ? 1 : 0;
   const size_t q_floats = p.stage_q ? (size_t)spc * AK : 0;
   const int grid = (p.B + spc - 1) / spc;
   const int H = mode == kLaunchSample ? 0 : p.H;
@@ -444,8 +497,48 @@ extern "C" int consolver_policy_table_f32(const float* w1, const float* b1, cons
   return launch_policy(p, kLaunchTable, rows, static_cast<cudaStream_t>(stream));
 }
 
+static void set_rng(PolicyParams& p, const consolver_rng_t* rng, float* q_out) {
+  if (!rng) return;
+  p.rng_mode = 1;
+  p.rng_seed = rng->seed; p.rng_offset = rng->offset;
+  p.rng_state = reinterpret_cast<const unsigned long long*>(rng->state);
+  p.rng_nthreads = rng->nthreads;
+  p.q_out = q_out;
+}
+
+__global__ void rng_advance_kernel(unsigned long long* state, unsigned long long amount) { state[1] += amount; }
+
+extern "C" int consolver_rng_state_advance(uint64_t* state, uint64_t amount, consolver_stream_t stream) {
+  if (!state) return CONSOLVER_ERR_NULL;
+  rng_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(state),
+                                                                      (unsigned long long)amount);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int consolver_torch_philox_plan(int64_t numel, uint32_t* nthreads, uint64_t* offset_increment) {
+  // at::cuda::detail calc_execution_policy (ATen/native/cuda/DistributionTemplates.h): block 256, grid =
+  // min(ceil(numel/256), SMs * maxThreadsPerSM/256), increment = ceil(numel / (256*grid*4)) * 4
+  if (numel <= 0 || !nthreads || !offset_increment) return CONSOLVER_ERR_SIZE;
+  static int sms = 0, per_sm = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  }
+  const uint64_t n = (uint64_t)numel, block = 256;
+  uint64_t grid = (n + block - 1) / block;
+  const uint64_t cap = (uint64_t)sms * (uint64_t)(per_sm / (int)block);
+  if (grid > cap) grid = cap;
+  *nthreads = (uint32_t)(grid * block);
+  *offset_increment = ((n - 1) / (block * grid * 4) + 1) * 4;
+  return 0;
+}
+
 extern "C" int consolver_policy_sample_f32(const float* probs_in, const float* action_values, const float* q,
-                                           const int64_t* idx_in, int B, int A, int K, int order_dim,
+                                           const int64_t* idx_in, const consolver_rng_t* rng, float* q_out,
+                                           int B, int A, int K, int order_dim,
                                            int scaler_dim, int n_hist, int64_t* idx, float* actions,
                                            float* act_probs, float* act_logp, float* masks, float* coef,
                                            consolver_stream_t stream) {
@@ -455,6 +548,7 @@ extern "C" int consolver_policy_sample_f32(const float* probs_in, const float* a
   p.B = B; p.A = A; p.K = K; p.order_dim = order_dim; p.scaler_dim = scaler_dim; p.n_hist = n_hist;
   p.idx = reinterpret_cast<long long*>(idx); p.actions = actions; p.act_probs = act_probs; p.act_logp = act_logp;
   p.masks = masks; p.coef = coef;
+  if (!q && !idx_in) set_rng(p, rng, q_out);
   return launch_policy(p, kLaunchSample, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -462,7 +556,7 @@ extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, co
                                             const float* w3, const float* b3, const float* action_values,
                                             const float* probs_in,
                                             float x0, float x1, float x_div, float temp,
-                                            const float* q, const int64_t* idx_in,
+                                            const float* q, const int64_t* idx_in, const consolver_rng_t* rng,
                                             int H, int A, int K, int scaler_dim,
                                             float* probs_table, int64_t* idx, float* actions, float* act_probs,
                                             float* act_logp, float* masks, float* coef,
@@ -474,8 +568,8 @@ extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, co
                                             consolver_stream_t stream) {
   int rc;
   if (probs_in) {
-    rc = consolver_policy_sample_f32(probs_in, action_values, q, idx_in, B, A, K, order_dim, scaler_dim, n_hist,
-                                     idx, actions, act_probs, act_logp, masks, coef, stream);
+    rc = consolver_policy_sample_f32(probs_in, action_values, q, idx_in, rng, nullptr, B, A, K, order_dim,
+                                     scaler_dim, n_hist, idx, actions, act_probs, act_logp, masks, coef, stream);
   } else {
     rc = consolver_policy_f32(w1, b1, w2, b2, w3, b3, action_values, x0, x1, x_div, temp, nullptr, 0, q, idx_in,
                               B, H, A, K, order_dim, scaler_dim, n_hist, probs_table, idx, actions, act_probs,

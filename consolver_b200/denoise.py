@@ -80,10 +80,30 @@ class GraphedPreview:
         with torch.cuda.stream(s):
             preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
         torch.cuda.current_stream(dev).wait_stream(s)
+        # graph-safe fused RNG: the sample kernels read {seed, offset} from a device buffer that replay() refreshes
+        # from the default generator (and advances it), so every replay draws what eager execution would draw
+        from . import _lib, rng as _rng
+
+        tr = scheduler._traj
+        self._dev = dev
+        self._rng_inc = 0
+        if scheduler.use_fused_rng and _rng.fused_rng_available(dev):
+            tr.rng_plan = _lib.philox_plan(tr.q.numel())
+            tr.graph_rng = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._pinned = torch.zeros(64, 2, dtype=torch.int64).pin_memory()
+            self._pin_events = [None] * 64
+            self._k = 0
         self._rewind()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
+            if tr.graph_rng is not None and tr.graph_rng_used:
+                # last node: the device-resident offset advances by what this graph consumed, so back-to-back
+                # replays need no host refresh at all
+                self._rng_inc = tr.graph_rng_used * tr.rng_plan[1]
+                _lib.check(_lib.load().consolver_rng_state_advance(
+                    tr.graph_rng.data_ptr(), self._rng_inc, torch.cuda.current_stream(dev).cuda_stream), "rng advance")
+        self._expected = None      # (seed, offset) the device state holds for the next replay
         self._rewind()
 
     def _rewind(self):
@@ -93,8 +113,26 @@ class GraphedPreview:
         if sch._traj is not None:
             sch._traj.count = 0
             sch._traj.table_pass = -1      # the capture (and every replay) re-evaluates the probability tables
+            sch._traj.graph_rng_used = 0
 
     def replay(self) -> torch.Tensor:
+        if self._rng_inc:
+            from . import rng as _rng
+
+            seed, off = _rng.take(self._dev, self._rng_inc)     # torch's generator advances as eager code would
+            if self._expected != (seed, off):
+                # first replay, or somebody else used / reseeded the generator since: refresh the device state
+                j = self._k % 64
+                self._k += 1
+                if self._pin_events[j] is not None:
+                    self._pin_events[j].synchronize()                 # the copy that last used this slot is done
+                self._pinned[j, 0] = seed - (1 << 64) if seed >= (1 << 63) else seed
+                self._pinned[j, 1] = off
+                self.scheduler._traj.graph_rng.copy_(self._pinned[j], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pin_events[j] = ev
+            self._expected = (seed, off + self._rng_inc)
         self.graph.replay()
         return self.out
 

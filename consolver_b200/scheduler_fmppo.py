@@ -6,6 +6,7 @@ sigmas, mu, timesteps)`, `set_begin_index`, `step(...)` signature (incl. the ign
 `per_token_timesteps` (edit_ppo/scheduler_fmppo.py:363-371) is exercised by no caller and is not supported."""
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 import math
 from typing import Dict, List, Optional, Union
@@ -16,6 +17,7 @@ import torch
 from . import _lib
 from .config_utils import BaseOutput, ConfigMixin, LazyConds, SchedulerMixin, register_to_config
 from .factor_net import FactorNetPPOFM, alloc_policy_outputs
+from .scheduler_ppo import next_rng
 
 
 @dataclasses.dataclass
@@ -44,6 +46,7 @@ class _FMTrajectory:
         self.condx_host = host.float().numpy()
         self.count = 0
         self.table_pass = -1
+        self.rng_plan, self.graph_rng, self.graph_rng_used = None, None, 0
 
 
 class FMPPOScheduler(SchedulerMixin, ConfigMixin):
@@ -121,6 +124,7 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         self.use_pdl = True
         self.replay: Optional[Dict] = None    # see PPOScheduler.replay
         self.fixed_coefficients = None        # see PPOScheduler.fixed_coefficients
+        self.use_fused_rng = True             # see PPOScheduler.use_fused_rng
 
     # ---- small properties / helpers of the reference surface ---------------------------------------------------
     @property
@@ -297,11 +301,15 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         conds_x = tr.condx[si:si + 1].expand(B, 2)
 
         o = tr.out
-        q_ptr, idx_ptr = tr.q.data_ptr(), None
+        q_ptr, idx_ptr, rng_arg = tr.q.data_ptr(), None, None
         if self.fixed_coefficients is not None:
             pass                                        # baseline solvers draw nothing
         elif self.replay is None:
-            tr.q.exponential_(1)                        # the draw torch.multinomial makes
+            r = next_rng(self, tr, e0.device) if not fn.use_conv else None    # see scheduler_ppo.next_rng
+            if r is None:
+                tr.q.exponential_(1)                    # the draw torch.multinomial makes
+            else:
+                q_ptr, rng_arg = None, ctypes.byref(r)
         elif self.replay.get("idx") is not None:
             forced = self.replay["idx"][tr.count].to(device=e0.device, dtype=torch.int64).contiguous()
             q_ptr, idx_ptr = None, forced.data_ptr()
@@ -325,7 +333,8 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
                 fn.policy_tables(tr.condx_f32, o["probs_table"], stream)
                 tr.table_pass = tr.count // tr.n
             rc = lib.consolver_policy_sample_f32(
-                o["probs_table"][si].data_ptr(), w[6], q_ptr, idx_ptr, B, fn.action_dims, fn.num_actions, od,
+                o["probs_table"][si].data_ptr(), w[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
+                fn.num_actions, od,
                 cfg.scaler_dim, n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
                 o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
             _lib.check(rc, "consolver_policy_sample_f32")

@@ -19,6 +19,7 @@ There is no CPU path: inputs must be CUDA tensors and libconsolver.so must load.
 """
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 import math
 from typing import Dict, List, Optional, Tuple, Union
@@ -47,6 +48,30 @@ def _cosine_alpha_bar_betas(n: int, max_beta: float = 0.999) -> torch.Tensor:
     return torch.tensor([min(1 - bar((i + 1) / n) / bar(i / n), max_beta) for i in range(n)], dtype=torch.float32)
 
 
+def next_rng(sched, tr, device):
+    """consolver_rng_t for this step's in-kernel draw, or None to use the torch exponential_ launch."""
+    from . import rng as _rng
+
+    if not sched.use_fused_rng:
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        if tr.graph_rng is None or tr.rng_plan is None:
+            return None
+        nthreads, inc = tr.rng_plan
+        r = _lib.Rng(0, tr.graph_rng_used * inc, tr.graph_rng.data_ptr(), nthreads)
+        tr.graph_rng_used += 1
+    else:
+        if not _rng.fused_rng_available(device):
+            return None
+        if tr.rng_plan is None:
+            tr.rng_plan = _lib.philox_plan(tr.q.numel())
+        nthreads, inc = tr.rng_plan
+        seed, off = _rng.take(device, inc)
+        r = _lib.Rng(seed, off, None, nthreads)
+    tr._rng_keepalive = r
+    return r
+
+
 class _Trajectory:
     """Per-(set_timesteps, batch shape) device state: policy outputs for every step, the Exp(1) buffer, the
     history ring.  Allocated once; `step()` itself allocates only the returned latent."""
@@ -70,6 +95,9 @@ class _Trajectory:
         self.condx_host = host.float().numpy()
         self.count = 0
         self.table_pass = -1   # trajectory pass (count // n) whose probability tables are in out['probs_table']
+        self.rng_plan = None   # (nthreads, offset increment) of torch's exponential_ launch for q's numel
+        self.graph_rng = None  # device int64[2] {seed, offset} refreshed before every CUDA-graph replay
+        self.graph_rng_used = 0
 
     def conv_buffers(self, fn):
         """use_conv=True scratch: features [B,od-1], reduction workspace, per-sample tables [n,B,A,K]"""
@@ -162,6 +190,8 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         self.sync_free = True
         #: link the policy and step kernels with programmatic dependent launch
         self.use_pdl = True
+        #: generate the Exp(1) draw inside the sample kernel (bit-identical to torch's exponential_, see rng.py)
+        self.use_fused_rng = True
         #: replay instead of sampling: {'idx': seq of [B,A] int64 per step} forces the bins (PPO replay, parity
         #: tests with injected actions); {'q': seq of [B*A,K] fp32 per step} supplies the Exp(1) draw.
         self.replay: Optional[Dict] = None
@@ -278,11 +308,18 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         sa_p, sb_p = float(self._sqrt_abar[pi]), float(self._sqrt_1m_abar[pi])
 
         o = tr.out
-        q_ptr, idx_ptr = tr.q.data_ptr(), None
+        q_ptr, idx_ptr, rng_arg = tr.q.data_ptr(), None, None
+        on_grid = t == self._timesteps_host[i]
         if self.fixed_coefficients is not None:
             pass                                     # baseline solvers draw nothing
         elif self.replay is None:
-            tr.q.exponential_(1)                     # the draw torch.multinomial makes (factor_net_ppo.py:161)
+            # the draw torch.multinomial makes (factor_net_ppo.py:161): generated inside the sample kernel from the
+            # default generator's (seed, offset) when possible, else by the torch launch into tr.q
+            r = next_rng(self, tr, e0.device) if (on_grid and not fn.use_conv) else None
+            if r is None:
+                tr.q.exponential_(1)
+            else:
+                q_ptr, rng_arg = None, ctypes.byref(r)
         elif self.replay.get("idx") is not None:
             forced = self.replay["idx"][tr.count].to(device=e0.device, dtype=torch.int64).contiguous()
             q_ptr, idx_ptr = None, forced.data_ptr()
@@ -310,13 +347,12 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         elif not fn.use_conv:
             # The policy input row depends only on the timestep grid: evaluate the MLP + softmax for ALL n rows in
             # one launch at the first step of a pass; every step then only samples from its row of the table.
-            on_grid = t == self._timesteps_host[i]
             if on_grid and tr.table_pass != tr.count // tr.n:
                 fn.policy_tables(tr.condx_f32, o["probs_table"])
                 tr.table_pass = tr.count // tr.n
             probs_in = o["probs_table"][i].data_ptr() if on_grid else None
             rc = lib.consolver_sd_policy_and_step(
-                *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr,
+                *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr, rng_arg,
                 fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
                 o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
                 o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(),

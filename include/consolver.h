@@ -62,6 +62,18 @@ typedef void* consolver_stream_t; /* a cudaStream_t */
 #define CONSOLVER_API
 #endif
 
+/* In-kernel Exp(1) draw that reproduces torch's CUDA `Tensor.exponential_(1)` stream bit-for-bit, so the sample
+ * kernel needs no q buffer and no separate RNG launch: the value written at linear index i of a contiguous fp32
+ * tensor of `numel` elements for default-generator state (seed, offset).  nthreads and the generator's offset
+ * increment come from consolver_torch_philox_plan(numel).  `state` (nullable, device uint64[2] = {seed, offset})
+ * overrides `seed` and is ADDED to `offset`: CUDA-graph replays refresh it instead of re-recording parameters. */
+typedef struct consolver_rng {
+  uint64_t seed;
+  uint64_t offset;
+  const uint64_t* state;
+  uint32_t nthreads;
+} consolver_rng_t;
+
 CONSOLVER_API int consolver_abi_version(void);
 /* human-readable text for any return value of this library (static storage). */
 CONSOLVER_API const char* consolver_error_string(int err);
@@ -162,9 +174,16 @@ CONSOLVER_API int consolver_policy_table_f32(const float* w1, const float* b1, c
 /*
  * Sampling only, from a given probability table probs_in [A,K]: the draw, gathers, masks and coefficient assembly
  * of consolver_policy_f32 (factor_net_ppo.py:159-168; scheduler_ppo.py:248-259,:165-175).  Same outputs.
+ * Exactly one draw source: q [B*A,K] (given Exp(1) values), idx_in [B,A] (forced bins) or rng (host struct: the
+ * kernel generates torch's exponential_ values itself; q_out, nullable [B*A,K], receives them for checking).
  */
+CONSOLVER_API int consolver_torch_philox_plan(int64_t numel, uint32_t* nthreads, uint64_t* offset_increment);
+/* state[1] += amount on the stream (one thread): put it at the end of a captured graph so the device-resident
+ * generator state advances by the graph's total consumption and replays need no host refresh. */
+CONSOLVER_API int consolver_rng_state_advance(uint64_t* state, uint64_t amount, consolver_stream_t stream);
 CONSOLVER_API int consolver_policy_sample_f32(const float* probs_in, const float* action_values, const float* q,
-                                              const int64_t* idx_in, int B, int A, int K, int order_dim,
+                                              const int64_t* idx_in, const consolver_rng_t* rng, float* q_out,
+                                              int B, int A, int K, int order_dim,
                                               int scaler_dim, int n_hist, int64_t* idx, float* actions,
                                               float* act_probs, float* act_logp, float* masks, float* coef,
                                               consolver_stream_t stream);
@@ -179,7 +198,7 @@ CONSOLVER_API int consolver_sd_policy_and_step(const float* w1, const float* b1,
                                  const float* w3, const float* b3, const float* action_values,
                                  const float* probs_in,
                                  float x0, float x1, float x_div, float temp,
-                                 const float* q, const int64_t* idx_in,
+                                 const float* q, const int64_t* idx_in, const consolver_rng_t* rng,
                                  int H, int A, int K, int scaler_dim,
                                  float* probs_table, int64_t* idx, float* actions, float* act_probs,
                                  float* act_logp, float* masks, float* coef,

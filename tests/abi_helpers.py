@@ -1,5 +1,7 @@
 """Thin torch<->C-ABI helpers for the tests: every call goes through libconsolver.so exactly as a foreign
 host (cgo/JNI/ctypes) would — raw device pointers, sizes, a stream handle."""
+import ctypes
+
 import torch
 
 from consolver_b200 import _lib
@@ -77,7 +79,7 @@ def policy_table(sd, x_rows, x_div, temp):
     return out
 
 
-def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None):
+def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None, rng=None, q_out=None):
     lib = _lib.load()
     A, K = sd["action_values"].shape
     dev = table.device
@@ -87,7 +89,9 @@ def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=No
                coef=torch.zeros(B, order_dim + 2, **f))
     rc = lib.consolver_policy_sample_f32(
         table.data_ptr(), sd["action_values"].data_ptr(), q.data_ptr() if q is not None else None,
-        idx_in.data_ptr() if idx_in is not None else None, B, A, K, order_dim, scaler_dim, n_hist,
+        idx_in.data_ptr() if idx_in is not None else None,
+        ctypes.byref(rng) if rng is not None else None, q_out.data_ptr() if q_out is not None else None,
+        B, A, K, order_dim, scaler_dim, n_hist,
         out["idx"].data_ptr(), out["actions"].data_ptr(), out["probs"].data_ptr(), out["logp"].data_ptr(),
         out["masks"].data_ptr(), out["coef"].data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "consolver_policy_sample_f32")

@@ -317,3 +317,30 @@ def test_denoise_loop_without_cat_matches_manual_loop():
         x = b.step(u + 3.0 * (c - u), t, x, return_dict=False)[0]     # the reference's caller-side sequence
     assert torch.equal(lat, x)
     assert torch.equal(rec["idx"], b.trajectory()["idx"])
+
+
+@pytest.mark.parametrize("B,A,K", [(64, 3, 11), (5, 5, 161), (1, 1, 11), (4096, 3, 11), (12000, 3, 11)])
+def test_in_kernel_exponential_draw_is_torchs(B, A, K):
+    """The sample kernel's own Exp(1) draw == torch.empty(B*A,K).exponential_(1) for the same generator state,
+    bit for bit (incl. numel beyond one grid of the torch launch), and the generator advance matches."""
+    from consolver_b200 import _lib
+    sd = make_sd("sd", 64, K, A + 1, 0, 0, seed=B, last_std=0.5)
+    dsd = ah.sd_to_dev(sd)
+    table = torch.softmax(torch.randn(A, K), -1).cuda()
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    torch.manual_seed(1234 + B)
+    torch.empty(37, device="cuda").normal_()                      # move the offset off zero
+    seed, off = gen.initial_seed(), gen.get_offset()
+    ref = torch.empty(B * A, K, device="cuda").exponential_(1)
+    nthreads, inc = _lib.philox_plan(B * A * K)
+    assert gen.get_offset() - off == inc
+    q_out = torch.zeros(B * A, K, device="cuda")
+    out = ah.policy_sample(dsd, table, B, A + 1, 0, A + 1, rng=_lib.Rng(seed, off, None, nthreads), q_out=q_out)
+    assert torch.equal(q_out, ref)
+    via_q = ah.policy_sample(dsd, table, B, A + 1, 0, A + 1, q=ref)
+    for k in ("idx", "actions", "probs", "coef"):
+        assert torch.equal(out[k], via_q[k])
+    # device-resident state: {seed, base} + per-launch offset
+    state = torch.tensor([seed, off - 8], dtype=torch.int64, device="cuda")
+    out2 = ah.policy_sample(dsd, table, B, A + 1, 0, A + 1, rng=_lib.Rng(0, 8, state.data_ptr(), nthreads))
+    assert torch.equal(out2["idx"], out["idx"])
