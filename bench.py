@@ -406,9 +406,15 @@ def run_ours(args, rank, world, device):
         peak, src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks \
             else (6650.0, "fallback (B200_PROFILING.md)")
         us, nbytes, nsets = time_step_kernel(B, 4, device)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+        if os.path.exists(tpath):          # DRAM bytes per launch from the committed ncu --set full capture
+            rec = json.load(open(tpath))["step_kernel_f32_nh4_pair"].get(str(B))
+            if rec:
+                traffic = rec["dram_read"] + rec["dram_write"]
         out["roofline"] = {"bound": "hbm", "kernel": "step_kernel<f32,NH=4,CFG pair>", "batch": B,
                            "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
-                           "frac": round(nbytes / us / 1e3 / peak, 4), "traffic": None, "us_per_launch": round(us, 3),
+                           "frac": round(nbytes / us / 1e3 / peak, 4), "traffic": traffic, "us_per_launch": round(us, 3),
                            "algorithmic_bytes": nbytes, "peak_source": src}
         sweep = []
         for Bs in (256, 1024, 4096):
@@ -528,6 +534,10 @@ def main():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    if world > 1:
+        from consolver_b200.sharding import bind_to_gpu_numa
+
+        bind_to_gpu_numa(local)       # host buffers of the e2e leg stay on the GPU's own socket
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of stdout: one JSON line only

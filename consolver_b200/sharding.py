@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Iterator, List, Sequence, Tuple
+from typing import Iterator, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -53,6 +53,26 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
             kw["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend, **kw)
     return rank, world, local
+
+
+def bind_to_gpu_numa(local_rank: int) -> Optional[int]:
+    """Pin this process (and therefore its pinned host allocations, first-touch) to the CPUs NVML reports as local
+    to GPU `local_rank`.  With 8 ranks sharing two sockets this keeps every rank's host<->device copies on the
+    PCIe root of its own socket.  Returns the number of CPUs bound, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def gather_job_stats(n_done: int, elapsed_s: float, checksum: float, device=None) -> dict:
