@@ -269,6 +269,43 @@ def with_denoiser(B, device, sd, previews=3):
             "solver_share": round(solver_ms / ms, 6), "previews_timed": previews, "batch_per_gpu": B}
 
 
+def fm_preview_throughput(device, B=16, steps=200):
+    """BASELINE configs[3]: FLUX-Kontext-shaped FMPPOScheduler loop — packed latents [B,4096,64] bf16, 8 steps,
+    order_dim=2, resident synthetic velocities as the transformer stand-in, one CUDA graph per preview."""
+    import numpy as np
+
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedPreview
+
+    torch.manual_seed(0)
+    nbytes = (1 + N_STEPS) * B * 4096 * 64 * 2
+    pool_n = int(max(2, -(-2 * L2_BYTES // nbytes)))
+    pool = []
+    for j in range(pool_n):
+        s = cb.FMPPOScheduler(shift=3.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15, base_image_seq_len=256,
+                              max_image_seq_len=4096, order_dim=2, scaler_dim=0, mu_dim=0,
+                              factor_net_kwargs=dict(hidden_dim=256, num_actions=11))
+        s.factor_net.to(device)
+        x = torch.randn(B, 4096, 64, device=device).bfloat16()
+        vs = [torch.randn(B, 4096, 64, device=device).bfloat16() for _ in range(N_STEPS)]
+        pool.append(GraphedPreview(s, x, vs, None, N_STEPS, set_timesteps_kwargs=dict(
+            sigmas=np.linspace(1.0, 1 / N_STEPS, N_STEPS), mu=1.15)))
+    for k in range(5):
+        pool[k % pool_n].replay()
+    torch.cuda.synchronize(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for k in range(steps):
+        pool[k % pool_n].replay()
+    b.record()
+    torch.cuda.synchronize(device)
+    ms = a.elapsed_time(b) / steps
+    tensors = 3 + 7 * 4     # n = 1, then 2: (n+2) tensors per step
+    return {"value": round(B / (ms / 1e3), 1), "unit": "previews/s", "batch": B, "ms_per_preview_batch": round(ms, 4),
+            "shape": "[B,4096,64] bf16, 8 steps, order_dim=2", "algorithmic_gbs": round(
+                tensors * B * 4096 * 64 * 2 / (ms / 1e3) / 1e9, 1), "pool_batches": pool_n}
+
+
 def run_ours(args, rank, world, device):
     import consolver_b200  # noqa: F401  (fails loudly if libconsolver.so cannot be built/loaded)
     from consolver_b200.denoise import GraphedPreview, preview_from_pairs
@@ -431,6 +468,10 @@ def run_ours(args, rank, world, device):
                                         "packed 1024^2 latents), order_dim=2", "bytes_per_sample": 4 * 4096 * 64 * 2,
                                         "points": fm}
         out["cpu_baseline"] = cpu_baseline(B, budget_s=args.cpu_budget)
+        try:
+            out["fm_flux_preview"] = fm_preview_throughput(device)
+        except Exception as e:  # noqa: BLE001
+            out["fm_flux_preview"] = {"error": repr(e)[:200]}
     if not args.no_denoiser:
         try:
             wd = with_denoiser(B, device, sd)

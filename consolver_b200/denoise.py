@@ -59,6 +59,15 @@ def preview_from_pairs(scheduler: PPOScheduler, x_T: torch.Tensor, pairs: Sequen
     return x
 
 
+def preview_from_outputs(scheduler, x_T: torch.Tensor, outputs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Solver-only preview through the plain `step()` contract (no CFG): works for PPOScheduler and FMPPOScheduler.
+    `set_timesteps` (and, for FM, `set_begin_index`) must have been called."""
+    x = x_T
+    for i, mo in enumerate(outputs):
+        x = scheduler.step(mo, scheduler.timesteps[i], x, return_dict=False)[0]
+    return x
+
+
 class GraphedPreview:
     """One CUDA graph for a whole n-step solver-only preview over fixed device buffers.
 
@@ -67,18 +76,29 @@ class GraphedPreview:
     step, no host work at replay.  Inputs are read from the buffers given at capture time (refill them, or build
     one GraphedPreview per resident batch)."""
 
-    def __init__(self, scheduler: PPOScheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: float,
-                 num_inference_steps: int):
+    def __init__(self, scheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: Optional[float],
+                 num_inference_steps: int, set_timesteps_kwargs: Optional[dict] = None):
+        """`guidance` None: `pairs` are plain model outputs fed to `step()` (FMPPOScheduler, or SD without CFG);
+        `set_timesteps_kwargs` (e.g. sigmas=..., mu=... for FM) are passed through."""
         self.scheduler = scheduler
         self.x_T, self.pairs, self.guidance, self.n = x_T, list(pairs), guidance, num_inference_steps
-        self.out = torch.empty_like(x_T)
+        self.out = torch.empty_like(x_T) if guidance is not None else None
         dev = x_T.device
-        scheduler.set_timesteps(num_inference_steps, device=dev)
+        scheduler.set_timesteps(num_inference_steps, device=dev, **(set_timesteps_kwargs or {}))
+        if hasattr(scheduler, "set_begin_index"):
+            scheduler.set_begin_index(0)
+
+        def run():
+            if guidance is not None:
+                return preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
+            return preview_from_outputs(scheduler, x_T, self.pairs)
+
+        self._run = run
         # warm-up on a side stream (allocates the trajectory buffers and the ring outside the capture)
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
-            preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
+            run()
         torch.cuda.current_stream(dev).wait_stream(s)
         # graph-safe fused RNG: the sample kernels read {seed, offset} from a device buffer that replay() refreshes
         # from the default generator (and advances it), so every replay draws what eager execution would draw
@@ -96,7 +116,9 @@ class GraphedPreview:
         self._rewind()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
+            res = run()
+            if self.out is None:
+                self.out = res          # lives in the graph's private pool: valid after every replay
             if tr.graph_rng is not None and tr.graph_rng_used:
                 # last node: the device-resident offset advances by what this graph consumed, so back-to-back
                 # replays need no host refresh at all
@@ -109,7 +131,10 @@ class GraphedPreview:
     def _rewind(self):
         sch = self.scheduler
         sch._hist = []
-        sch._step_count = 0
+        if hasattr(sch, "_step_count"):
+            sch._step_count = 0
+        if hasattr(sch, "_step_index"):
+            sch._step_index = None         # FM: restart from begin_index
         if sch._traj is not None:
             sch._traj.count = 0
             sch._traj.table_pass = -1      # the capture (and every replay) re-evaluates the probability tables

@@ -81,3 +81,31 @@ def test_graphed_preview_matches_eager_and_advances_the_generator():
     assert torch.equal(e.trajectory()["idx"], idx_g)
     assert torch.equal(out_e, out_g)
     assert not torch.equal(out_g, out_g2)
+
+
+def test_graphed_fm_preview_matches_eager():
+    import numpy as np
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedPreview, preview_from_outputs
+
+    kw = dict(shift=3.0, use_dynamic_shifting=True, order_dim=2, scaler_dim=0, mu_dim=0,
+              factor_net_kwargs=dict(hidden_dim=256, num_actions=11))
+    torch.manual_seed(0)
+    s, e = cb.FMPPOScheduler(**kw), cb.FMPPOScheduler(**kw)
+    e.factor_net.load_state_dict(s.factor_net.state_dict())
+    s.factor_net.cuda(), e.factor_net.cuda()
+    B, n = 4, 8
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, 4096, 64, device="cuda", generator=g).bfloat16()
+    vs = [torch.randn(B, 4096, 64, device="cuda", generator=g).bfloat16() for _ in range(n)]
+    tk = dict(sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+    gp = GraphedPreview(s, x, vs, None, n, set_timesteps_kwargs=tk)
+    torch.manual_seed(9)
+    out_g = gp.replay().clone()
+    idx_g = gp.record()["idx"].clone()
+    e.set_timesteps(n, device="cuda", **tk)
+    e.set_begin_index(0)
+    torch.manual_seed(9)
+    out_e = preview_from_outputs(e, x, vs)
+    assert torch.equal(e.trajectory()["idx"], idx_g)
+    assert torch.equal(out_e, out_g)

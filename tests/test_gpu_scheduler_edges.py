@@ -1,0 +1,87 @@
+"""GPU: scheduler-level edge cases of the drop-in API (dtypes, layouts, off-grid timesteps, timestep read-back,
+batch changes, empty batches)."""
+import pytest
+import torch
+
+import consolver_oracle as orc
+from golden_io import Golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(name="sd_eps_s0_n8_B3"):
+    import consolver_b200 as cb
+    g = Golden(name)
+    m = g.meta
+    s = cb.PPOScheduler(factor_net_kwargs=dict(m["factor_net_kwargs"]), **m["config"])
+    s.factor_net.load_state_dict(g.state_dict)
+    s.factor_net.cuda()
+    o = orc.OracleSDScheduler(g.state_dict, **m["config"])
+    return g, m, s, o
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_16bit_pipeline_dtype(dtype):
+    """fp16/bf16 latents (gen_ppo.py runs the pipeline under fp16 autocast): fp32 math, one rounding per step."""
+    g, m, s, o = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    o.set_timesteps(m["n"])
+    s.replay = {"idx": [g[f"idx_{i}"] for i in range(m["n"])]}
+    x = g["x_T"].to(dtype)
+    xg = x.cuda()
+    for i, t in enumerate(o.timesteps):
+        pair = g[f"pair_{i}"].to(dtype)
+        xg = s.step_cfg(pair.cuda(), s.timesteps[i], xg, m["guidance"])[0]
+        assert xg.dtype == dtype
+        u, c = pair.float().chunk(2)
+        eps = orc.cfg_combine(u, c, m["guidance"]).to(dtype).float()
+        x = o.step(eps, t, x.float(), forced_idx=g[f"idx_{i}"])[0].to(dtype)
+        assert torch.equal(xg.cpu(), x), f"step {i}"
+
+
+def test_non_contiguous_inputs_and_off_grid_timesteps():
+    g, m, s, o = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    o.set_timesteps(m["n"])
+    x = g["x_T"]
+    xg = x.cuda()
+    for i in range(4):
+        t = int(o.timesteps[i]) - 7                    # not a grid point: the fused MLP+sample kernel is used
+        eps = g[f"eps_{i}"]
+        q = g[f"q_{i}"]
+        s.replay = {"q": {s._traj.count if s._traj else 0: q.cuda()}}
+        eps_nc = eps.cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)      # channels_last strides
+        assert not eps_nc.is_contiguous()
+        xg, actions, probs, conds, masks = s.step(eps_nc, t, xg, return_dict=False)
+        x, a_o, p_o, _, m_o = o.step(eps, t, x, q=q)
+        assert torch.equal(actions.cpu(), a_o) and torch.equal(masks.cpu(), m_o)
+        torch.testing.assert_close(probs.cpu(), p_o, rtol=0, atol=1e-6)
+        assert torch.equal(conds["x"].cpu(), torch.tensor([[t, t - 125]], dtype=torch.float32).repeat(3, 1))
+        assert torch.equal(xg.cpu(), x)
+
+
+def test_timestep_read_back_and_batch_change():
+    g, m, s, o = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    s.sync_free = False                               # .item() the CUDA timestep like the reference does
+    x = g["x_T"].cuda()
+    out = s.step(g["eps_0"].cuda(), s.timesteps[0], x, return_dict=True)
+    assert out.prev_sample.shape == x.shape and out.actions.shape == (3, 3)
+    # a different batch size mid-trajectory re-allocates the per-trajectory buffers and keeps working
+    x5 = torch.randn(5, *m["shape"], device="cuda")
+    s.set_timesteps(m["n"], device="cuda")
+    out5 = s.step(torch.randn_like(x5), s.timesteps[0], x5, return_dict=True)
+    assert out5.actions.shape == (5, 3)
+    with pytest.raises(TypeError):
+        s.step(torch.randn_like(x5).half(), s.timesteps[1], x5)
+    with pytest.raises(ValueError):
+        s.step_cfg(torch.randn(7, *m["shape"], device="cuda"), s.timesteps[1], x5, 3.0)
+
+
+def test_empty_batch_is_rejected_loudly():
+    from consolver_b200._lib import ConsolverError
+    g, m, s, o = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    x0 = torch.zeros(0, *m["shape"], device="cuda")
+    with pytest.raises((ConsolverError, ZeroDivisionError, RuntimeError, ValueError)):
+        s.step(x0.clone(), s.timesteps[0], x0)
