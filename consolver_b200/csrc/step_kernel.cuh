@@ -31,6 +31,10 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
   bool live[U];
 
   // ---- issue every load before the first use ------------------------------------------------------------
+  // CHAIN (back-to-back solver steps, each a programmatic dependent launch of the previous one): the latent x and
+  // the newest history slot are the previous step's outputs; everything else (the CFG pair, older slots) is not,
+  // so it is requested before waiting on the previous step.
+  const bool chain = p.flags & CONSOLVER_FLAG_CHAIN;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const long long v = v0 + (long long)u * blockDim.x;
@@ -39,16 +43,28 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
     if (live[u]) {
       r_e0[u].load(static_cast<const T*>(p.e0) + off[u]);
       if (pair) r_c[u].load(static_cast<const T*>(p.cond) + off[u]);
-      r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
+      if (!chain) r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
 #pragma unroll
       for (int j = 0; j < kOlder; ++j)
-        if (NH || j < nh - 1) r_h[u][j].load(static_cast<const T*>(p.hist[j]) + off[u]);
+        if ((NH || j < nh - 1) && !(chain && j == 0)) r_h[u][j].load(static_cast<const T*>(p.hist[j]) + off[u]);
     }
   }
 
   // ---- per-sample coefficients (CTA-uniform).  Under PDL the preceding policy kernel may still be running:
   //      the bulk loads above do not depend on it, only these few floats do. ------------------------------------
-  if (p.flags & CONSOLVER_FLAG_PDL) grid_dependency_wait();
+  if (p.flags & (CONSOLVER_FLAG_PDL | CONSOLVER_FLAG_CHAIN)) grid_dependency_wait();
+  if (chain) {
+    // every predecessor is complete now: let the NEXT step start its independent loads, then fetch what the
+    // previous step produced
+    grid_launch_dependents();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (live[u]) {
+        r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
+        if (kOlder > 0 && (NH || 0 < nh - 1)) r_h[u][0].load(static_cast<const T*>(p.hist[0]) + off[u]);
+      }
+    }
+  }
   const float* cf = p.coef + (long long)b * p.coef_stride;
   float c[kOlder + 1];
 #pragma unroll
@@ -130,7 +146,7 @@ static int launch_one(StepParams& p, int threads, cudaStream_t stream) {
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  if (p.flags & CONSOLVER_FLAG_PDL) {
+  if (p.flags & (CONSOLVER_FLAG_PDL | CONSOLVER_FLAG_CHAIN)) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;

@@ -88,6 +88,10 @@ class GraphedPreview:
         if hasattr(scheduler, "set_begin_index"):
             scheduler.set_begin_index(0)
 
+        if guidance is not None and getattr(scheduler, "use_fused_rng", False):
+            scheduler.policy_stream = torch.cuda.Stream(device=dev)   # sample chain becomes a parallel graph branch
+            scheduler.chain_steps = True       # resident model outputs: consecutive steps overlap via PDL
+
         def run():
             if guidance is not None:
                 return preview_from_pairs(scheduler, x_T, self.pairs, guidance, out=self.out)
@@ -139,6 +143,7 @@ class GraphedPreview:
             sch._traj.count = 0
             sch._traj.table_pass = -1      # the capture (and every replay) re-evaluates the probability tables
             sch._traj.graph_rng_used = 0
+            sch._traj.policy_forked = False
 
     def replay(self) -> torch.Tensor:
         if self._rng_inc:

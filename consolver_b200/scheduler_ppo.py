@@ -98,6 +98,7 @@ class _Trajectory:
         self.rng_plan = None   # (nthreads, offset increment) of torch's exponential_ launch for q's numel
         self.graph_rng = None  # device int64[2] {seed, offset} refreshed before every CUDA-graph replay
         self.graph_rng_used = 0
+        self.policy_forked = False   # the policy side stream has been forked off the main stream in this pass
 
     def conv_buffers(self, fn):
         """use_conv=True scratch: features [B,od-1], reduction workspace, per-sample tables [n,B,A,K]"""
@@ -192,6 +193,11 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         self.use_pdl = True
         #: generate the Exp(1) draw inside the sample kernel (bit-identical to torch's exponential_, see rng.py)
         self.use_fused_rng = True
+        #: optional side stream for the policy kernels (set by GraphedPreview): see the two-stream note in _step
+        self.policy_stream: Optional[torch.cuda.Stream] = None
+        #: solver-only replays (GraphedPreview): chain consecutive step kernels with programmatic dependent launch
+        #: (CONSOLVER_FLAG_CHAIN).  Only valid when the model outputs are NOT produced by the kernel right before.
+        self.chain_steps = False
         #: replay instead of sampling: {'idx': seq of [B,A] int64 per step} forces the bins (PPO replay, parity
         #: tests with injected actions); {'q': seq of [B*A,K] fp32 per step} supplies the Exp(1) draw.
         self.replay: Optional[Dict] = None
@@ -350,14 +356,39 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
             if on_grid and tr.table_pass != tr.count // tr.n:
                 fn.policy_tables(tr.condx_f32, o["probs_table"])
                 tr.table_pass = tr.count // tr.n
+                tr.policy_forked = False                          # the side stream must see the new tables
             probs_in = o["probs_table"][i].data_ptr() if on_grid else None
-            rc = lib.consolver_sd_policy_and_step(
-                *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr, rng_arg,
-                fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
-                o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
-                o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(),
-                o["coef"][i].data_ptr(), *step_args, od, sa_t, sb_t, sa_p, sb_p, flags, B, N, stream)
-            _lib.check(rc, "consolver_sd_policy_and_step")
+            ps = self.policy_stream
+            if ps is not None and on_grid and rng_arg is not None:
+                # Two-stream form: the sample kernel needs nothing from the step kernels (only the table and the
+                # generator state), so it runs on its own stream and the step kernel just waits for its event.
+                # Captured in a CUDA graph this makes the sample chain a parallel branch: every step's coefficients
+                # are ready before its step kernel starts, and the critical path is the step kernels alone.
+                main = torch.cuda.current_stream(e0.device)
+                if not tr.policy_forked:
+                    ps.wait_stream(main)                          # fork (also orders after the table launch above)
+                    tr.policy_forked = True
+                rc = lib.consolver_policy_sample_f32(
+                    probs_in, w[6], None, None, rng_arg, None, B, fn.action_dims, fn.num_actions, od, cfg.scaler_dim,
+                    n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
+                    o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), ps.cuda_stream)
+                _lib.check(rc, "consolver_policy_sample_f32")
+                ev = torch.cuda.Event()
+                ev.record(ps)
+                main.wait_event(ev)
+                sflags = (flags & ~_lib.FLAG_PDL) | (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | \
+                    (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0) | (_lib.FLAG_CHAIN if self.chain_steps else 0)
+                rc = lib.consolver_step_sd(*step_args, o["coef"][i].data_ptr(), od + 2, od, sa_t, sb_t, sa_p, sb_p,
+                                           sflags, B, N, stream)
+                _lib.check(rc, "consolver_step_sd")
+            else:
+                rc = lib.consolver_sd_policy_and_step(
+                    *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr, rng_arg,
+                    fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
+                    o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
+                    o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(),
+                    o["coef"][i].data_ptr(), *step_args, od, sa_t, sb_t, sa_p, sb_p, flags, B, N, stream)
+                _lib.check(rc, "consolver_sd_policy_and_step")
         else:
             # use_conv=True (factor_net_ppo.py:146-149): two passes.  Pass 1 reduces the cosine features of the
             # history against the newest output (formed from the CFG pair on the fly); the policy MLP then runs per

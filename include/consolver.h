@@ -49,6 +49,12 @@ extern "C" {
 #define CONSOLVER_FLAG_PDL          8   /* launch with programmatic dependent launch: the bulk loads are issued
                                            before waiting on the preceding (policy) kernel's coefficients        */
 
+#define CONSOLVER_FLAG_CHAIN       16   /* back-to-back solver steps on one stream: this step is a programmatic
+                                           dependent launch of the PREVIOUS STEP; loads of e0/cond and of history
+                                           entries older than the newest are issued before waiting on it, x and the
+                                           newest history entry after.  Only valid when e0/cond/older entries are not
+                                           written by the immediately preceding kernel (solver-only replays)        */
+
 #define CONSOLVER_ERR_NULL        (-1)
 #define CONSOLVER_ERR_SIZE        (-2)
 #define CONSOLVER_ERR_UNSUPPORTED (-3)

@@ -109,3 +109,32 @@ def test_graphed_fm_preview_matches_eager():
     out_e = preview_from_outputs(e, x, vs)
     assert torch.equal(e.trajectory()["idx"], idx_g)
     assert torch.equal(out_e, out_g)
+
+
+def test_graphed_preview_stress_matches_eager_over_many_replays():
+    """The graph uses a side stream for the policy and PDL-chained step kernels (early loads before the previous
+    step finishes): replay it many times at the bench batch size and demand bit equality with eager execution."""
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedPreview, preview_from_pairs
+
+    s, e = cb.PPOScheduler(**PROD), cb.PPOScheduler(**PROD)
+    with torch.no_grad():
+        s.factor_net.mlp[4].weight.normal_(0, 0.05)
+    e.factor_net.load_state_dict(s.factor_net.state_dict())
+    s.factor_net.cuda(), e.factor_net.cuda()
+    B, n = 64, 8
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, 4, 64, 64, device="cuda", generator=g)
+    pairs = [torch.randn(2 * B, 4, 64, 64, device="cuda", generator=g) for _ in range(n)]
+    gp = GraphedPreview(s, x, pairs, 3.0, n)
+    assert s.chain_steps and s.policy_stream is not None
+    torch.manual_seed(123)
+    outs = []
+    for _ in range(12):
+        outs.append(gp.replay().clone())              # back-to-back: replay k+1 is enqueued while k still runs
+    torch.cuda.synchronize()
+    torch.manual_seed(123)
+    for k in range(12):
+        e.set_timesteps(n, device="cuda")
+        ref = preview_from_pairs(e, x, pairs, 3.0)
+        assert torch.equal(ref, outs[k]), f"replay {k}"
