@@ -432,7 +432,7 @@ def run_ours(args, rank, world, device):
                    "launch": "eager" if args.eager else "cuda_graph(8-step loop)", "sharding": f"dp{world} by prompt/seed, no collective"},
         "e2e": {"value": round(e2e_val, 1), "unit": "previews/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
-        "gpu_launches": args.steps * (1 + N_STEPS * 2),   # per preview: 1 table + 8 x (sample + step) kernels
+        "gpu_launches": args.steps * (2 + N_STEPS * 2),   # per preview: table + 8 x (sample + step) + rng-advance kernels
         "clocks": clk.summary(),
     }
     if rank == 0:

@@ -71,10 +71,14 @@ def preview_from_outputs(scheduler, x_T: torch.Tensor, outputs: Sequence[torch.T
 class GraphedPreview:
     """One CUDA graph for a whole n-step solver-only preview over fixed device buffers.
 
-    The graph holds, per step: the Exp(1) draw (torch's graph-safe Philox: every replay advances the default
-    generator exactly as eager execution would), the policy kernel and the fused step kernel — 3 launches per
-    step, no host work at replay.  Inputs are read from the buffers given at capture time (refill them, or build
-    one GraphedPreview per resident batch)."""
+    The graph holds one probability-table launch, then per step a sample kernel (drawing torch's Exp(1) stream
+    itself from a device-resident generator state, see rng.py) and the fused step kernel, and a final one-thread
+    node that advances that state: every replay consumes the default generator exactly as eager execution would.
+    The sample kernels run on a side stream (a parallel branch of the graph: they depend only on the table and the
+    generator state), and consecutive step kernels are PDL-chained (CONSOLVER_FLAG_CHAIN) because the model
+    outputs are resident.  Inputs are read from the buffers given at capture time (refill them, or build one
+    GraphedPreview per resident batch).  If the fused RNG self-check fails the graph falls back to torch's
+    graph-safe exponential_ launch per step."""
 
     def __init__(self, scheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: Optional[float],
                  num_inference_steps: int, set_timesteps_kwargs: Optional[dict] = None):
@@ -88,7 +92,7 @@ class GraphedPreview:
         if hasattr(scheduler, "set_begin_index"):
             scheduler.set_begin_index(0)
 
-        if guidance is not None and getattr(scheduler, "use_fused_rng", False):
+        if getattr(scheduler, "use_fused_rng", False) and getattr(scheduler, "fixed_coefficients", None) is None:
             scheduler.policy_stream = torch.cuda.Stream(device=dev)   # sample chain becomes a parallel graph branch
             scheduler.chain_steps = True       # resident model outputs: consecutive steps overlap via PDL
 

@@ -47,6 +47,7 @@ class _FMTrajectory:
         self.count = 0
         self.table_pass = -1
         self.rng_plan, self.graph_rng, self.graph_rng_used = None, None, 0
+        self.policy_forked = False
 
 
 class FMPPOScheduler(SchedulerMixin, ConfigMixin):
@@ -125,6 +126,8 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         self.replay: Optional[Dict] = None    # see PPOScheduler.replay
         self.fixed_coefficients = None        # see PPOScheduler.fixed_coefficients
         self.use_fused_rng = True             # see PPOScheduler.use_fused_rng
+        self.policy_stream = None             # see PPOScheduler.policy_stream
+        self.chain_steps = False              # see PPOScheduler.chain_steps
 
     # ---- small properties / helpers of the reference surface ---------------------------------------------------
     @property
@@ -318,6 +321,7 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         x_out = torch.empty(sample.shape, device=e0.device, dtype=e0.dtype)
         lib = _lib.load()
         stream = torch.cuda.current_stream(e0.device).cuda_stream
+        side = False
         w = fn.kernel_weights() if self.fixed_coefficients is None else None
         coef_ptr = o["coef"][i].data_ptr()
         if self.fixed_coefficients is not None:
@@ -332,12 +336,25 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
             if tr.table_pass != tr.count // tr.n:
                 fn.policy_tables(tr.condx_f32, o["probs_table"], stream)
                 tr.table_pass = tr.count // tr.n
+                tr.policy_forked = False
+            ps = self.policy_stream if rng_arg is not None else None      # two-stream form: see PPOScheduler._step
+            if ps is not None:
+                main = torch.cuda.current_stream(e0.device)
+                if not tr.policy_forked:
+                    ps.wait_stream(main)
+                    tr.policy_forked = True
+                side = True
             rc = lib.consolver_policy_sample_f32(
                 o["probs_table"][si].data_ptr(), w[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
                 fn.num_actions, od,
                 cfg.scaler_dim, n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
-                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
+                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(),
+                ps.cuda_stream if ps is not None else stream)
             _lib.check(rc, "consolver_policy_sample_f32")
+            if ps is not None:
+                ev = torch.cuda.Event()
+                ev.record(ps)
+                main.wait_event(ev)
         else:
             # use_conv=True: cosine features of the history (pass 1), per-sample MLP, then the fused step (pass 2)
             from .features import cosine_features_cuda, workspace_bytes
@@ -354,8 +371,11 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
                 full[i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
                 o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
             _lib.check(rc, "consolver_policy_f32")
-        flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0) \
-            | (_lib.FLAG_PDL if self.use_pdl else 0)
+        flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
+        if side:
+            flags |= _lib.FLAG_CHAIN if self.chain_steps else 0       # previous node on this stream is a step kernel
+        elif self.use_pdl:
+            flags |= _lib.FLAG_PDL
         rc = lib.consolver_step_fm(
             _lib.dtype_code(e0.dtype), _lib.dtype_code(sample.dtype), e0.data_ptr(), None,
             _lib.ptr_array([h.data_ptr() for h in older]), n_hist, sample.data_ptr(), x_out.data_ptr(),
