@@ -191,6 +191,8 @@ def test_launch_config_knobs_do_not_change_results():
             assert torch.equal(out, base)
         out, _ = ah.step_sd(e0, cond, 3.0, h, x, c, od, scalars, 8)   # PDL launch attribute
         assert torch.equal(out, base)
+        out, _ = ah.step_sd(e0, cond, 3.0, h, x, c, od, scalars, 16)  # CHAIN: late loads of x and the newest slot
+        assert torch.equal(out, base)
     finally:
         lib.consolver_set_step_launch(0, 0)
 
