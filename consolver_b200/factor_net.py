@@ -74,12 +74,17 @@ class FactorNetPPO(nn.Module):
         if hidden_dim > _lib.MAX_HIDDEN or num_actions * self.action_dims > _lib.MAX_LOGITS:
             raise ValueError("policy too large for the kernel limits in include/consolver.h")
         self._w32_cache = None
+        self._kparams = None
 
     # ---- fp32 weight pointers for the kernel (the reference may cast the module to fp16, gen_ppo.py:193-195;
     #      the kernel always computes in fp32) -----------------------------------------------------------------
     def kernel_weights(self):
-        ps = [self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight, self.mlp[2].bias,
-              self.mlp[4].weight, self.mlp[4].bias, self.action_values]
+        # nn.Module attribute lookups cost ~1 us each: hold the six Parameter objects (stable across .to() /
+        # load_state_dict, which rewrite .data in place) and re-fetch only the buffer (a new tensor after .to())
+        mlp = self._modules["mlp"]
+        if self._kparams is None or self._kparams[0] is not mlp:
+            self._kparams = (mlp, [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias])
+        ps = self._kparams[1] + [self._buffers["action_values"]]
         key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
         c = self._w32_cache
         if c is None or c[0] != key:

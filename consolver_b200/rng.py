@@ -20,9 +20,15 @@ from . import _lib
 _verified: Dict[int, bool] = {}
 
 
+_gens: Dict[int, torch.Generator] = {}
+
+
 def generator(device: torch.device) -> torch.Generator:
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    return torch.cuda.default_generators[idx]
+    g = _gens.get(idx)
+    if g is None:
+        g = _gens[idx] = torch.cuda.default_generators[idx]
+    return g
 
 
 def take(device: torch.device, increment: int) -> Tuple[int, int]:
@@ -62,9 +68,13 @@ def draw_reference_check(device: torch.device, numel: int = 5 * 3 * 11) -> bool:
 
 
 def fused_rng_available(device: torch.device) -> bool:
-    if os.environ.get("CONSOLVER_FUSED_RNG", "1") != "1":
-        return False
     idx = device.index if device.index is not None else torch.cuda.current_device()
+    v = _verified.get(idx)
+    if v is not None:
+        return v
+    if os.environ.get("CONSOLVER_FUSED_RNG", "1") != "1":
+        _verified[idx] = False
+        return False
     if idx not in _verified:
         if torch.cuda.is_current_stream_capturing():
             return False          # decide outside of a capture

@@ -37,6 +37,8 @@ class _FMTrajectory:
         self.n = max(int(sched.num_inference_steps), 1)
         A, K, od = fn.action_dims, fn.num_actions, sched.config.order_dim
         self.out = alloc_policy_outputs(B, A, K, od, device, lead=(self.n,))
+        # row pointers by arithmetic: indexing a tensor costs ~2 us of host time, a step needs seven of them
+        self._row = {k: (v.data_ptr(), v.stride(0) * v.element_size()) for k, v in self.out.items()}
         self.q = torch.empty((B * A, K), device=device, dtype=torch.float32)
         s = sched._sigmas_host
         rows = [[float(s[i]), float(s[i + 1])] for i in range(len(s) - 1)]
@@ -48,6 +50,11 @@ class _FMTrajectory:
         self.table_pass = -1
         self.rng_plan, self.graph_rng, self.graph_rng_used = None, None, 0
         self.policy_forked = False
+
+
+    def p(self, name, i):
+        base, stride = self._row[name]
+        return base + i * stride
 
 
 class FMPPOScheduler(SchedulerMixin, ConfigMixin):
@@ -320,10 +327,10 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
             tr.q.copy_(self.replay["q"][tr.count].reshape(tr.q.shape))
         x_out = torch.empty(sample.shape, device=e0.device, dtype=e0.dtype)
         lib = _lib.load()
-        stream = torch.cuda.current_stream(e0.device).cuda_stream
+        stream = torch._C._cuda_getCurrentRawStream(e0.device.index)
         side = False
         w = fn.kernel_weights() if self.fixed_coefficients is None else None
-        coef_ptr = o["coef"][i].data_ptr()
+        coef_ptr = tr.p("coef", i)
         if self.fixed_coefficients is not None:
             cache = tr.__dict__.setdefault("_fixed", {})
             if n_hist not in cache:
@@ -345,10 +352,10 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
                     tr.policy_forked = True
                 side = True
             rc = lib.consolver_policy_sample_f32(
-                o["probs_table"][si].data_ptr(), w[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
+                tr.p("probs_table", si), w[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
                 fn.num_actions, od,
-                cfg.scaler_dim, n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
-                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(),
+                cfg.scaler_dim, n_hist, tr.p("idx", i), tr.p("actions", i), tr.p("probs", i),
+                tr.p("logp", i), tr.p("masks", i), tr.p("coef", i),
                 ps.cuda_stream if ps is not None else stream)
             _lib.check(rc, "consolver_policy_sample_f32")
             if ps is not None:
@@ -368,8 +375,8 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
             rc = lib.consolver_policy_f32(
                 *w, x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
                 B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
-                full[i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
-                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
+                full[i].data_ptr(), tr.p("idx", i), tr.p("actions", i), tr.p("probs", i),
+                tr.p("logp", i), tr.p("masks", i), tr.p("coef", i), stream)
             _lib.check(rc, "consolver_policy_f32")
         flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
         if side:

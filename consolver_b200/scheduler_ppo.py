@@ -82,6 +82,8 @@ class _Trajectory:
         self.n = max(int(sched.num_inference_steps), 1)
         A, K, od = fn.action_dims, fn.num_actions, sched.config.order_dim
         self.out = alloc_policy_outputs(B, A, K, od, device, lead=(self.n,))
+        # row pointers by arithmetic: indexing a tensor costs ~2 us of host time, a step needs seven of them
+        self._row = {k: (v.data_ptr(), v.stride(0) * v.element_size()) for k, v in self.out.items()}
         self.q = torch.empty((B * A, K), device=device, dtype=torch.float32)
         self.ring = None  # [order_dim, B, *shape], allocated on the first step_cfg()
         self.ring_shape = (od, B, *shape)
@@ -99,6 +101,10 @@ class _Trajectory:
         self.graph_rng = None  # device int64[2] {seed, offset} refreshed before every CUDA-graph replay
         self.graph_rng_used = 0
         self.policy_forked = False   # the policy side stream has been forked off the main stream in this pass
+
+    def p(self, name, i):
+        base, stride = self._row[name]
+        return base + i * stride
 
     def conv_buffers(self, fn):
         """use_conv=True scratch: features [B,od-1], reduction workspace, per-sample tables [n,B,A,K]"""
@@ -338,7 +344,7 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
         hist_ptrs = _lib.ptr_array([h.data_ptr() for h in older])
         w = fn.kernel_weights() if self.fixed_coefficients is None else None
         lib = _lib.load()
-        stream = torch.cuda.current_stream(e0.device).cuda_stream
+        stream = torch._C._cuda_getCurrentRawStream(e0.device.index)
         step_args = (_lib.dtype_code(e0.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, guidance,
                      slot.data_ptr() if slot is not None else None, hist_ptrs, n_hist, sample.data_ptr(),
                      x_out.data_ptr(), out2.data_ptr() if out2 is not None else None,
@@ -357,7 +363,7 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
                 fn.policy_tables(tr.condx_f32, o["probs_table"])
                 tr.table_pass = tr.count // tr.n
                 tr.policy_forked = False                          # the side stream must see the new tables
-            probs_in = o["probs_table"][i].data_ptr() if on_grid else None
+            probs_in = tr.p("probs_table", i) if on_grid else None
             ps = self.policy_stream
             if ps is not None and on_grid and rng_arg is not None:
                 # Two-stream form: the sample kernel needs nothing from the step kernels (only the table and the
@@ -370,24 +376,24 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
                     tr.policy_forked = True
                 rc = lib.consolver_policy_sample_f32(
                     probs_in, w[6], None, None, rng_arg, None, B, fn.action_dims, fn.num_actions, od, cfg.scaler_dim,
-                    n_hist, o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
-                    o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), ps.cuda_stream)
+                    n_hist, tr.p("idx", i), tr.p("actions", i), tr.p("probs", i),
+                    tr.p("logp", i), tr.p("masks", i), tr.p("coef", i), ps.cuda_stream)
                 _lib.check(rc, "consolver_policy_sample_f32")
                 ev = torch.cuda.Event()
                 ev.record(ps)
                 main.wait_event(ev)
                 sflags = (flags & ~_lib.FLAG_PDL) | (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | \
                     (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0) | (_lib.FLAG_CHAIN if self.chain_steps else 0)
-                rc = lib.consolver_step_sd(*step_args, o["coef"][i].data_ptr(), od + 2, od, sa_t, sb_t, sa_p, sb_p,
+                rc = lib.consolver_step_sd(*step_args, tr.p("coef", i), od + 2, od, sa_t, sb_t, sa_p, sb_p,
                                            sflags, B, N, stream)
                 _lib.check(rc, "consolver_step_sd")
             else:
                 rc = lib.consolver_sd_policy_and_step(
                     *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr, rng_arg,
                     fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
-                    o["probs_table"][i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(),
-                    o["probs"][i].data_ptr(), o["logp"][i].data_ptr(), o["masks"][i].data_ptr(),
-                    o["coef"][i].data_ptr(), *step_args, od, sa_t, sb_t, sa_p, sb_p, flags, B, N, stream)
+                    tr.p("probs_table", i), tr.p("idx", i), tr.p("actions", i),
+                    tr.p("probs", i), tr.p("logp", i), tr.p("masks", i),
+                    tr.p("coef", i), *step_args, od, sa_t, sb_t, sa_p, sb_p, flags, B, N, stream)
                 _lib.check(rc, "consolver_sd_policy_and_step")
         else:
             # use_conv=True (factor_net_ppo.py:146-149): two passes.  Pass 1 reduces the cosine features of the
@@ -400,12 +406,12 @@ class PPOScheduler(SchedulerMixin, ConfigMixin):
             rc = lib.consolver_policy_f32(
                 *w, x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
                 B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
-                full[i].data_ptr(), o["idx"][i].data_ptr(), o["actions"][i].data_ptr(), o["probs"][i].data_ptr(),
-                o["logp"][i].data_ptr(), o["masks"][i].data_ptr(), o["coef"][i].data_ptr(), stream)
+                full[i].data_ptr(), tr.p("idx", i), tr.p("actions", i), tr.p("probs", i),
+                tr.p("logp", i), tr.p("masks", i), tr.p("coef", i), stream)
             _lib.check(rc, "consolver_policy_f32")
             sflags = flags | (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | \
                 (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
-            rc = lib.consolver_step_sd(*step_args, o["coef"][i].data_ptr(), od + 2, od, sa_t, sb_t, sa_p, sb_p,
+            rc = lib.consolver_step_sd(*step_args, tr.p("coef", i), od + 2, od, sa_t, sb_t, sa_p, sb_p,
                                        sflags, B, N, stream)
             _lib.check(rc, "consolver_step_sd")
 
