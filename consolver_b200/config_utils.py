@@ -38,6 +38,30 @@ except Exception:  # noqa: BLE001
             params = inspect.signature(cls.__init__).parameters
             return cls(**{k: v for k, v in cfg.items() if k in params})
 
+        @classmethod
+        def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **kwargs):
+            """Local-directory form of diffusers' loader: read `<path>[/<subfolder>]/scheduler_config.json`, let
+            kwargs override (edit_ppo/train_ppo.py:87 passes order_dim=... this way).  No hub access."""
+            import json
+            import os
+
+            d = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+            with open(os.path.join(d, cls.config_name)) as f:
+                cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+            return cls.from_config(cfg, **kwargs)
+
+        def save_config(self, save_directory):
+            import json
+            import os
+
+            os.makedirs(save_directory, exist_ok=True)
+            cfg = {"_class_name": type(self).__name__}
+            cfg.update({k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in self.config.items()})
+            with open(os.path.join(save_directory, self.config_name), "w") as f:
+                json.dump(cfg, f, indent=2, sort_keys=True)
+
+        save_pretrained = save_config
+
     class SchedulerMixin:
         pass
 

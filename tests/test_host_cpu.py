@@ -156,3 +156,33 @@ def test_fp16_cast_of_the_policy_keeps_a_loadable_state_dict():
     s.factor_net.load_state_dict(sd)
     s.factor_net.to(dtype=torch.float16)
     assert s.factor_net.action_values.dtype == torch.float16
+
+
+def test_config_round_trip_through_scheduler_config_json(tmp_path):
+    """edit_ppo/train_ppo.py:87: FMPPOScheduler.from_pretrained(path, subfolder="scheduler", order_dim=..., ...)."""
+    import json
+    import os
+    d = tmp_path / "flux" / "scheduler"
+    os.makedirs(d)
+    json.dump({"_class_name": "FlowMatchEulerDiscreteScheduler", "_diffusers_version": "0.30.0", "shift": 3.0,
+               "use_dynamic_shifting": True, "base_shift": 0.5, "max_shift": 1.15, "num_train_timesteps": 1000,
+               "unknown_key": 1}, open(d / "scheduler_config.json", "w"))
+    if not hasattr(cb.FMPPOScheduler, "from_pretrained"):
+        pytest.skip("diffusers mixin without local loader")
+    f = cb.FMPPOScheduler.from_pretrained(str(tmp_path / "flux"), subfolder="scheduler", order_dim=2, scaler_dim=0, mu_dim=0,
+                                          factor_net_kwargs=dict(hidden_dim=256, num_actions=11))
+    assert f.config.shift == 3.0 and f.config.use_dynamic_shifting and f.config.order_dim == 2
+    assert f.factor_net.action_dims == 1
+    f.save_pretrained(str(tmp_path / "out"))
+    again = cb.FMPPOScheduler.from_pretrained(str(tmp_path / "out"))
+    assert dict(again.config) == dict(f.config)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU / PyTorch fallback: if libconsolver.so is absent and cannot be built, loading raises."""
+    from consolver_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setenv("CONSOLVER_NO_AUTOBUILD", "1")
+    with pytest.raises(_lib.ConsolverError, match="not found"):
+        _lib.load()
