@@ -1,0 +1,93 @@
+"""GPU parity at BASELINE.json's full sizes.  The oracle cannot chew 2 GiB per step in seconds, so at these sizes
+the kernels are checked (a) bit-for-bit against the oracle on a random subset of samples — samples are independent,
+so any subset is a complete check of those rows — and (b) through size-independent properties: every sample of a
+replicated batch must equal the single-sample result, and the whole-batch result must not depend on the launch
+geometry (unroll / CTA size)."""
+import pytest
+import torch
+
+import abi_helpers as ah
+import consolver_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SCAL = (0.8378, 0.5460, 0.9151, 0.4033)
+
+
+def _coef(B, od, g):
+    c = torch.randn(B, od + 2, generator=g)
+    c[:, od:] = 1
+    return c
+
+
+@pytest.mark.parametrize("B", [256, 4096])
+def test_sd_step_full_size_subset_vs_oracle(B):
+    N, od = 4 * 64 * 64, 4
+    g = torch.Generator(device="cuda").manual_seed(B)
+    mk = lambda: torch.randn(B, N, device="cuda", generator=g)  # noqa: E731
+    u, c, x, h = mk(), mk(), mk(), [mk(), mk(), mk()]
+    coef = _coef(B, od, torch.Generator().manual_seed(1)).cuda()
+    out, slot = ah.step_sd(u, c, 3.0, h, x, coef, od, SCAL, 0, slot=True)
+    pick = torch.randperm(B, generator=torch.Generator().manual_seed(2))[:12].tolist() + [0, B - 1]
+    for b in pick:
+        eps = orc.cfg_combine(u[b].cpu(), c[b].cpu(), 3.0)
+        cf = [coef[b, j].cpu().view(1) for j in range(4)]
+        eff, xs = orc.combine_history([eps.view(1, -1)] + [t[b].cpu().view(1, -1) for t in h], cf, [], x[b].cpu().view(1, -1))
+        ref = orc.ddim_update(xs, eff, [torch.tensor(v) for v in SCAL])
+        assert torch.equal(out[b].cpu(), ref[0]), f"sample {b}"
+        assert torch.equal(slot[b].cpu(), eps)
+    # launch geometry must not matter at full size
+    from consolver_b200 import _lib
+    lib = _lib.load()
+    try:
+        for threads, unroll in ((128, 1), (512, 2)):
+            assert lib.consolver_set_step_launch(threads, unroll) == 0
+            o2, _ = ah.step_sd(u, c, 3.0, h, x, coef, od, SCAL, 0)
+            assert torch.equal(o2, out)
+    finally:
+        lib.consolver_set_step_launch(0, 0)
+
+
+def test_sd_replicated_batch_equals_single_sample():
+    """B replicas of one (pair, latent, history) with identical coefficients: every row must be bit-identical to
+    the B=1 launch (the PPO rollout layout, data_processing.py:65-80)."""
+    N, od, B = 4 * 64 * 64, 4, 1024
+    g = torch.Generator(device="cuda").manual_seed(7)
+    one = [torch.randn(1, N, device="cuda", generator=g) for _ in range(6)]
+    coef1 = _coef(1, od, torch.Generator().manual_seed(3)).cuda()
+    ref, _ = ah.step_sd(one[0], one[1], 3.0, one[3:6], one[2], coef1, od, SCAL, 0)
+    rep = [t.expand(B, N).contiguous() for t in one]
+    out, _ = ah.step_sd(rep[0], rep[1], 3.0, rep[3:6], rep[2], coef1.expand(B, od + 2).contiguous(), od, SCAL, 0)
+    assert torch.equal(out, ref.expand(B, N))
+
+
+def test_fm_step_flux_size_subset_vs_oracle():
+    B, N, od = 512, 4096 * 64, 2
+    g = torch.Generator(device="cuda").manual_seed(11)
+    mk = lambda: torch.randn(B, N, device="cuda", generator=g).bfloat16()  # noqa: E731
+    v, x, h1 = mk(), mk(), mk()
+    coef = _coef(B, od, torch.Generator().manual_seed(5)).cuda()
+    dt = torch.tensor(0.8403) - torch.tensor(0.9045)
+    out = ah.step_fm(v, [h1], x, coef, od, float(dt), 0)
+    for b in (0, 17, 255, 511):
+        cf = [coef[b, j].cpu().view(1) for j in range(2)]
+        eff, xs = orc.combine_history([v[b].cpu().view(1, -1), h1[b].cpu().view(1, -1)], cf, [],
+                                      x[b].cpu().float().view(1, -1))
+        ref = orc.fm_update(xs, eff, dt, torch.bfloat16)
+        assert torch.equal(out[b].cpu(), ref[0]), f"sample {b}"
+
+
+def test_policy_sampling_distribution_at_large_batch():
+    """Statistical sanity at B=4096: empirical bin frequencies of the in-kernel draw follow the table (chi-square)."""
+    from consolver_b200 import _lib
+    A, K, B = 3, 11, 4096
+    table = torch.softmax(torch.randn(A, K, generator=torch.Generator().manual_seed(0)), -1).cuda()
+    sd = {"action_values": torch.zeros(A, K, device="cuda"), "mlp.0.weight": torch.zeros(8, 2, device="cuda")}
+    nthreads, inc = _lib.philox_plan(B * A * K)
+    out = ah.policy_sample(sd, table, B, 4, 0, 4, rng=_lib.Rng(20260101, 0, None, nthreads))
+    idx = out["idx"].cpu()
+    for a in range(A):
+        obs = torch.bincount(idx[:, a], minlength=K).double()
+        exp = table[a].cpu().double() * B
+        chi2 = ((obs - exp) ** 2 / exp).sum().item()
+        assert chi2 < 40.0, f"dim {a}: chi2 {chi2}"       # 10 dof: P(chi2 > 40) ~ 2e-5
