@@ -1,0 +1,206 @@
+"""Pieces shared by PPOScheduler and FMPPOScheduler: the per-trajectory device state, the draw-source selection
+(in-kernel RNG / torch launch / replay), the lazy `conds` value and the rollout-record views."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .config_utils import LazyConds
+from .factor_net import alloc_policy_outputs
+
+
+class Trajectory:
+    """Per-(set_timesteps, batch shape) device state: policy outputs for every step, the Exp(1) buffer, the
+    history ring, the condition rows of the whole grid.  Allocated once per trajectory; a step allocates only the
+    latent it returns, and its `actions / probs / masks` are views of row i of these buffers."""
+
+    def __init__(self, fn, n_steps: int, order_dim: int, B: int, shape, dtype, device, rows: Sequence[Sequence[float]]):
+        self.key = (B, tuple(shape), dtype, device)
+        self.n = max(int(n_steps), 1)
+        self.order_dim = order_dim
+        A, K = fn.action_dims, fn.num_actions
+        self.out = alloc_policy_outputs(B, A, K, order_dim, device, lead=(self.n,))
+        # row pointers by arithmetic: indexing a tensor costs ~2 us of host time, a step needs seven of them
+        self._row = {k: (v.data_ptr(), v.stride(0) * v.element_size()) for k, v in self.out.items()}
+        self.q = torch.empty((B * A, K), device=device, dtype=torch.float32)
+        self.ring = None                       # [order_dim, B, *shape], allocated on the first fused-CFG step
+        self.ring_shape = (order_dim, B, *shape)
+        self.dtype, self.device = dtype, device
+        # conds['x'] rows of the whole grid, rounded through the model dtype as the reference's
+        # torch.tensor([[a, b]], dtype=model_output.dtype) does: one H2D copy per trajectory, not one per step
+        host = torch.tensor([list(map(float, r)) for r in rows], dtype=dtype)
+        self.condx = host.to(device, non_blocking=True)
+        self.condx_f32 = host.float().to(device, non_blocking=True)    # policy-table kernel input [n,2]
+        self.condx_host = host.float().numpy()
+        self.count = 0
+        self.table_pass = -1       # pass (count // n) whose probability tables are in out['probs_table']
+        self.rng_plan = None       # (nthreads, offset increment) of torch's exponential_ launch for q's numel
+        self.graph_rng = None      # device int64[2] {seed, offset} for CUDA-graph replays
+        self.graph_rng_used = 0
+        self.policy_forked = False  # the policy side stream has been forked off the main stream in this pass
+        self._conv = None
+        self._fixed: Dict[int, torch.Tensor] = {}
+
+    def p(self, name: str, i: int) -> int:
+        base, stride = self._row[name]
+        return base + i * stride
+
+    def rewind(self):
+        """restart the pass (GraphedPreview): same buffers, tables re-evaluated, RNG bookkeeping reset"""
+        self.count = 0
+        self.table_pass = -1
+        self.graph_rng_used = 0
+        self.policy_forked = False
+
+    def slot(self, i: int) -> torch.Tensor:
+        if self.ring is None:
+            self.ring = torch.empty(self.ring_shape, device=self.device, dtype=self.dtype)
+        return self.ring[i % self.ring_shape[0]]
+
+    def conv_buffers(self, fn):
+        """use_conv=True scratch: features [B,od-1], reduction workspace, per-sample tables [n,B,A,K]"""
+        if self._conv is None:
+            from .features import workspace_bytes
+
+            B, od = self.key[0], self.order_dim
+            self._conv = (torch.empty(B, od - 1, device=self.device, dtype=torch.float32),
+                          torch.empty(workspace_bytes(B, od) // 8 + 1, device=self.device, dtype=torch.float64),
+                          torch.empty(self.n, B, fn.action_dims, fn.num_actions, device=self.device))
+        return self._conv
+
+    def fixed_rows(self, coef_fn, n_hist: int) -> torch.Tensor:
+        """coefficient records [B, od+2] of a fixed-coefficient (baseline) solver at history depth n_hist"""
+        if n_hist not in self._fixed:
+            c = [float(v) for v in coef_fn(n_hist)]
+            if len(c) != n_hist:
+                raise ValueError("fixed_coefficients(n_hist) must return n_hist values")
+            od, B = self.order_dim, self.key[0]
+            row = torch.tensor(c + [0.0] * (od - n_hist) + [1.0, 1.0], dtype=torch.float32)
+            self._fixed[n_hist] = row.to(self.device).expand(B, od + 2).contiguous()
+        return self._fixed[n_hist]
+
+    def record(self, skip_first: bool = True) -> Dict[str, torch.Tensor]:
+        """The rollout record denoise_ppo.py:105-118 assembles with unsqueeze + cat, as views:
+        x [B,n',2], probs / actions / masks / idx / logp [B,n',A] for steps 1..count-1 (or 0.. if not skip_first)."""
+        lo, hi = (1 if skip_first else 0), min(self.count, self.n)
+        B = self.key[0]
+        pick = lambda k: self.out[k][lo:hi].transpose(0, 1)  # noqa: E731
+        return dict(x=self.condx[lo:hi].unsqueeze(0).expand(B, hi - lo, 2), probs=pick("probs"),
+                    actions=pick("actions"), masks=pick("masks"), idx=pick("idx"), logp=pick("logp"))
+
+    def last(self, table_row: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """table [A,K] (or [B,A,K] with use_conv), indices [B,A], coefficient records and log-probs of the latest step"""
+        i = (self.count - 1) % self.n
+        table = self._conv[2][i] if self._conv is not None else self.out["probs_table"][i if table_row is None else table_row]
+        return dict(probs_table=table, idx=self.out["idx"][i], coef=self.out["coef"][i], logp=self.out["logp"][i])
+
+
+def next_rng(sched, tr: Trajectory, device):
+    """consolver_rng_t for this step's in-kernel draw, or None to use the torch exponential_ launch."""
+    from . import rng as _rng
+
+    if not sched.use_fused_rng:
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        if tr.graph_rng is None or tr.rng_plan is None:
+            return None
+        nthreads, inc = tr.rng_plan
+        r = _lib.Rng(0, tr.graph_rng_used * inc, tr.graph_rng.data_ptr(), nthreads)
+        tr.graph_rng_used += 1
+    else:
+        if not _rng.fused_rng_available(device):
+            return None
+        if tr.rng_plan is None:
+            tr.rng_plan = _lib.philox_plan(tr.q.numel())
+        nthreads, inc = tr.rng_plan
+        seed, off = _rng.take(device, inc)
+        r = _lib.Rng(seed, off, None, nthreads)
+    tr._rng_keepalive = r
+    return r
+
+
+def draw_source(sched, tr: Trajectory, device, fused_ok: bool):
+    """Where this step's categorical draw comes from -> (q_ptr, idx_ptr, rng_arg), exactly one non-null unless the
+    scheduler runs with fixed coefficients:
+      * in-kernel RNG (torch's exponential_ stream regenerated by the sample kernel) when `fused_ok`,
+      * else the torch launch `q.exponential_(1)` — the draw torch.multinomial makes (factor_net_ppo.py:161),
+      * `replay['idx']`: forced bins,  `replay['q']`: supplied Exp(1) values."""
+    if sched.fixed_coefficients is not None:
+        return None, None, None                       # baseline solvers draw nothing
+    rp = sched.replay
+    if rp is None:
+        r = next_rng(sched, tr, device) if fused_ok else None
+        if r is not None:
+            return None, None, ctypes.byref(r)
+        tr.q.exponential_(1)
+        return tr.q.data_ptr(), None, None
+    if rp.get("idx") is not None:
+        forced = rp["idx"][tr.count].to(device=device, dtype=torch.int64).contiguous()
+        tr._forced_keepalive = forced
+        return None, forced.data_ptr(), None
+    tr.q.copy_(rp["q"][tr.count].reshape(tr.q.shape))
+    return tr.q.data_ptr(), None, None
+
+
+def lazy_conds(conds_x: torch.Tensor, hist_now: List[torch.Tensor], order_dim: int) -> LazyConds:
+    """`conds` of the reference's return: 'x' now, 'epsilon' (newest-first zero-padded stack, scheduler_ppo.py:222-237)
+    only when somebody reads it."""
+    def stack():
+        s = torch.stack(hist_now, dim=1)
+        if len(hist_now) < order_dim:
+            pad = s.new_zeros(s.shape[0], order_dim - len(hist_now), *s.shape[2:])
+            s = torch.cat([s, pad], dim=1)
+        return s
+
+    return LazyConds(conds_x, stack)
+
+
+class SolverOptions:
+    """Optional knobs shared by both schedulers (none of them changes a number)."""
+
+    def _init_solver_options(self):
+        #: True (default): a CUDA `timestep` tensor is NOT read back; the value is taken from the host copy of the grid
+        #: at the current step count (pipelines step in grid order).  False: `.item()` it (one sync per step).
+        self.sync_free = True
+        #: link the policy and step kernels with programmatic dependent launch
+        self.use_pdl = True
+        #: generate the Exp(1) draw inside the sample kernel (bit-identical to torch's exponential_, see rng.py)
+        self.use_fused_rng = True
+        #: optional side stream for the policy kernels (set by GraphedPreview): the sample kernel needs nothing from the
+        #: step kernels, so in a captured graph the sample chain becomes a parallel branch
+        self.policy_stream: Optional[torch.cuda.Stream] = None
+        #: solver-only replays (GraphedPreview): chain consecutive step kernels with programmatic dependent launch
+        #: (CONSOLVER_FLAG_CHAIN).  Only valid when the model outputs are NOT produced by the kernel right before.
+        self.chain_steps = False
+        #: replay instead of sampling: {'idx': per-step [B,A] int64} forces the bins (PPO replay, parity tests with
+        #: injected actions); {'q': per-step [B*A,K] fp32} supplies the Exp(1) draw
+        self.replay: Optional[Dict] = None
+        #: None, or a callable n_hist -> n_hist multipliers (newest first, summing to 1): the policy is bypassed and the
+        #: fused step runs with these fixed coefficients (consolver_b200.baselines); `fixed_depth` caps the history
+        self.fixed_coefficients = None
+        self.fixed_depth: Optional[int] = None
+        self._hist: List[torch.Tensor] = []    # model outputs, NEWEST FIRST (references or ring slots)
+        self._traj: Optional[Trajectory] = None
+
+    @property
+    def factor_net_module(self):
+        fn = self.factor_net
+        return fn.module if hasattr(fn, "module") else fn    # DDP-wrapped during training (scheduler_ppo.py:239)
+
+    @property
+    def ets(self) -> List[torch.Tensor]:
+        """History oldest-first, the reference's attribute name (scheduler_ppo.py:123)."""
+        return self._hist[::-1]
+
+    def _history_depth(self, order_dim: int) -> int:
+        if self.fixed_coefficients is None:
+            return order_dim
+        return min(order_dim, self.fixed_depth or order_dim)
+
+    def trajectory(self, skip_first: bool = True) -> Dict[str, torch.Tensor]:
+        if self._traj is None:
+            raise ValueError("no trajectory recorded; call step() first")
+        return self._traj.record(skip_first)

@@ -116,7 +116,7 @@ static int launch_feat(FeatParams& p, bool vec_ok, cudaStream_t stream) {
   p.nvec_per_sample = vec_ok ? p.n_per_sample / E : p.n_per_sample;
   const long long per_cta = (long long)kFeatThreads * 4;                 // >= 4 vectors per thread
   long long chunks = (p.nvec_per_sample + per_cta - 1) / per_cta;
-  const long long want = (2LL * 148 + p.B - 1) / p.B;                    // enough CTAs for ~2 per SM ...
+  const long long want = (2LL * sm_count() + p.B - 1) / p.B;                    // enough CTAs for ~2 per SM ...
   if (chunks > want) chunks = want < 1 ? 1 : want;                        // ... but no more than that
   p.chunks_per_sample = (int)chunks;
   const long long grid = chunks * p.B;

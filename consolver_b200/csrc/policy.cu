@@ -423,11 +423,11 @@ static int launch_policy(const PolicyParams& pp, int mode, int rows, cudaStream_
   const int AK = p.A * p.K;
   int spc;
   if (p.feat) {
-    spc = (p.B + 147) / 148;                       // per-sample MLP: spread the batch over the SMs
+    spc = (p.B + sm_count() - 1) / sm_count();     // per-sample MLP: spread the batch over the SMs
   } else {
     spc = kQSlabBytes / (AK * (int)sizeof(float));
     // sampling-only launches carry no per-CTA MLP cost: use more, smaller CTAs
-    if (mode == kLaunchSample) spc = min(spc, max(p.rng_mode ? 16 : 64, (p.B + 147) / 148));
+    if (mode == kLaunchSample) spc = min(spc, max(p.rng_mode ? 16 : 64, (p.B + sm_count() - 1) / sm_count()));
     spc = max(1, min(spc, kMaxSamplesPerCta));
     spc = min(spc, p.B);
     if (spc >= 4) spc &= ~3;                       // keeps every CTA's q slab 16-byte aligned

@@ -170,7 +170,7 @@ static int launch_nh(StepParams& p, bool vec_ok, cudaStream_t stream) {
   if (unroll <= 0) {
     // default: 2 vectors/thread once the grid is at least ~8 CTAs per SM, else 1 (small batches need CTAs)
     const long long ctas_u2 = ((p.nvec_per_sample + 2LL * threads - 1) / (2LL * threads)) * p.B;
-    unroll = ctas_u2 >= 148LL * 8 ? 2 : 1;
+    unroll = ctas_u2 >= (long long)sm_count() * 8 ? 2 : 1;
   }
   if (unroll >= 2) return launch_one<T, TX, NH, MODE, E, 2>(p, threads, stream);
   return launch_one<T, TX, NH, MODE, E, 1>(p, threads, stream);

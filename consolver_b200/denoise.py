@@ -144,10 +144,7 @@ class GraphedPreview:
         if hasattr(sch, "_step_index"):
             sch._step_index = None         # FM: restart from begin_index
         if sch._traj is not None:
-            sch._traj.count = 0
-            sch._traj.table_pass = -1      # the capture (and every replay) re-evaluates the probability tables
-            sch._traj.graph_rng_used = 0
-            sch._traj.policy_forked = False
+            sch._traj.rewind()             # the capture (and every replay) re-evaluates the probability tables
 
     def replay(self) -> torch.Tensor:
         if self._rng_inc:

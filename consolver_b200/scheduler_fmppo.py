@@ -6,7 +6,6 @@ sigmas, mu, timesteps)`, `set_begin_index`, `step(...)` signature (incl. the ign
 `per_token_timesteps` (edit_ppo/scheduler_fmppo.py:363-371) is exercised by no caller and is not supported."""
 from __future__ import annotations
 
-import ctypes
 import dataclasses
 import math
 from typing import Dict, List, Optional, Union
@@ -15,9 +14,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from .config_utils import BaseOutput, ConfigMixin, LazyConds, SchedulerMixin, register_to_config
-from .factor_net import FactorNetPPOFM, alloc_policy_outputs
-from .scheduler_ppo import next_rng
+from ._sched_common import SolverOptions, Trajectory, draw_source, lazy_conds
+from .config_utils import BaseOutput, ConfigMixin, SchedulerMixin, register_to_config
+from .factor_net import FactorNetPPOFM
 
 
 @dataclasses.dataclass
@@ -30,34 +29,7 @@ class FMPPOSchedulerOutput(BaseOutput):
     masks: Optional[torch.Tensor] = None
 
 
-class _FMTrajectory:
-    def __init__(self, sched: "FMPPOScheduler", B, shape, dtype, device):
-        fn = sched.factor_net_module
-        self.key = (B, tuple(shape), dtype, device)
-        self.n = max(int(sched.num_inference_steps), 1)
-        A, K, od = fn.action_dims, fn.num_actions, sched.config.order_dim
-        self.out = alloc_policy_outputs(B, A, K, od, device, lead=(self.n,))
-        # row pointers by arithmetic: indexing a tensor costs ~2 us of host time, a step needs seven of them
-        self._row = {k: (v.data_ptr(), v.stride(0) * v.element_size()) for k, v in self.out.items()}
-        self.q = torch.empty((B * A, K), device=device, dtype=torch.float32)
-        s = sched._sigmas_host
-        rows = [[float(s[i]), float(s[i + 1])] for i in range(len(s) - 1)]
-        host = torch.tensor(rows, dtype=dtype)          # (sigma, sigma_next) rounded through the model dtype (:383)
-        self.condx = host.to(device, non_blocking=True)
-        self.condx_f32 = host.float().to(device, non_blocking=True)
-        self.condx_host = host.float().numpy()
-        self.count = 0
-        self.table_pass = -1
-        self.rng_plan, self.graph_rng, self.graph_rng_used = None, None, 0
-        self.policy_forked = False
-
-
-    def p(self, name, i):
-        base, stride = self._row[name]
-        return base + i * stride
-
-
-class FMPPOScheduler(SchedulerMixin, ConfigMixin):
+class FMPPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
     """Learned linear-multistep Euler-form solver (ConsistencySolver) for flow-matching models."""
 
     _compatibles = []
@@ -125,27 +97,10 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
                                       "(edit_ppo/scheduler_fmppo.py:169-170)")
         kw.setdefault("num_actions", 161)
         self.factor_net = FactorNetPPOFM(**kw)
-        self._hist: List[torch.Tensor] = []
-        self._traj: Optional[_FMTrajectory] = None
+        self._init_solver_options()
         self._curr_sigma = None
-        self.sync_free = True
-        self.use_pdl = True
-        self.replay: Optional[Dict] = None    # see PPOScheduler.replay
-        self.fixed_coefficients = None        # see PPOScheduler.fixed_coefficients
-        self.use_fused_rng = True             # see PPOScheduler.use_fused_rng
-        self.policy_stream = None             # see PPOScheduler.policy_stream
-        self.chain_steps = False              # see PPOScheduler.chain_steps
 
     # ---- small properties / helpers of the reference surface ---------------------------------------------------
-    @property
-    def factor_net_module(self):
-        fn = self.factor_net
-        return fn.module if hasattr(fn, "module") else fn
-
-    @property
-    def ets(self):
-        return self._hist[::-1]
-
     @property
     def step_index(self):
         return self._step_index
@@ -298,50 +253,45 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         N = sample.numel() // B
         tr = self._traj
         if tr is None or tr.key != (B, tuple(sample.shape[1:]), e0.dtype, e0.device):
-            tr = self._traj = _FMTrajectory(self, B, sample.shape[1:], e0.dtype, e0.device)
+            sg = self._sigmas_host
+            rows = [[float(sg[j]), float(sg[j + 1])] for j in range(len(sg) - 1)]      # (sigma, sigma_next): :383
+            tr = self._traj = Trajectory(fn, self.num_inference_steps, od, B, sample.shape[1:], e0.dtype, e0.device, rows)
         si = self._step_index
         if si + 1 >= len(self._sigmas_host):
             raise IndexError("FMPPOScheduler.step called past the end of the sigma schedule")
         i = tr.count % tr.n
-        depth = od if self.fixed_coefficients is None else min(od, getattr(self, "fixed_depth", od) or od)
-        older = self._hist[: depth - 1]
+        older = self._hist[: self._history_depth(od) - 1]
         n_hist = len(older) + 1
+        fixed = self.fixed_coefficients is not None
         dt = float(np.float32(self._sigmas_host[si + 1]) - np.float32(self._sigmas_host[si]))   # :373-376
         x0, x1 = float(tr.condx_host[si, 0]), float(tr.condx_host[si, 1])
         conds_x = tr.condx[si:si + 1].expand(B, 2)
 
-        o = tr.out
-        q_ptr, idx_ptr, rng_arg = tr.q.data_ptr(), None, None
-        if self.fixed_coefficients is not None:
-            pass                                        # baseline solvers draw nothing
-        elif self.replay is None:
-            r = next_rng(self, tr, e0.device) if not fn.use_conv else None    # see scheduler_ppo.next_rng
-            if r is None:
-                tr.q.exponential_(1)                    # the draw torch.multinomial makes
-            else:
-                q_ptr, rng_arg = None, ctypes.byref(r)
-        elif self.replay.get("idx") is not None:
-            forced = self.replay["idx"][tr.count].to(device=e0.device, dtype=torch.int64).contiguous()
-            q_ptr, idx_ptr = None, forced.data_ptr()
-        else:
-            tr.q.copy_(self.replay["q"][tr.count].reshape(tr.q.shape))
+        q_ptr, idx_ptr, rng_arg = draw_source(self, tr, e0.device, fused_ok=not fn.use_conv)
         x_out = torch.empty(sample.shape, device=e0.device, dtype=e0.dtype)
         lib = _lib.load()
         stream = torch._C._cuda_getCurrentRawStream(e0.device.index)
-        side = False
-        w = fn.kernel_weights() if self.fixed_coefficients is None else None
-        coef_ptr = tr.p("coef", i)
-        if self.fixed_coefficients is not None:
-            cache = tr.__dict__.setdefault("_fixed", {})
-            if n_hist not in cache:
-                c = [float(v) for v in self.fixed_coefficients(n_hist)]
-                row = torch.tensor(c + [0.0] * (od - n_hist) + [1.0, 1.0], dtype=torch.float32)
-                cache[n_hist] = row.to(e0.device).expand(B, od + 2).contiguous()
-            coef_ptr = cache[n_hist].data_ptr()
-        elif not fn.use_conv:
+        outs = tuple(tr.p(k, i) for k in ("idx", "actions", "probs", "logp", "masks", "coef"))
+        coef_ptr = outs[5]
+        flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
+        if fixed:
+            coef_ptr = tr.fixed_rows(self.fixed_coefficients, n_hist).data_ptr()      # baseline solvers: no policy
+        elif fn.use_conv:
+            # use_conv=True: cosine features of the history (pass 1), per-sample MLP, then the fused step (pass 2)
+            from .features import cosine_features_cuda
+
+            feat, ws, full = tr.conv_buffers(fn)
+            cosine_features_cuda(e0, None, 0.0, older, od, feat, ws, stream)
+            rc = lib.consolver_policy_f32(
+                *fn.kernel_weights(), x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
+                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
+                full[i].data_ptr(), *outs, stream)
+            _lib.check(rc, "consolver_policy_f32")
+            flags |= _lib.FLAG_PDL if self.use_pdl else 0
+        else:
             # all n (sigma, sigma_next) rows of the schedule go through the MLP in one launch per pass
             if tr.table_pass != tr.count // tr.n:
-                fn.policy_tables(tr.condx_f32, o["probs_table"], stream)
+                fn.policy_tables(tr.condx_f32, tr.out["probs_table"], stream)
                 tr.table_pass = tr.count // tr.n
                 tr.policy_forked = False
             ps = self.policy_stream if rng_arg is not None else None      # two-stream form: see PPOScheduler._step
@@ -350,39 +300,17 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
                 if not tr.policy_forked:
                     ps.wait_stream(main)
                     tr.policy_forked = True
-                side = True
             rc = lib.consolver_policy_sample_f32(
-                tr.p("probs_table", si), w[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
-                fn.num_actions, od,
-                cfg.scaler_dim, n_hist, tr.p("idx", i), tr.p("actions", i), tr.p("probs", i),
-                tr.p("logp", i), tr.p("masks", i), tr.p("coef", i),
-                ps.cuda_stream if ps is not None else stream)
+                tr.p("probs_table", si), fn.kernel_weights()[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
+                fn.num_actions, od, cfg.scaler_dim, n_hist, *outs, ps.cuda_stream if ps is not None else stream)
             _lib.check(rc, "consolver_policy_sample_f32")
             if ps is not None:
                 ev = torch.cuda.Event()
                 ev.record(ps)
                 main.wait_event(ev)
-        else:
-            # use_conv=True: cosine features of the history (pass 1), per-sample MLP, then the fused step (pass 2)
-            from .features import cosine_features_cuda, workspace_bytes
-
-            if getattr(tr, "_conv", None) is None:
-                tr._conv = (torch.empty(B, od - 1, device=e0.device, dtype=torch.float32),
-                            torch.empty(workspace_bytes(B, od) // 8 + 1, device=e0.device, dtype=torch.float64),
-                            torch.empty(tr.n, B, fn.action_dims, fn.num_actions, device=e0.device))
-            feat, ws, full = tr._conv
-            cosine_features_cuda(e0, None, 0.0, older, od, feat, ws, stream)
-            rc = lib.consolver_policy_f32(
-                *w, x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
-                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
-                full[i].data_ptr(), tr.p("idx", i), tr.p("actions", i), tr.p("probs", i),
-                tr.p("logp", i), tr.p("masks", i), tr.p("coef", i), stream)
-            _lib.check(rc, "consolver_policy_f32")
-        flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
-        if side:
-            flags |= _lib.FLAG_CHAIN if self.chain_steps else 0       # previous node on this stream is a step kernel
-        elif self.use_pdl:
-            flags |= _lib.FLAG_PDL
+                flags |= _lib.FLAG_CHAIN if self.chain_steps else 0   # previous node on this stream is a step kernel
+            elif self.use_pdl:
+                flags |= _lib.FLAG_PDL
         rc = lib.consolver_step_fm(
             _lib.dtype_code(e0.dtype), _lib.dtype_code(sample.dtype), e0.data_ptr(), None,
             _lib.ptr_array([h.data_ptr() for h in older]), n_hist, sample.data_ptr(), x_out.data_ptr(),
@@ -395,39 +323,16 @@ class FMPPOScheduler(SchedulerMixin, ConfigMixin):
         tr.count += 1
         self._curr_sigma = self.sigmas[si + 1]
 
-        hist_now = list(self._hist)
-        shape = tuple(sample.shape[1:])
-
-        def _stack():
-            s = torch.stack(hist_now, dim=1)
-            if len(hist_now) < od:
-                s = torch.cat([s, s.new_zeros(B, od - len(hist_now), *shape)], dim=1)
-            return s
-
-        actions, probs, masks = o["actions"][i], o["probs"][i], o["masks"][i]
-        if self.fixed_coefficients is not None:
-            actions = probs = masks = None
-        conds = LazyConds(conds_x, _stack)
+        o = tr.out
+        actions, probs, masks = (None, None, None) if fixed else (o["actions"][i], o["probs"][i], o["masks"][i])
+        conds = lazy_conds(conds_x, list(self._hist), od)
         if not return_dict:
             return (x_out, actions, probs, conds, masks)
         return FMPPOSchedulerOutput(prev_sample=x_out, actions=actions, probs=probs, conds=conds, masks=masks)
 
-    def trajectory(self, skip_first: bool = True):
-        tr = self._traj
-        if tr is None:
-            raise ValueError("no trajectory recorded; call step() first")
-        lo, hi = (1 if skip_first else 0), min(tr.count, tr.n)
-        B = tr.key[0]
-        pick = lambda k: tr.out[k][lo:hi].transpose(0, 1)  # noqa: E731
-        return dict(x=tr.condx[lo:hi].unsqueeze(0).expand(B, hi - lo, 2), probs=pick("probs"),
-                    actions=pick("actions"), masks=pick("masks"), idx=pick("idx"), logp=pick("logp"))
-
     def last_policy(self):
-        tr = self._traj
-        i = (tr.count - 1) % tr.n
-        table = tr._conv[2][i] if getattr(tr, "_conv", None) is not None else \
-            tr.out["probs_table"][(self._step_index - 1) % tr.n]
-        return dict(probs_table=table, idx=tr.out["idx"][i], coef=tr.out["coef"][i], logp=tr.out["logp"][i])
+        """see PPOScheduler.last_policy; the table row is indexed by the sigma index of the step"""
+        return self._traj.last(table_row=(self._step_index - 1) % self._traj.n)
 
     def scale_noise(self, sample: torch.Tensor, timestep, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward process of flow matching (edit_ppo/scheduler_fmppo.py:457-484); not on the hot path."""
