@@ -31,6 +31,8 @@ SIGNATURES = {
     "consolver_sd_policy_and_step": (_i, [_p] * 8 + [_f] * 4 + [_p, _p, _p] + [_i] * 4 + [_p] * 7 +
                                      [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_set_step_launch": (_i, [_i, _i]),
+    "consolver_ppo_workspace": (C.c_size_t, [_i, _i, _i, _i]),
+    "consolver_ppo_loss_grad_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i] + [_p] * 3 + [_i, _f, _f] + [_p] * 3 + [_p]),
     "consolver_cosine_features_workspace": (C.c_size_t, [_i, _i]),
     "consolver_cosine_features": (_i, [_i, _p, _p, _f, _p, _i, _i, _i, _i64, _p, _p, _p]),
 }

@@ -1,0 +1,127 @@
+// mlp_device.cuh — device-side building blocks of the policy MLP shared by the sampling kernels (policy.cu) and the
+// PPO update kernel (ppo.cu): warp reductions, L2 prefetch / cp.async helpers, the one-warp-per-row dense layer and
+// the MLP + softmax forward for one input row.  See policy.cu for the design notes.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace consolver {
+
+struct MlpView {
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  int H, A, K;
+  float temp;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// pull `bytes` starting at p into L2, one 128-byte line per thread per round
+__device__ __forceinline__ void prefetch_range_l2(const void* p, size_t bytes) {
+  const char* c = static_cast<const char*>(p);
+  for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128) prefetch_l2(c + o);
+}
+
+// y[r] = act(b[r] + W[r,:] . x) for r in [0,R): one warp per row, ROWS rows of loads in flight per warp.
+template <bool RELU>
+__device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias,
+                                            const float* x_s, float* y_s, int R, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const bool vec = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15u) == 0);
+  constexpr int ROWS = 8;
+  for (int r0 = warp * ROWS; r0 < R; r0 += nwarp * ROWS) {
+    float acc[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) acc[i] = 0.f;
+    if (vec) {
+      const int C4 = C >> 2;
+      for (int c = lane; c < C4; c += 32) {
+        float4 w[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i)
+          w[i] = (r0 + i < R) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(r0 + i) * C) + c)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 xv = reinterpret_cast<const float4*>(x_s)[c];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          acc[i] = fmaf(w[i].x, xv.x, acc[i]);
+          acc[i] = fmaf(w[i].y, xv.y, acc[i]);
+          acc[i] = fmaf(w[i].z, xv.z, acc[i]);
+          acc[i] = fmaf(w[i].w, xv.w, acc[i]);
+        }
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i)
+          if (r0 + i < R) acc[i] = fmaf(__ldg(W + (size_t)(r0 + i) * C + c), x_s[c], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      const double s = warp_sum((double)acc[i]);
+      if (lane == 0 && r0 + i < R) {
+        float v = (float)(s + (double)__ldg(bias + r0 + i));
+        y_s[r0 + i] = RELU ? fmaxf(v, 0.f) : v;
+      }
+    }
+  }
+}
+
+// MLP + softmax for one input row held in x_s[0..in_dim); leaves probs in p_s[0..A*K).
+__device__ __forceinline__ void mlp_softmax(const MlpView& p, int in_dim, const float* x_s, float* h1_s,
+                                            float* h2_s, float* lg_s, float* p_s) {
+  const int H = p.H, AK = p.A * p.K;
+  // layer 0: in_dim is 2 (or 2 + order_dim - 1): one thread per hidden unit
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    double acc = 0.0;
+    for (int i = 0; i < in_dim; ++i) acc = fma((double)__ldg(p.w1 + j * in_dim + i), (double)x_s[i], acc);
+    h1_s[j] = fmaxf((float)(acc + (double)__ldg(p.b1 + j)), 0.f);
+  }
+  __syncthreads();
+  dense_layer<true>(p.w2, p.b2, h1_s, h2_s, H, H);
+  __syncthreads();
+  dense_layer<false>(p.w3, p.b3, h2_s, lg_s, AK, H);
+  __syncthreads();
+  // softmax(logits / temp) per action dim: one warp per dim
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int a = warp; a < p.A; a += nwarp) {
+    float* l = lg_s + a * p.K;
+    float m = -INFINITY;
+    for (int k = lane; k < p.K; k += 32) {
+      const float v = __fdiv_rn(l[k], p.temp);
+      l[k] = v;
+      m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    double s = 0.0;
+    for (int k = lane; k < p.K; k += 32) {
+      const float e = expf(__fsub_rn(l[k], m));
+      l[k] = e;
+      s += (double)e;
+    }
+    const float sum = (float)warp_sum(s);
+    for (int k = lane; k < p.K; k += 32) p_s[a * p.K + k] = __fdiv_rn(l[k], sum);
+  }
+  __syncthreads();
+}
+
+}  // namespace consolver

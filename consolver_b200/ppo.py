@@ -126,17 +126,70 @@ def ppo_loss(factor_net, x_rows: torch.Tensor, idx: torch.Tensor, old_probs: tor
     return loss, dict(policy_loss=policy_loss.detach(), entropy=ent.mean().detach(), ratio_mean=ratio.mean().detach())
 
 
+def ppo_loss_grad_cuda(factor_net, flat: FlatParams, x_rows: torch.Tensor, idx_rba: torch.Tensor,
+                       old_rba: torch.Tensor, adv_rba: torch.Tensor, clip_range: float, entropy_coef: float,
+                       workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Hand-written CUDA forward + loss + backward (csrc/ppo.cu): writes d loss / d params into `flat.grad` and
+    returns stats [4] = {loss, policy_loss, mean entropy, mean ratio} (device tensor, no sync).
+    Inputs in the trajectory buffers' native layout: idx / old probs / advantages as [R, B, A]."""
+    from . import _lib
+
+    fn = factor_net.module if hasattr(factor_net, "module") else factor_net
+    if fn.use_conv:
+        raise NotImplementedError("the PPO kernel covers the shared-row policy (use_conv=False)")
+    lib = _lib.load()
+    R, B, A = idx_rba.shape
+    dev = idx_rba.device
+    need = int(lib.consolver_ppo_workspace(R, fn.hidden_dim, fn.action_dims, fn.num_actions))
+    if workspace is None or workspace.numel() * 4 < need:
+        workspace = torch.empty((need + 3) // 4, device=dev, dtype=torch.float32)
+    stats = torch.empty(4, device=dev, dtype=torch.float32)
+    w = fn.kernel_weights()
+    expected = sum(p.numel() for p in fn.parameters())
+    if flat.grad.numel() != expected or flat.grad.dtype != torch.float32:
+        raise ValueError("flat gradient buffer does not match the policy's parameters")
+    rc = lib.consolver_ppo_loss_grad_f32(
+        *w[:6], x_rows.data_ptr(), R, fn.x_div, fn.temperature, fn.hidden_dim, fn.action_dims, fn.num_actions,
+        idx_rba.data_ptr(), old_rba.data_ptr(), adv_rba.data_ptr(), B, float(clip_range), float(entropy_coef),
+        workspace.data_ptr(), flat.grad.data_ptr(), stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "consolver_ppo_loss_grad_f32")
+    return stats
+
+
 def ppo_update(factor_net, flat: FlatParams, optimizer, record: Dict[str, torch.Tensor], rewards: torch.Tensor,
                ppo_epochs: int = 1, clip_range: float = 0.2, entropy_coef: float = 0.0,
-               max_grad_norm: Optional[float] = 1.0) -> Dict[str, float]:
+               max_grad_norm: Optional[float] = 1.0, native: Optional[bool] = None) -> Dict[str, float]:
     """ppo_epochs x (loss, backward, flat all-reduce, clip, optimizer step) — train_ppo.py:406-437.
     `record` is `scheduler.trajectory()` (views); it is detached/cloned here because the next rollout reuses the
-    buffers."""
+    buffers.  `native` (default: on for CUDA tensors with the shared-row policy) runs forward + loss + backward as the
+    hand-written kernels of csrc/ppo.cu; otherwise torch autograd on the distinct rows."""
     x_rows = record["x"][0].detach().float().clone()
     idx = record["idx"].detach().clone()
     old_probs = record["probs"].detach().clone()
     adv = advantages_from_rewards(rewards.detach(), record["masks"].detach()).clone()
+    fn = factor_net.module if hasattr(factor_net, "module") else factor_net
+    if native is None:
+        native = bool(idx.is_cuda and not fn.use_conv and flat.grad.dtype == torch.float32)
     stats = {}
+    if native:
+        idx_r, old_r, adv_r = (t.transpose(0, 1).contiguous() for t in (idx, old_probs, adv))   # [R,B,A]
+        x_rows = x_rows.contiguous()
+        ws = None
+        for _ in range(ppo_epochs):
+            for p, (o, k) in zip(flat.params, flat._spans()):       # keep p.grad aliased to the flat buffer
+                if p.grad is None or p.grad.data_ptr() != flat.grad[o:o + k].data_ptr():
+                    p.grad = flat.grad[o:o + k].view_as(p)
+            st = ppo_loss_grad_cuda(fn, flat, x_rows, idx_r, old_r, adv_r, clip_range, entropy_coef, ws)
+            allreduce_gradients(flat)
+            if max_grad_norm is not None:
+                norm = flat.grad.norm()
+                flat.grad.mul_(torch.clamp(max_grad_norm / (norm + 1e-6), max=1.0))
+            optimizer.step()
+        vals = st.tolist()      # one read-back per update, after the last epoch
+        stats.update(loss=vals[0], policy_loss=vals[1], entropy=vals[2], ratio_mean=vals[3])
+        if max_grad_norm is not None:
+            stats["grad_norm"] = float(norm)
+        return stats
     for _ in range(ppo_epochs):
         flat.zero_grad()
         loss, info = ppo_loss(factor_net, x_rows, idx, old_probs, adv, clip_range, entropy_coef)

@@ -227,6 +227,27 @@ CONSOLVER_API int consolver_cosine_features(int dtype, const void* e0, const voi
                                             int64_t n_per_sample, void* workspace, float* feat,
                                             consolver_stream_t stream);
 
+/*
+ * PPO update of the policy: forward + clipped-ratio loss + entropy bonus + backward of
+ * `factor_net(conds, actions)` (factor_net_ppo.py:170-184) and the loss of train_ppo.py:406-427, evaluated on the
+ * `rows` DISTINCT condition rows of a rollout instead of B*(n-1) replicas.
+ *   x_rows [rows,2]              (t, prev_t) / (sigma, sigma_next) of steps 1..n-1
+ *   idx, old_probs, advantages   [rows,B,A]: sampled bins, their probabilities at rollout time, advantages * masks
+ *   workspace                    consolver_ppo_workspace(rows,H,A,K) bytes of scratch (per-row partial gradients)
+ *   grad_flat [P]                d loss / d parameters in nn.Module.parameters() order: mlp.0.weight [H,2], mlp.0.bias,
+ *                                mlp.2.weight [H,H], mlp.2.bias, mlp.4.weight [A*K,H], mlp.4.bias   (overwritten)
+ *   stats [4]                    {loss, policy_loss, mean normalised entropy, mean ratio}
+ * The sum over rows runs in a fixed order: results are deterministic run to run.
+ */
+CONSOLVER_API size_t consolver_ppo_workspace(int rows, int H, int A, int K);
+CONSOLVER_API int consolver_ppo_loss_grad_f32(const float* w1, const float* b1, const float* w2, const float* b2,
+                                              const float* w3, const float* b3, const float* x_rows, int rows,
+                                              float x_div, float temp, int H, int A, int K,
+                                              const int64_t* idx, const float* old_probs, const float* advantages,
+                                              int B, float clip_range, float entropy_coef,
+                                              void* workspace, float* grad_flat, float* stats,
+                                              consolver_stream_t stream);
+
 /* Tuning knobs for benchmarking (process-global; not part of the numerical contract).
  *   threads: CTA size of the step kernels (32..512, multiple of 32; 0 = default)
  *   unroll : 16-byte vectors per thread per stream (1, 2 or 4; 0 = default)                          */

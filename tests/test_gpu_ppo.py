@@ -138,3 +138,55 @@ def test_graphed_preview_stress_matches_eager_over_many_replays():
         e.set_timesteps(n, device="cuda")
         ref = preview_from_pairs(e, x, pairs, 3.0)
         assert torch.equal(ref, outs[k]), f"replay {k}"
+
+
+@pytest.mark.parametrize("variant", ["sd", "fm"])
+def test_native_ppo_kernel_matches_autograd(variant):
+    """csrc/ppo.cu (forward + clipped loss + entropy + backward on the distinct rows) vs torch autograd."""
+    import consolver_b200 as cb
+    from consolver_b200 import ppo
+
+    torch.manual_seed(3)
+    if variant == "sd":
+        fn = cb.FactorNetPPO(hidden_dim=256, num_actions=11, order_dim=4, scaler_dim=0)
+        with torch.no_grad():
+            fn.mlp[4].weight.normal_(0, 0.3)
+            fn.mlp[4].bias.normal_(0, 0.1)
+        t = torch.tensor([874., 749., 624., 499., 374.])
+        x_rows = torch.stack([t, t - 125], 1)
+    else:
+        fn = cb.FactorNetPPOFM(hidden_dim=256, num_actions=11, order_dim=4, scaler_dim=2, mu_dim=0)
+        with torch.no_grad():
+            fn.mlp[4].weight.mul_(0.05)          # temperature 0.01: keep the softmax away from one-hot
+        x_rows = torch.rand(5, 2)
+    fn.cuda()
+    x_rows = x_rows.cuda()
+    flat = ppo.FlatParams(fn)
+    B, R, A, K = 48, x_rows.shape[0], fn.action_dims, fn.num_actions
+    g = torch.Generator(device="cuda").manual_seed(1)
+    idx = torch.randint(0, K, (B, R, A), device="cuda", generator=g)
+    with torch.no_grad():
+        tables = fn.forward_({"x": x_rows})
+    old = tables.unsqueeze(0).expand(B, R, A, K).gather(3, idx.unsqueeze(-1)).squeeze(-1)
+    old = (old * (1 + 0.3 * torch.randn(old.shape, device="cuda", generator=g))).clamp(1e-4, 1.0)
+    masks = torch.ones(B, R, A, device="cuda")
+    masks[:, 0, 1:] = 0
+    adv = ppo.advantages_from_rewards(torch.randn(B, 1, device="cuda", generator=g), masks)
+    for clip, ent in ((0.2, 0.01), (0.05, 0.0)):
+        flat.zero_grad()
+        loss, info = ppo.ppo_loss(fn, x_rows, idx, old, adv, clip, ent)
+        loss.backward()
+        g_ref = flat.grad.clone()
+        flat.grad.zero_()
+        st = ppo.ppo_loss_grad_cuda(fn, flat, x_rows, *(t.transpose(0, 1).contiguous() for t in (idx, old, adv)), clip, ent)
+        scale = g_ref.abs().max()
+        assert scale > 0
+        torch.testing.assert_close(flat.grad, g_ref, rtol=2e-3, atol=float(scale) * 2e-4)
+        torch.testing.assert_close(st[0], loss.detach(), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(st[1], info["policy_loss"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(st[2], info["entropy"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(st[3], info["ratio_mean"], rtol=1e-4, atol=1e-6)
+    # deterministic: same inputs, same bits
+    a = flat.grad.clone()
+    ppo.ppo_loss_grad_cuda(fn, flat, x_rows, *(t.transpose(0, 1).contiguous() for t in (idx, old, adv)), 0.05, 0.0)
+    assert torch.equal(a, flat.grad)
