@@ -441,3 +441,24 @@ def run_sd_preview(sched: OracleSDScheduler, x_T: torch.Tensor, pairs: Sequence[
         x = out[0]
         rec.append(out)
     return x, rec
+
+
+# --------------------------------------------------------------------------------------------
+# PPO update side
+# --------------------------------------------------------------------------------------------
+def ppo_loss_replicated(sd: Dict[str, torch.Tensor], x: torch.Tensor, actions: torch.Tensor, old_probs: torch.Tensor,
+                        masks: torch.Tensor, rewards: torch.Tensor, variant: str, clip_range: float,
+                        entropy_coef: float) -> torch.Tensor:
+    """train_ppo.py:376-427 restated literally on the reference's layout: x [B,n',2] (B replicated condition rows
+    per step), actions / old_probs / masks [B,n',A], rewards [B,1].  `sd` entries may require grad."""
+    B, n1, A = actions.shape
+    adv = (rewards - rewards.mean()) / (rewards.std() + 1e-8) * 10                 # :376
+    adv = adv.repeat(1, n1).reshape(B * n1, -1)                                    # :377-379
+    adv = adv * masks.reshape(B * n1, A)                                           # :390
+    cur, ent = action_probs_entropy(sd, x.reshape(B * n1, 2), actions.reshape(B * n1, A), variant)   # :408
+    logp = (cur + 1e-9).log().sum(dim=1).unsqueeze(1)                              # :410
+    old = (old_probs.reshape(B * n1, A) + 1e-9).log().sum(dim=1).unsqueeze(1)      # :411
+    ratio = (logp - old).exp()
+    clipped = torch.clamp(ratio, 1 - clip_range, 1 + clip_range)
+    policy_loss = -torch.min(adv * ratio, adv * clipped).mean()                    # :416-420
+    return policy_loss + (-entropy_coef * ent.mean())                              # :424-427

@@ -190,3 +190,39 @@ def test_native_ppo_kernel_matches_autograd(variant):
     a = flat.grad.clone()
     ppo.ppo_loss_grad_cuda(fn, flat, x_rows, *(t.transpose(0, 1).contiguous() for t in (idx, old, adv)), 0.05, 0.0)
     assert torch.equal(a, flat.grad)
+
+
+def test_native_ppo_kernel_matches_the_oracle_restatement_of_the_training_loss():
+    """Kernel (distinct rows, recorded indices) vs the oracle's literal restatement of train_ppo.py:376-427 on
+    B*(n-1) replicated rows with bins re-derived from the action values — loss and gradients."""
+    import consolver_b200 as cb
+    import consolver_oracle as orc
+    from consolver_b200 import ppo
+
+    torch.manual_seed(11)
+    fn = cb.FactorNetPPO(hidden_dim=256, num_actions=11, order_dim=4, scaler_dim=0)
+    with torch.no_grad():
+        fn.mlp[4].weight.normal_(0, 0.3)
+    B, R, A, K = 24, 6, 3, 11
+    g = torch.Generator().manual_seed(2)
+    t = torch.tensor([874., 749., 624., 499., 374., 249.])
+    x_rows = torch.stack([t, t - 125], 1)
+    idx = torch.randint(0, K, (B, R, A), generator=g)
+    actions = fn.action_values[torch.arange(A).view(1, 1, A).expand(B, R, A), idx]
+    old = torch.rand(B, R, A, generator=g) * 0.3 + 0.02
+    masks = torch.ones(B, R, A)
+    masks[:, 0, 1:] = 0
+    masks[:, 1, 2:] = 0
+    rewards = torch.randn(B, 1, generator=g)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k != "action_values")
+          for k, v in fn.state_dict().items()}
+    ref = orc.ppo_loss_replicated(sd, x_rows.unsqueeze(0).expand(B, R, 2), actions, old, masks, rewards, "sd", 0.2, 0.01)
+    names = [n for n, _ in fn.named_parameters()]
+    g_ref = torch.cat([gr.reshape(-1) for gr in torch.autograd.grad(ref, [sd[n] for n in names])])
+    fn.cuda()
+    flat = ppo.FlatParams(fn)
+    adv = ppo.advantages_from_rewards(rewards, masks).cuda()
+    st = ppo.ppo_loss_grad_cuda(fn, flat, x_rows.cuda(), idx.transpose(0, 1).contiguous().cuda(),
+                                old.transpose(0, 1).contiguous().cuda(), adv.transpose(0, 1).contiguous(), 0.2, 0.01)
+    torch.testing.assert_close(st[0].cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(flat.grad.cpu(), g_ref, rtol=2e-3, atol=float(g_ref.abs().max()) * 2e-4)

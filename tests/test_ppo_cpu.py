@@ -45,24 +45,12 @@ def _fake_record(fn, B, n1, seed, variant="sd"):
 
 
 def _reference_loss(fn, rec, rewards, clip, ent_coef, variant):
-    """train_ppo.py:376-427 restated literally on B*(n-1) replicated rows through the oracle."""
-    B, n1, A = rec["idx"].shape
+    """train_ppo.py:376-427 restated literally on B*(n-1) replicated rows: oracle.ppo_loss_replicated."""
     sd = dict(fn.state_dict())
     for k, v in fn.named_parameters():
         sd[k] = v                                               # keep autograd
-    adv = (rewards - rewards.mean()) / (rewards.std() + 1e-8) * 10
-    adv = adv.repeat(1, n1).reshape(B * n1, -1)
-    x = rec["x"].reshape(B * n1, 2)
-    actions = rec["actions"].reshape(B * n1, A)
-    probs = rec["probs"].reshape(B * n1, A)
-    masks = rec["masks"].reshape(B * n1, A)
-    adv = adv * masks
-    cur, ent = orc.action_probs_entropy(sd, x, actions, variant)
-    logp = (cur + 1e-9).log().sum(dim=1).unsqueeze(1)
-    old = (probs + 1e-9).log().sum(dim=1).unsqueeze(1)
-    ratio = (logp - old).exp()
-    pl = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
-    return pl + (-ent_coef * ent.mean())
+    return orc.ppo_loss_replicated(sd, rec["x"], rec["actions"], rec["probs"], rec["masks"], rewards, variant, clip,
+                                   ent_coef)
 
 
 @pytest.mark.parametrize("variant", ["sd", "fm"])
