@@ -429,7 +429,9 @@ def run_ours(args, rank, world, device):
                                "synthetic CFG pairs", "batch_per_gpu": B, "solver_steps": N_STEPS,
                    "l2_policy": f"inputs larger than L2: rotating pool of {pool_n} resident batches "
                                 f"({pool_n * bytes_per_batch >> 20} MiB)",
-                   "launch": "eager" if args.eager else "cuda_graph(8-step loop)", "sharding": f"dp{world} by prompt/seed, no collective"},
+                   "launch": "eager python launches" if args.eager else
+                   "one CUDA graph per 8-step preview (table kernel, sample kernels on a side stream, PDL-chained step "
+                   "kernels, rng-advance node); valid because the stand-in model outputs are resident", "sharding": f"dp{world} by prompt/seed, no collective"},
         "e2e": {"value": round(e2e_val, 1), "unit": "previews/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "gpu_launches": args.steps * (2 + N_STEPS * 2),   # per preview: table + 8 x (sample + step) + rng-advance kernels
