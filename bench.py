@@ -519,11 +519,28 @@ def cpu_baseline(B, budget_s=10.0):
         best = min(best, time.perf_counter() - t1)
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": round(n * B / dt, 1), "unit": "previews/s", "cores": torch.get_num_threads(), "kind": "port",
+    cores = torch.get_num_threads()
+    # second row: the same port on ONE host thread, a short bounded sample
+    torch.set_num_threads(1)
+    t1 = time.perf_counter()
+    n1 = 0
+    while n1 < 2 or (time.perf_counter() - t1 < min(2.0, budget_s / 4) and n1 < 200):
+        run()
+        n1 += 1
+    dt1 = time.perf_counter() - t1
+    torch.set_num_threads(cores)
+    model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
+    except OSError:
+        pass
+    return {"value": round(n * B / dt, 1), "unit": "previews/s", "cores": cores, "kind": "port",
             "sample": f"{n} full 8-step previews of batch {B} (same workload unit, ~{dt:.1f} s of CPU work), torch-CPU "
                       f"oracle port of the reference scheduler incl. CFG combine, no debug prints",
             "best_ms_per_step": round(best * 1e3, 2), "algorithmic_gbs": round(
-                TENSORS_PER_PREVIEW * B * 65536 / best / 1e9, 2)}
+                TENSORS_PER_PREVIEW * B * 65536 / best / 1e9, 2),
+            "value_1_thread": round(n1 * B / dt1, 1), "host_cpus": os.cpu_count(), "cpu_model": model}
 
 
 def run_reference(args, rank, world):

@@ -1,0 +1,91 @@
+"""Host-side schedules of the drop-in schedulers against the UNMODIFIED reference, for option combinations the
+committed golden vectors do not cover.  Runs only where the reference tree exists (the build container);
+skipped elsewhere — the GPU box never reads /root/reference."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import consolver_b200 as cb
+import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("spacing,schedule,n", list(itertools.product(
+    ["leading", "trailing", "linspace"], ["linear", "scaled_linear", "squaredcos_cap_v2"], [2, 7, 15, 50])))
+def test_sd_schedules_match_reference(spacing, schedule, n):
+    ref = ref_shim.load_reference()
+    kw = dict(timestep_spacing=spacing, beta_schedule=schedule, steps_offset=1, order_dim=4, scaler_dim=0,
+              factor_net_kwargs=dict(hidden_dim=8, num_actions=3))
+    with ref_shim.quiet():
+        r = ref.PPOScheduler(**kw)
+    m = cb.PPOScheduler(**kw)
+    assert torch.equal(r.alphas_cumprod, m.alphas_cumprod)
+    r.set_timesteps(n)
+    m.set_timesteps(n)
+    assert torch.equal(r.timesteps, m.timesteps)
+    x0, noise, t = torch.randn(2, 4, 4, 4), torch.randn(2, 4, 4, 4), torch.tensor([3, 700])
+    assert torch.equal(r.add_noise(x0, noise, t), m.add_noise(x0, noise, t))
+    # the per-step scalars the kernel receives are the reference's 0-d fp32 values
+    for tt in m.timesteps.tolist():
+        a = r.alphas_cumprod[tt]
+        assert float(a ** 0.5) == float(m._sqrt_abar[tt]) and float((1 - a) ** 0.5) == float(m._sqrt_1m_abar[tt])
+
+
+FM_VARIANTS = [dict(shift=3.0), dict(use_dynamic_shifting=True), dict(use_karras_sigmas=True),
+               dict(use_exponential_sigmas=True), dict(use_beta_sigmas=True), dict(shift=2.0, shift_terminal=0.02),
+               dict(invert_sigmas=True), dict(use_dynamic_shifting=True, time_shift_type="linear")]
+
+
+@pytest.mark.parametrize("variant", FM_VARIANTS)
+@pytest.mark.parametrize("mode", ["n", "sigmas", "timesteps"])
+def test_fm_schedules_match_reference(variant, mode):
+    ref = ref_shim.load_reference()
+    kw = dict(order_dim=2, scaler_dim=0, mu_dim=0, factor_net_kwargs=dict(hidden_dim=8, num_actions=3), **variant)
+    with ref_shim.quiet():
+        r = ref.FMPPOScheduler(**kw)
+    m = cb.FMPPOScheduler(**kw)
+    assert torch.equal(r.sigmas, m.sigmas) and torch.equal(r.timesteps, m.timesteps)
+    assert r.sigma_min == m.sigma_min and r.sigma_max == m.sigma_max
+    n = 6
+    mu = 0.9 if variant.get("use_dynamic_shifting") else None
+    args = dict(n=dict(num_inference_steps=n), sigmas=dict(sigmas=np.linspace(1.0, 1 / n, n)),
+                timesteps=dict(timesteps=[900.0, 700.0, 500.0, 300.0, 200.0, 100.0]))[mode]
+    r.set_timesteps(mu=mu, **args)
+    m.set_timesteps(mu=mu, **args)
+    assert torch.equal(r.sigmas, m.sigmas), (r.sigmas, m.sigmas)
+    assert torch.equal(r.timesteps, m.timesteps)
+    assert r.index_for_timestep(r.timesteps[3]) == m.index_for_timestep(m.timesteps[3])
+    lat, noise = torch.randn(2, 8, 4), torch.randn(2, 8, 4)
+    assert torch.equal(r.scale_noise(lat, r.timesteps[:2], noise), m.scale_noise(lat, m.timesteps[:2], noise))
+
+
+def test_policy_modules_match_reference_at_init_and_on_the_update_side():
+    ref = ref_shim.load_reference()
+    for Ref, Mine, kw in ((ref.FactorNetPPO_SD, cb.FactorNetPPO, dict(hidden_dim=32, num_actions=11, order_dim=4, scaler_dim=2)),
+                          (ref.FactorNetPPO_FM, cb.FactorNetPPOFM, dict(hidden_dim=32, num_actions=11, order_dim=3, scaler_dim=1, mu_dim=1)),
+                          (ref.FactorNetPPO_SD, cb.FactorNetPPO, dict(hidden_dim=32, num_actions=7, order_dim=4, scaler_dim=0, use_conv=True))):
+        with ref_shim.quiet():
+            torch.manual_seed(5)
+            r = Ref(**kw)
+        torch.manual_seed(5)
+        m = Mine(**kw)
+        rs, ms = r.state_dict(), m.state_dict()
+        assert list(rs) == list(ms) and all(torch.equal(rs[k], ms[k]) for k in rs)    # same init stream, same buffers
+        with torch.no_grad():
+            for mod in (r, m):
+                torch.manual_seed(9)
+                mod.mlp[4].weight.normal_(0, 0.2)
+        x = torch.tensor([[874.0, 749.0], [499.0, 374.0]]) if Ref is ref.FactorNetPPO_SD else torch.rand(2, 2)
+        d = {"x": x}
+        if kw.get("use_conv"):
+            d["epsilon"] = torch.randn(2, 4, 4, 8, 8)
+        idx = torch.randint(0, kw["num_actions"], (2, r.action_dims))
+        actions = r.action_values[torch.arange(r.action_dims), idx]
+        with ref_shim.quiet():
+            pr, er = r(d, actions)
+        pm, em = m(d, actions)
+        torch.testing.assert_close(pm, pr, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(em, er, rtol=1e-5, atol=1e-6)
