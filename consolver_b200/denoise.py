@@ -134,6 +134,12 @@ class GraphedPreview:
                 _lib.check(_lib.load().consolver_rng_state_advance(
                     tr.graph_rng.data_ptr(), self._rng_inc, torch.cuda.current_stream(dev).cuda_stream), "rng advance")
         self._expected = None      # (seed, offset) the device state holds for the next replay
+        # the two-stream / chained form is baked into the graph; eager calls on this scheduler go back to the
+        # general single-stream form (CHAIN is only valid for resident model outputs)
+        self.used_policy_stream = scheduler.policy_stream is not None
+        self.used_chain = bool(scheduler.chain_steps)
+        scheduler.policy_stream = None
+        scheduler.chain_steps = False
         self._rewind()
 
     def _rewind(self):

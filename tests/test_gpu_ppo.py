@@ -127,7 +127,7 @@ def test_graphed_preview_stress_matches_eager_over_many_replays():
     x = torch.randn(B, 4, 64, 64, device="cuda", generator=g)
     pairs = [torch.randn(2 * B, 4, 64, 64, device="cuda", generator=g) for _ in range(n)]
     gp = GraphedPreview(s, x, pairs, 3.0, n)
-    assert s.chain_steps and s.policy_stream is not None
+    assert gp.used_chain and gp.used_policy_stream and not s.chain_steps and s.policy_stream is None
     torch.manual_seed(123)
     outs = []
     for _ in range(12):
