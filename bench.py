@@ -339,24 +339,19 @@ def run_ours(args, rank, world, device):
     # Independent preview batches (different prompts/seeds) have no dependency on each other: keep `streams` of them
     # in flight on separate CUDA streams so one batch's launch ramp / tail overlaps another's streaming phase.
     # Pool entry j always runs on stream j % streams, so no two streams touch the same buffers.
-    n_streams = max(1, min(args.streams, pool_n))
-    while pool_n % n_streams:
-        n_streams -= 1
-    main_stream = torch.cuda.current_stream(device)
-    streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)] if n_streams > 1 else [main_stream]
+    from consolver_b200.denoise import PreviewPool
+
+    ppool = None if args.eager else PreviewPool([p[3] for p in pool], streams=args.streams)
+    n_streams = 1 if ppool is None else len(ppool.streams)
 
     def run_steps(first, count):
-        if n_streams == 1:
+        if ppool is None:
             for k in range(first, first + count):
                 one_step(k)
             return
-        for st in streams:
-            st.wait_stream(main_stream)
         for k in range(first, first + count):
-            with torch.cuda.stream(streams[k % n_streams]):
-                one_step(k)
-        for st in streams:
-            main_stream.wait_stream(st)
+            ppool.submit(k % pool_n)
+        ppool.join()
 
     run_steps(0, args.warmup)
     barrier()

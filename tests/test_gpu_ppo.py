@@ -226,3 +226,45 @@ def test_native_ppo_kernel_matches_the_oracle_restatement_of_the_training_loss()
                                 old.transpose(0, 1).contiguous().cuda(), adv.transpose(0, 1).contiguous(), 0.2, 0.01)
     torch.testing.assert_close(st[0].cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(flat.grad.cpu(), g_ref, rtol=2e-3, atol=float(g_ref.abs().max()) * 2e-4)
+
+
+def test_preview_pool_concurrent_replays_match_serial_execution():
+    """4 independent previews in flight on 4 streams: same bits as running them one after the other."""
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedPreview, PreviewPool, preview_from_pairs
+
+    B, n = 32, 8
+    g = torch.Generator(device="cuda").manual_seed(9)
+    batches, previews, eager = [], [], []
+    for j in range(4):
+        s = cb.PPOScheduler(**PROD)
+        with torch.no_grad():
+            torch.manual_seed(50 + j)
+            s.factor_net.mlp[4].weight.normal_(0, 0.05)
+        s.factor_net.cuda()
+        e = cb.PPOScheduler(**PROD)
+        e.factor_net.load_state_dict(s.factor_net.state_dict())
+        e.factor_net.cuda()
+        x = torch.randn(B, 4, 64, 64, device="cuda", generator=g)
+        pairs = [torch.randn(2 * B, 4, 64, 64, device="cuda", generator=g) for _ in range(n)]
+        batches.append((x, pairs))
+        previews.append(GraphedPreview(s, x, pairs, 3.0, n))
+        eager.append(e)
+    pool = PreviewPool(previews, streams=4)
+    assert len(pool.streams) == 4
+    torch.manual_seed(321)
+    outs = []
+    for rnd in range(3):
+        for j in range(4):
+            outs.append(pool.submit(j))
+        pool.join()
+        outs = [o.clone() for o in outs[:-4]] + [o.clone() for o in outs[-4:]]
+    torch.cuda.synchronize()
+    torch.manual_seed(321)
+    k = 0
+    for rnd in range(3):
+        for j in range(4):
+            eager[j].set_timesteps(n, device="cuda")
+            ref = preview_from_pairs(eager[j], *batches[j], 3.0)
+            assert torch.equal(ref, outs[k]), f"round {rnd} preview {j}"
+            k += 1
