@@ -216,3 +216,86 @@ class PreviewPool:
             for st in self.streams:
                 self.main.wait_stream(st)
         self._open = False
+
+
+class GraphedDenoiseLoop:
+    """The WHOLE n-step CFG sampling loop — denoiser forward passes included — as one CUDA graph over static
+    buffers.  For interactive previews (batch 1-4) the denoiser is launch-bound, so replaying one
+    graph instead of ~10^4 eager launches is where the latency goes; the scheduler's part is the same kernels as in
+    `denoise_loop` (fused CFG + step writing x' into both halves of the next denoiser input, sample kernels on a
+    side stream, in-kernel RNG from a device-resident generator state).
+
+    `denoiser(model_in [2B,...], t, i)` must be capturable (static shapes, no host sync); `t` is the python int of
+    step i.  Fill `self.noise` (or pass `noise=` to `replay`) and call `replay()`; the result is `self.latents`."""
+
+    def __init__(self, scheduler: PPOScheduler, denoiser: Callable, noise: torch.Tensor, cfg: float,
+                 num_inference_steps: int):
+        from . import _lib, rng as _rng
+
+        self.scheduler, self.denoiser, self.cfg, self.n = scheduler, denoiser, float(cfg), num_inference_steps
+        dev = noise.device
+        B = noise.shape[0]
+        self.noise = noise.clone()
+        self._bufs = [noise.new_empty((2 * B, *noise.shape[1:])) for _ in range(2)]
+        scheduler.set_timesteps(num_inference_steps, device=dev)
+        ts = [int(t) for t in scheduler._timesteps_host]
+        if scheduler.use_fused_rng and scheduler.fixed_coefficients is None:
+            scheduler.policy_stream = torch.cuda.Stream(device=dev)
+
+        def run():
+            bufs = self._bufs
+            bufs[0][:B].copy_(self.noise)
+            bufs[0][B:].copy_(self.noise)
+            for i, t in enumerate(ts):
+                cur, nxt = bufs[i % 2], bufs[(i + 1) % 2]
+                pred = self.denoiser(cur, t, i)
+                scheduler.step_cfg(pred, t, cur[:B], self.cfg, out=nxt[:B], out2=nxt[B:])
+            return bufs[len(ts) % 2][:B]
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            run()
+            run()                                     # second pass: library autotuning / lazy allocations settle
+        torch.cuda.current_stream(dev).wait_stream(side)
+        tr = scheduler._traj
+        self._dev, self._rng_inc, self._expected = dev, 0, None
+        if scheduler.use_fused_rng and _rng.fused_rng_available(dev):
+            tr.rng_plan = _lib.philox_plan(tr.q.numel())
+            tr.graph_rng = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._rewind()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.latents = run()
+            if tr.graph_rng is not None and tr.graph_rng_used:
+                self._rng_inc = tr.graph_rng_used * tr.rng_plan[1]
+                _lib.check(_lib.load().consolver_rng_state_advance(
+                    tr.graph_rng.data_ptr(), self._rng_inc, torch.cuda.current_stream(dev).cuda_stream), "rng advance")
+        scheduler.policy_stream = None
+        self._rewind()
+
+    def _rewind(self):
+        sch = self.scheduler
+        sch._hist = []
+        sch._step_count = 0
+        if sch._traj is not None:
+            sch._traj.rewind()
+
+    def replay(self, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if noise is not None:
+            self.noise.copy_(noise)
+        if self._rng_inc:
+            from . import rng as _rng
+
+            seed, off = _rng.take(self._dev, self._rng_inc)
+            if self._expected != (seed, off):
+                state = torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, off], dtype=torch.int64)
+                self.scheduler._traj.graph_rng.copy_(state)       # pageable source: staged synchronously, rare
+            self._expected = (seed, off + self._rng_inc)
+        self.graph.replay()
+        return self.latents
+
+    def record(self):
+        tr = self.scheduler._traj
+        tr.count = self.n
+        return self.scheduler.trajectory()

@@ -268,3 +268,32 @@ def test_preview_pool_concurrent_replays_match_serial_execution():
             ref = preview_from_pairs(eager[j], *batches[j], 3.0)
             assert torch.equal(ref, outs[k]), f"round {rnd} preview {j}"
             k += 1
+
+
+def test_graphed_denoise_loop_with_a_denoiser_matches_eager():
+    """Whole CFG loop (denoiser included) in one CUDA graph == eager denoise_loop, bit for bit, seeds included."""
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedDenoiseLoop, denoise_loop
+
+    s, e = cb.PPOScheduler(**PROD), cb.PPOScheduler(**PROD)
+    with torch.no_grad():
+        s.factor_net.mlp[4].weight.normal_(0, 0.05)
+    e.factor_net.load_state_dict(s.factor_net.state_dict())
+    s.factor_net.cuda(), e.factor_net.cuda()
+    @torch.no_grad()
+    def den(x, t, i):      # element-wise only: library convolutions may pick different algorithms under capture
+        scale = 1.0 + 0.0005 * float(t)      # python scalar in both modes (eager hands a 0-d tensor, the graph an int)
+        return 0.6 * x + 0.3 * torch.roll(x, 1, dims=2) - 0.2 * torch.roll(x, 1, dims=1) * scale
+
+    noise = torch.randn(2, 4, 32, 32, device="cuda")
+    noise2 = torch.randn_like(noise)                 # drawn up front: nothing else may touch the generator below
+    g = GraphedDenoiseLoop(s, den, noise, cfg=3.0, num_inference_steps=6)
+    torch.manual_seed(4)
+    out1 = g.replay().clone()
+    idx1 = g.record()["idx"].clone()
+    out2 = g.replay(noise2).clone()
+    torch.manual_seed(4)
+    ref1, rec1 = denoise_loop(e, den, noise, cfg=3.0, num_inference_steps=6)
+    assert torch.equal(rec1["idx"], idx1) and torch.equal(ref1, out1)
+    ref2, _ = denoise_loop(e, den, noise2, cfg=3.0, num_inference_steps=6)
+    assert torch.equal(ref2, out2)
