@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kPpoThreads) ppo_row_kernel(const PpoParams p)
   const long long oW1 = 0, ob1 = 2LL * H, oW2 = 3LL * H, ob2 = oW2 + (long long)H * H, oW3 = ob2 + H,
                   ob3 = oW3 + (long long)AK * H;
   for (int i = tid; i < AK; i += nt) part[ob3 + i] = lg_s[i];
-  for (long long e = tid; e < (long long)AK * H; e += nt) part[oW3 + e] = lg_s[e / H] * h2_s[e % H];
+  for (int e = tid; e < AK * H; e += nt) part[oW3 + e] = lg_s[e / H] * h2_s[e % H];       // 32-bit index math
   for (int j = tid; j < H; j += nt) {
     float acc = 0.f;
     for (int q = 0; q < AK; ++q) acc = fmaf(__ldg(p.m.w3 + (size_t)q * H + j), lg_s[q], acc);
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kPpoThreads) ppo_row_kernel(const PpoParams p)
   __syncthreads();
   // ---- layer 2 backward ---------------------------------------------------------------------------------------------
   for (int j = tid; j < H; j += nt) part[ob2 + j] = dz2_s[j];
-  for (long long e = tid; e < (long long)H * H; e += nt) part[oW2 + e] = dz2_s[e / H] * h1_s[e % H];
+  for (int e = tid; e < H * H; e += nt) part[oW2 + e] = dz2_s[e / H] * h1_s[e % H];
   for (int i = tid; i < H; i += nt) {
     float acc = 0.f;
     for (int j = 0; j < H; ++j) acc = fmaf(__ldg(p.m.w2 + (size_t)j * H + i), dz2_s[j], acc);

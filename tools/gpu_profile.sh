@@ -14,3 +14,6 @@ ncu --set full --clock-control none --import-source on -k regex:policy -s 12 -c 
     python bench.py --steps 2 --warmup 3 --no-extras --eager > gpurun_out/ncu_policy.log 2>&1
 cat gpurun_out/launch_summary_$R.txt | head -8
 ls -la gpurun_out/*.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:ppo_ -s 4 -c 2 -o gpurun_out/ppo_$R \
+    python tools/ppo_bench.py --iters 3 > gpurun_out/ncu_ppo.log 2>&1
+ls -la gpurun_out/ppo_$R.ncu-rep
