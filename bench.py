@@ -413,6 +413,22 @@ def run_ours(args, rank, world, device):
         ms = t.item()
     value = world * args.steps * B / (ms / 1e3)
 
+    # for transparency: the same loop with ONE preview batch in flight (no cross-batch overlap), rank-local
+    single = None
+    if ppool is not None and n_streams > 1:
+        k1 = min(args.steps, 500)
+        for k in range(8):
+            one_step(k)
+        torch.cuda.synchronize(device)
+        a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a1.record()
+        for k in range(k1):
+            one_step(k)
+        b1.record()
+        torch.cuda.synchronize(device)
+        single = {"value_per_gpu": round(k1 * B / (a1.elapsed_time(b1) / 1e3), 1),
+                  "us_per_preview_batch": round(a1.elapsed_time(b1) * 1e3 / k1, 2)}
+
     if args.no_extras:
         return {"metric": "sd15_8step_solver_previews_per_s", "value": round(value, 1), "unit": "previews/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4)}
@@ -503,7 +519,7 @@ def run_ours(args, rank, world, device):
     # whole-loop HBM rate: 58 latent-sized transfers per sample per 8-step preview, per GPU
     loop_gbs = value / world * TENSORS_PER_PREVIEW * SHAPE[0] * SHAPE[1] * SHAPE[2] * 4 / 1e9
     out["solver_loop"] = {"algorithmic_bytes_per_preview": TENSORS_PER_PREVIEW * SHAPE[0] * SHAPE[1] * SHAPE[2] * 4,
-                          "achieved_gbs_per_gpu": round(loop_gbs, 1)}
+                          "achieved_gbs_per_gpu": round(loop_gbs, 1), "one_batch_in_flight": single}
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
