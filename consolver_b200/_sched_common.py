@@ -23,6 +23,9 @@ class Trajectory:
         self.order_dim = order_dim
         A, K = fn.action_dims, fn.num_actions
         self.out = alloc_policy_outputs(B, A, K, order_dim, device, lead=(self.n,))
+        # rows 0..n-1: tables of the grid (one table-kernel launch per pass); row n: scratch for an off-grid timestep
+        self.out["probs_table"] = torch.empty(self.n + 1, A, K, device=device, dtype=torch.float32)
+        self.last_table_row = 0
         # row pointers by arithmetic: indexing a tensor costs ~2 us of host time, a step needs seven of them
         self._row = {k: (v.data_ptr(), v.stride(0) * v.element_size()) for k, v in self.out.items()}
         self.q = torch.empty((B * A, K), device=device, dtype=torch.float32)
@@ -94,7 +97,8 @@ class Trajectory:
     def last(self, table_row: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """table [A,K] (or [B,A,K] with use_conv), indices [B,A], coefficient records and log-probs of the latest step"""
         i = (self.count - 1) % self.n
-        table = self._conv[2][i] if self._conv is not None else self.out["probs_table"][i if table_row is None else table_row]
+        row = self.last_table_row if table_row is None else table_row
+        table = self._conv[2][i] if self._conv is not None else self.out["probs_table"][row]
         return dict(probs_table=table, idx=self.out["idx"][i], coef=self.out["coef"][i], logp=self.out["logp"][i])
 
 

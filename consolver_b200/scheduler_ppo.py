@@ -116,6 +116,7 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
 
         self._init_solver_options()
         self._step_count = 0
+        self._grid_offset = None
         self._stride = 0
 
     # ------------------------------------------------------------------------------------------------------
@@ -141,19 +142,36 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         self._hist = []
         self._traj = None
         self._step_count = 0
+        self._grid_offset = None
 
     def scale_model_input(self, sample: torch.Tensor, timestep: Optional[int] = None) -> torch.Tensor:
         return sample
 
     # ------------------------------------------------------------------------------------------------------
     def _host_timestep(self, timestep) -> int:
-        if isinstance(timestep, torch.Tensor):
-            if timestep.is_cuda:
-                if self.sync_free:
-                    return int(self._timesteps_host[self._step_count % len(self._timesteps_host)])
-                return int(timestep.item())
+        """Value of `timestep` without a per-step device read-back.  Host ints / CPU tensors are read directly.  A CUDA
+        tensor (pipelines iterate `scheduler.timesteps` on the device) is read back ONCE per trajectory to locate the
+        starting position in the grid — img2img-style callers start at `timesteps[t_start:]` — and consecutive steps
+        are then taken from the host copy of the grid.  `sync_free = False` reads every timestep back instead."""
+        if not isinstance(timestep, torch.Tensor):
             return int(timestep)
-        return int(timestep)
+        if not timestep.is_cuda:
+            return int(timestep)
+        if not self.sync_free:
+            return int(timestep.item())
+        grid = self._timesteps_host
+        if self._grid_offset is None:
+            if torch.cuda.is_current_stream_capturing():
+                self._grid_offset = -self._step_count           # cannot read back while capturing: grid order
+            else:
+                hits = np.nonzero(grid == int(timestep.item()))[0]
+                if len(hits) == 0:
+                    return int(timestep.item())                 # off-grid: keep reading back
+                self._grid_offset = int(hits[0]) - self._step_count
+        j = self._step_count + self._grid_offset
+        if 0 <= j < len(grid):
+            return int(grid[j])
+        return int(timestep.item())
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True):
         """Same contract as scheduler_ppo.py:178-299.  `return_dict=False` ->
@@ -208,11 +226,14 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         n_hist = len(older) + 1
         fixed = self.fixed_coefficients is not None
 
-        # policy input row (t, prev_t) rounded through the model dtype (scheduler_ppo.py:207)
-        on_grid = t == self._timesteps_host[i]
+        # policy input row (t, prev_t) rounded through the model dtype (scheduler_ppo.py:207).  gi = position of t in
+        # the grid (normally the step count; elsewhere when the caller starts mid-grid), None when t is off the grid
+        grid = self._timesteps_host
+        gi = i if grid[i] == t else next(iter(np.nonzero(grid == t)[0].tolist()), None)
+        on_grid = gi is not None
         if on_grid:
-            x0, x1 = float(tr.condx_host[i, 0]), float(tr.condx_host[i, 1])
-            conds_x = tr.condx[i:i + 1].expand(B, 2)
+            x0, x1 = float(tr.condx_host[gi, 0]), float(tr.condx_host[gi, 1])
+            conds_x = tr.condx[gi:gi + 1].expand(B, 2)
         else:
             row = torch.tensor([[t, prev_t]], dtype=e0.dtype)
             x0, x1 = (float(v) for v in row.float()[0])
@@ -266,7 +287,7 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
                 fn.policy_tables(tr.condx_f32, tr.out["probs_table"])
                 tr.table_pass = tr.count // tr.n
                 tr.policy_forked = False                          # the side stream must see the new tables
-            probs_in = tr.p("probs_table", i) if on_grid else None
+            probs_in = tr.p("probs_table", gi) if on_grid else None
             ps = self.policy_stream
             if ps is not None and on_grid and rng_arg is not None:
                 # Two-stream form: the sample kernel needs nothing from the step kernels (only the table and the
@@ -291,9 +312,10 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
                 rc = lib.consolver_sd_policy_and_step(
                     *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr, rng_arg,
                     fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
-                    tr.p("probs_table", i), *outs, *step_args, *tail, vflag | pdl, B, N, stream)
+                    tr.p("probs_table", gi if on_grid else tr.n), *outs, *step_args, *tail, vflag | pdl, B, N, stream)
                 _lib.check(rc, "consolver_sd_policy_and_step")
 
+        tr.last_table_row = gi if on_grid else tr.n
         newest = slot if cond is not None else e0     # plain step keeps the caller's tensor by reference, as
         self._hist = [newest] + older                 # the reference does (scheduler_ppo.py:214-218)
         tr.count += 1

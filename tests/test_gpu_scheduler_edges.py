@@ -112,3 +112,22 @@ def test_fp16_cast_policy_and_sample_action_api():
         fn.mlp[4].bias.add_(1.0)
     p2 = fn.sample_action({"x": x})[1]
     assert p2.shape == (5, 3)
+
+
+def test_cuda_timesteps_starting_mid_grid_like_img2img():
+    """A pipeline that starts at timesteps[t_start:] (img2img strength < 1) hands CUDA timestep tensors from the middle
+    of the grid: the scheduler locates the start with one read-back and follows the grid from there."""
+    g, m, s, o = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    o.set_timesteps(m["n"])
+    start = 3
+    x = g["x_T"]
+    xg = x.cuda()
+    s.replay = {"q": {k: g[f"q_{start + k}"].cuda() for k in range(m["n"] - start)}}
+    for k, i in enumerate(range(start, m["n"])):
+        eps = g[f"eps_{i}"]
+        xg, actions, _, conds, _ = s.step(eps.cuda(), s.timesteps[i], xg, return_dict=False)     # CUDA 0-d tensor
+        x, a_o, _, c_o, _ = o.step(eps, o.timesteps[i], x, q=g[f"q_{i}"])
+        assert torch.equal(conds["x"].cpu(), c_o["x"]), f"step {i}: wrong timestep row"
+        assert torch.equal(actions.cpu(), a_o)
+        assert torch.equal(xg.cpu(), x)
