@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
   const float cs0 = eff_scale ? __ldg(cf + p.order_dim) : 1.f;
   const float cs1 = x_scale ? __ldg(cf + p.order_dim + 1) : 1.f;
   const bool vpred = p.flags & CONSOLVER_FLAG_VPRED;
+  const bool lowp = p.flags & CONSOLVER_FLAG_LOWP_COMBINE;
   const float g = p.guidance;
 
 #pragma unroll
@@ -111,8 +112,11 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
         // edit_ppo/scheduler_fmppo.py:429.  First step without scalers: `dt * model_output` is a 0-d fp32
         // tensor times a 16-bit tensor, which torch evaluates in the 16-bit dtype — dt is rounded to it, the
         // product is formed in fp32 and rounded to it — before the fp32 add with the upcast sample.
+        // LOWP_COMBINE extends that to the baseline solvers' multi-term form (edit_ppo/scheduler_fm.py:430),
+        // where the history sum itself is a 16-bit tensor expression.
         float prod;
-        if (Elem<T>::k16 && nh == 1 && !eff_scale) {
+        if (Elem<T>::k16 && !eff_scale && (nh == 1 || lowp)) {
+          if (nh > 1) eff = Elem<T>::to_f(Elem<T>::from_f(eff));
           const float dt16 = Elem<T>::to_f(Elem<T>::from_f(p.k0));
           prod = Elem<T>::to_f(Elem<T>::from_f(__fmul_rn(dt16, eff)));
         } else {

@@ -54,6 +54,13 @@ extern "C" {
                                            entries older than the newest are issued before waiting on it, x and the
                                            newest history entry after.  Only valid when e0/cond/older entries are not
                                            written by the immediately preceding kernel (solver-only replays)        */
+#define CONSOLVER_FLAG_LOWP_COMBINE 32  /* consolver_step_fm, 16-bit model outputs only: form the history combination
+                                           and its product with dt in the MODEL dtype, the way torch evaluates the
+                                           baseline solvers' `0.5 * dt * (v_old + v_new)` on bf16/fp16 tensors
+                                           (edit_ppo/scheduler_fm.py:430): sum rounded to the model dtype, dt rounded
+                                           to it, product rounded to it, then the fp32 add with the sample.  Without
+                                           the flag the combination is fp32 (per-sample fp32 coefficients promote,
+                                           edit_ppo/scheduler_fmppo.py:413-429).  Ignored for fp32 model outputs     */
 
 #define CONSOLVER_ERR_NULL        (-1)
 #define CONSOLVER_ERR_SIZE        (-2)

@@ -427,6 +427,75 @@ class OracleFMScheduler:
         return prev, actions, act_probs, {"x": x, "epsilon": eps_stack}, masks
 
 
+class OracleFMGeneralScheduler:
+    """The reference's training-free flow-matching baselines restated:
+    FlowMatchGeneralDiscreteScheduler.step, edit_ppo/scheduler_fm.py:384-488, `type` in
+    euler / heun / dpm-solver / dpm-solver-multistep.  The sigma schedule is the same code as FMPPOScheduler's
+    (edit_ppo/scheduler_fm.py:259-353).  The two-stage kinds keep the first stage's fp32 sample, model output and
+    step size between calls; that state is NOT cleared by set_timesteps in the reference (its one-line
+    set_timesteps override at :141-145 is shadowed by the full definition at :259), and is not cleared here."""
+
+    KINDS = ("euler", "heun", "dpm-solver", "dpm-solver-multistep")
+
+    def __init__(self, *, kind="euler", num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False,
+                 time_shift_type="exponential", shift_terminal=None, invert_sigmas=False,
+                 use_karras_sigmas=False, use_exponential_sigmas=False):
+        self.kw = dict(num_train_timesteps=num_train_timesteps, shift=shift,
+                       use_dynamic_shifting=use_dynamic_shifting, time_shift_type=time_shift_type,
+                       shift_terminal=shift_terminal, invert_sigmas=invert_sigmas,
+                       use_karras_sigmas=use_karras_sigmas, use_exponential_sigmas=use_exponential_sigmas)
+        self.kind = kind
+        self.n = None
+        self.prev_dt = self.prev_sample = self.prev_model_output = None
+
+    def set_timesteps(self, num_inference_steps=None, sigmas=None, mu=None, timesteps=None):
+        self.timesteps, self.sigmas = fm_sigmas(num_inference_steps, sigmas, mu, timesteps, **self.kw)
+        self.n = len(self.timesteps)
+        self.step_index = None
+        self.begin_index = None
+
+    def set_begin_index(self, i=0):
+        self.begin_index = i
+
+    def step(self, model_output, timestep, sample):
+        if self.step_index is None:
+            if self.begin_index is None:
+                hits = (self.timesteps == timestep).nonzero()
+                self.step_index = hits[1 if len(hits) > 1 else 0].item()
+            else:
+                self.step_index = self.begin_index
+        sample = sample.to(F32)                                           # :399
+        i, sg = self.step_index, self.sigmas
+        if self.kind == "euler":                                          # :405-410
+            nxt = sg[i + 1] if i + 1 < len(sg) else sg[-1]
+            prev = sample + (nxt - sg[i]) * model_output
+        elif self.kind == "heun":                                         # :412-430
+            if i % 2 == 0:
+                nxt = sg[i + 2] if i + 2 < len(sg) else sg[-1]
+                self.prev_dt, self.prev_sample, self.prev_model_output = nxt - sg[i], sample, model_output
+                prev = sample + self.prev_dt * model_output
+            else:
+                prev = self.prev_sample + 0.5 * self.prev_dt * (self.prev_model_output + model_output)
+        elif self.kind == "dpm-solver":                                   # :431-452
+            if i % 2 == 0:
+                self.prev_dt, self.prev_sample, self.prev_model_output = sg[i + 1] - sg[i], sample, model_output
+                prev = sample + self.prev_dt * model_output
+            else:
+                prev = self.prev_sample + (self.prev_dt + (sg[i + 1] - sg[i])) * model_output
+        elif self.kind == "dpm-solver-multistep":                         # :454-483
+            if i == 0:
+                self.prev_dt, self.prev_sample, self.prev_model_output = sg[1] - sg[0], sample, model_output
+                prev = sample + self.prev_dt * model_output
+            else:
+                prev = self.prev_sample + (self.prev_dt + (sg[i + 1] - sg[i])) * model_output
+                self.prev_dt, self.prev_sample = sg[i + 1] - sg[i], sample
+        else:
+            # the reference falls through with `prev_sample` unbound (UnboundLocalError); a clear error here
+            raise ValueError(f"unknown solver type {self.kind!r}")
+        self.step_index += 1
+        return prev.to(model_output.dtype)                                # :488
+
+
 def run_sd_preview(sched: OracleSDScheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: float,
                    qs: Optional[Sequence[torch.Tensor]] = None, forced_idx=None):
     """The caller loop of denoise_ppo.py:62-113 with the denoiser replaced by given CFG pairs

@@ -162,6 +162,36 @@ def gen_fm(name, *, B, shape, n, seed, dtype, last_std=0.02, use_begin_index=Tru
     print("wrote", name, "A=%d K=%d" % (A, K))
 
 
+def gen_fm_general(name, *, kind, B, shape, n, seed, dtype, use_begin_index=True, **cfg_over):
+    """Baseline flow-matching solvers (edit_ppo/scheduler_fm.py:384-488): no policy, no RNG."""
+    ref = ref_shim.load_reference()
+    cfg = dict(dict(shift=3.0, use_dynamic_shifting=True, type=kind), **cfg_over)
+    s = ref.FlowMatchGeneralDiscreteScheduler(**cfg)
+    if cfg["use_dynamic_shifting"]:
+        s.set_timesteps(n, sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+    else:
+        s.set_timesteps(n)
+    if use_begin_index:
+        s.set_begin_index(0)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, *shape, generator=g).to(dtype)
+    bf, d = [], {}
+    d["x_T"] = _np(x, bf, "x_T")
+    d["timesteps"] = s.timesteps.numpy()
+    d["sigmas"] = s.sigmas.numpy()
+    for i, t in enumerate(s.timesteps):
+        v = torch.randn(B, *shape, generator=g).to(dtype)
+        x = s.step(v, t, x, return_dict=False)[0]
+        d[f"v_{i}"] = _np(v, bf, f"v_{i}")
+        d[f"prev_{i}"] = _np(x, bf, f"prev_{i}")
+    meta = dict(kind="fm_general", solver=kind, B=B, shape=list(shape), n=n, seed=seed, config=cfg,
+                dtype=str(dtype).split(".")[-1], mu=1.15, use_begin_index=use_begin_index, torch=torch.__version__)
+    d["__meta__"] = np.array(json.dumps(meta))
+    d["__bf16__"] = np.array(json.dumps(bf))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name)
+
+
 def gen_update_side(name, variant, seed, **kw):
     """FactorNetPPO.get_action_probs (factor_net_ppo.py:170-184): the PPO-update-side evaluation."""
     ref = ref_shim.load_reference()
@@ -186,8 +216,22 @@ def gen_update_side(name, variant, seed, **kw):
     print("wrote", name)
 
 
+def main_fm_general():
+    """`python oracle/make_golden.py fm_general` writes only these."""
+    tok = (16, 8)
+    for j, kind in enumerate(("euler", "heun", "dpm-solver", "dpm-solver-multistep")):
+        tag = kind.replace("-", "")
+        gen_fm_general(f"fmgen_{tag}_bf16_n8_B3", kind=kind, B=3, shape=tok, n=8, seed=50 + j, dtype=torch.bfloat16)
+        gen_fm_general(f"fmgen_{tag}_f32_n7_B2", kind=kind, B=2, shape=(5, 7), n=7, seed=60 + j, dtype=torch.float32,
+                       use_begin_index=False)
+    gen_fm_general("fmgen_heun_f16_static_n6_B2", kind="heun", B=2, shape=tok, n=6, seed=70, dtype=torch.float16,
+                   use_dynamic_shifting=False)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["fm_general"]:
+        return main_fm_general()
     small = (4, 8, 8)
     # --- SD / PPOScheduler: production config at several step counts (warm-up depths, n=7 quirk) -------
     for n in (2, 5, 7, 8, 12):
@@ -230,6 +274,8 @@ def main():
     gen_update_side("update_sd_o4_s0", "sd", 41, hidden_dim=256, num_actions=11, order_dim=4, scaler_dim=0)
     gen_update_side("update_fm_o2_s0_m0", "fm", 42, hidden_dim=256, num_actions=11, order_dim=2, scaler_dim=0,
                     mu_dim=0)
+    # --- baseline flow-matching solvers -------------------------------------------------
+    main_fm_general()
 
 
 if __name__ == "__main__":

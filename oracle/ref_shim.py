@@ -140,8 +140,9 @@ def _load(name: str, path: str, aliases: dict):
 
 @functools.lru_cache(maxsize=None)
 def load_reference():
-    """Returns a namespace with the reference's PPOScheduler, FMPPOScheduler and both FactorNetPPO
-    classes (sd / fm), loaded from REFERENCE_ROOT without modification."""
+    """Returns a namespace with the reference's PPOScheduler, FMPPOScheduler, the baseline
+    FlowMatchGeneralDiscreteScheduler and both FactorNetPPO classes (sd / fm), loaded from REFERENCE_ROOT
+    without modification."""
     if not reference_available():
         raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
     _install_diffusers_standins()
@@ -161,7 +162,9 @@ def load_reference():
     fn_fm = _load("_ref_factor_net_fm", os.path.join(r, "edit_ppo", "factor_net_ppo.py"), {"conv_net": conv_fm})
     sched_fm = _load("_ref_scheduler_fmppo", os.path.join(r, "edit_ppo", "scheduler_fmppo.py"),
                      {"factor_net_ppo": fn_fm, "conv_net": conv_fm})
+    sched_fm_base = _load("_ref_scheduler_fm", os.path.join(r, "edit_ppo", "scheduler_fm.py"), {})
     return types.SimpleNamespace(
+        FlowMatchGeneralDiscreteScheduler=sched_fm_base.FlowMatchGeneralDiscreteScheduler,
         PPOScheduler=sched_sd.PPOScheduler,
         FMPPOScheduler=sched_fm.FMPPOScheduler,
         FactorNetPPO_SD=fn_sd.FactorNetPPO,

@@ -186,3 +186,33 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setenv("CONSOLVER_NO_AUTOBUILD", "1")
     with pytest.raises(_lib.ConsolverError, match="not found"):
         _lib.load()
+
+
+@pytest.mark.parametrize("name", names("fmgen_"))
+def test_fm_baseline_scheduler_schedule_matches_reference(name):
+    """FlowMatchGeneralDiscreteScheduler (edit_ppo/scheduler_fm.py): constructor surface and sigma schedule."""
+    g = Golden(name)
+    m = g.meta
+    s = cb.FlowMatchGeneralDiscreteScheduler(**m["config"])
+    assert s.config.type == m["solver"] == s.type and s.order == 1 and len(s) == 1000
+    if m["config"]["use_dynamic_shifting"]:
+        s.set_timesteps(m["n"], sigmas=np.linspace(1.0, 1 / m["n"], m["n"]), mu=m["mu"])
+    else:
+        s.set_timesteps(m["n"])
+    assert torch.equal(s.timesteps, g["timesteps"]) and torch.equal(s.sigmas, g["sigmas"])
+    assert s.step_index is None and s.begin_index is None
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        s.step(g["v_0"], s.timesteps[0], g["x_T"])
+
+
+def test_fm_baseline_scheduler_errors():
+    with pytest.raises(ValueError):
+        cb.FlowMatchGeneralDiscreteScheduler(use_karras_sigmas=True, use_exponential_sigmas=True)
+    with pytest.raises(ValueError):
+        cb.FlowMatchGeneralDiscreteScheduler(time_shift_type="cubic")
+    s = cb.FlowMatchGeneralDiscreteScheduler(use_dynamic_shifting=True)
+    with pytest.raises(ValueError, match="mu"):
+        s.set_timesteps(4)
+    d = cb.FlowMatchGeneralDiscreteScheduler()                # reference defaults (edit_ppo/scheduler_fm.py:92-109)
+    assert d.config.type == "euler" and d.config.shift == 1.0 and d.shift == 1.0
+    assert d.sigma_max == 1.0 and abs(d.sigma_min - 1e-3) < 1e-9

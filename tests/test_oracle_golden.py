@@ -61,6 +61,33 @@ def test_fm_oracle_matches_reference(name):
         assert torch.equal(x, g[f"prev_{i}"]), f"step {i} latent not bit-exact"
 
 
+def _fmgen_set_timesteps(s, m):
+    import numpy as np
+    if m["config"]["use_dynamic_shifting"]:
+        s.set_timesteps(m["n"], sigmas=np.linspace(1.0, 1 / m["n"], m["n"]), mu=m["mu"])
+    else:
+        s.set_timesteps(m["n"])
+    if m["use_begin_index"]:
+        s.set_begin_index(0)
+
+
+@pytest.mark.parametrize("name", names("fmgen_"))
+def test_fm_baseline_solvers_oracle_matches_reference(name):
+    """euler / heun / dpm-solver / dpm-solver-multistep of edit_ppo/scheduler_fm.py:384-488, bit-exact."""
+    g = Golden(name)
+    m = g.meta
+    cfg = dict(m["config"])
+    s = orc.OracleFMGeneralScheduler(kind=cfg.pop("type"), **cfg)
+    _fmgen_set_timesteps(s, m)
+    assert torch.equal(s.timesteps, g["timesteps"])
+    assert torch.equal(s.sigmas, g["sigmas"])
+    x = g["x_T"]
+    for i, t in enumerate(s.timesteps):
+        x = s.step(g[f"v_{i}"], t, x)
+        assert x.dtype == g[f"prev_{i}"].dtype
+        assert torch.equal(x, g[f"prev_{i}"]), f"step {i} latent not bit-exact"
+
+
 @pytest.mark.parametrize("name", names("update_"))
 def test_update_side_oracle(name):
     g = Golden(name)
