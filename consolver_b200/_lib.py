@@ -12,6 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libconsolver.so")
 
 F32, F16, BF16 = 0, 1, 2
+DPM_CONVERT_NONE, DPM_CONVERT_DIV, DPM_CONVERT_LIN = 0, 1, 2
 FLAG_VPRED, FLAG_EFF_SCALE, FLAG_X_SCALE, FLAG_PDL, FLAG_CHAIN, FLAG_LOWP_COMBINE = 1, 2, 4, 8, 16, 32
 MAX_ORDER, MAX_HIDDEN, MAX_LOGITS, MAX_IN = 8, 1024, 4096, 16
 
@@ -24,6 +25,7 @@ SIGNATURES = {
     "consolver_policy_f32": (_i, [_p] * 7 + [_f] * 4 + [_p, _i] + [_p, _p] + [_i] * 7 + [_p] * 7 + [_p]),
     "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
+    "consolver_step_dpm": (_i, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _i64, _p]),
     "consolver_policy_table_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i, _p, _p]),
     "consolver_policy_sample_f32": (_i, [_p] * 4 + [_p, _p] + [_i] * 6 + [_p] * 6 + [_p]),
     "consolver_rng_state_advance": (_i, [_p, C.c_uint64, _p]),

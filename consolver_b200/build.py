@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libconsolver.so")
-SOURCES = ["policy.cu", "step_sd.cu", "step_fm.cu", "features.cu", "ppo.cu"]
+SOURCES = ["policy.cu", "step_sd.cu", "step_fm.cu", "step_dpm.cu", "features.cu", "ppo.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

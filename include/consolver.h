@@ -173,6 +173,28 @@ CONSOLVER_API int consolver_step_fm(int dtype, int x_dtype, const void* e0, void
                       int B, int64_t n_per_sample, consolver_stream_t stream);
 
 /*
+ * Fused multistep DPM-Solver / DPM-Solver++ step with AMED direction scaling — replaces, per step,
+ * the caller's CFG combine (gen_pretrain/pipeline.py:1069-1071), diffusers' convert_model_output (diffusers 0.26.3
+ * DPMSolverMultistepScheduler; not part of the reference tree) and the plugin's first/second-order updates
+ * (diffusers_amed_plugin_dpmpp.py:70-138, :140-262) with one pass over HBM.  Scalars are computed by the host the way
+ * the plugin computes them (0-d fp32 tensors) and handed in:
+ *   m0 = e                            convert == CONSOLVER_DPM_CONVERT_NONE
+ *      = (x - ck0*e) / ck1                        CONSOLVER_DPM_CONVERT_DIV   (dpmsolver++ / epsilon: ck0 = sigma_s, ck1 = alpha_s)
+ *      = ck1*x + ck0*e                            CONSOLVER_DPM_CONVERT_LIN   (v-prediction forms)
+ *   x'  = cx*x - a0*m0                                      when m1 == NULL (first order, :121/:123)
+ *       = (cx*x - a0*m0) - a1*(rinv*(m0 - m1))              otherwise       (second order, :201-208)
+ * e = e0, or e0 + guidance*(cond - e0) when cond != NULL.  m0 is written to slot_out when non-NULL (the caller's
+ * two-slot ring).  fp32 arithmetic in exactly this order; 16-bit dtypes round e, m0 and x' once each.
+ */
+#define CONSOLVER_DPM_CONVERT_NONE 0
+#define CONSOLVER_DPM_CONVERT_DIV  1
+#define CONSOLVER_DPM_CONVERT_LIN  2
+CONSOLVER_API int consolver_step_dpm(int dtype, int x_dtype, const void* e0, const void* cond, float guidance,
+                      void* slot_out, const void* m1, const void* x, void* x_out, void* x_out2,
+                      int64_t out2_stride, int convert, float ck0, float ck1, float cx, float a0, float a1,
+                      float rinv, int B, int64_t n_per_sample, consolver_stream_t stream);
+
+/*
  * Probability tables only: MLP + softmax (factor_net_ppo.py:137-157) for `rows` input rows in one launch (one CTA
  * per row).  The schedulers call it once per trajectory with the (t, prev_t) / (sigma, sigma_next) rows of the
  * whole timestep grid — the policy input does not depend on the sample — and then run only

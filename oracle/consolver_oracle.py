@@ -496,6 +496,128 @@ class OracleFMGeneralScheduler:
         return prev.to(model_output.dtype)                                # :488
 
 
+class OracleDPMSolverAMED:
+    """The AMED baseline restated: the reference's plugin `diffusers_amed_plugin_dpmpp.py`
+    (custom-timestep set_timesteps :29-68, first-order update :70-138, second-order update :140-262, step :350-436,
+    `scale_dir` use :417-423) on top of diffusers 0.26.3 `DPMSolverMultistepScheduler`.  diffusers is a third-party
+    dependency ABSENT from the reference tree and from this image (pinned `diffusers==0.26.3`, env.yaml:52); the
+    inherited pieces (beta tables, `_sigma_to_alpha_sigma_t`, `convert_model_output`, stock `set_timesteps`) are a
+    restatement of the published library algorithm.  PARITY PIN: tests/golden/amed_*.npz are produced by running
+    the UNMODIFIED plugin file over a stand-in of that base (oracle/ref_shim.py::_dpm_base) — this pins every line
+    that lives in the reference; the inherited pieces are pinned only to the restatement ("parity unpinned" for
+    those).  ODE variants only (dpmsolver / dpmsolver++), solver_order <= 2, no thresholding."""
+
+    def __init__(self, *, num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear",
+                 trained_betas=None, solver_order=2, prediction_type="epsilon", algorithm_type="dpmsolver++",
+                 solver_type="midpoint", lower_order_final=True, euler_at_final=False, final_sigmas_type="zero",
+                 timestep_spacing="linspace", steps_offset=0, scale_dirs=None, scale_times=None):
+        if algorithm_type not in ("dpmsolver", "dpmsolver++") or solver_order not in (1, 2):
+            raise NotImplementedError
+        self.T = num_train_timesteps
+        self.alphas_cumprod = sd_alphas_cumprod(sd_betas(num_train_timesteps, beta_start, beta_end, beta_schedule,
+                                                         trained_betas))
+        self.order, self.prediction_type, self.algo, self.solver_type = (solver_order, prediction_type,
+                                                                         algorithm_type, solver_type)
+        self.lower_order_final, self.euler_at_final, self.final_sigmas_type = (lower_order_final, euler_at_final,
+                                                                               final_sigmas_type)
+        self.spacing, self.offset = timestep_spacing, steps_offset
+        self.scale_dirs, self.scale_times = scale_dirs, scale_times
+        self.n = None
+
+    def set_timesteps(self, num_inference_steps=None, timesteps=None):
+        all_sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        if timesteps is None:                         # stock diffusers grid (restated; basic interpolation only)
+            n, T = num_inference_steps, self.T
+            if self.spacing == "linspace":
+                ts = np.linspace(0, T - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+            elif self.spacing == "leading":
+                ts = (np.arange(0, n + 1) * (T // (n + 1))).round()[::-1][:-1].copy().astype(np.int64) + self.offset
+            elif self.spacing == "trailing":
+                ts = np.arange(T, 0, -(T / n)).round().copy().astype(np.int64) - 1
+            else:
+                raise ValueError(self.spacing)
+            sig = np.interp(ts, np.arange(0, len(all_sigmas)), all_sigmas)
+            last = all_sigmas[0] if self.final_sigmas_type == "sigma_min" else 0
+            self.sigmas = torch.from_numpy(np.concatenate([sig, [last]]).astype(np.float32))
+            self.timesteps = torch.from_numpy(ts)
+            self.n = len(ts)
+        else:                                         # plugin :47-60
+            self.sigmas = torch.from_numpy(all_sigmas[timesteps])
+            self.timesteps = torch.tensor(timesteps[:-1], dtype=torch.int64)
+            for i in range(len(self.scale_times)):
+                if i % 2 == 1:
+                    target = self.sigmas[i] * self.scale_times[i]
+                    src = torch.tensor(all_sigmas[timesteps[i + 1] + 1:timesteps[i - 1]])
+                    self.timesteps[i] = timesteps[i + 1] + 1 + torch.argmin(torch.abs(src - target))
+            self.n = len(timesteps)                   # :60 counts the trailing 0 as well
+        self.hist: List[torch.Tensor] = []            # converted model outputs, newest first
+        self.lower_order_nums = 0
+        self.step_index = None
+
+    @staticmethod
+    def _alpha_sigma(sigma):
+        alpha = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return alpha, sigma * alpha
+
+    def _convert(self, e, sample):
+        alpha, sig = self._alpha_sigma(self.sigmas[self.step_index])
+        pp = self.algo == "dpmsolver++"
+        if self.prediction_type == "epsilon":
+            return (sample - sig * e) / alpha if pp else e
+        if self.prediction_type == "sample":
+            return e if pp else (sample - alpha * e) / sig
+        if self.prediction_type == "v_prediction":
+            return alpha * sample - sig * e if pp else alpha * e + sig * sample
+        raise ValueError(self.prediction_type)
+
+    def step(self, model_output, timestep, sample):
+        if self.n is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
+                             "the scheduler")
+        if self.step_index is None:
+            hits = (self.timesteps == timestep).nonzero()
+            self.step_index = (len(self.timesteps) - 1 if len(hits) == 0 else
+                               hits[1].item() if len(hits) > 1 else hits[0].item())
+        i, nts = self.step_index, len(self.timesteps)
+        final_first = (i == nts - 1) and (self.euler_at_final or (self.lower_order_final and nts < 15)
+                                          or self.final_sigmas_type == "zero")                         # :394-398
+        m0 = self._convert(model_output, sample)
+        self.hist = ([m0] + self.hist)[: self.order]
+        sample = sample.to(F32)                                                                          # :409
+        sd = 1.0 if self.scale_dirs is None else self.scale_dirs[i]                                     # :417
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i + 1])
+        alpha_s, sigma_s = self._alpha_sigma(self.sigmas[i])
+        h = (torch.log(alpha_t) - torch.log(sigma_t)) - (torch.log(alpha_s) - torch.log(sigma_s))
+        pp = self.algo == "dpmsolver++"
+        if self.order == 1 or self.lower_order_nums < 1 or final_first:                                 # :418-419
+            if pp:
+                x = (sigma_t / sigma_s) * sample - sd * (alpha_t * (torch.exp(-h) - 1.0)) * m0          # :121
+            else:
+                x = (alpha_t / alpha_s) * sample - sd * (sigma_t * (torch.exp(h) - 1.0)) * m0           # :123
+        else:                                                                                           # :420-421
+            alpha_p, sigma_p = self._alpha_sigma(self.sigmas[i - 1])
+            lam_s = torch.log(alpha_s) - torch.log(sigma_s)
+            h_0 = lam_s - (torch.log(alpha_p) - torch.log(sigma_p))
+            r0 = h_0 / h
+            d1 = (1.0 / r0) * (m0 - self.hist[1])                                                       # :201
+            if pp and self.solver_type == "midpoint":                                                   # :205-209
+                x = ((sigma_t / sigma_s) * sample - sd * (alpha_t * (torch.exp(-h) - 1.0)) * m0
+                     - sd * 0.5 * (alpha_t * (torch.exp(-h) - 1.0)) * d1)
+            elif pp:                                                                                    # :211-215
+                x = ((sigma_t / sigma_s) * sample - sd * (alpha_t * (torch.exp(-h) - 1.0)) * m0
+                     + sd * (alpha_t * ((torch.exp(-h) - 1.0) / h + 1.0)) * d1)
+            elif self.solver_type == "midpoint":                                                        # :219-223
+                x = ((alpha_t / alpha_s) * sample - sd * (sigma_t * (torch.exp(h) - 1.0)) * m0
+                     - sd * 0.5 * (sigma_t * (torch.exp(h) - 1.0)) * d1)
+            else:                                                                                       # :225-229
+                x = ((alpha_t / alpha_s) * sample - sd * (sigma_t * (torch.exp(h) - 1.0)) * m0
+                     - sd * (sigma_t * ((torch.exp(h) - 1.0) / h - 1.0)) * d1)
+        if self.lower_order_nums < self.order:
+            self.lower_order_nums += 1
+        self.step_index += 1
+        return x.to(m0.dtype)                                                                            # :429
+
+
 def run_sd_preview(sched: OracleSDScheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: float,
                    qs: Optional[Sequence[torch.Tensor]] = None, forced_idx=None):
     """The caller loop of denoise_ppo.py:62-113 with the denoiser replaced by given CFG pairs

@@ -192,6 +192,64 @@ def gen_fm_general(name, *, kind, B, shape, n, seed, dtype, use_begin_index=True
     print("wrote", name)
 
 
+# gen_ppo.py:24-55: the AMED schedules, gradient ("direction") scales and time scales the reference ships
+AMED_SCHEDULES = {
+    4: ([999, 694, 500, 110, 0], [1.0, 0.991, 1.0, 0.9912, 1.0], [1.0, 1.0333, 1.0, 0.9861, 1.0]),
+    6: ([999, 758, 666, 495, 333, 107, 0], [1.0, 0.9924, 1.0, 0.9916, 1.0, 0.9906, 1.0],
+        [1.0, 1.052, 1.0, 0.9998, 1.0, 0.9781, 1.0]),
+    8: ([999, 831, 749, 623, 500, 394, 250, 88, 0], [1.0, 0.9976, 1.0, 0.991, 1.0, 0.9907, 1.0, 0.9905, 1.0],
+        [1.0, 1.0257, 1.0, 0.9989, 1.0, 1.0022, 1.0, 0.9747, 1.0]),
+}
+SD15_SCHED = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1)
+
+
+def gen_amed(name, *, n, B, shape, seed, amed=True, **cfg_over):
+    """diffusers_amed_plugin_dpmpp.py (UNMODIFIED) over the stand-in of its diffusers base class — see
+    ref_shim._dpm_base for what that pins and what it does not."""
+    ref = ref_shim.load_reference()
+    cfg = dict(SD15_SCHED, **cfg_over)
+    s = ref.AMEDDPMSolverMultistepScheduler(**cfg)
+    if amed:
+        ts, dirs, times = AMED_SCHEDULES[n]
+        s.scale_dirs, s.scale_times = dirs, times
+        s.set_timesteps(n, timesteps=ts)
+    else:
+        ts, dirs, times = None, [1.0] * (n + 1), None
+        s.scale_dirs = dirs                          # the plugin's step() reads it unconditionally (:417)
+        s.set_timesteps(n)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, *shape, generator=g)
+    d = dict(x_T=x.numpy(), timesteps=s.timesteps.numpy(), sigmas=s.sigmas.numpy())
+    for i, t in enumerate(s.timesteps):
+        e = torch.randn(B, *shape, generator=g)
+        x = s.step(e, t, x, return_dict=False)[0]
+        d[f"eps_{i}"] = e.numpy()
+        d[f"prev_{i}"] = x.numpy()
+    meta = dict(kind="amed", B=B, shape=list(shape), n=n, seed=seed, config=cfg, amed=amed, schedule=ts,
+                scale_dirs=dirs, scale_times=times, dtype="float32", torch=torch.__version__)
+    d["__meta__"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name)
+
+
+def main_amed():
+    """`python oracle/make_golden.py amed` writes only these."""
+    small = (4, 8, 8)
+    gen_amed("amed_n8_B3", n=8, B=3, shape=small, seed=80)                               # gen_ppo.py `type == "amed"`
+    gen_amed("amed_n4_B2", n=4, B=2, shape=small, seed=81)
+    gen_amed("amed_n6_heun_B2_ragged", n=6, B=2, shape=(3, 5, 7), seed=82, solver_type="heun")
+    gen_amed("amed_n8_dpmsolver_B2", n=8, B=2, shape=small, seed=83, algorithm_type="dpmsolver")
+    gen_amed("amed_n6_dpmsolver_heun_v_B2", n=6, B=2, shape=small, seed=84, algorithm_type="dpmsolver",
+             solver_type="heun", prediction_type="v_prediction")
+    gen_amed("amed_n8_v_B2", n=8, B=2, shape=small, seed=85, prediction_type="v_prediction")
+    gen_amed("amed_n4_order1_sample_B2", n=4, B=2, shape=small, seed=86, solver_order=1, prediction_type="sample")
+    # stock grids (no AMED schedule): gen_ppo.py `type == "dpm"` uses dpmsolver + final sigma_min
+    gen_amed("amed_stock_n8_dpmsolver_sigmamin_B2", n=8, B=2, shape=small, seed=87, amed=False,
+             algorithm_type="dpmsolver", final_sigmas_type="sigma_min")
+    gen_amed("amed_stock_n5_trailing_zero_B2", n=5, B=2, shape=small, seed=88, amed=False, timestep_spacing="trailing")
+    gen_amed("amed_stock_n20_leading_B1", n=20, B=1, shape=small, seed=89, amed=False, timestep_spacing="leading")
+
+
 def gen_update_side(name, variant, seed, **kw):
     """FactorNetPPO.get_action_probs (factor_net_ppo.py:170-184): the PPO-update-side evaluation."""
     ref = ref_shim.load_reference()
@@ -232,6 +290,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1:] == ["fm_general"]:
         return main_fm_general()
+    if sys.argv[1:] == ["amed"]:
+        return main_amed()
     small = (4, 8, 8)
     # --- SD / PPOScheduler: production config at several step counts (warm-up depths, n=7 quirk) -------
     for n in (2, 5, 7, 8, 12):
@@ -276,6 +336,7 @@ def main():
                     mu_dim=0)
     # --- baseline flow-matching solvers -------------------------------------------------
     main_fm_general()
+    main_amed()
 
 
 if __name__ == "__main__":

@@ -96,6 +96,19 @@ def _install_diffusers_standins():
 
             return logging.getLogger(name)
 
+    tu = types.ModuleType("diffusers.utils.torch_utils")
+
+    def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+        import torch
+
+        return torch.randn(shape, generator=generator, device=device, dtype=dtype)
+
+    tu.randn_tensor = randn_tensor
+    ut.torch_utils = tu
+    ut.deprecate = lambda *a, **k: None
+    diffusers.DPMSolverMultistepScheduler = _dpm_base(ConfigMixin, SchedulerMixin)
+    sys.modules["diffusers.utils.torch_utils"] = tu
+
     cu.ConfigMixin = ConfigMixin
     cu.register_to_config = _register_to_config
     su.SchedulerMixin = SchedulerMixin
@@ -115,6 +128,161 @@ def _install_diffusers_standins():
         "diffusers.schedulers.scheduling_utils": su,
         "diffusers.utils": ut,
     })
+
+
+def _dpm_base(ConfigMixin, SchedulerMixin):
+    """Stand-in for diffusers 0.26.3 `DPMSolverMultistepScheduler`, the base class of the reference's AMED plugin
+    (diffusers_amed_plugin_dpmpp.py:22,:27).  diffusers is NOT in this image and not in the reference tree, so this
+    is a restatement of the published library code — only the pieces the plugin inherits: the beta/sigma tables,
+    `_sigma_to_alpha_sigma_t`, `convert_model_output`, step-index bookkeeping and the stock `set_timesteps`
+    (basic sigma interpolation; Karras / Lu spacings and dynamic thresholding are not restated).  Everything
+    the plugin overrides (custom-timestep `set_timesteps`, both update formulas, `step`) runs from the unmodified
+    reference file on top of this.  PARITY NOTE: goldens made this way pin the plugin's own arithmetic; the
+    inherited pieces are pinned only to this restatement."""
+    import numpy as np
+    import torch
+
+    class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
+        order = 1
+
+        @_register_to_config
+        def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                     trained_betas=None, solver_order=2, prediction_type="epsilon", thresholding=False,
+                     dynamic_thresholding_ratio=0.995, sample_max_value=1.0, algorithm_type="dpmsolver++",
+                     solver_type="midpoint", lower_order_final=True, euler_at_final=False,
+                     use_karras_sigmas=False, use_lu_lambdas=False, final_sigmas_type="zero",
+                     lambda_min_clipped=-float("inf"), variance_type=None, timestep_spacing="linspace",
+                     steps_offset=0):
+            if trained_betas is not None:
+                self.betas = torch.tensor(trained_betas, dtype=torch.float32)
+            elif beta_schedule == "linear":
+                self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+            elif beta_schedule == "scaled_linear":
+                self.betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps,
+                                            dtype=torch.float32) ** 2
+            else:
+                raise NotImplementedError(f"{beta_schedule} is not implemented for {self.__class__}")
+            self.alphas = 1.0 - self.betas
+            self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+            self.alpha_t = torch.sqrt(self.alphas_cumprod)
+            self.sigma_t = torch.sqrt(1 - self.alphas_cumprod)
+            self.lambda_t = torch.log(self.alpha_t) - torch.log(self.sigma_t)
+            self.sigmas = ((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5
+            self.init_noise_sigma = 1.0
+            if algorithm_type not in ("dpmsolver", "dpmsolver++", "sde-dpmsolver", "sde-dpmsolver++"):
+                raise NotImplementedError(f"{algorithm_type} is not implemented for {self.__class__}")
+            if solver_type not in ("midpoint", "heun"):
+                raise NotImplementedError(f"{solver_type} is not implemented for {self.__class__}")
+            self.num_inference_steps = None
+            timesteps = np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=np.float32)[::-1].copy()
+            self.timesteps = torch.from_numpy(timesteps)
+            self.model_outputs = [None] * solver_order
+            self.lower_order_nums = 0
+            self._step_index = None
+            self._begin_index = None
+            self.sigmas = self.sigmas.to("cpu")
+
+        @property
+        def step_index(self):
+            return self._step_index
+
+        @property
+        def begin_index(self):
+            return self._begin_index
+
+        def set_begin_index(self, begin_index=0):
+            self._begin_index = begin_index
+
+        def set_timesteps(self, num_inference_steps=None, device=None):
+            cfg = self.config
+            clipped_idx = torch.searchsorted(torch.flip(self.lambda_t, [0]), cfg.lambda_min_clipped)
+            last_timestep = ((cfg.num_train_timesteps - clipped_idx).numpy()).item()
+            if cfg.timestep_spacing == "linspace":
+                timesteps = (np.linspace(0, last_timestep - 1, num_inference_steps + 1).round()[::-1][:-1]
+                             .copy().astype(np.int64))
+            elif cfg.timestep_spacing == "leading":
+                step_ratio = last_timestep // (num_inference_steps + 1)
+                timesteps = (np.arange(0, num_inference_steps + 1) * step_ratio).round()[::-1][:-1].copy().astype(np.int64)
+                timesteps += cfg.steps_offset
+            elif cfg.timestep_spacing == "trailing":
+                step_ratio = cfg.num_train_timesteps / num_inference_steps
+                timesteps = np.arange(last_timestep, 0, -step_ratio).round().copy().astype(np.int64)
+                timesteps -= 1
+            else:
+                raise ValueError(f"{cfg.timestep_spacing} is not supported.")
+            sigmas = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+            if cfg.use_karras_sigmas or cfg.use_lu_lambdas:
+                raise NotImplementedError("Karras / Lu spacings are not restated in this stand-in")
+            sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
+            if cfg.final_sigmas_type == "sigma_min":
+                sigma_last = ((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5
+            elif cfg.final_sigmas_type == "zero":
+                sigma_last = 0
+            else:
+                raise ValueError(f"`final_sigmas_type` must be one of 'zero', or 'sigma_min', got {cfg.final_sigmas_type}")
+            sigmas = np.concatenate([sigmas, [sigma_last]]).astype(np.float32)
+            self.sigmas = torch.from_numpy(sigmas)
+            self.timesteps = torch.from_numpy(timesteps).to(device=device, dtype=torch.int64)
+            self.num_inference_steps = len(timesteps)
+            self.model_outputs = [None] * cfg.solver_order
+            self.lower_order_nums = 0
+            self._step_index = None
+            self._begin_index = None
+            self.sigmas = self.sigmas.to("cpu")
+
+        def _sigma_to_alpha_sigma_t(self, sigma):
+            alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+            sigma_t = sigma * alpha_t
+            return alpha_t, sigma_t
+
+        def convert_model_output(self, model_output, *args, sample=None, **kwargs):
+            cfg = self.config
+            if cfg.thresholding:
+                raise NotImplementedError("dynamic thresholding is not restated in this stand-in")
+            sigma = self.sigmas[self.step_index]
+            alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma)
+            if cfg.algorithm_type in ("dpmsolver++", "sde-dpmsolver++"):
+                if cfg.prediction_type == "epsilon":
+                    return (sample - sigma_t * model_output) / alpha_t
+                if cfg.prediction_type == "sample":
+                    return model_output
+                if cfg.prediction_type == "v_prediction":
+                    return alpha_t * sample - sigma_t * model_output
+            else:
+                if cfg.prediction_type == "epsilon":
+                    return model_output
+                if cfg.prediction_type == "sample":
+                    return (sample - alpha_t * model_output) / sigma_t
+                if cfg.prediction_type == "v_prediction":
+                    return alpha_t * model_output + sigma_t * sample
+            raise ValueError(f"prediction_type given as {cfg.prediction_type} must be one of `epsilon`, `sample`, or"
+                             " `v_prediction` for the DPMSolverMultistepScheduler.")
+
+        def index_for_timestep(self, timestep, schedule_timesteps=None):
+            if schedule_timesteps is None:
+                schedule_timesteps = self.timesteps
+            cand = (schedule_timesteps == timestep).nonzero()
+            if len(cand) == 0:
+                return len(self.timesteps) - 1
+            if len(cand) > 1:
+                return cand[1].item()
+            return cand[0].item()
+
+        def _init_step_index(self, timestep):
+            if self.begin_index is None:
+                if isinstance(timestep, torch.Tensor):
+                    timestep = timestep.to(self.timesteps.device)
+                self._step_index = self.index_for_timestep(timestep)
+            else:
+                self._step_index = self._begin_index
+
+        def scale_model_input(self, sample, *args, **kwargs):
+            return sample
+
+        def __len__(self):
+            return self.config.num_train_timesteps
+
+    return DPMSolverMultistepScheduler
 
 
 def _load(name: str, path: str, aliases: dict):
@@ -162,9 +330,11 @@ def load_reference():
     fn_fm = _load("_ref_factor_net_fm", os.path.join(r, "edit_ppo", "factor_net_ppo.py"), {"conv_net": conv_fm})
     sched_fm = _load("_ref_scheduler_fmppo", os.path.join(r, "edit_ppo", "scheduler_fmppo.py"),
                      {"factor_net_ppo": fn_fm, "conv_net": conv_fm})
+    amed = _load("_ref_amed_plugin", os.path.join(r, "diffusers_amed_plugin_dpmpp.py"), {})
     sched_fm_base = _load("_ref_scheduler_fm", os.path.join(r, "edit_ppo", "scheduler_fm.py"), {})
     return types.SimpleNamespace(
         FlowMatchGeneralDiscreteScheduler=sched_fm_base.FlowMatchGeneralDiscreteScheduler,
+        AMEDDPMSolverMultistepScheduler=amed.DPMSolverMultistepScheduler,
         PPOScheduler=sched_sd.PPOScheduler,
         FMPPOScheduler=sched_fm.FMPPOScheduler,
         FactorNetPPO_SD=fn_sd.FactorNetPPO,

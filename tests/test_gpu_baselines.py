@@ -123,3 +123,81 @@ def test_fm_baseline_second_stage_without_first_is_an_error():
     bad.set_timesteps(4, device="cuda")
     with pytest.raises(ValueError, match="unknown solver type"):
         bad.step(v, bad.timesteps[0], v)
+
+
+# ---- AMED-scaled multistep DPM-Solver(++) (diffusers_amed_plugin_dpmpp.py), one fused kernel per step --------------
+def _amed(g, dev="cuda"):
+    import consolver_b200 as cb
+    m = g.meta
+    s = cb.DPMSolverMultistepScheduler(**m["config"])
+    if m["amed"]:
+        s.scale_dirs, s.scale_times = m["scale_dirs"], m["scale_times"]
+        s.set_timesteps(m["n"], device=dev, timesteps=m["schedule"])
+    else:
+        s.set_timesteps(m["n"], device=dev)
+    return s
+
+
+@pytest.mark.parametrize("name", golden_names("amed_"))
+def test_amed_dpm_solver_bit_exact_on_golden(name):
+    """Every latent of every step identical to the plugin's (fp32): first / second order, midpoint / heun,
+    dpmsolver / dpmsolver++, epsilon / sample / v-prediction, AMED and stock grids, ragged sizes."""
+    g = Golden(name)
+    s = _amed(g)
+    assert torch.equal(s.timesteps.cpu(), g["timesteps"])
+    x = g["x_T"].cuda()
+    for i, t in enumerate(s.timesteps):          # CUDA scalars, as a pipeline passes them
+        x = s.step(g[f"eps_{i}"].cuda(), t, x).prev_sample
+        assert torch.equal(x.cpu(), g[f"prev_{i}"]), f"{name} step {i}: latent not bit-identical"
+
+
+def _amed_pair(kind="amed", **over):
+    import consolver_b200 as cb
+    cfg = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1, **over)
+    ts = [999, 831, 749, 623, 500, 394, 250, 88, 0]
+    dirs = [1.0, 0.9976, 1.0, 0.991, 1.0, 0.9907, 1.0, 0.9905, 1.0]
+    times = [1.0, 1.0257, 1.0, 0.9989, 1.0, 1.0022, 1.0, 0.9747, 1.0]
+    s = cb.DPMSolverMultistepScheduler(**cfg)
+    s.scale_dirs, s.scale_times = dirs, times
+    s.set_timesteps(8, device="cuda", timesteps=ts)
+    o = orc.OracleDPMSolverAMED(scale_dirs=dirs, scale_times=times, **cfg)
+    o.set_timesteps(8, timesteps=ts)
+    return s, o
+
+
+def test_amed_step_cfg_full_size_matches_oracle_and_feeds_next_input():
+    """SD1.5 latent shape, B=8, 8 AMED steps, CFG fused; the next latent also lands in both halves of the next
+    [2B] denoiser input (out2 written twice is the caller's business: here one half)."""
+    s, o = _amed_pair()
+    gen = torch.Generator().manual_seed(11)
+    B, shape = 8, (4, 64, 64)
+    x_ref = torch.randn(B, *shape, generator=gen)
+    x = x_ref.cuda()
+    nxt = torch.zeros(2 * B, *shape, device="cuda")
+    for i, t in enumerate(s.timesteps):
+        pair = torch.randn(2 * B, *shape, generator=gen)
+        (x,) = s.step_cfg(pair.cuda(), t, x, 7.5, out2=nxt[B:])
+        u, c = pair.chunk(2)
+        x_ref = o.step(orc.cfg_combine(u, c, 7.5), o.timesteps[i], x_ref)
+        assert torch.equal(x.cpu(), x_ref), f"step {i}"
+        assert torch.equal(nxt[B:], x) and not nxt[:B].any()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_amed_16bit_io_tracks_fp32(dtype):
+    """16-bit model outputs / latents: fp32 arithmetic in registers, e, m0 and x' rounded once each.  The plugin's
+    own 16-bit path rounds after every torch op, so this is compared to the fp32 oracle on the same (rounded)
+    inputs within the dtype's resolution, not bit for bit."""
+    s, o = _amed_pair()
+    gen = torch.Generator().manual_seed(12)
+    x_ref = torch.randn(2, 4, 32, 32, generator=gen).to(dtype).float()
+    x = x_ref.to(dtype).cuda()
+    eps_rel = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    for i, t in enumerate(s.timesteps):
+        e = torch.randn(2, 4, 32, 32, generator=gen).to(dtype)
+        x = s.step(e.cuda(), t, x, return_dict=False)[0]
+        assert x.dtype == dtype
+        x_ref = o.step(e.float(), o.timesteps[i], x_ref)
+        err = (x.float().cpu() - x_ref).abs().max() / x_ref.abs().max()
+        assert err < 6 * eps_rel * (i + 1), f"step {i}: {err}"
+        x_ref = x.float().cpu()                 # re-anchor: compare single steps, not accumulated drift

@@ -216,3 +216,74 @@ def test_fm_baseline_scheduler_errors():
     d = cb.FlowMatchGeneralDiscreteScheduler()                # reference defaults (edit_ppo/scheduler_fm.py:92-109)
     assert d.config.type == "euler" and d.config.shift == 1.0 and d.shift == 1.0
     assert d.sigma_max == 1.0 and abs(d.sigma_min - 1e-3) < 1e-9
+
+
+# ---- DPMSolverMultistepScheduler with AMED scaling (diffusers_amed_plugin_dpmpp.py) -----------------------------
+def _amed(g):
+    m = g.meta
+    s = cb.DPMSolverMultistepScheduler(**m["config"])
+    if m["amed"]:
+        s.scale_dirs, s.scale_times = m["scale_dirs"], m["scale_times"]
+        s.set_timesteps(m["n"], timesteps=m["schedule"])
+    else:
+        s.set_timesteps(m["n"])
+    return s
+
+
+def _dpm_kernel_arithmetic(p, first, e, x, m1):
+    """include/consolver.h's statement of consolver_step_dpm, in torch-CPU fp32 ops (same roundings)."""
+    from consolver_b200 import _lib
+    if p.convert == _lib.DPM_CONVERT_DIV:
+        m0 = (x - p.ck0 * e) / p.ck1
+    elif p.convert == _lib.DPM_CONVERT_LIN:
+        m0 = p.ck1 * x + p.ck0 * e
+    else:
+        m0 = e
+    out = p.cx * x - p.a0 * m0
+    if not first:
+        out = out - p.a1 * (p.rinv * (m0 - m1))
+    return out, m0
+
+
+@pytest.mark.parametrize("name", names("amed_"))
+def test_amed_scheduler_grid_and_host_scalars_reproduce_the_plugin(name):
+    """The host half of the AMED / DPM-Solver scheduler without a GPU: grids equal the plugin's, and the per-step
+    scalars + order selection, pushed through the kernel's documented arithmetic, give the plugin's latents
+    bit for bit (the GPU tests then only have to show that the kernel does that arithmetic)."""
+    g = Golden(name)
+    s = _amed(g)
+    assert torch.equal(s.timesteps, g["timesteps"]) and torch.equal(s.sigmas, g["sigmas"])
+    x, m1 = g["x_T"], None
+    for i, t in enumerate(s.timesteps):
+        idx, plan, first = s._plan_for_step(t)
+        assert idx == i
+        x, m1 = _dpm_kernel_arithmetic(plan, first, g[f"eps_{i}"], x, m1)
+        s._advance()
+        assert torch.equal(x, g[f"prev_{i}"]), f"step {i}"
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        s.step(g["eps_0"], 0, x)
+
+
+def test_amed_scheduler_surface_and_errors():
+    D = cb.DPMSolverMultistepScheduler
+    s = D(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1)
+    assert s.config.solver_order == 2 and s.config.algorithm_type == "dpmsolver++" and s.order == 1
+    assert s.init_noise_sigma == 1.0 and len(s) == 1000
+    with pytest.raises(ValueError, match="set_timesteps"):
+        s._plan_for_step(999)
+    with pytest.raises(AssertionError):                      # plugin :48-49
+        s.set_timesteps(4, timesteps=[999, 694, 500, 110, 0])
+    for bad in (dict(algorithm_type="sde-dpmsolver++"), dict(solver_order=3), dict(thresholding=True),
+                dict(solver_type="bh1"), dict(beta_schedule="squaredcos_cap_v2")):
+        with pytest.raises(NotImplementedError):
+            D(**bad)
+    with pytest.raises(ValueError):
+        D(prediction_type="flow")
+    # SD1.5's scheduler_config.json carries PNDM-only keys; from_config must ignore them (gen_ppo.py:160-163)
+    cfg = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+               set_alpha_to_one=False, skip_prk_steps=True, steps_offset=1, clip_sample=False, trained_betas=None)
+    s2 = D.from_config(cfg)
+    s2.scale_dirs, s2.scale_times = [1.0, 0.991, 1.0, 0.9912, 1.0], [1.0, 1.0333, 1.0, 0.9861, 1.0]
+    s2.set_timesteps(4, timesteps=[999, 694, 500, 110, 0])
+    assert s2.timesteps.tolist()[0] == 999 and s2.timesteps.tolist()[2] == 500 and len(s2.timesteps) == 4
+    assert s2.num_inference_steps == 5                        # plugin :60 counts the trailing 0

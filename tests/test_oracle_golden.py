@@ -88,6 +88,22 @@ def test_fm_baseline_solvers_oracle_matches_reference(name):
         assert torch.equal(x, g[f"prev_{i}"]), f"step {i} latent not bit-exact"
 
 
+@pytest.mark.parametrize("name", names("amed_"))
+def test_amed_dpm_solver_oracle_matches_plugin(name):
+    """diffusers_amed_plugin_dpmpp.py run unmodified (over a stand-in of its diffusers base, see
+    oracle/ref_shim.py::_dpm_base) vs the oracle restatement: grids and every latent bit-exact."""
+    g = Golden(name)
+    m = g.meta
+    s = orc.OracleDPMSolverAMED(scale_dirs=m["scale_dirs"], scale_times=m["scale_times"], **m["config"])
+    s.set_timesteps(m["n"], timesteps=m["schedule"])
+    assert torch.equal(s.timesteps, g["timesteps"])
+    assert torch.equal(s.sigmas, g["sigmas"])
+    x = g["x_T"]
+    for i, t in enumerate(s.timesteps):
+        x = s.step(g[f"eps_{i}"], t, x)
+        assert torch.equal(x, g[f"prev_{i}"]), f"step {i} latent not bit-exact"
+
+
 @pytest.mark.parametrize("name", names("update_"))
 def test_update_side_oracle(name):
     g = Golden(name)
