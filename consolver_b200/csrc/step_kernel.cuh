@@ -6,6 +6,8 @@
 // Reference arithmetic being fused: denoise_ppo.py:96-100, scheduler_ppo.py:263-280 and :306-332,
 // edit_ppo/scheduler_fmppo.py:354,:413-436.
 #pragma once
+#include <type_traits>
+
 #include "step_common.cuh"
 
 namespace consolver {
@@ -14,8 +16,13 @@ enum : int { kModeSD = 0, kModeFM = 1 };
 
 // NH  > 0 : history depth known at compile time (1..4), loads fully unrolled
 // NH == 0 : runtime depth (5..8), guarded loads
+// T  : element type of model outputs, history and ring slot;  TX : element type of the incoming latent.
+// The next latent is written as T by the FM step (the reference casts back to the model dtype,
+// edit_ppo/scheduler_fmppo.py:436) and as TX by the SD step (torch promotion: fp32 latents with 16-bit model outputs
+// under accelerator.autocast stay fp32, train_ppo.py:353).
 template <typename T, typename TX, int NH, int MODE, int E, int U>
 __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
+  using TO = typename std::conditional<MODE == kModeSD, TX, T>::type;
   constexpr int kOlder = NH ? NH - 1 : kMaxOlder;
   const int b = blockIdx.x / p.chunks_per_sample;
   const int chunk = blockIdx.x - b * p.chunks_per_sample;
@@ -80,7 +87,8 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (!live[u]) continue;
-    Raw<T, E> r_slot, r_out;
+    Raw<T, E> r_slot;
+    Raw<TO, E> r_out;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       // CFG: u + g*(c - u)                                            denoise_ppo.py:100
@@ -126,8 +134,8 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
       }
       r_out.set(i, out);
     }
-    r_out.store(static_cast<T*>(p.x_out) + off[u]);
-    if (p.x_out2) r_out.store(static_cast<T*>(p.x_out2) + (long long)b * p.out2_stride + (off[u] - base));
+    r_out.store(static_cast<TO*>(p.x_out) + off[u]);
+    if (p.x_out2) r_out.store(static_cast<TO*>(p.x_out2) + (long long)b * p.out2_stride + (off[u] - base));
     if (pair && p.slot_out) r_slot.store(static_cast<T*>(p.slot_out) + off[u]);
   }
   // plain (non-pair) step with a ring slot requested: copy e0 through

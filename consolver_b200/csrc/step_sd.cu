@@ -30,12 +30,16 @@ extern "C" int consolver_step_sd(int dtype, const void* e0, const void* cond, fl
   p.k0 = sa_t; p.k1 = sb_t; p.k2 = sa_p; p.k3 = sb_p;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool al = all_aligned(p);
+  const bool x32 = flags & CONSOLVER_FLAG_X_F32;      // fp32 latents with 16-bit model outputs (autocast pipelines)
   switch (dtype) {
     case CONSOLVER_F32:
       return launch_step<float, float, kModeSD>(p, al && n_per_sample % Elem<float>::kPerVec == 0, s);
     case CONSOLVER_F16:
+      if (x32) return launch_step<__half, float, kModeSD>(p, al && n_per_sample % Elem<__half>::kPerVec == 0, s);
       return launch_step<__half, __half, kModeSD>(p, al && n_per_sample % Elem<__half>::kPerVec == 0, s);
     case CONSOLVER_BF16:
+      if (x32)
+        return launch_step<__nv_bfloat16, float, kModeSD>(p, al && n_per_sample % Elem<__nv_bfloat16>::kPerVec == 0, s);
       return launch_step<__nv_bfloat16, __nv_bfloat16, kModeSD>(
           p, al && n_per_sample % Elem<__nv_bfloat16>::kPerVec == 0, s);
     default:

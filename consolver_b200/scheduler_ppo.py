@@ -207,8 +207,17 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
         if not (e0.is_cuda and sample.is_cuda):
             raise RuntimeError("consolver_b200 has no CPU path: model_output and sample must be CUDA tensors")
+        # Mixed precision as torch promotion resolves it in the reference: fp32 latents with a 16-bit model output
+        # (accelerate autocast, train_ppo.py:353) keep the latents fp32 — the kernel reads/writes x as fp32 and the
+        # model outputs / history as 16-bit; a 16-bit latent with an fp32 model output is promoted to fp32 up front.
+        mixed = 0
         if sample.dtype != e0.dtype:
-            raise TypeError(f"sample ({sample.dtype}) and model_output ({e0.dtype}) must share a dtype")
+            if sample.dtype == torch.float32 and e0.dtype in (torch.float16, torch.bfloat16):
+                mixed = _lib.FLAG_X_F32
+            elif e0.dtype == torch.float32 and sample.dtype in (torch.float16, torch.bfloat16):
+                sample = sample.float()
+            else:
+                raise TypeError(f"sample ({sample.dtype}) and model_output ({e0.dtype}) cannot be combined")
         cfg = self.config
         fn = self.factor_net_module
         od = cfg.order_dim
@@ -246,7 +255,7 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         q_ptr, idx_ptr, rng_arg = draw_source(self, tr, e0.device, fused_ok=on_grid and not fn.use_conv)
         x_out = out if out is not None else torch.empty_like(sample)
         slot = tr.slot(tr.count) if cond is not None else None
-        vflag = _lib.FLAG_VPRED if cfg.prediction_type == "v_prediction" else 0
+        vflag = (_lib.FLAG_VPRED if cfg.prediction_type == "v_prediction" else 0) | mixed
         sflag = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
         pdl = _lib.FLAG_PDL if self.use_pdl else 0
         lib = _lib.load()

@@ -62,6 +62,13 @@ extern "C" {
                                            the flag the combination is fp32 (per-sample fp32 coefficients promote,
                                            edit_ppo/scheduler_fmppo.py:413-429).  Ignored for fp32 model outputs     */
 
+#define CONSOLVER_FLAG_X_F32        64   /* consolver_step_sd with a 16-bit dtype: x, x_out and x_out2 are fp32 (the model
+                                           outputs, history and ring slot stay `dtype`).  This is the layout of the
+                                           reference's mixed-precision training loop (train_ppo.py:353, accelerate
+                                           fp16/bf16 autocast): fp32 latents, 16-bit U-Net output, and torch promotion
+                                           keeps every later product and the returned latent in fp32
+                                           (scheduler_ppo.py:272,:323-330).  Ignored when dtype is CONSOLVER_F32    */
+
 #define CONSOLVER_ERR_NULL        (-1)
 #define CONSOLVER_ERR_SIZE        (-2)
 #define CONSOLVER_ERR_UNSUPPORTED (-3)

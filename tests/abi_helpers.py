@@ -42,9 +42,12 @@ def step_sd(e0, cond, guidance, hist, x, coef, order_dim, scalars, flags=0, slot
     B = x.shape[0]
     N = x.numel() // B
     x_out = torch.empty_like(x)
-    slot_t = torch.empty_like(x) if slot else None
+    slot_t = torch.empty_like(e0) if slot else None
+    if x.dtype != e0.dtype:                      # fp32 latents, 16-bit model outputs (autocast pipelines)
+        assert x.dtype == torch.float32
+        flags |= _lib.FLAG_X_F32
     rc = lib.consolver_step_sd(
-        _lib.dtype_code(x.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, float(guidance),
+        _lib.dtype_code(e0.dtype), e0.data_ptr(), cond.data_ptr() if cond is not None else None, float(guidance),
         slot_t.data_ptr() if slot else None, _lib.ptr_array([h.data_ptr() for h in hist]), len(hist) + 1,
         x.data_ptr(), x_out.data_ptr(), out2.data_ptr() if out2 is not None else None,
         out2.stride(0) if out2 is not None else 0, coef.data_ptr(), coef.shape[1], order_dim,

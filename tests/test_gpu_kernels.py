@@ -346,3 +346,30 @@ def test_in_kernel_exponential_draw_is_torchs(B, A, K):
     state = torch.tensor([seed, off - 8], dtype=torch.int64, device="cuda")
     out2 = ah.policy_sample(dsd, table, B, A + 1, 0, A + 1, rng=_lib.Rng(0, 8, state.data_ptr(), nthreads))
     assert torch.equal(out2["idx"], out["idx"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n_hist", [1, 2, 4])
+@pytest.mark.parametrize("pair,vpred,sdim", [(False, False, 0), (True, False, 0), (False, True, 2)])
+def test_step_sd_fp32_latents_with_16bit_model_outputs(dtype, n_hist, pair, vpred, sdim):
+    """CONSOLVER_FLAG_X_F32 — the mixed-precision layout of the reference's training loop (train_ppo.py:353):
+    16-bit model outputs / history, fp32 latent in and out.  fp32 arithmetic on the upcast values, so from the second
+    step on (n_hist >= 2, where torch promotion makes the reference's arithmetic fp32 too) the result is the
+    oracle's bit for bit; ragged size included."""
+    B, shape, od = 3, (4, 9, 7), 4
+    g = torch.Generator().manual_seed(17)
+    r16 = lambda: torch.randn(B, *shape, generator=g).to(dtype)  # noqa: E731
+    e0, cond = r16(), (r16() if pair else None)
+    hist = [r16() for _ in range(n_hist - 1)]
+    x = torch.randn(B, *shape, generator=g)
+    c = _rand_coef(B, od, g, sdim)
+    scalars = (0.8378, 0.5460, 0.9151, 0.4033)
+    eps = orc.cfg_combine(e0.float(), cond.float(), 3.0).to(dtype) if pair else e0
+    ref, _ = _oracle_sd(eps.float(), None, 0.0, [h.float() for h in hist], x, c, od, scalars, vpred, sdim)
+    flags = (1 if vpred else 0) | (2 if sdim >= 1 else 0) | (4 if sdim >= 2 else 0)
+    out, slot = ah.step_sd(e0.cuda(), cond.cuda() if pair else None, 3.0, [h.cuda() for h in hist], x.cuda(), c.cuda(),
+                           od, scalars, flags, slot=pair)
+    assert out.dtype == torch.float32
+    assert torch.equal(out.cpu(), ref)
+    if pair:
+        assert slot.dtype == dtype and torch.equal(slot.cpu(), eps)

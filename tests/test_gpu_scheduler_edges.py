@@ -131,3 +131,36 @@ def test_cuda_timesteps_starting_mid_grid_like_img2img():
         assert torch.equal(conds["x"].cpu(), c_o["x"]), f"step {i}: wrong timestep row"
         assert torch.equal(actions.cpu(), a_o)
         assert torch.equal(xg.cpu(), x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_autocast_style_mixed_precision_matches_reference_promotion(dtype):
+    """train_ppo.py:353 runs the rollout under accelerate autocast: the U-Net output is 16-bit, the latents fp32.
+    The reference's torch ops then promote: the returned latent is fp32, and from the second step on every product
+    is fp32 arithmetic on the upcast model outputs — which the oracle (fed the same mixed dtypes) and the kernel
+    must agree on bit for bit.  At the first step (eff is the 16-bit output itself) the reference rounds two
+    products to 16 bits; the kernel keeps fp32 there, so that step is compared within 16-bit resolution."""
+    g, m, s, o = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    o.set_timesteps(m["n"])
+    s.replay = {"idx": [g[f"idx_{i}"] for i in range(m["n"])]}
+    x = g["x_T"]
+    for i, t in enumerate(o.timesteps):
+        eps = g[f"eps_{i}"].to(dtype)
+        out = s.step(eps.cuda(), s.timesteps[i], x.cuda(), return_dict=False)
+        ref = o.step(eps, t, x, forced_idx=g[f"idx_{i}"])
+        assert out[0].dtype == torch.float32 and ref[0].dtype == torch.float32
+        if i == 0:
+            tol = (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10) * ref[0].abs().max()
+            assert (out[0].cpu() - ref[0]).abs().max() <= 2 * tol
+        else:
+            assert torch.equal(out[0].cpu(), ref[0]), f"step {i}"
+        assert torch.equal(out[1].cpu(), ref[1]) and torch.equal(out[4].cpu(), ref[4])
+        x = out[0].cpu()
+    # the other direction: 16-bit latent with an fp32 model output is promoted to fp32
+    s.set_timesteps(m["n"], device="cuda")
+    s.replay = {"idx": [g[f"idx_{i}"] for i in range(m["n"])]}
+    y = s.step(g["eps_0"].cuda(), s.timesteps[0], g["x_T"].to(dtype).cuda(), return_dict=False)[0]
+    assert y.dtype == torch.float32
+    with pytest.raises(TypeError):
+        s.step(g["eps_1"].half().cuda(), s.timesteps[1], y.bfloat16(), return_dict=False)
