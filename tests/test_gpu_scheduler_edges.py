@@ -164,3 +164,23 @@ def test_autocast_style_mixed_precision_matches_reference_promotion(dtype):
     assert y.dtype == torch.float32
     with pytest.raises(TypeError):
         s.step(g["eps_1"].half().cuda(), s.timesteps[1], y.bfloat16(), return_dict=False)
+
+
+def test_denoise_loop_with_a_16bit_denoiser_output_keeps_fp32_latents():
+    """The rollout loop (denoise_ppo.py:52-120) under autocast: fp32 ping-pong latents, fp16 denoiser output."""
+    from consolver_b200.denoise import denoise_loop
+    g, m, s, _ = _pair()
+    w = torch.randn(4, 4, device="cuda") * 0.3
+    den = lambda x, t, i: torch.einsum("oc,bchw->bohw", w, x).half()  # noqa: E731
+    noise = g["x_T"].cuda()
+    torch.manual_seed(3)
+    lat, rec = denoise_loop(s, den, noise, cfg=3.0, num_inference_steps=6)
+    assert lat.dtype == torch.float32 and rec["actions"].shape[:2] == (3, 5)
+    # the same loop spelled out, replaying the sampled actions
+    idx = s._traj.out["idx"][:6].clone()
+    s.set_timesteps(6, device="cuda")
+    s.replay = {"idx": [idx[i] for i in range(6)]}
+    x = noise
+    for i, t in enumerate(s.timesteps):
+        x = s.step_cfg(den(torch.cat([x] * 2), t, i), t, x, 3.0)[0]
+    assert torch.equal(x, lat)

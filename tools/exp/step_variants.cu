@@ -97,6 +97,77 @@ __global__ void __launch_bounds__(256) k_persist(const P p, long long total_vec)
   }
 }
 
+// ---- TMA variant: 1-D bulk copies (cp.async.bulk) global -> shared, mbarrier-completed, STAGES-deep ring per CTA, persistent
+// grid.  One elected thread produces; all 256 threads consume from shared memory and store with st.global.cs.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n));
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+template <int U, int STAGES>
+__global__ void __launch_bounds__(256) k_tma(const P p, long long total_tiles, int tiles_per_sample) {
+  constexpr int TILE = 256 * 4 * U;                      // floats per tensor per tile
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* buf = reinterpret_cast<float*>(smem_raw);       // [STAGES][6][TILE]
+  __shared__ unsigned long long bar[STAGES];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const float* src[6] = {p.u, p.c, p.x, p.h1, p.h2, p.h3};
+  const long long first = blockIdx.x;
+  const long long n_my = first < total_tiles ? (total_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](long long k) {
+    const int s = (int)(k % STAGES);
+    const long long off = (first + k * gridDim.x) * TILE;
+    mbar_expect(&bar[s], 6u * TILE * 4u);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) bulk_g2s(buf + ((size_t)s * 6 + j) * TILE, src[j] + off, TILE * 4u, &bar[s]);
+  };
+  if (threadIdx.x == 0)
+    for (long long k = 0; k < STAGES && k < n_my; ++k) issue(k);
+  for (long long k = 0; k < n_my; ++k) {
+    const int s = (int)(k % STAGES);
+    mbar_wait(&bar[s], (unsigned)((k / STAGES) & 1));
+    const long long tile = first + k * gridDim.x;
+    const int b = (int)(tile / tiles_per_sample);
+    float cf[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cf[j] = __ldg(p.coef + b * 6 + j);
+    const float* sb = buf + (size_t)s * 6 * TILE;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int e = (threadIdx.x + i * 256) * 4;
+      const float4 ru = *reinterpret_cast<const float4*>(sb + 0 * TILE + e), rc = *reinterpret_cast<const float4*>(sb + 1 * TILE + e),
+                   rx = *reinterpret_cast<const float4*>(sb + 2 * TILE + e), r1 = *reinterpret_cast<const float4*>(sb + 3 * TILE + e),
+                   r2 = *reinterpret_cast<const float4*>(sb + 4 * TILE + e), r3 = *reinterpret_cast<const float4*>(sb + 5 * TILE + e);
+      float4 o, ee;
+      math<true>(ru.x, rc.x, rx.x, r1.x, r2.x, r3.x, cf, 3.f, o.x, ee.x);
+      math<true>(ru.y, rc.y, rx.y, r1.y, r2.y, r3.y, cf, 3.f, o.y, ee.y);
+      math<true>(ru.z, rc.z, rx.z, r1.z, r2.z, r3.z, cf, 3.f, o.z, ee.z);
+      math<true>(ru.w, rc.w, rx.w, r1.w, r2.w, r3.w, cf, 3.f, o.w, ee.w);
+      st<ST_CS>(p.out + tile * TILE + e, o);
+      st<ST_CS>(p.slot + tile * TILE + e, ee);
+    }
+    __syncthreads();                                     // stage s fully consumed
+    if (threadIdx.x == 0 && k + STAGES < n_my) issue(k + STAGES);
+  }
+}
+
 struct Set { float* t[8]; };
 
 int main(int argc, char** argv) {
@@ -145,6 +216,17 @@ int main(int argc, char** argv) {
       char nm[64]; snprintf(nm, sizeof nm, "persistent grid=148x%d exact", k);
       run(nm, [&](const Set& s) { P p = mkp(s, 1); k_persist<LD_NC_NOALLOC, ST_PLAIN, true><<<148 * k, 256>>>(p, (long long)B * N / 4); });
     }
+#define RUN_TMA(NAME, U, STG, CTAS_PER_SM) do { \
+      const int smem = STG * 6 * 256 * 4 * U * 4; \
+      CK(cudaFuncSetAttribute(k_tma<U, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      const long long tiles = (long long)B * N / (256 * 4 * U); \
+      const int grid = (int)std::min<long long>(tiles, 148LL * CTAS_PER_SM); \
+      run(NAME, [&](const Set& s) { P p = mkp(s, U); k_tma<U, STG><<<grid, 256, smem>>>(p, tiles, (int)(N / (256 * 4 * U))); }); \
+    } while (0)
+    RUN_TMA("TMA bulk U1 (4 KiB/tensor) 4 stages, 2 CTA/SM st.cs", 1, 4, 2);
+    RUN_TMA("TMA bulk U2 (8 KiB/tensor) 2 stages, 2 CTA/SM st.cs", 2, 2, 2);
+    RUN_TMA("TMA bulk U2 (8 KiB/tensor) 4 stages, 1 CTA/SM st.cs", 2, 4, 1);
+    RUN_TMA("TMA bulk U1 (4 KiB/tensor) 2 stages, 4 CTA/SM st.cs", 1, 2, 4);
     for (auto& s : sets) for (int i = 0; i < 8; ++i) cudaFree(s.t[i]);
     cudaFree(coef);
   }
