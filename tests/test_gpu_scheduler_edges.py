@@ -73,7 +73,7 @@ def test_timestep_read_back_and_batch_change():
     out5 = s.step(torch.randn_like(x5), s.timesteps[0], x5, return_dict=True)
     assert out5.actions.shape == (5, 3)
     with pytest.raises(TypeError):
-        s.step(torch.randn_like(x5).half(), s.timesteps[1], x5)
+        s.step(torch.randn_like(x5).half(), s.timesteps[1], x5.bfloat16())     # two different 16-bit types
     with pytest.raises(ValueError):
         s.step_cfg(torch.randn(7, *m["shape"], device="cuda"), s.timesteps[1], x5, 3.0)
 
