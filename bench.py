@@ -127,10 +127,12 @@ def synth_batch(B, seed, device, pin=False):
     return x.to(device), pairs.to(device)
 
 
-def time_step_kernel(B, n_hist, device, iters=64, pool_bytes=3 * L2_BYTES):
+def time_step_kernel(B, n_hist, device, iters=64, pool_bytes=3 * L2_BYTES, flags=0):
     """Average device time of ONE fused-step launch (CFG pair, n_hist deep) over `iters` launches on rotating
     buffer sets larger than L2, captured in a CUDA graph so host launch gaps do not enter; CUDA events on the
-    launch stream."""
+    launch stream.  `flags` = CONSOLVER_FLAG_CHAIN times the launch form the product's replay graphs use
+    (each step a programmatic dependent launch of the previous one, so one launch's tail overlaps the next one's
+    ramp); the launches here are independent, which is what the flag requires of everything but x / hist[0]."""
     from consolver_b200 import _lib
 
     lib = _lib.load()
@@ -145,8 +147,8 @@ def time_step_kernel(B, n_hist, device, iters=64, pool_bytes=3 * L2_BYTES):
     def launch(st, stream):
         rc = lib.consolver_step_sd(0, st["u"].data_ptr(), st["c"].data_ptr(), GUIDANCE, st["s"].data_ptr(),
                                    _lib.ptr_array([t.data_ptr() for t in st["h"]]), n_hist, st["x"].data_ptr(),
-                                   st["o"].data_ptr(), None, 0, coef.data_ptr(), 6, 4, 0.8378, 0.5460, 0.9151, 0.4033, 0,
-                                   B, N, stream)
+                                   st["o"].data_ptr(), None, 0, coef.data_ptr(), 6, 4, 0.8378, 0.5460, 0.9151, 0.4033,
+                                   flags, B, N, stream)
         assert rc == 0, rc
 
     side = torch.cuda.Stream(device=device)
@@ -538,6 +540,13 @@ def run_ours(args, rank, world, device):
                            "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
                            "frac": round(nbytes / us / 1e3 / peak, 4), "traffic": traffic, "us_per_launch": round(us, 3),
                            "algorithmic_bytes": nbytes, "peak_source": src}
+        from consolver_b200._lib import FLAG_CHAIN
+        us_c, _, _ = time_step_kernel(B, 4, device, flags=FLAG_CHAIN)
+        out["roofline"]["chained"] = {
+            "us_per_launch": round(us_c, 3), "achieved": round(nbytes / us_c / 1e3, 1),
+            "frac": round(nbytes / us_c / 1e3 / peak, 4),
+            "note": "same launches as programmatic dependent launches of one another (CONSOLVER_FLAG_CHAIN), the form "
+                    "the replay graphs of the `value` leg use; `frac` above is the plain, fully serialised launch"}
         sweep = []
         for Bs in (256, 1024, 4096):
             us, nbytes, nsets = time_step_kernel(Bs, 4, device, iters=32)

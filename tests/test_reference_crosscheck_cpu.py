@@ -89,3 +89,62 @@ def test_policy_modules_match_reference_at_init_and_on_the_update_side():
         pm, em = m(d, actions)
         torch.testing.assert_close(pm, pr, rtol=1e-6, atol=1e-7)
         torch.testing.assert_close(em, er, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("variant", FM_VARIANTS)
+@pytest.mark.parametrize("kind", ["euler", "heun", "dpm-solver", "dpm-solver-multistep"])
+def test_fm_baseline_scheduler_grids_match_reference(variant, kind):
+    """FlowMatchGeneralDiscreteScheduler (edit_ppo/scheduler_fm.py): every sigma-grid option against the live class."""
+    ref = ref_shim.load_reference()
+    r = ref.FlowMatchGeneralDiscreteScheduler(type=kind, **variant)
+    m = cb.FlowMatchGeneralDiscreteScheduler(type=kind, **variant)
+    assert torch.equal(r.sigmas, m.sigmas) and torch.equal(r.timesteps, m.timesteps)
+    mu = 0.9 if variant.get("use_dynamic_shifting") else None
+    r.set_timesteps(7, mu=mu)
+    m.set_timesteps(7, mu=mu)
+    assert torch.equal(r.sigmas, m.sigmas) and torch.equal(r.timesteps, m.timesteps)
+    assert r.index_for_timestep(r.timesteps[2]) == m.index_for_timestep(m.timesteps[2])
+    lat, noise = torch.randn(2, 8, 4), torch.randn(2, 8, 4)
+    assert torch.equal(r.scale_noise(lat, r.timesteps[:2], noise), m.scale_noise(lat, m.timesteps[:2], noise))
+
+
+AMED_ALL = {   # gen_ppo.py:24-55
+    4: ([999, 694, 500, 110, 0], [1.0, 0.991, 1.0, 0.9912, 1.0], [1.0, 1.0333, 1.0, 0.9861, 1.0]),
+    6: ([999, 758, 666, 495, 333, 107, 0], [1.0, 0.9924, 1.0, 0.9916, 1.0, 0.9906, 1.0],
+        [1.0, 1.052, 1.0, 0.9998, 1.0, 0.9781, 1.0]),
+    8: ([999, 831, 749, 623, 500, 394, 250, 88, 0], [1.0, 0.9976, 1.0, 0.991, 1.0, 0.9907, 1.0, 0.9905, 1.0],
+        [1.0, 1.0257, 1.0, 0.9989, 1.0, 1.0022, 1.0, 0.9747, 1.0]),
+    10: ([999, 885, 799, 705, 599, 492, 400, 329, 200, 73, 0],
+         [1.0, 0.9974, 1.0, 0.9904, 1.0, 0.991, 1.0, 0.9905, 1.0, 0.9904, 1.0],
+         [1.0, 0.9872, 1.0, 1.0152, 1.0, 1.0186, 1.0, 0.9934, 1.0, 0.9731, 1.0]),
+    14: ([999, 924, 856, 790, 714, 623, 571, 494, 428, 374, 285, 241, 143, 55, 0],
+         [1.0, 0.9922, 1.0, 0.9909, 1.0, 0.9914, 1.0, 0.9908, 1.0, 0.9904, 1.0, 0.9903, 1.0, 0.9904, 1.0],
+         [1.0, 0.9835, 1.0, 1.0293, 1.0, 1.0216, 1.0, 1.0241, 1.0, 1.0021, 1.0, 0.9844, 1.0, 0.9714, 1.0]),
+}
+
+
+@pytest.mark.parametrize("n", sorted(AMED_ALL))
+def test_amed_grids_and_step_scalars_match_the_plugin_for_every_shipped_schedule(n):
+    """All five AMED schedules of gen_ppo.py through the unmodified plugin (over the stand-in of its diffusers base):
+    time-scaled timesteps, sigmas, and — via the kernel's documented arithmetic — every latent of a full run."""
+    from test_host_cpu import _dpm_kernel_arithmetic
+    ref = ref_shim.load_reference()
+    cfg = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1)
+    ts, dirs, times = AMED_ALL[n]
+    r = ref.AMEDDPMSolverMultistepScheduler(**cfg)
+    m = cb.DPMSolverMultistepScheduler(**cfg)
+    for s in (r, m):
+        s.scale_dirs, s.scale_times = dirs, times
+        s.set_timesteps(n, timesteps=ts)
+    assert torch.equal(r.timesteps, m.timesteps) and torch.equal(r.sigmas, m.sigmas)
+    assert r.num_inference_steps == m.num_inference_steps
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(2, 4, 8, 8, generator=g)
+    xm, m1 = x, None
+    for t in r.timesteps:
+        e = torch.randn(2, 4, 8, 8, generator=g)
+        x = r.step(e, t, x, return_dict=False)[0]
+        _, plan, first = m._plan_for_step(t)
+        xm, m1 = _dpm_kernel_arithmetic(plan, first, e, xm, m1)
+        m._advance()
+        assert torch.equal(x, xm)
