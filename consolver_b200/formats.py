@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import os
 import random
-from typing import Dict, Iterator, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 

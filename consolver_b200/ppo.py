@@ -15,9 +15,8 @@ What is different from the reference, none of it numerical:
 This module is training-side torch code (autograd); it is not the sampling hot path and runs on any device."""
 from __future__ import annotations
 
-import math
 import random
-from typing import Dict, Iterable, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist

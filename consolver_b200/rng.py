@@ -11,7 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import warnings
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 

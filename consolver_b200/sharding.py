@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Iterator, List, Optional, Sequence, Tuple
+from typing import Iterator, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
