@@ -61,6 +61,9 @@ template <> struct Elem<__nv_bfloat16> {
   static constexpr bool k16 = true;
 };
 
+// v rounded to T and back: the value a torch op with a T result would hold
+template <typename T> __device__ __forceinline__ float round_to(float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); }
+
 // ---- 128-bit streaming accessors ------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   uint4 r;

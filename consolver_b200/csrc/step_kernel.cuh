@@ -94,8 +94,13 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
       // CFG: u + g*(c - u)                                            denoise_ppo.py:100
       float eps = r_e0[u].get(i);
       if (pair) {
-        eps = __fadd_rn(eps, __fmul_rn(g, __fsub_rn(r_c[u].get(i), eps)));
-        if (Elem<T>::k16) eps = Elem<T>::to_f(Elem<T>::from_f(eps));  // the value the ring keeps
+        if (Elem<T>::k16) {
+          // the caller's combine on 16-bit tensors rounds after every op; the python scalar g stays fp32
+          const float d = round_to<T>(__fsub_rn(r_c[u].get(i), eps));
+          eps = round_to<T>(__fadd_rn(eps, round_to<T>(__fmul_rn(g, d))));
+        } else {
+          eps = __fadd_rn(eps, __fmul_rn(g, __fsub_rn(r_c[u].get(i), eps)));
+        }
         r_slot.set(i, eps);
       }
       // eff = ((0 + c0*e0) + c1*e1) + ...                              scheduler_ppo.py:263-272
@@ -112,7 +117,29 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
       float xs = r_x[u].get(i);
       if (x_scale) xs = __fmul_rn(xs, cs1);                           // :278
       float out;
-      if (MODE == kModeSD) {
+      if (MODE == kModeSD && Elem<T>::k16 && nh == 1 && !eff_scale && !x_scale) {
+        // First step of a 16-bit pipeline: `eff` is still the raw 16-bit model output (scheduler_ppo.py:263-265), so
+        // torch evaluates every `0-d fp32 scalar * eff` of :316-330 in the 16-bit dtype — scalar rounded to it, product
+        // rounded to it — while `tensor / 0-d scalar` keeps the scalar in fp32.  With a 16-bit latent every
+        // intermediate is rounded as well; with an fp32 latent (autocast) the rest promotes to fp32.
+        float e = eff;
+        if (Elem<TX>::k16) {
+          if (vpred)
+            e = round_to<T>(__fadd_rn(round_to<T>(__fmul_rn(round_to<T>(p.k0), e)),
+                                      round_to<T>(__fmul_rn(round_to<T>(p.k1), xs))));
+          const float t2 = round_to<T>(__fsub_rn(xs, round_to<T>(__fmul_rn(round_to<T>(p.k1), e))));
+          const float x0 = round_to<T>(__fdiv_rn(t2, p.k0));
+          out = round_to<T>(__fadd_rn(round_to<T>(__fmul_rn(round_to<T>(p.k2), x0)),
+                                      round_to<T>(__fmul_rn(round_to<T>(p.k3), e))));
+        } else if (vpred) {
+          e = __fadd_rn(round_to<T>(__fmul_rn(round_to<T>(p.k0), e)), __fmul_rn(p.k1, xs));     // fp32 from here on
+          const float x0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.k1, e)), p.k0);
+          out = __fadd_rn(__fmul_rn(p.k2, x0), __fmul_rn(p.k3, e));
+        } else {
+          const float x0 = __fdiv_rn(__fsub_rn(xs, round_to<T>(__fmul_rn(round_to<T>(p.k1), e))), p.k0);
+          out = __fadd_rn(__fmul_rn(p.k2, x0), round_to<T>(__fmul_rn(round_to<T>(p.k3), e)));
+        }
+      } else if (MODE == kModeSD) {
         if (vpred) eff = __fadd_rn(__fmul_rn(p.k0, eff), __fmul_rn(p.k1, xs));          // :316-317
         const float x0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.k1, eff)), p.k0);          // :323
         out = __fadd_rn(__fmul_rn(p.k2, x0), __fmul_rn(p.k3, eff));                     // :329-330

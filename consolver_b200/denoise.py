@@ -41,8 +41,14 @@ def denoise_loop(scheduler: PPOScheduler, denoiser: Callable[[torch.Tensor, torc
     bufs[0][:B].copy_(noise)
     bufs[0][B:].copy_(noise)
     for i, t in enumerate(scheduler.timesteps):
-        cur, nxt = bufs[i % 2], bufs[(i + 1) % 2]
+        cur = bufs[i % 2]
         pred = denoiser(scheduler.scale_model_input(cur, t), t, i)
+        # with a 16-bit denoiser output the latent may turn fp32 (torch promotion in the reference, see
+        # PPOScheduler.next_latent_dtype): give the step a destination of the dtype it is going to return
+        want = scheduler.next_latent_dtype(pred.dtype, cur.dtype)
+        if bufs[(i + 1) % 2].dtype != want:
+            bufs[(i + 1) % 2] = cur.new_empty(cur.shape, dtype=want)
+        nxt = bufs[(i + 1) % 2]
         scheduler.step_cfg(pred, t, cur[:B], cfg, out=nxt[:B], out2=nxt[B:])
     latents = bufs[len(scheduler.timesteps) % 2][:B]
     return latents, (scheduler.trajectory() if record and num_inference_steps > 1 else None)

@@ -191,11 +191,19 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             raise ValueError("step_cfg expects the [2B, ...] classifier-free-guidance pair")
         if not noise_pred.is_contiguous():
             noise_pred = noise_pred.contiguous()
-        if out2 is not None and (out2.shape != sample.shape or out2.dtype != sample.dtype or
-                                 not out2[0].is_contiguous()):
-            raise ValueError("out2 must have the sample's shape/dtype with contiguous samples")
+        if out2 is not None and (out2.shape != sample.shape or not out2[0].is_contiguous()):
+            raise ValueError("out2 must have the sample's shape with contiguous samples")
         return self._step(noise_pred[:B], noise_pred[B:], float(guidance_scale), timestep, sample, return_dict, out,
                           out2)
+
+    def next_latent_dtype(self, model_dtype: torch.dtype, sample_dtype: torch.dtype) -> torch.dtype:
+        """dtype of the latent the next `step` returns — what torch promotion makes of the reference's arithmetic
+        (see the note in `_step`): fp32, except for an all-16-bit step whose estimate is still the raw model output."""
+        if model_dtype in (torch.float16, torch.bfloat16) and sample_dtype == model_dtype:
+            n_hist = len(self._hist[: self._history_depth(self.config.order_dim) - 1]) + 1
+            if n_hist == 1 and self.config.scaler_dim == 0:
+                return model_dtype
+        return torch.float32
 
     def _new_trajectory(self, B, shape, dtype, device) -> Trajectory:
         rows = [[float(t), float(t - self._stride)] for t in self._timesteps_host]      # (t, prev_t): scheduler_ppo.py:203-207
@@ -207,17 +215,6 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
         if not (e0.is_cuda and sample.is_cuda):
             raise RuntimeError("consolver_b200 has no CPU path: model_output and sample must be CUDA tensors")
-        # Mixed precision as torch promotion resolves it in the reference: fp32 latents with a 16-bit model output
-        # (accelerate autocast, train_ppo.py:353) keep the latents fp32 — the kernel reads/writes x as fp32 and the
-        # model outputs / history as 16-bit; a 16-bit latent with an fp32 model output is promoted to fp32 up front.
-        mixed = 0
-        if sample.dtype != e0.dtype:
-            if sample.dtype == torch.float32 and e0.dtype in (torch.float16, torch.bfloat16):
-                mixed = _lib.FLAG_X_F32
-            elif e0.dtype == torch.float32 and sample.dtype in (torch.float16, torch.bfloat16):
-                sample = sample.float()
-            else:
-                raise TypeError(f"sample ({sample.dtype}) and model_output ({e0.dtype}) cannot be combined")
         cfg = self.config
         fn = self.factor_net_module
         od = cfg.order_dim
@@ -234,6 +231,30 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         older = self._hist[: self._history_depth(od) - 1]
         n_hist = len(older) + 1
         fixed = self.fixed_coefficients is not None
+
+        # Latent dtype, resolved the way torch promotion resolves it in the reference (scheduler_ppo.py:263-280,
+        # :316-330).  With a 16-bit model output the combined estimate turns fp32 as soon as an fp32 per-sample
+        # coefficient or scaler multiplies it (every step but a scaler-free first one), and the latent with it: an
+        # fp16 pipeline (gen_ppo.py) gets fp32 latents back from its second step on, an autocast rollout
+        # (train_ppo.py:353: fp32 latents, 16-bit U-Net output) keeps fp32 throughout.  The kernel then reads / writes x
+        # as fp32 (CONSOLVER_FLAG_X_F32) with the model outputs and history still 16-bit.
+        mixed = 0
+        lowp = e0.dtype in (torch.float16, torch.bfloat16)
+        if sample.dtype != e0.dtype and not (lowp and sample.dtype == torch.float32) and not (
+                e0.dtype == torch.float32 and sample.dtype in (torch.float16, torch.bfloat16)):
+            raise TypeError(f"sample ({sample.dtype}) and model_output ({e0.dtype}) cannot be combined")
+        if lowp:
+            raw_estimate = n_hist == 1 and cfg.scaler_dim == 0
+            if sample.dtype != torch.float32 and not raw_estimate:
+                sample = sample.float()
+            if sample.dtype == torch.float32:
+                mixed = _lib.FLAG_X_F32
+        elif sample.dtype != torch.float32:
+            sample = sample.float()
+        for name, dst in (("out", out), ("out2", out2)):
+            if dst is not None and dst.dtype != sample.dtype:
+                raise ValueError(f"{name} is {dst.dtype} but this step returns a {sample.dtype} latent "
+                                 "(16-bit model outputs promote the latent to fp32 from the second step on)")
 
         # policy input row (t, prev_t) rounded through the model dtype (scheduler_ppo.py:207).  gi = position of t in
         # the grid (normally the step count; elsewhere when the caller starts mid-grid), None when t is off the grid

@@ -141,8 +141,17 @@ CONSOLVER_API int consolver_policy_f32(const float* w1, const float* b1, const f
  * Fused SD solver step: CFG combine (denoise_ppo.py:96-100) + linear-multistep combine over the history
  * (scheduler_ppo.py:263-280) + DDIM update (scheduler_ppo.py:306-332), one pass over HBM.
  *
- *   dtype            CONSOLVER_F32 / F16 / BF16: element type of every latent-sized buffer (math is fp32; for
- *                    F32 the result is bit-identical to the reference's op-by-op fp32 arithmetic)
+ *   dtype            CONSOLVER_F32 / F16 / BF16: element type of the model outputs, history and ring slot, and of
+ *                    x / x_out / x_out2 unless CONSOLVER_FLAG_X_F32 is set.  F32: bit-identical to the reference's
+ *                    op-by-op fp32 arithmetic.  16-bit: the arithmetic torch performs on those dtypes —
+ *                      CFG combine: a rounding to `dtype` after each op, guidance kept in fp32;
+ *                      n_hist == 1 without scaler flags (the estimate is the raw 16-bit output): every
+ *                        `scalar * tensor` product of scheduler_ppo.py:316-330 is a 16-bit product (scalar and
+ *                        product rounded), `tensor / scalar` keeps the fp32 scalar; with a 16-bit latent all
+ *                        intermediates are rounded too, with CONSOLVER_FLAG_X_F32 the rest is fp32;
+ *                      otherwise (n_hist > 1 or scalers): fp32 arithmetic on the upcast values — exactly torch's
+ *                        promotion when the latent is fp32 (X_F32); with a 16-bit latent (a layout the reference
+ *                        never produces there) the fp32 result is rounded once
  *   e0               newest model output [B,N]; if `cond` != NULL it is the UNCONDITIONAL half and
  *                    eps = e0 + guidance*(cond - e0) is formed in the kernel
  *   slot_out         NULL, or [B,N]: receives eps (the in-place history-ring slot of this step)

@@ -65,7 +65,10 @@ def _hook_probs(fn, store):
     fn.forward_ = wrapped
 
 
-def gen_sd(name, *, B, shape, n, guidance, seed, last_std=0.5, dtype=torch.float32, **cfg_over):
+def gen_sd(name, *, B, shape, n, guidance, seed, last_std=0.5, dtype=torch.float32, latent_dtype=None, **cfg_over):
+    """`dtype`: dtype of the denoiser output (and of the caller-side CFG combine); `latent_dtype`: dtype of the
+    initial latent (default = dtype).  16-bit `dtype` with fp32 latents is the autocast layout of train_ppo.py:353;
+    16-bit both is gen_ppo.py's fp16 pipeline, whose latents torch promotion turns fp32 after the second step."""
     ref = ref_shim.load_reference()
     cfg = dict(SD_PROD, **cfg_over)
     fkw = dict(embedding_dim=64, hidden_dim=cfg.pop("hidden_dim", 256), num_actions=cfg.pop("num_actions", 11))
@@ -76,7 +79,7 @@ def gen_sd(name, *, B, shape, n, guidance, seed, last_std=0.5, dtype=torch.float
     _hook_probs(s.factor_net, full)
     s.set_timesteps(n)
     g = torch.Generator().manual_seed(seed + 1)
-    x = torch.randn(B, *shape, generator=g).to(dtype)
+    x = torch.randn(B, *shape, generator=g).to(latent_dtype or dtype)
     bf, d = [], {}
     d["x_T"] = _np(x, bf, "x_T")
     for k, v in s.factor_net.state_dict().items():
@@ -107,11 +110,29 @@ def gen_sd(name, *, B, shape, n, guidance, seed, last_std=0.5, dtype=torch.float
         assert conds["epsilon"].shape == (B, cfg["order_dim"], *shape)
         assert torch.equal(conds["epsilon"][:, 0], eps)
     meta = dict(kind="sd", B=B, shape=list(shape), n=n, guidance=guidance, seed=seed, config=cfg,
-                factor_net_kwargs=fkw, dtype=str(dtype).split(".")[-1], torch=torch.__version__)
+                factor_net_kwargs=fkw, dtype=str(dtype).split(".")[-1],
+                latent_dtype=str(latent_dtype or dtype).split(".")[-1], torch=torch.__version__)
     d["__meta__"] = np.array(json.dumps(meta))
     d["__bf16__"] = np.array(json.dumps(bf))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
     print("wrote", name, "A=%d K=%d" % (A, K))
+
+
+def main_sd16():
+    """`python oracle/make_golden.py sd16`: 16-bit denoiser outputs (prefix sd16_ keeps them out of the fp32 sweeps)."""
+    small = (4, 8, 8)
+    f16, b16, f32 = torch.float16, torch.bfloat16, torch.float32
+    gen_sd("sd16_f16_pipeline_eps_s0_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=90, dtype=f16)
+    gen_sd("sd16_bf16_pipeline_v_s0_n6_B2", hidden_dim=64, B=2, shape=small, n=6, guidance=3.0, seed=91, dtype=b16,
+           prediction_type="v_prediction")
+    gen_sd("sd16_f16_autocast_eps_s0_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=92, dtype=f16,
+           latent_dtype=f32)                                                               # train_ppo.py:353
+    gen_sd("sd16_bf16_autocast_v_s0_n5_B2_ragged", hidden_dim=64, B=2, shape=(3, 5, 7), n=5, guidance=3.0, seed=93,
+           dtype=b16, latent_dtype=f32, prediction_type="v_prediction")
+    gen_sd("sd16_f16_pipeline_eps_s2_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=94, dtype=f16,
+           scaler_dim=2)
+    gen_sd("sd16_bf16_autocast_eps_s1_o3_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=95, dtype=b16,
+           latent_dtype=f32, scaler_dim=1, order_dim=3)
 
 
 def gen_fm(name, *, B, shape, n, seed, dtype, last_std=0.02, use_begin_index=True, **cfg_over):
@@ -292,6 +313,8 @@ def main():
         return main_fm_general()
     if sys.argv[1:] == ["amed"]:
         return main_amed()
+    if sys.argv[1:] == ["sd16"]:
+        return main_sd16()
     small = (4, 8, 8)
     # --- SD / PPOScheduler: production config at several step counts (warm-up depths, n=7 quirk) -------
     for n in (2, 5, 7, 8, 12):
@@ -337,6 +360,7 @@ def main():
     # --- baseline flow-matching solvers -------------------------------------------------
     main_fm_general()
     main_amed()
+    main_sd16()
 
 
 if __name__ == "__main__":

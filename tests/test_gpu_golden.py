@@ -134,3 +134,32 @@ def test_sd_default_generator_reproduces_torch_multinomial():
         torch.manual_seed(1234 + i)
         ref_idx = torch.multinomial(table.unsqueeze(0).expand(B, A, K).reshape(-1, K), num_samples=1).view(B, A)
         assert torch.equal(lp["idx"], ref_idx), f"step {i}"
+
+
+# ---- 16-bit denoiser outputs: gen_ppo.py's fp16 pipeline and train_ppo.py's autocast rollout -------------------------
+@pytest.mark.parametrize("mode", ["plain", "cfg_fused"])
+@pytest.mark.parametrize("name", names("sd16_"))
+def test_sd_16bit_model_outputs_reproduce_the_reference_bit_for_bit(name, mode):
+    """Fixtures made by the unmodified reference on 16-bit model outputs (fp16 / bf16; latents 16-bit or fp32).  What
+    the reference's torch ops do there is part of its behaviour: the estimate — and with it the returned latent — is
+    promoted to fp32 as soon as an fp32 coefficient or scaler multiplies it, and while the estimate is still the raw
+    16-bit output, `0-d scalar * tensor` products are 16-bit products.  Every latent and its dtype must match, both
+    through step() on the caller-combined estimate and through step_cfg() on the raw pair."""
+    g = Golden(name)
+    m = g.meta
+    s = _sd(g)
+    s.replay = {"q": {i: g[f"q_{i}"].cuda() for i in range(m["n"])}}
+    x = g["x_T"].cuda()
+    for i, t in enumerate(s.timesteps):
+        if mode == "plain":
+            out = s.step(g[f"eps_{i}"].cuda(), t, x, return_dict=False)
+        else:
+            out = s.step_cfg(g[f"pair_{i}"].cuda(), t, x, m["guidance"])
+        x = out[0]
+        ref = g[f"prev_{i}"]
+        assert x.dtype == ref.dtype, f"step {i}: latent dtype {x.dtype} vs reference {ref.dtype}"
+        assert torch.equal(x.cpu(), ref), f"step {i}: latent not bit-identical"
+        assert torch.equal(s.last_policy()["idx"].cpu(), g[f"idx_{i}"])
+        assert torch.equal(out[1].cpu(), g[f"actions_{i}"]) and torch.equal(out[4].cpu(), g[f"masks_{i}"])
+        assert torch.equal(out[3]["x"].cpu(), g[f"condx_{i}"])
+        torch.testing.assert_close(out[2].cpu(), g[f"probs_{i}"], rtol=0, atol=PROB_ATOL)

@@ -135,8 +135,10 @@ def test_step_sd_unaligned_pointers_use_scalar_path():
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("n_hist", [1, 4])
 def test_step_sd_16bit_io(dtype, n_hist):
-    """16-bit I/O: fp32 math on the upcast inputs, one rounding at the end (the reference's fp16 pipeline rounds
-    after every op; bit parity with that arithmetic is not a goal — SURVEY §7)."""
+    """All-16-bit I/O at the C ABI.  The CFG combine rounds after every op like the caller's torch expression on
+    16-bit tensors.  n_hist == 1 (the estimate is the raw 16-bit output): torch's own 16-bit evaluation of
+    scheduler_ppo.py:316-330, bit for bit.  n_hist > 1 with a 16-bit latent is a layout the schedulers never request
+    (torch promotion makes the latent fp32 there, see CONSOLVER_FLAG_X_F32): fp32 math, one rounding."""
     B, shape, od = 3, (4, 16, 16), 4
     g = torch.Generator().manual_seed(7)
     rn = lambda: torch.randn(B, *shape, generator=g).to(dtype)  # noqa: E731
@@ -144,8 +146,13 @@ def test_step_sd_16bit_io(dtype, n_hist):
     hist = [rn() for _ in range(n_hist - 1)]
     c = _rand_coef(B, od, g, 0)
     scalars = (0.8378, 0.5460, 0.9151, 0.4033)
-    eps = orc.cfg_combine(e0.float(), cond.float(), 3.0).to(dtype)
-    ref, _ = _oracle_sd(eps.float(), None, 0.0, [h.float() for h in hist], x.float(), c, od, scalars, False, 0)
+    eps = orc.cfg_combine(e0, cond, 3.0)                      # torch's 16-bit evaluation: a rounding per op
+    assert eps.dtype == dtype
+    if n_hist == 1:
+        ref, _ = _oracle_sd(eps, None, 0.0, [], x, c, od, scalars, False, 0)        # 16-bit tensors, 0-d fp32 scalars
+        assert ref.dtype == dtype
+    else:
+        ref, _ = _oracle_sd(eps.float(), None, 0.0, [h.float() for h in hist], x.float(), c, od, scalars, False, 0)
     out, slot = ah.step_sd(e0.cuda(), cond.cuda(), 3.0, [h.cuda() for h in hist], x.cuda(), c.cuda(), od, scalars, 0,
                            slot=True)
     assert torch.equal(slot.cpu(), eps)
@@ -353,9 +360,10 @@ def test_in_kernel_exponential_draw_is_torchs(B, A, K):
 @pytest.mark.parametrize("pair,vpred,sdim", [(False, False, 0), (True, False, 0), (False, True, 2)])
 def test_step_sd_fp32_latents_with_16bit_model_outputs(dtype, n_hist, pair, vpred, sdim):
     """CONSOLVER_FLAG_X_F32 — the mixed-precision layout of the reference's training loop (train_ppo.py:353):
-    16-bit model outputs / history, fp32 latent in and out.  fp32 arithmetic on the upcast values, so from the second
-    step on (n_hist >= 2, where torch promotion makes the reference's arithmetic fp32 too) the result is the
-    oracle's bit for bit; ragged size included."""
+    16-bit model outputs / history, fp32 latent in and out.  From the second step on torch promotion makes the
+    reference's arithmetic fp32 on the upcast values; at the first step (no scalers) the two products with the raw
+    16-bit output are 16-bit products.  Either way: the oracle's torch expressions on these dtypes, bit for bit;
+    ragged size included."""
     B, shape, od = 3, (4, 9, 7), 4
     g = torch.Generator().manual_seed(17)
     r16 = lambda: torch.randn(B, *shape, generator=g).to(dtype)  # noqa: E731
@@ -364,8 +372,10 @@ def test_step_sd_fp32_latents_with_16bit_model_outputs(dtype, n_hist, pair, vpre
     x = torch.randn(B, *shape, generator=g)
     c = _rand_coef(B, od, g, sdim)
     scalars = (0.8378, 0.5460, 0.9151, 0.4033)
-    eps = orc.cfg_combine(e0.float(), cond.float(), 3.0).to(dtype) if pair else e0
-    ref, _ = _oracle_sd(eps.float(), None, 0.0, [h.float() for h in hist], x, c, od, scalars, vpred, sdim)
+    eps = orc.cfg_combine(e0, cond, 3.0) if pair else e0      # the caller's 16-bit combine (a rounding per op)
+    # the reference's torch expressions on exactly these dtypes: 16-bit estimate / history, fp32 latent and coefficients
+    ref, _ = _oracle_sd(eps, None, 0.0, hist, x, c, od, scalars, vpred, sdim)
+    assert ref.dtype == torch.float32
     flags = (1 if vpred else 0) | (2 if sdim >= 1 else 0) | (4 if sdim >= 2 else 0)
     out, slot = ah.step_sd(e0.cuda(), cond.cuda() if pair else None, 3.0, [h.cuda() for h in hist], x.cuda(), c.cuda(),
                            od, scalars, flags, slot=pair)

@@ -119,3 +119,22 @@ def test_action_value_tables_match_reference_buffers():
         tab = orc.action_value_table(g.meta["kind"], f["num_actions"], c["order_dim"], c["scaler_dim"],
                                      c.get("mu_dim", 0))
         assert torch.equal(tab, g.state_dict["action_values"]), name
+
+
+@pytest.mark.parametrize("name", names("sd16_"))
+def test_sd_oracle_matches_reference_on_16bit_model_outputs(name):
+    """fp16 / bf16 denoiser outputs with 16-bit or fp32 latents: the oracle is the reference's torch ops, so it must
+    follow torch's promotion (latent dtype trajectory) and 16-bit scalar-product roundings exactly."""
+    g = Golden(name)
+    m = g.meta
+    s = orc.OracleSDScheduler(g.state_dict, **m["config"])
+    s.set_timesteps(m["n"])
+    x = g["x_T"]
+    for i, t in enumerate(s.timesteps):
+        u, c = g[f"pair_{i}"].chunk(2)
+        eps = orc.cfg_combine(u, c, m["guidance"])
+        assert torch.equal(eps, g[f"eps_{i}"])
+        x, actions, probs, conds, masks = s.step(eps, t, x, q=g[f"q_{i}"])
+        assert torch.equal(s.last_idx, g[f"idx_{i}"]) and torch.equal(actions, g[f"actions_{i}"])
+        assert torch.equal(conds["x"], g[f"condx_{i}"])
+        assert x.dtype == g[f"prev_{i}"].dtype and torch.equal(x, g[f"prev_{i}"]), f"step {i}"
