@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libconsolver.so")
 
 F32, F16, BF16 = 0, 1, 2
 DPM_CONVERT_NONE, DPM_CONVERT_DIV, DPM_CONVERT_LIN = 0, 1, 2
-FLAG_VPRED, FLAG_EFF_SCALE, FLAG_X_SCALE, FLAG_PDL, FLAG_CHAIN, FLAG_LOWP_COMBINE, FLAG_X_F32 = 1, 2, 4, 8, 16, 32, 64
+FLAG_VPRED, FLAG_EFF_SCALE, FLAG_X_SCALE, FLAG_PDL, FLAG_CHAIN, FLAG_LOWP_COMBINE, FLAG_X_F32, FLAG_X_WAS_LOWP = 1, 2, 4, 8, 16, 32, 64, 128
 MAX_ORDER, MAX_HIDDEN, MAX_LOGITS, MAX_IN = 8, 1024, 4096, 16
 
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64

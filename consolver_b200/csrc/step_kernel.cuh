@@ -140,7 +140,14 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
           out = __fadd_rn(__fmul_rn(p.k2, x0), round_to<T>(__fmul_rn(round_to<T>(p.k3), e)));
         }
       } else if (MODE == kModeSD) {
-        if (vpred) eff = __fadd_rn(__fmul_rn(p.k0, eff), __fmul_rn(p.k1, xs));          // :316-317
+        if (vpred) {                                                                     // :316-317
+          // X_WAS_LOWP: the sample is still a 16-bit tensor in the reference at this step, so its product with the
+          // 0-d scalar is a 16-bit product; everything else has been promoted to fp32 by the coefficients
+          const float sx = (Elem<T>::k16 && (p.flags & CONSOLVER_FLAG_X_WAS_LOWP) && !x_scale)
+                               ? round_to<T>(__fmul_rn(round_to<T>(p.k1), xs))
+                               : __fmul_rn(p.k1, xs);
+          eff = __fadd_rn(__fmul_rn(p.k0, eff), sx);
+        }
         const float x0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.k1, eff)), p.k0);          // :323
         out = __fadd_rn(__fmul_rn(p.k2, x0), __fmul_rn(p.k3, eff));                     // :329-330
       } else {

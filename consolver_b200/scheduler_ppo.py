@@ -246,9 +246,10 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         if lowp:
             raw_estimate = n_hist == 1 and cfg.scaler_dim == 0
             if sample.dtype != torch.float32 and not raw_estimate:
-                sample = sample.float()
+                sample = sample.float()                   # exact; the reference's sample is still 16-bit at this step,
+                mixed = _lib.FLAG_X_WAS_LOWP              # which only v-prediction's scalar*sample product can see
             if sample.dtype == torch.float32:
-                mixed = _lib.FLAG_X_F32
+                mixed |= _lib.FLAG_X_F32
         elif sample.dtype != torch.float32:
             sample = sample.float()
         for name, dst in (("out", out), ("out2", out2)):

@@ -69,6 +69,12 @@ extern "C" {
                                            keeps every later product and the returned latent in fp32
                                            (scheduler_ppo.py:272,:323-330).  Ignored when dtype is CONSOLVER_F32    */
 
+#define CONSOLVER_FLAG_X_WAS_LOWP  128   /* with CONSOLVER_FLAG_X_F32: the fp32 latent handed in is an exact upcast of a
+                                           `dtype` latent (the step at which torch promotion turns a 16-bit pipeline's
+                                           latent fp32).  The one place the reference multiplies the still-16-bit
+                                           sample by a scalar — v-prediction's sqrt(1-abar_t)*sample,
+                                           scheduler_ppo.py:317 — is then a 16-bit product; ignored with X_SCALE     */
+
 #define CONSOLVER_ERR_NULL        (-1)
 #define CONSOLVER_ERR_SIZE        (-2)
 #define CONSOLVER_ERR_UNSUPPORTED (-3)

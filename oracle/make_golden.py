@@ -131,6 +131,8 @@ def main_sd16():
            dtype=b16, latent_dtype=f32, prediction_type="v_prediction")
     gen_sd("sd16_f16_pipeline_eps_s2_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=94, dtype=f16,
            scaler_dim=2)
+    gen_sd("sd16_f16_pipeline_v_s1_n4_B2", hidden_dim=64, B=2, shape=small, n=4, guidance=3.0, seed=96, dtype=f16,
+           scaler_dim=1, prediction_type="v_prediction")
     gen_sd("sd16_bf16_autocast_eps_s1_o3_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=95, dtype=b16,
            latent_dtype=f32, scaler_dim=1, order_dim=3)
 
