@@ -201,9 +201,18 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         (see the note in `_step`): fp32, except for an all-16-bit step whose estimate is still the raw model output."""
         if model_dtype in (torch.float16, torch.bfloat16) and sample_dtype == model_dtype:
             n_hist = len(self._hist[: self._history_depth(self.config.order_dim) - 1]) + 1
-            if n_hist == 1 and self.config.scaler_dim == 0:
+            if self._estimate_stays_lowp(model_dtype, n_hist):
                 return model_dtype
         return torch.float32
+
+    def _estimate_stays_lowp(self, model_dtype: torch.dtype, n_hist: int) -> bool:
+        """Does the combined estimate keep the 16-bit model dtype at this step?  In the reference the per-sample
+        coefficients and scalers are gathered from the policy's `action_values` buffer (factor_net_ppo.py:163) and
+        carry ITS dtype: an fp32 policy promotes the estimate at every step that multiplies by one (all but a
+        scaler-free first step), a policy cast to the pipeline's own 16-bit dtype (gen_ppo.py:193-195) never does."""
+        if self.factor_net_module.action_values.dtype == model_dtype:
+            return True
+        return n_hist == 1 and self.config.scaler_dim == 0
 
     def _new_trajectory(self, B, shape, dtype, device) -> Trajectory:
         rows = [[float(t), float(t - self._stride)] for t in self._timesteps_host]      # (t, prev_t): scheduler_ppo.py:203-207
@@ -244,7 +253,7 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
                 e0.dtype == torch.float32 and sample.dtype in (torch.float16, torch.bfloat16)):
             raise TypeError(f"sample ({sample.dtype}) and model_output ({e0.dtype}) cannot be combined")
         if lowp:
-            raw_estimate = n_hist == 1 and cfg.scaler_dim == 0
+            raw_estimate = self._estimate_stays_lowp(e0.dtype, n_hist)
             if sample.dtype != torch.float32 and not raw_estimate:
                 sample = sample.float()                   # exact; the reference's sample is still 16-bit at this step,
                 mixed = _lib.FLAG_X_WAS_LOWP              # which only v-prediction's scalar*sample product can see

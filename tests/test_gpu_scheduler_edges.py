@@ -183,3 +183,27 @@ def test_denoise_loop_with_a_16bit_denoiser_output_ends_with_fp32_latents(noise_
     for i, t in enumerate(s.timesteps):
         x = s.step_cfg(den(torch.cat([x] * 2), t, i), t, x, 3.0)[0]
     assert torch.equal(x, lat)
+
+
+def test_policy_cast_to_the_pipeline_dtype_keeps_16bit_latents():
+    """gen_ppo.py:193-195 casts the policy, bin buffer included, to the pipeline's fp16: the reference's coefficients are
+    then fp16 tensors, nothing promotes, and the latents stay fp16 at every step (each torch op rounding to fp16).
+    The scheduler follows the dtype trajectory; its arithmetic is fp32 with one rounding per step, so values are
+    compared step by step within fp16 resolution against the reference's per-op fp16 evaluation."""
+    g, m, s, _ = _pair()
+    s.factor_net.to("cuda", dtype=torch.float16)
+    mixed_sd = dict(g.state_dict, action_values=g.state_dict["action_values"].half())     # fp16 bins => fp16 coefficients
+    o = orc.OracleSDScheduler(mixed_sd, **m["config"])
+    s.set_timesteps(m["n"], device="cuda")
+    o.set_timesteps(m["n"])
+    s.replay = {"idx": [g[f"idx_{i}"] for i in range(m["n"])]}
+    x = g["x_T"].half()
+    for i, t in enumerate(o.timesteps):
+        eps = g[f"eps_{i}"].half()
+        assert s.next_latent_dtype(eps.dtype, x.dtype) == torch.float16
+        out = s.step(eps.cuda(), s.timesteps[i], x.cuda(), return_dict=False)[0]
+        ref = o.step(eps, t, x, forced_idx=g[f"idx_{i}"])[0]
+        assert out.dtype == ref.dtype == torch.float16, f"step {i}"
+        err = (out.float().cpu() - ref.float()).abs().max() / ref.float().abs().max()
+        assert err < 8 * 2.0 ** -10, f"step {i}: {err}"
+        x = out.cpu()
