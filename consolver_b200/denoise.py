@@ -54,6 +54,49 @@ def denoise_loop(scheduler: PPOScheduler, denoiser: Callable[[torch.Tensor, torc
     return latents, (scheduler.trajectory() if record and num_inference_steps > 1 else None)
 
 
+def denoise_loop_flow(scheduler, denoiser: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor],
+                      initial_latents: torch.Tensor, image_latents: Optional[torch.Tensor] = None,
+                      num_inference_steps: int = 8, sigmas=None, mu: Optional[float] = None,
+                      record: bool = True) -> Tuple[torch.Tensor, Optional[Dict[str, torch.Tensor]]]:
+    """Flow-matching sampling loop of the editing model (edit_ppo/denoise_diffusion.py:84-160): packed latents
+    `[B, L, D]`, optionally followed along the sequence axis by the reference-image latents `[B, Li, D]`.
+
+    `denoiser(latent_model_input [B, L(+Li), D], t, i)` returns the velocity for the whole sequence (or for the first L
+    tokens); only the first L tokens are used (:140).  The step kernel writes the next latent straight into the head of
+    the next `[B, L+Li, D]` transformer input (`out2`, strided by L+Li), whose image-latent tail was filled once, so the
+    per-step `torch.cat([latents, image_latents], dim=1)` (:100 — read and write L+Li tokens) never runs.  Works with
+    FMPPOScheduler (returns the rollout record: x [B,n-1,2], probs / actions / masks [B,n-1,A]) and with
+    FlowMatchGeneralDiscreteScheduler (`use_naive_scheduler` in the reference; record is None)."""
+    dev = initial_latents.device
+    kw = {}
+    if sigmas is not None:
+        kw["sigmas"] = sigmas
+    if mu is not None:
+        kw["mu"] = mu
+    scheduler.set_timesteps(num_inference_steps, device=dev, **kw)
+    scheduler.set_begin_index(0)                      # edit_ppo/pipeline.py:1072; avoids the timestep search read-back
+    B, L = initial_latents.shape[:2]
+    learned = hasattr(scheduler, "factor_net")
+    latents = initial_latents
+    if image_latents is None:
+        for i, t in enumerate(scheduler.timesteps):
+            pred = denoiser(latents, t, i)
+            latents = scheduler.step(pred, t, latents, return_dict=False)[0]
+    else:
+        Li = image_latents.shape[1]
+        wide = [initial_latents.new_empty((B, L + Li, *initial_latents.shape[2:])) for _ in range(2)]
+        for w in wide:
+            w[:, L:].copy_(image_latents)
+        wide[0][:, :L].copy_(initial_latents)
+        for i, t in enumerate(scheduler.timesteps):
+            pred = denoiser(wide[i % 2], t, i)
+            if pred.shape[1] != L:
+                pred = pred[:, :L]
+            latents = scheduler.step(pred, t, latents, return_dict=False, out2=wide[(i + 1) % 2][:, :L])[0]
+    rec = scheduler.trajectory() if (record and learned and num_inference_steps > 1) else None
+    return latents, rec
+
+
 def preview_from_pairs(scheduler: PPOScheduler, x_T: torch.Tensor, pairs: Sequence[torch.Tensor], guidance: float,
                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Solver-only preview: the denoiser is replaced by given per-step CFG pairs ([2B,...] each) — BASELINE

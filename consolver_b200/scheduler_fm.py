@@ -102,6 +102,8 @@ class FlowMatchGeneralDiscreteScheduler(FlowSigmaSchedule, SchedulerMixin, Confi
         sample = sample if sample.is_contiguous() else sample.contiguous()
         if sample.dtype not in (e0.dtype, torch.float32):
             sample = sample.float()                                       # :399
+        if out2 is not None and (out2.dtype != e0.dtype or out2.shape != e0.shape or not out2[0].is_contiguous()):
+            raise ValueError("out2 must have the model output's dtype and shape, with contiguous samples")
         i, sg, f32 = self._step_index, self._sigmas_host, np.float32
 
         def sigma(j, clamp):

@@ -117,6 +117,9 @@ class FMPPOScheduler(FlowSigmaSchedule, SolverOptions, SchedulerMixin, ConfigMix
         sample = sample if sample.is_contiguous() else sample.contiguous()
         if sample.dtype != e0.dtype:
             sample = sample.float()                     # the reference upcasts the sample anyway (:354)
+        if out2 is not None and (out2.dtype != e0.dtype or out2.shape != e0.shape or not out2[0].is_contiguous()):
+            raise ValueError("out2 must have the model output's dtype and shape, with contiguous samples "
+                             "(the next latent is returned in the model dtype, :436)")
         B = sample.shape[0]
         N = sample.numel() // B
         tr = self._traj

@@ -207,3 +207,52 @@ def test_policy_cast_to_the_pipeline_dtype_keeps_16bit_latents():
         err = (out.float().cpu() - ref.float()).abs().max() / ref.float().abs().max()
         assert err < 8 * 2.0 ** -10, f"step {i}: {err}"
         x = out.cpu()
+
+
+@pytest.mark.parametrize("kind", ["learned", "heun"])
+def test_flow_denoise_loop_writes_into_the_packed_transformer_input(kind):
+    """edit_ppo/denoise_diffusion.py:84-160 with reference-image latents appended along the sequence axis: the ready-made
+    loop (no per-step torch.cat) against the reference's loop spelled out with torch.cat and noise_pred[:, :L]."""
+    import numpy as np
+    import consolver_b200 as cb
+    from consolver_b200.denoise import denoise_loop_flow
+    B, L, Li, D, n = 2, 64, 32, 16, 6
+    kw = dict(shift=3.0, use_dynamic_shifting=True)
+    if kind == "learned":
+        s = cb.FMPPOScheduler(order_dim=2, scaler_dim=0, mu_dim=0, factor_net_kwargs=dict(hidden_dim=32, num_actions=11),
+                              **kw)
+        with torch.no_grad():
+            s.factor_net.mlp[4].weight.normal_(0, 0.02)
+        s.factor_net.cuda()
+    else:
+        s = cb.FlowMatchGeneralDiscreteScheduler(type="heun", **kw)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x0 = torch.randn(B, L, D, device="cuda", generator=gen).bfloat16()
+    img = torch.randn(B, Li, D, device="cuda", generator=gen).bfloat16()
+    w = (torch.randn(D, D, device="cuda", generator=gen) * 0.2).bfloat16()
+    seen = []
+
+    def den(inp, t, i):
+        assert inp.shape == (B, L + Li, D)
+        seen.append(inp.clone())
+        return (inp @ w) * (1.0 + 0.01 * i)
+
+    sig = np.linspace(1.0, 1 / n, n)
+    torch.manual_seed(5)
+    lat, rec = denoise_loop_flow(s, den, x0, img, num_inference_steps=n, sigmas=sig, mu=1.15)
+    assert lat.dtype == torch.bfloat16 and all(torch.equal(v[:, L:], img) for v in seen)
+    if kind == "learned":
+        assert rec["actions"].shape == (B, n - 1, 1) and rec["x"].shape == (B, n - 1, 2)
+        idx = s._traj.out["idx"][:n].clone()
+        s.replay = {"idx": [idx[i] for i in range(n)]}
+    else:
+        assert rec is None
+    # the reference's loop, spelled out
+    s.set_timesteps(n, device="cuda", sigmas=sig, mu=1.15)
+    s.set_begin_index(0)
+    x = x0
+    for i, t in enumerate(s.timesteps):
+        inp = torch.cat([x, img], dim=1)
+        assert torch.equal(inp, seen[i]), f"step {i}: transformer input differs"
+        x = s.step(den(inp, t, i)[:, :L], t, x, return_dict=False)[0]
+    assert torch.equal(x, lat)
