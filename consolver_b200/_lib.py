@@ -25,6 +25,7 @@ SIGNATURES = {
     "consolver_policy_f32": (_i, [_p] * 7 + [_f] * 4 + [_p, _i] + [_p, _p] + [_i] * 7 + [_p] * 7 + [_p]),
     "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
+    "consolver_step_fm_strided": (_i, [_i, _i, _p, _i64, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
     "consolver_step_dpm": (_i, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _i64, _p]),
     "consolver_policy_table_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i, _p, _p]),
     "consolver_policy_sample_f32": (_i, [_p] * 4 + [_p, _p] + [_i] * 6 + [_p] * 6 + [_p]),

@@ -208,3 +208,19 @@ class SolverOptions:
         if self._traj is None:
             raise ValueError("no trajectory recorded; call step() first")
         return self._traj.record(skip_first)
+
+
+def strided_model_outputs(e0: torch.Tensor, older: List[torch.Tensor]):
+    """Model outputs for `consolver_step_fm_strided` -> (e0, older, e_stride).  When the newest output and the history
+    are all views with contiguous samples and ONE common sample stride (the `noise_pred[:, :L]` slices of a wider
+    transformer output, edit_ppo/denoise_diffusion.py:140) they are consumed in place (e_stride = that stride);
+    contiguous tensors give e_stride 0; any other mix is made contiguous (one copy each)."""
+    every = [e0] + list(older)
+    if all(t.is_contiguous() for t in every):
+        return e0, older, 0
+    n = e0[0].numel()
+    stride = e0.stride(0)
+    if stride % 8 == 0 and stride >= n and all(
+            t.dim() > 1 and t[0].is_contiguous() and t.stride(0) == stride and t.shape == e0.shape for t in every):
+        return e0, older, stride
+    return e0.contiguous(), [h.contiguous() for h in older], 0

@@ -34,6 +34,7 @@ struct StepParams {
   int flags;
   float guidance;
   float k0, k1, k2, k3;  // SD: sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev), sqrt(1-abar_prev); FM: k0 = dt
+  long long e_stride;       // FM: elements between consecutive samples of e0 / hist (>= n_per_sample)
   long long n_per_sample;   // elements
   long long nvec_per_sample;  // thread-vectors per sample (n_per_sample / ELEMS)
   int chunks_per_sample;

@@ -30,6 +30,9 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
   const long long v0 = (long long)chunk * ((long long)blockDim.x * U) + threadIdx.x;
   const int nh = NH ? NH : p.n_hist;
   const bool pair = p.cond != nullptr;
+  // FM only: model outputs (e0 and the history) may be sample-strided views, e.g. the first L tokens of a wider packed
+  // transformer output (edit_ppo/denoise_diffusion.py:140); the SD instantiations keep one offset for every stream
+  const long long edelta = (MODE == kModeFM) ? (long long)b * (p.e_stride - p.n_per_sample) : 0;
 
   Raw<T, E> r_e0[U], r_c[U];
   Raw<T, E> r_h[U][kOlder > 0 ? kOlder : 1];
@@ -48,12 +51,12 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
     live[u] = v < p.nvec_per_sample;
     off[u] = base + v * E;
     if (live[u]) {
-      r_e0[u].load(static_cast<const T*>(p.e0) + off[u]);
+      r_e0[u].load(static_cast<const T*>(p.e0) + off[u] + edelta);
       if (pair) r_c[u].load(static_cast<const T*>(p.cond) + off[u]);
       if (!chain) r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
 #pragma unroll
       for (int j = 0; j < kOlder; ++j)
-        if ((NH || j < nh - 1) && !(chain && j == 0)) r_h[u][j].load(static_cast<const T*>(p.hist[j]) + off[u]);
+        if ((NH || j < nh - 1) && !(chain && j == 0)) r_h[u][j].load(static_cast<const T*>(p.hist[j]) + off[u] + edelta);
     }
   }
 
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
     for (int u = 0; u < U; ++u) {
       if (live[u]) {
         r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
-        if (kOlder > 0 && (NH || 0 < nh - 1)) r_h[u][0].load(static_cast<const T*>(p.hist[0]) + off[u]);
+        if (kOlder > 0 && (NH || 0 < nh - 1)) r_h[u][0].load(static_cast<const T*>(p.hist[0]) + off[u] + edelta);
       }
     }
   }
@@ -251,6 +254,7 @@ inline int fill_common(StepParams& p, const void* e0, const void* cond, void* sl
   }
   p.coef = coef; p.coef_stride = coef_stride; p.order_dim = order_dim; p.n_hist = n_hist; p.flags = flags;
   p.n_per_sample = n_per_sample; p.B = B;
+  p.e_stride = n_per_sample;
   return 0;
 }
 

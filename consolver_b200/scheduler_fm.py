@@ -29,6 +29,7 @@ import torch
 
 from . import _lib
 from ._fm_schedule import FlowSigmaSchedule
+from ._sched_common import strided_model_outputs
 from .config_utils import BaseOutput, ConfigMixin, SchedulerMixin, register_to_config
 
 SOLVER_TYPES = ("euler", "heun", "dpm-solver", "dpm-solver-multistep")
@@ -98,7 +99,7 @@ class FlowMatchGeneralDiscreteScheduler(FlowSigmaSchedule, SchedulerMixin, Confi
             raise ValueError(f"unknown solver type {self.type!r}; expected one of {SOLVER_TYPES}")
         if self._step_index is None:
             self._init_step_index(timestep)
-        e0 = model_output if model_output.is_contiguous() else model_output.contiguous()
+        e0 = model_output             # may be a sample-strided view (noise_pred[:, :L]); resolved before the launch
         sample = sample if sample.is_contiguous() else sample.contiguous()
         if sample.dtype not in (e0.dtype, torch.float32):
             sample = sample.float()                                       # :399
@@ -146,16 +147,17 @@ class FlowMatchGeneralDiscreteScheduler(FlowSigmaSchedule, SchedulerMixin, Confi
         if older and older[0].dtype != e0.dtype:
             raise ValueError("model outputs of the two stages must have one dtype")
 
+        e0, older, e_stride = strided_model_outputs(e0, older)
         B = e0.shape[0]
         N = e0.numel() // B
         x_out = torch.empty(e0.shape, device=e0.device, dtype=e0.dtype)    # :485: result in the model dtype
         stream = torch._C._cuda_getCurrentRawStream(e0.device.index)
-        rc = _lib.load().consolver_step_fm(
-            _lib.dtype_code(e0.dtype), _lib.dtype_code(base.dtype), e0.data_ptr(), None,
+        rc = _lib.load().consolver_step_fm_strided(
+            _lib.dtype_code(e0.dtype), _lib.dtype_code(base.dtype), e0.data_ptr(), e_stride, None,
             _lib.ptr_array([h.data_ptr() for h in older]), len(older) + 1, base.data_ptr(), x_out.data_ptr(),
             out2.data_ptr() if out2 is not None else None, out2.stride(0) if out2 is not None else 0,
             self._unit_coefficients(B, e0.device).data_ptr(), _ORDER_DIM + 2, _ORDER_DIM, float(dt), flags, B, N, stream)
-        _lib.check(rc, "consolver_step_fm")
+        _lib.check(rc, "consolver_step_fm_strided")
         self._step_index += 1
         if not return_dict:
             return (x_out,)

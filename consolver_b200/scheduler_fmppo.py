@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._fm_schedule import FlowSigmaSchedule
-from ._sched_common import SolverOptions, Trajectory, draw_source, lazy_conds
+from ._sched_common import SolverOptions, Trajectory, draw_source, lazy_conds, strided_model_outputs
 from .config_utils import BaseOutput, ConfigMixin, SchedulerMixin, register_to_config
 from .factor_net import FactorNetPPOFM
 
@@ -113,7 +113,7 @@ class FMPPOScheduler(FlowSigmaSchedule, SolverOptions, SchedulerMixin, ConfigMix
         cfg = self.config
         fn = self.factor_net_module
         od = cfg.order_dim
-        e0 = model_output if model_output.is_contiguous() else model_output.contiguous()
+        e0 = model_output                               # may be a sample-strided view: see strided_model_outputs below
         sample = sample if sample.is_contiguous() else sample.contiguous()
         if sample.dtype != e0.dtype:
             sample = sample.float()                     # the reference upcasts the sample anyway (:354)
@@ -132,6 +132,10 @@ class FMPPOScheduler(FlowSigmaSchedule, SolverOptions, SchedulerMixin, ConfigMix
             raise IndexError("FMPPOScheduler.step called past the end of the sigma schedule")
         i = tr.count % tr.n
         older = self._hist[: self._history_depth(od) - 1]
+        if fn.use_conv and self.fixed_coefficients is None:      # the feature reduction reads contiguous tensors
+            e0, e_stride = (e0 if e0.is_contiguous() else e0.contiguous()), 0
+        else:
+            e0, older, e_stride = strided_model_outputs(e0, older)
         n_hist = len(older) + 1
         fixed = self.fixed_coefficients is not None
         dt = float(np.float32(self._sigmas_host[si + 1]) - np.float32(self._sigmas_host[si]))   # :373-376
@@ -182,12 +186,12 @@ class FMPPOScheduler(FlowSigmaSchedule, SolverOptions, SchedulerMixin, ConfigMix
                 flags |= _lib.FLAG_CHAIN if self.chain_steps else 0   # previous node on this stream is a step kernel
             elif self.use_pdl:
                 flags |= _lib.FLAG_PDL
-        rc = lib.consolver_step_fm(
-            _lib.dtype_code(e0.dtype), _lib.dtype_code(sample.dtype), e0.data_ptr(), None,
+        rc = lib.consolver_step_fm_strided(
+            _lib.dtype_code(e0.dtype), _lib.dtype_code(sample.dtype), e0.data_ptr(), e_stride, None,
             _lib.ptr_array([h.data_ptr() for h in older]), n_hist, sample.data_ptr(), x_out.data_ptr(),
             out2.data_ptr() if out2 is not None else None, out2.stride(0) if out2 is not None else 0,
             coef_ptr, od + 2, od, dt, flags, B, N, stream)
-        _lib.check(rc, "consolver_step_fm")
+        _lib.check(rc, "consolver_step_fm_strided")
 
         self._hist = [e0] + older
         self._step_index += 1

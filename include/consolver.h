@@ -195,6 +195,18 @@ CONSOLVER_API int consolver_step_fm(int dtype, int x_dtype, const void* e0, void
                       int B, int64_t n_per_sample, consolver_stream_t stream);
 
 /*
+ * consolver_step_fm with sample-strided model outputs: e0 and every hist entry are views with `e_stride` elements
+ * between consecutive samples (each sample contiguous; e_stride >= n_per_sample, a multiple of 8 for the vector path;
+ * 0 = n_per_sample).  This is `noise_pred[:, :L]` of a transformer output that covers [latents | image latents]
+ * (edit_ppo/denoise_diffusion.py:140): the slice is consumed in place instead of being copied out first.
+ */
+CONSOLVER_API int consolver_step_fm_strided(int dtype, int x_dtype, const void* e0, int64_t e_stride, void* slot_out,
+                      const void* const* hist, int n_hist, const void* x, void* x_out,
+                      void* x_out2, int64_t out2_stride,
+                      const float* coef, int coef_stride, int order_dim, float dt, int flags,
+                      int B, int64_t n_per_sample, consolver_stream_t stream);
+
+/*
  * Fused multistep DPM-Solver / DPM-Solver++ step with AMED direction scaling — replaces, per step,
  * the caller's CFG combine (gen_pretrain/pipeline.py:1069-1071), diffusers' convert_model_output (diffusers 0.26.3
  * DPMSolverMultistepScheduler; not part of the reference tree) and the plugin's first/second-order updates

@@ -383,3 +383,33 @@ def test_step_sd_fp32_latents_with_16bit_model_outputs(dtype, n_hist, pair, vpre
     assert torch.equal(out.cpu(), ref)
     if pair:
         assert slot.dtype == dtype and torch.equal(slot.cpu(), eps)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_step_fm_strided_model_outputs_equal_contiguous(dtype):
+    """consolver_step_fm_strided: e0 and the history as `[:, :L]` views of wider tensors (sample stride (L+Li)*D) give
+    exactly what contiguous copies give; a stride that is not a multiple of 8 elements takes the scalar path."""
+    from consolver_b200 import _lib
+    lib = _lib.load()
+    B, L, Li, D, od = 3, 64, 32, 8, 2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for extra in (Li, 3):                                     # (L+3)*D = 536 elements: not a multiple of 8*... still %8==0
+        wide_v = torch.randn(B, L + extra, D, device="cuda", generator=g).to(dtype)
+        wide_h = torch.randn(B, L + extra, D, device="cuda", generator=g).to(dtype)
+        x = torch.randn(B, L, D, device="cuda", generator=g).to(dtype)
+        coef = torch.tensor([[1.3, -0.3, 1.0, 1.0]], device="cuda").repeat(B, 1).contiguous()
+        v, h = wide_v[:, :L], wide_h[:, :L]
+        assert not v.is_contiguous()
+        ref = ah.step_fm(v.contiguous(), [h.contiguous()], x, coef, od, -0.0433)
+        out = torch.empty_like(x)
+        rc = lib.consolver_step_fm_strided(
+            _lib.dtype_code(dtype), _lib.dtype_code(dtype), v.data_ptr(), v.stride(0), None,
+            _lib.ptr_array([h.data_ptr()]), 2, x.data_ptr(), out.data_ptr(), None, 0, coef.data_ptr(), od + 2, od,
+            -0.0433, 0, B, L * D, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "consolver_step_fm_strided")
+        assert torch.equal(out, ref)
+    # a stride smaller than one sample is rejected
+    rc = lib.consolver_step_fm_strided(_lib.dtype_code(dtype), _lib.dtype_code(dtype), v.data_ptr(), L * D - 8, None,
+                                       _lib.ptr_array([h.data_ptr()]), 2, x.data_ptr(), out.data_ptr(), None, 0,
+                                       coef.data_ptr(), od + 2, od, -0.0433, 0, B, L * D, None)
+    assert rc == -2
