@@ -388,12 +388,12 @@ def test_step_sd_fp32_latents_with_16bit_model_outputs(dtype, n_hist, pair, vpre
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_step_fm_strided_model_outputs_equal_contiguous(dtype):
     """consolver_step_fm_strided: e0 and the history as `[:, :L]` views of wider tensors (sample stride (L+Li)*D) give
-    exactly what contiguous copies give; a stride that is not a multiple of 8 elements takes the scalar path."""
+    exactly what contiguous copies give."""
     from consolver_b200 import _lib
     lib = _lib.load()
     B, L, Li, D, od = 3, 64, 32, 8, 2
     g = torch.Generator(device="cuda").manual_seed(3)
-    for extra in (Li, 3):                                     # (L+3)*D = 536 elements: not a multiple of 8*... still %8==0
+    for extra in (Li, 3):                                     # sample strides of 768 and 536 elements
         wide_v = torch.randn(B, L + extra, D, device="cuda", generator=g).to(dtype)
         wide_h = torch.randn(B, L + extra, D, device="cuda", generator=g).to(dtype)
         x = torch.randn(B, L, D, device="cuda", generator=g).to(dtype)
