@@ -26,7 +26,7 @@ SIGNATURES = {
     "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
     "consolver_step_fm_strided": (_i, [_i, _i, _p, _i64, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
-    "consolver_step_dpm": (_i, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _i64, _p]),
+    "consolver_step_dpm": (_i, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _p, _i, _i64, _p]),
     "consolver_policy_table_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i, _p, _p]),
     "consolver_policy_sample_f32": (_i, [_p] * 4 + [_p, _p] + [_i] * 6 + [_p] * 6 + [_p]),
     "consolver_rng_state_advance": (_i, [_p, C.c_uint64, _p]),
@@ -43,6 +43,11 @@ SIGNATURES = {
 class Rng(C.Structure):
     """consolver_rng_t"""
     _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("state", C.c_void_p), ("nthreads", C.c_uint32)]
+
+
+class DpmUpdate(C.Structure):
+    """consolver_dpm_update_t"""
+    _fields_ = [(n, C.c_float) for n in ("cx", "a0", "a1", "rinv", "a2", "rinv1", "w", "rs")]
 
 
 def philox_plan(numel: int):

@@ -6,7 +6,7 @@
 // One launch per solver step: CFG combine of the denoiser pair, conversion of the noise prediction to the quantity the
 // solver integrates (m0; the data prediction for dpmsolver++), the first/second-order update, and the write of m0 into
 // the two-slot ring — every latent-sized operand read once and written once:
-//   reads  u, c, x (+ m1 for the second-order step)    writes x', m0      => 5 or 6 tensors per step
+//   reads  u, c, x (+ m1, + m2 for the second / third-order step)    writes x', m0      => 5, 6 or 7 tensors per step
 // against 3 (CFG) + 4 (convert) + 9 (update) + casts for the op-by-op version.  Same streaming skeleton as step_kernel.cuh.
 #include "step_common.cuh"
 
@@ -17,6 +17,7 @@ struct DpmParams {
   const void* cond;   // non-null: CFG pair, e0 is the unconditional half
   void* slot_out;     // nullable: where m0 goes
   const void* m1;     // nullable: previous step's m (second-order update when present)
+  const void* m2;     // nullable: the one before (third-order update when present; needs m1)
   const void* x;
   void* x_out;
   void* x_out2;
@@ -24,7 +25,7 @@ struct DpmParams {
   float guidance;
   int convert;
   float ck0, ck1;     // DIV: m0 = (x - ck0 e) / ck1     LIN: m0 = ck1 x + ck0 e
-  float cx, a0, a1, rinv;   // x' = (cx x - a0 m0) - a1 (rinv (m0 - m1))
+  consolver_dpm_update_t k;  // see include/consolver.h
   long long n_per_sample, nvec_per_sample;
   int chunks_per_sample;
   int B;
@@ -38,8 +39,9 @@ __global__ void __launch_bounds__(512) dpm_step_kernel(const DpmParams p) {
   const long long v0 = (long long)chunk * ((long long)blockDim.x * U) + threadIdx.x;
   const bool pair = p.cond != nullptr;
   const bool second = p.m1 != nullptr;
+  const bool third = second && p.m2 != nullptr;
 
-  Raw<T, E> r_e0[U], r_c[U], r_m1[U];
+  Raw<T, E> r_e0[U], r_c[U], r_m1[U], r_m2[U];
   Raw<TX, E> r_x[U];
   long long off[U];
   bool live[U];
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(512) dpm_step_kernel(const DpmParams p) {
       if (pair) r_c[u].load(static_cast<const T*>(p.cond) + off[u]);
       r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
       if (second) r_m1[u].load(static_cast<const T*>(p.m1) + off[u]);
+      if (third) r_m2[u].load(static_cast<const T*>(p.m2) + off[u]);
     }
   }
   const float g = p.guidance;
@@ -78,10 +81,18 @@ __global__ void __launch_bounds__(512) dpm_step_kernel(const DpmParams p) {
       }
       if (Elem<T>::k16) m0 = Elem<T>::to_f(Elem<T>::from_f(m0));                // the value the ring keeps
       r_m0.set(i, m0);
-      float out = __fsub_rn(__fmul_rn(p.cx, xs), __fmul_rn(p.a0, m0));         // plugin :121 / :205-207
-      if (second) {
-        const float d1 = __fmul_rn(p.rinv, __fsub_rn(m0, r_m1[u].get(i)));       // plugin :201
-        out = __fsub_rn(out, __fmul_rn(p.a1, d1));                              // plugin :208
+      float out = __fsub_rn(__fmul_rn(p.k.cx, xs), __fmul_rn(p.k.a0, m0));     // plugin :121 / :205-207 / :335-336
+      if (third) {
+        const float m1 = r_m1[u].get(i);
+        const float d10 = __fmul_rn(p.k.rinv, __fsub_rn(m0, m1));                // plugin :328
+        const float d11 = __fmul_rn(p.k.rinv1, __fsub_rn(m1, r_m2[u].get(i)));
+        const float dd = __fsub_rn(d10, d11);
+        const float d1 = __fadd_rn(d10, __fmul_rn(p.k.w, dd));                   // :329
+        const float d2 = __fmul_rn(p.k.rs, dd);                                  // :330
+        out = __fsub_rn(__fsub_rn(out, __fmul_rn(p.k.a1, d1)), __fmul_rn(p.k.a2, d2));   // :337-338 / :345-346
+      } else if (second) {
+        const float d1 = __fmul_rn(p.k.rinv, __fsub_rn(m0, r_m1[u].get(i)));     // plugin :201
+        out = __fsub_rn(out, __fmul_rn(p.k.a1, d1));                              // plugin :208
       }
       r_out.set(i, out);
     }
@@ -122,22 +133,24 @@ static int launch_dpm(DpmParams& p, bool vec_ok, cudaStream_t stream) {
 using namespace consolver;
 
 extern "C" int consolver_step_dpm(int dtype, int x_dtype, const void* e0, const void* cond, float guidance,
-                                  void* slot_out, const void* m1, const void* x, void* x_out, void* x_out2,
-                                  int64_t out2_stride, int convert, float ck0, float ck1, float cx, float a0,
-                                  float a1, float rinv, int B, int64_t n_per_sample, consolver_stream_t stream) {
-  if (!e0 || !x || !x_out) return CONSOLVER_ERR_NULL;
+                                  void* slot_out, const void* m1, const void* m2, const void* x, void* x_out,
+                                  void* x_out2, int64_t out2_stride, int convert, float ck0, float ck1,
+                                  const consolver_dpm_update_t* upd, int B, int64_t n_per_sample,
+                                  consolver_stream_t stream) {
+  if (!e0 || !x || !x_out || !upd) return CONSOLVER_ERR_NULL;
+  if (m2 && !m1) return CONSOLVER_ERR_NULL;
   if (B <= 0 || n_per_sample <= 0) return CONSOLVER_ERR_SIZE;
   if (convert < CONSOLVER_DPM_CONVERT_NONE || convert > CONSOLVER_DPM_CONVERT_LIN) return CONSOLVER_ERR_UNSUPPORTED;
   if (x_dtype != dtype && x_dtype != CONSOLVER_F32) return CONSOLVER_ERR_DTYPE;
   DpmParams p{};
-  p.e0 = e0; p.cond = cond; p.slot_out = slot_out; p.m1 = m1; p.x = x; p.x_out = x_out; p.x_out2 = x_out2;
+  p.e0 = e0; p.cond = cond; p.slot_out = slot_out; p.m1 = m1; p.m2 = m2; p.x = x; p.x_out = x_out; p.x_out2 = x_out2;
   p.out2_stride = out2_stride > 0 ? (long long)out2_stride : (long long)n_per_sample;
   if (x_out2 && p.out2_stride < (long long)n_per_sample) return CONSOLVER_ERR_SIZE;
   p.guidance = guidance; p.convert = convert; p.ck0 = ck0; p.ck1 = ck1;
-  p.cx = cx; p.a0 = a0; p.a1 = a1; p.rinv = rinv;
+  p.k = *upd;
   p.n_per_sample = (long long)n_per_sample; p.B = B;
   bool al = aligned16(e0) && aligned16(x) && aligned16(x_out) && (!cond || aligned16(cond)) &&
-            (!slot_out || aligned16(slot_out)) && (!m1 || aligned16(m1)) &&
+            (!slot_out || aligned16(slot_out)) && (!m1 || aligned16(m1)) && (!m2 || aligned16(m2)) &&
             (!x_out2 || (aligned16(x_out2) && p.out2_stride % 8 == 0));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (dtype) {

@@ -8,19 +8,21 @@ per-step `scale_dirs[i]` that multiplies every model-output term of the update (
 attributes before `set_timesteps(..., timesteps=[...])`, exactly like gen_ppo.py:292-296.  Without a timestep list
 the stock diffusers grid is used and `scale_dirs` defaults to ones (the plugin itself requires it to be set).
 
-The update of step i is   x' = cx*x - a0*m0 [- a1*(m0 - m1)/r0]   with m the converted model outputs
+The update of step i is   x' = cx*x - a0*m0 [- a1*D1 [- a2*D2]]   with m the converted model outputs, D1 / D2 their
+first / second divided differences
 (data prediction for dpmsolver++).  All scalars are evaluated on the host with the same 0-d fp32 torch expressions
 the plugin uses (so they carry its roundings) once per `set_timesteps`; `consolver_step_dpm` then does CFG combine,
-conversion, update and the write of m0 into a two-slot ring in one pass over HBM (5-6 latent-sized tensors per
+conversion, update and the write of m0 into a three-slot ring in one pass over HBM (5-7 latent-sized tensors per
 step instead of ~20 for the op-by-op version).
 
-Scope: the ODE variants (`dpmsolver++`, `dpmsolver`), solver_order 1-2, midpoint / heun, epsilon / sample /
+Scope: the ODE variants (`dpmsolver++`, `dpmsolver`), solver_order 1-3, midpoint / heun, epsilon / sample /
 v_prediction; no dynamic thresholding, no SDE variants, no Karras / Lu spacings (the reference's AMED run uses none
 of them).  diffusers itself (0.26.3, env.yaml:52) is not part of the reference tree: the inherited pieces
 (`convert_model_output`, sigma tables, stock grid) follow the published library algorithm; see DESIGN.md §7 for
 what the golden vectors pin."""
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 from typing import List, Optional, Union
 
@@ -46,6 +48,7 @@ class _StepPlan:
     a0: float
     a1: Optional[float]       # second-order terms; None at step 0 (no previous model output)
     rinv: Optional[float]
+    third: Optional[tuple] = None     # (a1, rinv, a2, rinv1, w, rs) of the third-order form; None at steps 0 and 1
 
 
 class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
@@ -90,8 +93,8 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
                                       "'dpmsolver++' are built on the fused kernel")
         if solver_type not in ("midpoint", "heun"):
             raise NotImplementedError(f"{solver_type} is not implemented for {self.__class__}")
-        if solver_order not in (1, 2):
-            raise NotImplementedError("solver_order 3 is not built (the reference's AMED run uses the default 2)")
+        if solver_order not in (1, 2, 3):
+            raise NotImplementedError(f"solver_order {solver_order}: the multistep solver has orders 1 to 3")
         if thresholding or use_karras_sigmas or use_lu_lambdas or variance_type in ("learned", "learned_range"):
             raise NotImplementedError("thresholding / Karras / Lu spacings / learned variance are not built")
         if prediction_type not in ("epsilon", "sample", "v_prediction"):
@@ -110,7 +113,7 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
         self._begin_index = None
         self._plans = None
         self._ring = None
-        self._have_prev = False
+        self._n_prev = 0
 
     # ---- reference / diffusers surface -------------------------------------------------------------------------
     @property
@@ -179,7 +182,7 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
         self._step_index = None
         self._begin_index = None
         self._plans = None
-        self._have_prev = False
+        self._n_prev = 0
 
     def index_for_timestep(self, timestep, schedule_timesteps=None):
         grid = self._timesteps_host if schedule_timesteps is None else schedule_timesteps.detach().cpu().numpy()
@@ -238,8 +241,21 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
                     a1 = sd * 0.5 * (sigma_t * (torch.exp(h) - 1.0))                      # :222
                 else:
                     a1 = sd * (sigma_t * ((torch.exp(h) - 1.0) / h - 1.0))                # :228
+            third = None
+            if i > 1 and cfg.solver_order == 3:                                           # :307-346
+                alpha_q, sigma_q = self._alpha_sigma(sg[i - 2])
+                h_1 = (torch.log(alpha_p) - torch.log(sigma_p)) - (torch.log(alpha_q) - torch.log(sigma_q))
+                r0, r1 = h_0 / h, h_1 / h
+                if pp:
+                    b1 = -(sd * (alpha_t * ((torch.exp(-h) - 1.0) / h + 1.0)))            # :337 (added there)
+                    b2 = sd * (alpha_t * ((torch.exp(-h) - 1.0 + h) / h ** 2 - 0.5))      # :338
+                else:
+                    b1 = sd * (sigma_t * ((torch.exp(h) - 1.0) / h - 1.0))                # :345
+                    b2 = sd * (sigma_t * ((torch.exp(h) - 1.0 - h) / h ** 2 - 0.5))       # :346
+                third = tuple(float(v) for v in (b1, 1.0 / r0, b2, 1.0 / r1, r0 / (r0 + r1), 1.0 / (r0 + r1)))
             f = lambda v: None if v is None else float(v)  # noqa: E731
-            plans.append(_StepPlan(conv[0], float(conv[1]), float(conv[2]), float(cx), float(a0), f(a1), f(rinv)))
+            plans.append(_StepPlan(conv[0], float(conv[1]), float(conv[2]), float(cx), float(a0), f(a1), f(rinv),
+                                   third))
         self._plans = plans
         self._plans_dirs = None if dirs is None else tuple(dirs)
 
@@ -262,7 +278,7 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
         return SchedulerOutput(prev_sample=x) if return_dict else (x,)
 
     def _plan_for_step(self, timestep):
-        """(step index, host scalars, first-order?) of the step about to be taken; no device work"""
+        """(step index, host scalars, order of the update) of the step about to be taken; no device work"""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
                              "the scheduler")
@@ -277,8 +293,14 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
             raise IndexError("DPMSolverMultistepScheduler.step called past the end of the sigma schedule")
         final_first = (i == nts - 1) and (cfg.euler_at_final or (cfg.lower_order_final and nts < 15)
                                           or cfg.final_sigmas_type == "zero")               # :394-398
-        first = cfg.solver_order == 1 or self.lower_order_nums < 1 or final_first          # :418
-        return i, self._plans[i], first
+        second_only = (i == nts - 2) and cfg.lower_order_final and nts < 15                # :399-401
+        if cfg.solver_order == 1 or self.lower_order_nums < 1 or final_first:              # :418-423
+            order = 1
+        elif cfg.solver_order == 2 or self.lower_order_nums < 2 or second_only:
+            order = 2
+        else:
+            order = 3
+        return i, self._plans[i], order
 
     def _advance(self):
         if self.lower_order_nums < self.config.solver_order:                               # :425-426
@@ -288,7 +310,7 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
     def _step(self, e0, cond, guidance, timestep, sample, out2):
         if not (e0.is_cuda and sample.is_cuda):
             raise RuntimeError("consolver_b200 has no CPU path: model_output and sample must be CUDA tensors")
-        i, p, first = self._plan_for_step(timestep)
+        i, p, order = self._plan_for_step(timestep)
         e0 = e0 if e0.is_contiguous() else e0.contiguous()
         sample = sample if sample.is_contiguous() else sample.contiguous()
         if sample.dtype not in (e0.dtype, torch.float32):
@@ -297,21 +319,28 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
         N = e0.numel() // B
         ring = self._ring
         if ring is None or ring.shape[1:] != e0.shape or ring.dtype != e0.dtype or ring.device != e0.device:
-            ring = self._ring = torch.empty((2,) + tuple(e0.shape), device=e0.device, dtype=e0.dtype)
-            self._have_prev = False
-        slot, prev = ring[i % 2], ring[(i + 1) % 2]
-        if not first and not self._have_prev:
-            raise RuntimeError("second-order step without a previous model output in the ring")
+            ring = self._ring = torch.empty((3,) + tuple(e0.shape), device=e0.device, dtype=e0.dtype)
+            self._n_prev = 0
+        if order - 1 > self._n_prev:
+            raise RuntimeError(f"order-{order} step with only {self._n_prev} earlier model outputs in the ring")
+        slot = ring[i % 3]                              # converted outputs of steps i, i-1, i-2 live in i, i-1, i-2 mod 3
+        m1 = ring[(i - 1) % 3].data_ptr() if order >= 2 else None
+        m2 = ring[(i - 2) % 3].data_ptr() if order == 3 else None
+        upd = _lib.DpmUpdate(cx=p.cx, a0=p.a0)
+        if order == 2:
+            upd.a1, upd.rinv = p.a1, p.rinv
+        elif order == 3:
+            upd.a1, upd.rinv, upd.a2, upd.rinv1, upd.w, upd.rs = p.third
         x_out = torch.empty(e0.shape, device=e0.device, dtype=e0.dtype)                    # :429: model dtype
         stream = torch._C._cuda_getCurrentRawStream(e0.device.index)
         rc = _lib.load().consolver_step_dpm(
             _lib.dtype_code(e0.dtype), _lib.dtype_code(sample.dtype), e0.data_ptr(),
-            cond.data_ptr() if cond is not None else None, guidance, slot.data_ptr(),
-            None if first else prev.data_ptr(), sample.data_ptr(), x_out.data_ptr(),
+            cond.data_ptr() if cond is not None else None, guidance, slot.data_ptr(), m1, m2,
+            sample.data_ptr(), x_out.data_ptr(),
             out2.data_ptr() if out2 is not None else None, out2.stride(0) if out2 is not None else 0,
-            p.convert, p.ck0, p.ck1, p.cx, p.a0, 0.0 if first else p.a1, 0.0 if first else p.rinv, B, N, stream)
+            p.convert, p.ck0, p.ck1, ctypes.byref(upd), B, N, stream)
         _lib.check(rc, "consolver_step_dpm")
-        self._have_prev = True
+        self._n_prev = min(self._n_prev + 1, 2)
         self._advance()
         return x_out
 

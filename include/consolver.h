@@ -209,24 +209,33 @@ CONSOLVER_API int consolver_step_fm_strided(int dtype, int x_dtype, const void* 
 /*
  * Fused multistep DPM-Solver / DPM-Solver++ step with AMED direction scaling — replaces, per step,
  * the caller's CFG combine (gen_pretrain/pipeline.py:1069-1071), diffusers' convert_model_output (diffusers 0.26.3
- * DPMSolverMultistepScheduler; not part of the reference tree) and the plugin's first/second-order updates
- * (diffusers_amed_plugin_dpmpp.py:70-138, :140-262) with one pass over HBM.  Scalars are computed by the host the way
+ * DPMSolverMultistepScheduler; not part of the reference tree) and the plugin's first/second/third-order updates
+ * (diffusers_amed_plugin_dpmpp.py:70-138, :140-262, :264-348) with one pass over HBM.  Scalars are computed by the host the way
  * the plugin computes them (0-d fp32 tensors) and handed in:
  *   m0 = e                            convert == CONSOLVER_DPM_CONVERT_NONE
  *      = (x - ck0*e) / ck1                        CONSOLVER_DPM_CONVERT_DIV   (dpmsolver++ / epsilon: ck0 = sigma_s, ck1 = alpha_s)
  *      = ck1*x + ck0*e                            CONSOLVER_DPM_CONVERT_LIN   (v-prediction forms)
- *   x'  = cx*x - a0*m0                                      when m1 == NULL (first order, :121/:123)
- *       = (cx*x - a0*m0) - a1*(rinv*(m0 - m1))              otherwise       (second order, :201-208)
+ *   x'  = cx*x - a0*m0                                          m1 == NULL            (first order,  :121/:123)
+ *       = (cx*x - a0*m0) - a1*D                                 m1 != NULL, m2 == NULL (second order, :201-208)
+ *             D   = rinv*(m0 - m1)
+ *       = ((cx*x - a0*m0) - a1*D1) - a2*D2                      m1, m2 != NULL         (third order,  :326-346)
+ *             D10 = rinv*(m0 - m1), D11 = rinv1*(m1 - m2), D1 = D10 + w*(D10 - D11), D2 = rs*(D10 - D11)
+ * (a term the plugin ADDS is passed with its sign flipped: a - (-b) == a + b exactly.)
  * e = e0, or e0 + guidance*(cond - e0) when cond != NULL.  m0 is written to slot_out when non-NULL (the caller's
- * two-slot ring).  fp32 arithmetic in exactly this order; 16-bit dtypes round e, m0 and x' once each.
+ * ring of converted outputs).  fp32 arithmetic in exactly this order; 16-bit dtypes round e, m0 and x' once each.
  */
 #define CONSOLVER_DPM_CONVERT_NONE 0
 #define CONSOLVER_DPM_CONVERT_DIV  1
 #define CONSOLVER_DPM_CONVERT_LIN  2
+typedef struct consolver_dpm_update {   /* host struct, fp32 values of the plugin's 0-d tensors */
+  float cx, a0;              /* all orders                                                                 */
+  float a1, rinv;            /* second and third order: rinv = 1/r0                                        */
+  float a2, rinv1, w, rs;    /* third order: rinv1 = 1/r1, w = r0/(r0+r1), rs = 1/(r0+r1)                  */
+} consolver_dpm_update_t;
 CONSOLVER_API int consolver_step_dpm(int dtype, int x_dtype, const void* e0, const void* cond, float guidance,
-                      void* slot_out, const void* m1, const void* x, void* x_out, void* x_out2,
-                      int64_t out2_stride, int convert, float ck0, float ck1, float cx, float a0, float a1,
-                      float rinv, int B, int64_t n_per_sample, consolver_stream_t stream);
+                      void* slot_out, const void* m1, const void* m2, const void* x, void* x_out, void* x_out2,
+                      int64_t out2_stride, int convert, float ck0, float ck1, const consolver_dpm_update_t* upd,
+                      int B, int64_t n_per_sample, consolver_stream_t stream);
 
 /*
  * Probability tables only: MLP + softmax (factor_net_ppo.py:137-157) for `rows` input rows in one launch (one CTA

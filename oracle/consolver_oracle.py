@@ -505,13 +505,13 @@ class OracleDPMSolverAMED:
     restatement of the published library algorithm.  PARITY PIN: tests/golden/amed_*.npz are produced by running
     the UNMODIFIED plugin file over a stand-in of that base (oracle/ref_shim.py::_dpm_base) — this pins every line
     that lives in the reference; the inherited pieces are pinned only to the restatement ("parity unpinned" for
-    those).  ODE variants only (dpmsolver / dpmsolver++), solver_order <= 2, no thresholding."""
+    those).  ODE variants only (dpmsolver / dpmsolver++), solver_order 1-3, no thresholding."""
 
     def __init__(self, *, num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear",
                  trained_betas=None, solver_order=2, prediction_type="epsilon", algorithm_type="dpmsolver++",
                  solver_type="midpoint", lower_order_final=True, euler_at_final=False, final_sigmas_type="zero",
                  timestep_spacing="linspace", steps_offset=0, scale_dirs=None, scale_times=None):
-        if algorithm_type not in ("dpmsolver", "dpmsolver++") or solver_order not in (1, 2):
+        if algorithm_type not in ("dpmsolver", "dpmsolver++") or solver_order not in (1, 2, 3):
             raise NotImplementedError
         self.T = num_train_timesteps
         self.alphas_cumprod = sd_alphas_cumprod(sd_betas(num_train_timesteps, beta_start, beta_end, beta_schedule,
@@ -594,6 +594,27 @@ class OracleDPMSolverAMED:
                 x = (sigma_t / sigma_s) * sample - sd * (alpha_t * (torch.exp(-h) - 1.0)) * m0          # :121
             else:
                 x = (alpha_t / alpha_s) * sample - sd * (sigma_t * (torch.exp(h) - 1.0)) * m0           # :123
+        elif not (self.order == 2 or self.lower_order_nums < 2 or
+                  ((i == nts - 2) and self.lower_order_final and nts < 15)):                            # :422-423
+            alpha_p, sigma_p = self._alpha_sigma(self.sigmas[i - 1])                                    # third order
+            alpha_q, sigma_q = self._alpha_sigma(self.sigmas[i - 2])                                    # :307-346
+            lam_s = torch.log(alpha_s) - torch.log(sigma_s)
+            lam_p = torch.log(alpha_p) - torch.log(sigma_p)
+            lam_q = torch.log(alpha_q) - torch.log(sigma_q)
+            h_0, h_1 = lam_s - lam_p, lam_p - lam_q
+            r0, r1 = h_0 / h, h_1 / h
+            m1, m2 = self.hist[1], self.hist[2]
+            d1_0, d1_1 = (1.0 / r0) * (m0 - m1), (1.0 / r1) * (m1 - m2)
+            d1 = d1_0 + (r0 / (r0 + r1)) * (d1_0 - d1_1)
+            d2 = (1.0 / (r0 + r1)) * (d1_0 - d1_1)
+            if pp:
+                x = ((sigma_t / sigma_s) * sample - sd * (alpha_t * (torch.exp(-h) - 1.0)) * m0
+                     + sd * (alpha_t * ((torch.exp(-h) - 1.0) / h + 1.0)) * d1
+                     - sd * (alpha_t * ((torch.exp(-h) - 1.0 + h) / h ** 2 - 0.5)) * d2)
+            else:
+                x = ((alpha_t / alpha_s) * sample - sd * (sigma_t * (torch.exp(h) - 1.0)) * m0
+                     - sd * (sigma_t * ((torch.exp(h) - 1.0) / h - 1.0)) * d1
+                     - sd * (sigma_t * ((torch.exp(h) - 1.0 - h) / h ** 2 - 0.5)) * d2)
         else:                                                                                           # :420-421
             alpha_p, sigma_p = self._alpha_sigma(self.sigmas[i - 1])
             lam_s = torch.log(alpha_s) - torch.log(sigma_s)

@@ -266,6 +266,9 @@ def main_amed():
              solver_type="heun", prediction_type="v_prediction")
     gen_amed("amed_n8_v_B2", n=8, B=2, shape=small, seed=85, prediction_type="v_prediction")
     gen_amed("amed_n4_order1_sample_B2", n=4, B=2, shape=small, seed=86, solver_order=1, prediction_type="sample")
+    gen_amed("amed_n8_order3_B2", n=8, B=2, shape=small, seed=97, solver_order=3)       # 1st, 2nd, 3rd x4, 2nd, 1st
+    gen_amed("amed_stock_n16_order3_dpmsolver_v_B2", n=16, B=2, shape=small, seed=98, amed=False, solver_order=3,
+             algorithm_type="dpmsolver", final_sigmas_type="sigma_min", prediction_type="v_prediction")
     # stock grids (no AMED schedule): gen_ppo.py `type == "dpm"` uses dpmsolver + final sigma_min
     gen_amed("amed_stock_n8_dpmsolver_sigmamin_B2", n=8, B=2, shape=small, seed=87, amed=False,
              algorithm_type="dpmsolver", final_sigmas_type="sigma_min")

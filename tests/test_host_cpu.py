@@ -230,8 +230,9 @@ def _amed(g):
     return s
 
 
-def _dpm_kernel_arithmetic(p, first, e, x, m1):
-    """include/consolver.h's statement of consolver_step_dpm, in torch-CPU fp32 ops (same roundings)."""
+def _dpm_kernel_arithmetic(p, order, e, x, hist):
+    """include/consolver.h's statement of consolver_step_dpm, in torch-CPU fp32 ops (same roundings).
+    `hist`: converted outputs of the earlier steps, newest first.  Returns (x', [m0] + hist)."""
     from consolver_b200 import _lib
     if p.convert == _lib.DPM_CONVERT_DIV:
         m0 = (x - p.ck0 * e) / p.ck1
@@ -240,9 +241,14 @@ def _dpm_kernel_arithmetic(p, first, e, x, m1):
     else:
         m0 = e
     out = p.cx * x - p.a0 * m0
-    if not first:
-        out = out - p.a1 * (p.rinv * (m0 - m1))
-    return out, m0
+    if order == 2:
+        out = out - p.a1 * (p.rinv * (m0 - hist[0]))
+    elif order == 3:
+        a1, rinv, a2, rinv1, w, rs = p.third
+        d10, d11 = rinv * (m0 - hist[0]), rinv1 * (hist[0] - hist[1])
+        dd = d10 - d11
+        out = (out - a1 * (d10 + w * dd)) - a2 * (rs * dd)
+    return out, ([m0] + hist)[:2]
 
 
 @pytest.mark.parametrize("name", names("amed_"))
@@ -253,11 +259,11 @@ def test_amed_scheduler_grid_and_host_scalars_reproduce_the_plugin(name):
     g = Golden(name)
     s = _amed(g)
     assert torch.equal(s.timesteps, g["timesteps"]) and torch.equal(s.sigmas, g["sigmas"])
-    x, m1 = g["x_T"], None
+    x, hist = g["x_T"], []
     for i, t in enumerate(s.timesteps):
-        idx, plan, first = s._plan_for_step(t)
+        idx, plan, order = s._plan_for_step(t)
         assert idx == i
-        x, m1 = _dpm_kernel_arithmetic(plan, first, g[f"eps_{i}"], x, m1)
+        x, hist = _dpm_kernel_arithmetic(plan, order, g[f"eps_{i}"], x, hist)
         s._advance()
         assert torch.equal(x, g[f"prev_{i}"]), f"step {i}"
     with pytest.raises(RuntimeError, match="no CPU path"):
@@ -273,7 +279,7 @@ def test_amed_scheduler_surface_and_errors():
         s._plan_for_step(999)
     with pytest.raises(AssertionError):                      # plugin :48-49
         s.set_timesteps(4, timesteps=[999, 694, 500, 110, 0])
-    for bad in (dict(algorithm_type="sde-dpmsolver++"), dict(solver_order=3), dict(thresholding=True),
+    for bad in (dict(algorithm_type="sde-dpmsolver++"), dict(solver_order=4), dict(thresholding=True),
                 dict(solver_type="bh1"), dict(beta_schedule="squaredcos_cap_v2")):
         with pytest.raises(NotImplementedError):
             D(**bad)

@@ -123,13 +123,15 @@ AMED_ALL = {   # gen_ppo.py:24-55
 }
 
 
+@pytest.mark.parametrize("solver_order", [2, 3])
 @pytest.mark.parametrize("n", sorted(AMED_ALL))
-def test_amed_grids_and_step_scalars_match_the_plugin_for_every_shipped_schedule(n):
+def test_amed_grids_and_step_scalars_match_the_plugin_for_every_shipped_schedule(n, solver_order):
     """All five AMED schedules of gen_ppo.py through the unmodified plugin (over the stand-in of its diffusers base):
     time-scaled timesteps, sigmas, and — via the kernel's documented arithmetic — every latent of a full run."""
     from test_host_cpu import _dpm_kernel_arithmetic
     ref = ref_shim.load_reference()
-    cfg = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1)
+    cfg = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1,
+               solver_order=solver_order)
     ts, dirs, times = AMED_ALL[n]
     r = ref.AMEDDPMSolverMultistepScheduler(**cfg)
     m = cb.DPMSolverMultistepScheduler(**cfg)
@@ -140,11 +142,11 @@ def test_amed_grids_and_step_scalars_match_the_plugin_for_every_shipped_schedule
     assert r.num_inference_steps == m.num_inference_steps
     g = torch.Generator().manual_seed(n)
     x = torch.randn(2, 4, 8, 8, generator=g)
-    xm, m1 = x, None
+    xm, hist = x, []
     for t in r.timesteps:
         e = torch.randn(2, 4, 8, 8, generator=g)
         x = r.step(e, t, x, return_dict=False)[0]
-        _, plan, first = m._plan_for_step(t)
-        xm, m1 = _dpm_kernel_arithmetic(plan, first, e, xm, m1)
+        _, plan, order = m._plan_for_step(t)
+        xm, hist = _dpm_kernel_arithmetic(plan, order, e, xm, hist)
         m._advance()
         assert torch.equal(x, xm)

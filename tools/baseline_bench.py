@@ -3,6 +3,7 @@ step with a CFG pair (reads u, c, x, m1; writes x', m0 = 6 latent-sized tensors)
 stage (reads v, kept v, kept x; writes x' = 4 tensors), graph-captured, rotating buffer sets larger than L2,
 CUDA-event timed.  One JSON object per point."""
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -50,12 +51,14 @@ def bench_dpm(B, N=4 * 64 * 64, dtype=torch.float32, iters=200):
     sets = [dict(u=mk(), c=mk(), x=mk(), m1=mk(), out=torch.empty(B, N, device="cuda", dtype=dtype),
                  slot=torch.empty(B, N, device="cuda", dtype=dtype)) for _ in range(nsets)]
     code = _lib.dtype_code(dtype)
+    upd = _lib.DpmUpdate(cx=0.71, a0=-0.21, a1=-0.105, rinv=1.3)
+    upd_ref = ctypes.byref(upd)
 
     def launch(k, st):
         s = sets[k]
         rc = lib.consolver_step_dpm(code, code, s["u"].data_ptr(), s["c"].data_ptr(), 7.5, s["slot"].data_ptr(),
-                                    s["m1"].data_ptr(), s["x"].data_ptr(), s["out"].data_ptr(), None, 0,
-                                    _lib.DPM_CONVERT_DIV, 0.83, 0.55, 0.71, -0.21, -0.105, 1.3, B, N, st)
+                                    s["m1"].data_ptr(), None, s["x"].data_ptr(), s["out"].data_ptr(), None, 0,
+                                    _lib.DPM_CONVERT_DIV, 0.83, 0.55, upd_ref, B, N, st)
         assert rc == 0, rc
 
     med, best = _time(launch, nsets, iters)
