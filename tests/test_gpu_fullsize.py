@@ -91,3 +91,39 @@ def test_policy_sampling_distribution_at_large_batch():
         exp = table[a].cpu().double() * B
         chi2 = ((obs - exp) ** 2 / exp).sum().item()
         assert chi2 < 40.0, f"dim {a}: chi2 {chi2}"       # 10 dof: P(chi2 > 40) ~ 2e-5
+
+
+def test_whole_preview_is_invariant_to_how_the_batch_is_split():
+    """Size-independent property of the WHOLE path (policy draw + coefficients + fused CFG step, 8 steps, SD1.5
+    latents): a batch of 512 previews run at once equals eight batches of 64 run one after the other on the
+    corresponding slices of the same inputs and the same Exp(1) draw — bit for bit, latents and sampled actions.
+    Samples never interact, so the result must not depend on batch size, grid shape or unroll choice."""
+    import consolver_b200 as cb
+    from consolver_b200.denoise import preview_from_pairs
+    B, sub, n, shape = 512, 64, 8, (4, 64, 64)
+    cfg = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, steps_offset=1,
+               timestep_spacing="trailing", order_dim=4, scaler_dim=0,
+               factor_net_kwargs=dict(embedding_dim=64, hidden_dim=256, num_actions=11))
+    s = cb.PPOScheduler(**cfg)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        s.factor_net.mlp[4].weight.normal_(0, 0.05)
+    s.factor_net.cuda()
+    A, K = s.factor_net.action_dims, s.factor_net.num_actions
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x_T = torch.randn(B, *shape, device="cuda", generator=g)
+    pairs = [torch.randn(2 * B, *shape, device="cuda", generator=g) for _ in range(n)]
+    qs = [torch.empty(B * A, K, device="cuda").exponential_(1, generator=g) for _ in range(n)]
+
+    s.set_timesteps(n, device="cuda")
+    s.replay = {"q": qs}
+    whole = preview_from_pairs(s, x_T, pairs, 3.0).clone()
+    whole_actions = s._traj.out["actions"][:n].clone()                 # [n, B, A]
+    for k in range(B // sub):
+        rows = slice(k * sub, (k + 1) * sub)
+        s.set_timesteps(n, device="cuda")
+        s.replay = {"q": [q.view(B, A, K)[rows].reshape(sub * A, K).contiguous() for q in qs]}
+        sub_pairs = [torch.cat([p[:B][rows], p[B:][rows]]) for p in pairs]
+        part = preview_from_pairs(s, x_T[rows].contiguous(), sub_pairs, 3.0)
+        assert torch.equal(part, whole[rows]), f"sub-batch {k}"
+        assert torch.equal(s._traj.out["actions"][:n], whole_actions[:, rows])
