@@ -149,7 +149,17 @@ class FlowSigmaSchedule:
             grid = self._timesteps_host
         else:
             grid = schedule_timesteps.detach().float().cpu().numpy()
-        tv = np.float32(timestep.item() if isinstance(timestep, torch.Tensor) else timestep)
+        tv = None
+        ts = self.timesteps
+        if (schedule_timesteps is None and isinstance(timestep, torch.Tensor) and timestep.dim() == 0 and ts.is_cuda
+                and timestep.dtype == ts.dtype
+                and timestep.untyped_storage().data_ptr() == ts.untyped_storage().data_ptr()):
+            # `for t in scheduler.timesteps` hands out views of the grid tensor: read the value from the host copy
+            j = timestep.storage_offset() - ts.storage_offset()
+            if 0 <= j < len(grid):
+                tv = np.float32(grid[j])
+        if tv is None:
+            tv = np.float32(timestep.item() if isinstance(timestep, torch.Tensor) else timestep)
         hits = np.nonzero(grid == tv)[0]
         return int(hits[1 if len(hits) > 1 else 0])
 

@@ -186,7 +186,16 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
 
     def index_for_timestep(self, timestep, schedule_timesteps=None):
         grid = self._timesteps_host if schedule_timesteps is None else schedule_timesteps.detach().cpu().numpy()
-        tv = int(timestep.item() if isinstance(timestep, torch.Tensor) else timestep)
+        tv = None
+        ts = self.timesteps
+        if (schedule_timesteps is None and isinstance(timestep, torch.Tensor) and timestep.dim() == 0 and ts.is_cuda
+                and timestep.dtype == ts.dtype
+                and timestep.untyped_storage().data_ptr() == ts.untyped_storage().data_ptr()):
+            j = timestep.storage_offset() - ts.storage_offset()       # a view of our own grid tensor: no read-back
+            if 0 <= j < len(grid):
+                tv = int(grid[j])
+        if tv is None:
+            tv = int(timestep.item() if isinstance(timestep, torch.Tensor) else timestep)
         hits = np.nonzero(grid == tv)[0]
         if len(hits) == 0:
             return len(self._timesteps_host) - 1

@@ -160,6 +160,14 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         if not self.sync_free:
             return int(timestep.item())
         grid = self._timesteps_host
+        # `for t in scheduler.timesteps` (and `timesteps[t_start:]`) hands out 0-d VIEWS of our own grid tensor: the
+        # position is the storage offset, no read-back at all
+        ts = self.timesteps
+        if (timestep.dim() == 0 and ts.is_cuda and timestep.dtype == ts.dtype and
+                timestep.untyped_storage().data_ptr() == ts.untyped_storage().data_ptr()):
+            j = timestep.storage_offset() - ts.storage_offset()
+            if 0 <= j < len(grid):
+                return int(grid[j])
         if self._grid_offset is None:
             if torch.cuda.is_current_stream_capturing():
                 self._grid_offset = -self._step_count           # cannot read back while capturing: grid order

@@ -256,3 +256,69 @@ def test_flow_denoise_loop_writes_into_the_packed_transformer_input(kind):
         assert torch.equal(inp, seen[i]), f"step {i}: transformer input differs"
         x = s.step(den(inp, t, i)[:, :L], t, x, return_dict=False)[0]
     assert torch.equal(x, lat)
+
+
+def _no_sync():
+    """context: any synchronising torch call (.item(), nonzero, blocking copies ...) raises"""
+    import contextlib
+
+    @contextlib.contextmanager
+    def ctx():
+        prev = torch.cuda.get_sync_debug_mode()
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            yield
+        finally:
+            torch.cuda.set_sync_debug_mode(prev)
+    return ctx()
+
+
+def test_pipeline_style_loops_never_synchronise_with_the_host():
+    """`for t in scheduler.timesteps: scheduler.step(model_output, t, latents)` — the loop every diffusers pipeline
+    runs, with `t` a CUDA 0-d tensor — completes without a single host synchronisation for all four schedulers (the
+    reference reads the timestep back several times per step).  The first pass allocates the per-trajectory buffers;
+    the checked pass is a second trajectory, including its first step."""
+    import numpy as np
+    import consolver_b200 as cb
+    g, m, s, _ = _pair()
+    x0 = g["x_T"].cuda()
+    eps = [g[f"eps_{i}"].cuda() for i in range(m["n"])]
+
+    def run_sd():
+        s.set_timesteps(m["n"], device="cuda")
+        x = x0
+        for i, t in enumerate(s.timesteps):
+            x = s.step(eps[i], t, x, return_dict=False)[0]
+        x = x0
+        for i, t in enumerate(s.timesteps[2:]):                   # a pipeline that starts mid-grid
+            x = s.step(eps[i], t, x, return_dict=False)[0] if i else x
+        return x
+
+    fm = cb.FMPPOScheduler(shift=3.0, use_dynamic_shifting=True, order_dim=2, scaler_dim=0, mu_dim=0,
+                           factor_net_kwargs=dict(hidden_dim=32, num_actions=11))
+    fm.factor_net.cuda()
+    base = cb.FlowMatchGeneralDiscreteScheduler(shift=3.0, use_dynamic_shifting=True, type="heun")
+    dpm = cb.DPMSolverMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    v = torch.randn(2, 64, 16, device="cuda").bfloat16()
+    sig = np.linspace(1.0, 1 / 6, 6)
+
+    def run_flow(sched):
+        sched.set_timesteps(6, device="cuda", sigmas=sig, mu=1.15)       # no set_begin_index: the step has to find t
+        x = v
+        for t in sched.timesteps:
+            x = sched.step(v, t, x, return_dict=False)[0]
+        return x
+
+    def run_dpm():
+        dpm.set_timesteps(6, device="cuda")
+        x = x0
+        for i, t in enumerate(dpm.timesteps):
+            x = dpm.step(eps[i], t, x, return_dict=False)[0]
+        return x
+
+    for fn in (run_sd, lambda: run_flow(fm), lambda: run_flow(base), run_dpm):
+        fn()                                   # warm-up: allocations, table uploads
+        torch.cuda.synchronize()
+        with _no_sync():
+            fn()
+        torch.cuda.synchronize()
