@@ -98,6 +98,11 @@ class ClockSampler:
         self._stop.set()
         if self.ok:
             self.t.join()
+            if not self.samples:      # a region shorter than the thread's start-up: sample now, the GPU is still busy/hot
+                try:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                except Exception:  # noqa: BLE001
+                    pass
 
     def summary(self):
         s = sorted(self.samples)
@@ -486,12 +491,13 @@ def run_ours(args, rank, world, device):
         e2e_step(k)
     e2e_drain()
     barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(k)
-    e2e_drain()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    with ClockSampler(torch.cuda.current_device()) as clk_e2e:     # the second timed region: sampled as well
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_step(k)
+        e2e_drain()
+        barrier()
+        e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -517,6 +523,7 @@ def run_ours(args, rank, world, device):
                 "steps": e2e_steps},
         "gpu_launches": args.steps * (2 + N_STEPS * 2),   # per preview: table + 8 x (sample + step) + rng-advance kernels
         "clocks": clk.summary(),
+        "clocks_e2e": clk_e2e.summary(),       # the host-link-bound leg, where the SMs idle most of the time
     }
     # whole-loop HBM rate: 58 latent-sized transfers per sample per 8-step preview, per GPU
     loop_gbs = value / world * TENSORS_PER_PREVIEW * SHAPE[0] * SHAPE[1] * SHAPE[2] * 4 / 1e9
