@@ -3,6 +3,23 @@
 
 using namespace consolver;
 
+template <int MODE>
+static int dispatch_fm(StepParams& p, int dtype, int x_dtype, bool al, cudaStream_t s) {
+  const long long n = p.n_per_sample;
+  switch (dtype) {
+    case CONSOLVER_F32:
+      return launch_step<float, float, MODE>(p, al && n % 4 == 0, s);
+    case CONSOLVER_F16:
+      if (x_dtype == CONSOLVER_F32) return launch_step<__half, float, MODE>(p, al && n % 8 == 0, s);
+      return launch_step<__half, __half, MODE>(p, al && n % 8 == 0, s);
+    case CONSOLVER_BF16:
+      if (x_dtype == CONSOLVER_F32) return launch_step<__nv_bfloat16, float, MODE>(p, al && n % 8 == 0, s);
+      return launch_step<__nv_bfloat16, __nv_bfloat16, MODE>(p, al && n % 8 == 0, s);
+    default:
+      return CONSOLVER_ERR_DTYPE;
+  }
+}
+
 extern "C" int consolver_step_fm(int dtype, int x_dtype, const void* e0, void* slot_out,
                                  const void* const* hist, int n_hist, const void* x, void* x_out,
                                  void* x_out2, int64_t out2_stride,
@@ -27,17 +44,6 @@ extern "C" int consolver_step_fm_strided(int dtype, int x_dtype, const void* e0,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool al = all_aligned(p) && p.e_stride % 8 == 0;
   if (x_dtype != dtype && x_dtype != CONSOLVER_F32) return CONSOLVER_ERR_DTYPE;
-  switch (dtype) {
-    case CONSOLVER_F32:
-      return launch_step<float, float, kModeFM>(p, al && n_per_sample % 4 == 0, s);
-    case CONSOLVER_F16:
-      if (x_dtype == CONSOLVER_F32) return launch_step<__half, float, kModeFM>(p, al && n_per_sample % 8 == 0, s);
-      return launch_step<__half, __half, kModeFM>(p, al && n_per_sample % 8 == 0, s);
-    case CONSOLVER_BF16:
-      if (x_dtype == CONSOLVER_F32)
-        return launch_step<__nv_bfloat16, float, kModeFM>(p, al && n_per_sample % 8 == 0, s);
-      return launch_step<__nv_bfloat16, __nv_bfloat16, kModeFM>(p, al && n_per_sample % 8 == 0, s);
-    default:
-      return CONSOLVER_ERR_DTYPE;
-  }
+  return p.e_stride != p.n_per_sample ? dispatch_fm<kModeFMStrided>(p, dtype, x_dtype, al, s)
+                                      : dispatch_fm<kModeFM>(p, dtype, x_dtype, al, s);
 }

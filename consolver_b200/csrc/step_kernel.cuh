@@ -12,7 +12,10 @@
 
 namespace consolver {
 
-enum : int { kModeSD = 0, kModeFM = 1 };
+// kModeFMStrided: the FM step with sample-strided model outputs (a separate instantiation, so that the contiguous
+// form pays nothing for it: the extra address arithmetic cost ~0.3 us per launch at small batches when it was
+// folded into kModeFM)
+enum : int { kModeSD = 0, kModeFM = 1, kModeFMStrided = 2 };
 
 // NH  > 0 : history depth known at compile time (1..4), loads fully unrolled
 // NH == 0 : runtime depth (5..8), guarded loads
@@ -30,9 +33,9 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
   const long long v0 = (long long)chunk * ((long long)blockDim.x * U) + threadIdx.x;
   const int nh = NH ? NH : p.n_hist;
   const bool pair = p.cond != nullptr;
-  // FM only: model outputs (e0 and the history) may be sample-strided views, e.g. the first L tokens of a wider packed
-  // transformer output (edit_ppo/denoise_diffusion.py:140); the SD instantiations keep one offset for every stream
-  const long long edelta = (MODE == kModeFM) ? (long long)b * (p.e_stride - p.n_per_sample) : 0;
+  // kModeFMStrided: model outputs (e0 and the history) are sample-strided views, e.g. the first L tokens of a wider
+  // packed transformer output (edit_ppo/denoise_diffusion.py:140); every other instantiation keeps one offset
+  const long long edelta = (MODE == kModeFMStrided) ? (long long)b * (p.e_stride - p.n_per_sample) : 0;
 
   Raw<T, E> r_e0[U], r_c[U];
   Raw<T, E> r_h[U][kOlder > 0 ? kOlder : 1];
