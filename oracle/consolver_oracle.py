@@ -30,6 +30,60 @@ F32 = torch.float32
 
 
 # --------------------------------------------------------------------------------------------
+# where the reference runs: torch evaluates `0-d HOST scalar (op) tensor` differently for CPU and CUDA tensors
+# --------------------------------------------------------------------------------------------
+class TorchSemantics:
+    """The reference keeps its schedule scalars as 0-d fp32 tensors ON THE HOST (scheduler_ppo.py:110-114,:309-312)
+    while latents and model outputs live on the GPU.  ATen treats such a scalar differently per device:
+
+      device="cpu"   (the reference executed on CPU tensors — what the CPU-made fixtures tests/golden/{sd,sd16,fm}_* hold)
+          scalar * t16   -> the scalar is first rounded to t16's dtype, the product rounded again
+          t / scalar     -> true division
+      device="cuda"  (the reference executed the way its drivers run it — fixtures tests/golden/cuda_*, made on a B200)
+          scalar * t     -> the scalar enters the kernel as an fp32 opmath value: round_T(float(t) * k), one rounding
+                            (ATen opmath_symmetric_gpu_kernel_with_scalars)
+          t / scalar     -> t * (1 / scalar), the reciprocal taken once in fp32 (ATen div_true_kernel_cuda's
+                            CPU-scalar branch) — this changes fp32 results too, by an ulp here and there
+
+    `autocast` (None / torch.float16 / torch.bfloat16): the step runs inside torch.autocast("cuda", dtype)
+    (gen_ppo.py:309, train_ppo.py:353): nn.Linear runs in that dtype, softmax and torch.sum return fp32.
+    Everything here is torch-CPU arithmetic that restates those rules; tests/test_oracle_golden.py pins the
+    restatement against the cuda_* fixtures bit for bit."""
+
+    def __init__(self, device: str = "cpu", autocast: Optional[torch.dtype] = None):
+        if device not in ("cpu", "cuda"):
+            raise ValueError("device must be 'cpu' or 'cuda'")
+        self.device, self.autocast = device, autocast
+
+    @property
+    def cuda(self) -> bool:
+        return self.device == "cuda"
+
+    def smul(self, k, t: torch.Tensor) -> torch.Tensor:
+        """0-d host scalar * tensor"""
+        if not self.cuda:
+            return k * t
+        return (t.float() * torch.as_tensor(k, dtype=F32)).to(t.dtype)
+
+    def sdiv(self, t: torch.Tensor, k) -> torch.Tensor:
+        """tensor / 0-d host scalar (or python number)"""
+        if not self.cuda:
+            return t / k
+        inv = torch.tensor(1.0, dtype=F32) / torch.as_tensor(k, dtype=F32)
+        return (t.float() * inv).to(t.dtype)
+
+    def sum0(self, stacked: torch.Tensor) -> torch.Tensor:
+        """torch.sum(stacked, dim=0) — fp32 in, fp32 out under autocast"""
+        if self.autocast is not None and stacked.dtype in (torch.float16, torch.bfloat16):
+            stacked = stacked.float()
+        return torch.sum(stacked, dim=0)
+
+
+HOST = TorchSemantics("cpu")
+CUDA = TorchSemantics("cuda")
+
+
+# --------------------------------------------------------------------------------------------
 # schedules
 # --------------------------------------------------------------------------------------------
 def sd_betas(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear",
@@ -183,22 +237,40 @@ def cosine_features(epsilon: torch.Tensor, order_dim: int) -> torch.Tensor:
                       for i in range(1, order_dim)], dim=-1)
 
 
+def _linear_lowp(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    """nn.Linear under autocast: operands cast to `dt`, fp32 accumulation, bias added before the single rounding of
+    the output (cuBLAS; the accumulation order is the library's, so a logit can differ from this by one `dt` ulp)."""
+    acc = x.to(dt).double() @ w.to(dt).double().t() + b.to(dt).double()
+    return acc.float().to(dt)
+
+
 def policy_probs(sd: Dict[str, torch.Tensor], x: torch.Tensor, variant: str,
-                 epsilon: Optional[torch.Tensor] = None, order_dim: int = 4) -> torch.Tensor:
+                 epsilon: Optional[torch.Tensor] = None, order_dim: int = 4,
+                 sem: Optional["TorchSemantics"] = None) -> torch.Tensor:
     """forward_: factor_net_ppo.py:137-157 (sd: x/999, softmax) / edit_ppo/factor_net_ppo.py:149-169
     (fm: identity normalise, softmax(logits/0.01)).  x: [R, 2] in the model dtype; returns [R, A, K] fp32.
-    `epsilon` (stacked history [R, order_dim, ...]) switches on the use_conv feature path."""
+    `epsilon` (stacked history [R, order_dim, ...]) switches on the use_conv feature path.
+    `sem.autocast`: the three Linear layers run in that dtype (activations rounded to it after every layer), the
+    softmax in fp32 on the upcast logits; a policy whose parameters are already 16-bit (gen_ppo.py:194-195) is the
+    same computation."""
+    sem = sem or HOST
     av = sd["action_values"]
     A, K = av.shape
-    xn = x.float() / 999.0 if variant == "sd" else x.float()
+    xn = sem.sdiv(x.float(), 999.0) if variant == "sd" else x.float()
     if epsilon is not None:
         xn = torch.cat([xn, cosine_features(epsilon, order_dim)], dim=-1)
-    h = torch.relu(torch.nn.functional.linear(xn, sd["mlp.0.weight"].float(), sd["mlp.0.bias"].float()))
-    h = torch.relu(torch.nn.functional.linear(h, sd["mlp.2.weight"].float(), sd["mlp.2.bias"].float()))
-    logits = torch.nn.functional.linear(h, sd["mlp.4.weight"].float(), sd["mlp.4.bias"].float()).view(-1, A, K)
+    dt = sem.autocast
+    if dt is None:
+        h = torch.relu(torch.nn.functional.linear(xn, sd["mlp.0.weight"].float(), sd["mlp.0.bias"].float()))
+        h = torch.relu(torch.nn.functional.linear(h, sd["mlp.2.weight"].float(), sd["mlp.2.bias"].float()))
+        logits = torch.nn.functional.linear(h, sd["mlp.4.weight"].float(), sd["mlp.4.bias"].float()).view(-1, A, K)
+    else:
+        h = torch.relu(_linear_lowp(xn, sd["mlp.0.weight"], sd["mlp.0.bias"], dt))
+        h = torch.relu(_linear_lowp(h, sd["mlp.2.weight"], sd["mlp.2.bias"], dt))
+        logits = _linear_lowp(h, sd["mlp.4.weight"], sd["mlp.4.bias"], dt).view(-1, A, K)
     if variant == "fm":
-        logits = logits / 0.01
-    return torch.softmax(logits, dim=-1)
+        logits = sem.sdiv(logits, 0.01)
+    return torch.softmax(logits.float(), dim=-1)
 
 
 def sample_indices(probs: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
@@ -248,16 +320,20 @@ def step_masks(B: int, A: int, n_hist: int, order_dim: int) -> torch.Tensor:
     return m
 
 
-def coefficients(actions: torch.Tensor, n_hist: int, order_dim: int, scaler_dim: int):
+def coefficients(actions: torch.Tensor, n_hist: int, order_dim: int, scaler_dim: int,
+                 sem: Optional["TorchSemantics"] = None):
     """scheduler_ppo.py:253-259 + set_default_coefficients :165-175 (same in edit_ppo/scheduler_fmppo.py
     :249-268).  Returns (coef list of n_hist tensors [B] newest first — for n_hist==1 the reference
-    bypasses the coefficient and uses the estimate itself (:263-265) so coef is None —, scale list)."""
+    bypasses the coefficient and uses the estimate itself (:263-265) so coef is None —, scale list).
+    With 16-bit actions (policy cast to the pipeline dtype) under autocast, torch.sum returns fp32, so the LAST
+    coefficient is an fp32 tensor while the others keep the 16-bit dtype."""
+    sem = sem or HOST
     a = [actions[:, i] for i in range(order_dim - 1)]
     s = [actions[:, i] for i in range(order_dim - 1, order_dim + scaler_dim - 1)]
     a.append(a[-1] if a else None)  # placeholder (:166)
     a[0] = a[0] + 1
     if n_hist > 1:
-        a[n_hist - 1] = 1 - torch.sum(torch.stack(a[:n_hist - 1]), dim=0)
+        a[n_hist - 1] = 1 - sem.sum0(torch.stack(a[:n_hist - 1]))
     s = [v + 1 for v in s]
     return (a[:n_hist] if n_hist > 1 else None), s
 
@@ -290,15 +366,17 @@ def combine_history(hist: Sequence[torch.Tensor], coef, scale, sample: torch.Ten
     return eff, sample
 
 
-def ddim_update(sample, eff, scalars, prediction_type="epsilon"):
-    """scheduler_ppo.py:306-332 (_get_prev_sample), eta=0, no clipping."""
+def ddim_update(sample, eff, scalars, prediction_type="epsilon", sem: Optional["TorchSemantics"] = None):
+    """scheduler_ppo.py:306-332 (_get_prev_sample), eta=0, no clipping.  The four scalars are 0-d HOST tensors in the
+    reference: `sem` says how torch combines them with the (CPU or CUDA) latents."""
+    sem = sem or HOST
     sa_t, sb_t, sa_p, sb_p = scalars
     if prediction_type == "v_prediction":
-        eff = sa_t * eff + sb_t * sample
+        eff = sem.smul(sa_t, eff) + sem.smul(sb_t, sample)
     elif prediction_type != "epsilon":
         raise ValueError(f"Unsupported prediction_type: {prediction_type}")
-    x0 = (sample - sb_t * eff) / sa_t
-    return sa_p * x0 + sb_p * eff
+    x0 = sem.sdiv(sample - sem.smul(sb_t, eff), sa_t)
+    return sem.smul(sa_p, x0) + sem.smul(sb_p, eff)
 
 
 def fm_update(sample, eff, dt, out_dtype):
@@ -316,8 +394,14 @@ class OracleSDScheduler:
 
     def __init__(self, state_dict, *, num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02,
                  beta_schedule="linear", trained_betas=None, prediction_type="epsilon",
-                 timestep_spacing="leading", steps_offset=0, order_dim=4, scaler_dim=2, use_conv=False):
+                 timestep_spacing="leading", steps_offset=0, order_dim=4, scaler_dim=2, use_conv=False,
+                 sem: Optional[TorchSemantics] = None, policy_dtype: Optional[torch.dtype] = None):
+        """`sem`: where the reference being restated ran (TorchSemantics; default: CPU tensors, no autocast).
+        `policy_dtype`: the policy — bin buffer included — was cast to this dtype (gen_ppo.py:194-195)."""
         self.sd = {k: torch.as_tensor(v) for k, v in state_dict.items()}
+        if policy_dtype is not None:
+            self.sd = {k: v.to(policy_dtype) for k, v in self.sd.items()}
+        self.sem = sem or HOST
         self.T, self.order_dim, self.scaler_dim = num_train_timesteps, order_dim, scaler_dim
         self.prediction_type, self.spacing, self.offset = prediction_type, timestep_spacing, steps_offset
         self.use_conv = use_conv
@@ -344,7 +428,7 @@ class OracleSDScheduler:
         if n_hist < self.order_dim:
             pad = torch.zeros(B, self.order_dim - n_hist, *model_output.shape[1:], dtype=model_output.dtype)
             eps_stack = torch.cat([eps_stack, pad], dim=1)
-        probs = policy_probs(self.sd, x, "sd", eps_stack if self.use_conv else None, self.order_dim)
+        probs = policy_probs(self.sd, x, "sd", eps_stack if self.use_conv else None, self.order_dim, sem=self.sem)
         A, K = probs.shape[1:]
         if forced_idx is None:
             if q is None:
@@ -354,9 +438,9 @@ class OracleSDScheduler:
             idx = forced_idx
         actions, act_probs = gather_actions(self.sd, probs, idx)
         masks = step_masks(B, A, n_hist, self.order_dim)
-        coef, scale = coefficients(actions, n_hist, self.order_dim, self.scaler_dim)
+        coef, scale = coefficients(actions, n_hist, self.order_dim, self.scaler_dim, sem=self.sem)
         eff, smp = combine_history(self.hist, coef, scale, sample)
-        prev = ddim_update(smp, eff, ddim_scalars(self.alphas_cumprod, t, prev_t), self.prediction_type)
+        prev = ddim_update(smp, eff, ddim_scalars(self.alphas_cumprod, t, prev_t), self.prediction_type, sem=self.sem)
         self.last_idx, self.last_probs_full = idx, probs
         return prev, actions, act_probs, {"x": x, "epsilon": eps_stack}, masks
 
@@ -367,8 +451,9 @@ class OracleFMScheduler:
     def __init__(self, state_dict, *, num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False,
                  time_shift_type="exponential", shift_terminal=None, invert_sigmas=False,
                  use_karras_sigmas=False, use_exponential_sigmas=False, order_dim=4, scaler_dim=2, mu_dim=1,
-                 use_conv=False):
+                 use_conv=False, sem: Optional[TorchSemantics] = None):
         self.sd = {k: torch.as_tensor(v) for k, v in state_dict.items()}
+        self.sem = sem or HOST
         self.kw = dict(num_train_timesteps=num_train_timesteps, shift=shift,
                        use_dynamic_shifting=use_dynamic_shifting, time_shift_type=time_shift_type,
                        shift_terminal=shift_terminal, invert_sigmas=invert_sigmas,
@@ -409,7 +494,7 @@ class OracleFMScheduler:
         if n_hist < self.order_dim:
             pad = torch.zeros(B, self.order_dim - n_hist, *model_output.shape[1:], dtype=model_output.dtype)
             eps_stack = torch.cat([eps_stack, pad], dim=1)
-        probs = policy_probs(self.sd, x, "fm", eps_stack if self.use_conv else None, self.order_dim)
+        probs = policy_probs(self.sd, x, "fm", eps_stack if self.use_conv else None, self.order_dim, sem=self.sem)
         A, K = probs.shape[1:]
         if forced_idx is None:
             if q is None:
@@ -419,7 +504,7 @@ class OracleFMScheduler:
             idx = forced_idx
         actions, act_probs = gather_actions(self.sd, probs, idx)
         masks = step_masks(B, A, n_hist, self.order_dim)
-        coef, scale = coefficients(actions, n_hist, self.order_dim, self.scaler_dim)  # mu params unused (:409,:440)
+        coef, scale = coefficients(actions, n_hist, self.order_dim, self.scaler_dim, sem=self.sem)  # mu params unused (:409,:440)
         eff, smp = combine_history(self.hist, coef, scale, sample)
         prev = fm_update(smp, eff, dt, model_output.dtype)
         self.step_index += 1

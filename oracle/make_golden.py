@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_shim  # noqa: E402
 
-OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+OUT = os.environ.get("CONSOLVER_GOLDEN_OUT") or os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 SD_PROD = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, num_train_timesteps=1000,
                steps_offset=1, timestep_spacing="trailing", order_dim=4, scaler_dim=0, use_conv=False)
@@ -65,53 +65,73 @@ def _hook_probs(fn, store):
     fn.forward_ = wrapped
 
 
-def gen_sd(name, *, B, shape, n, guidance, seed, last_std=0.5, dtype=torch.float32, latent_dtype=None, **cfg_over):
+def _autocast(device, dtype):
+    import contextlib
+
+    return torch.autocast(torch.device(device).type, dtype) if dtype is not None else contextlib.nullcontext()
+
+
+def gen_sd(name, *, B, shape, n, guidance, seed, last_std=0.5, dtype=torch.float32, latent_dtype=None, device="cpu",
+           policy_dtype=None, autocast=None, **cfg_over):
     """`dtype`: dtype of the denoiser output (and of the caller-side CFG combine); `latent_dtype`: dtype of the
     initial latent (default = dtype).  16-bit `dtype` with fp32 latents is the autocast layout of train_ppo.py:353;
-    16-bit both is gen_ppo.py's fp16 pipeline, whose latents torch promotion turns fp32 after the second step."""
+    16-bit both is gen_ppo.py's fp16 pipeline, whose latents torch promotion turns fp32 after the second step.
+    `device="cuda"`: the reference runs on the GPU exactly as its drivers run it — policy moved with `.to(device)`,
+    `set_timesteps(device=...)`, CUDA 0-d timesteps, schedule tables left on the host (scheduler_ppo.py:110-114).
+    `policy_dtype`: gen_ppo.py:193-195 casts the policy, bin buffer included, to the pipeline dtype.
+    `autocast`: dtype of the `torch.autocast` region the CFG combine and `step` run in (gen_ppo.py:309,
+    train_ppo.py:353)."""
     ref = ref_shim.load_reference()
     cfg = dict(SD_PROD, **cfg_over)
     fkw = dict(embedding_dim=64, hidden_dim=cfg.pop("hidden_dim", 256), num_actions=cfg.pop("num_actions", 11))
     with ref_shim.quiet():
         s = ref.PPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
     _seed_policy(s.factor_net, seed, last_std)
+    bf, d = [], {}
+    for k, v in s.factor_net.state_dict().items():
+        d[f"sd.{k}"] = v.numpy().copy()                    # fp32 master weights, before any cast
+    if policy_dtype is not None:
+        s.factor_net.to(device, dtype=policy_dtype)        # gen_ppo.py:194-195
+    else:
+        s.factor_net.to(device)
     full = []
     _hook_probs(s.factor_net, full)
-    s.set_timesteps(n)
+    s.set_timesteps(n, device=device)
     g = torch.Generator().manual_seed(seed + 1)
-    x = torch.randn(B, *shape, generator=g).to(latent_dtype or dtype)
-    bf, d = [], {}
+    x = torch.randn(B, *shape, generator=g).to(latent_dtype or dtype).to(device)
     d["x_T"] = _np(x, bf, "x_T")
-    for k, v in s.factor_net.state_dict().items():
-        d[f"sd.{k}"] = v.numpy()
-    d["timesteps"] = s.timesteps.numpy()
+    d["timesteps"] = s.timesteps.cpu().numpy()
     A, K = s.factor_net.action_dims, s.factor_net.num_actions
     for i, t in enumerate(s.timesteps):
-        pair = torch.randn(2 * B, *shape, generator=g).to(dtype)
+        pair = torch.randn(2 * B, *shape, generator=g).to(dtype).to(device)
         u, c = pair.chunk(2)
-        eps = u + guidance * (c - u)                      # denoise_ppo.py:97-100
+        with _autocast(device, autocast):
+            eps = u + guidance * (c - u)                      # denoise_ppo.py:97-100, gen_pretrain/pipeline.py:1069-1071
+            torch.manual_seed(seed * 1000 + i)
+            with ref_shim.quiet():
+                x, actions, probs, conds, masks = s.step(eps, t, x, return_dict=False)
         torch.manual_seed(seed * 1000 + i)
-        with ref_shim.quiet():
-            x, actions, probs, conds, masks = s.step(eps, t, x, return_dict=False)
-        torch.manual_seed(seed * 1000 + i)
-        q = torch.empty(B * A, K).exponential_(1)
+        q = torch.empty(B * A, K, device=device).exponential_(1)
         idx = torch.argmax(full[i].view(-1, K) / q, dim=-1).view(B, A)
-        assert torch.equal(s.factor_net.action_values[torch.arange(A), idx], actions), "q recovery failed"
+        assert torch.equal(s.factor_net.action_values[torch.arange(A, device=device), idx], actions), "q recovery failed"
         d[f"pair_{i}"] = _np(pair, bf, f"pair_{i}")
         d[f"eps_{i}"] = _np(eps, bf, f"eps_{i}")
-        d[f"q_{i}"] = q.numpy()
-        d[f"idx_{i}"] = idx.numpy()
-        d[f"actions_{i}"] = actions.detach().numpy()
-        d[f"probs_{i}"] = probs.detach().numpy()
-        d[f"probs_full_{i}"] = full[i].numpy()
-        d[f"masks_{i}"] = masks.numpy()
+        d[f"q_{i}"] = q.cpu().numpy()
+        d[f"idx_{i}"] = idx.cpu().numpy()
+        d[f"actions_{i}"] = _np(actions, bf, f"actions_{i}")
+        d[f"probs_{i}"] = _np(probs, bf, f"probs_{i}")
+        d[f"probs_full_{i}"] = _np(full[i], bf, f"probs_full_{i}")
+        d[f"masks_{i}"] = _np(masks, bf, f"masks_{i}")
         d[f"condx_{i}"] = _np(conds["x"], bf, f"condx_{i}")
         d[f"prev_{i}"] = _np(x, bf, f"prev_{i}")
         assert conds["epsilon"].shape == (B, cfg["order_dim"], *shape)
         assert torch.equal(conds["epsilon"][:, 0], eps)
+    short = lambda t: None if t is None else str(t).split(".")[-1]  # noqa: E731
     meta = dict(kind="sd", B=B, shape=list(shape), n=n, guidance=guidance, seed=seed, config=cfg,
                 factor_net_kwargs=fkw, dtype=str(dtype).split(".")[-1],
-                latent_dtype=str(latent_dtype or dtype).split(".")[-1], torch=torch.__version__)
+                latent_dtype=str(latent_dtype or dtype).split(".")[-1], torch=torch.__version__,
+                device=torch.device(device).type, policy_dtype=short(policy_dtype), autocast=short(autocast),
+                gpu=torch.cuda.get_device_name(0) if torch.device(device).type == "cuda" else None)
     d["__meta__"] = np.array(json.dumps(meta))
     d["__bf16__"] = np.array(json.dumps(bf))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
@@ -137,48 +157,54 @@ def main_sd16():
            latent_dtype=f32, scaler_dim=1, order_dim=3)
 
 
-def gen_fm(name, *, B, shape, n, seed, dtype, last_std=0.02, use_begin_index=True, **cfg_over):
+def gen_fm(name, *, B, shape, n, seed, dtype, last_std=0.02, use_begin_index=True, device="cpu", autocast=None,
+           **cfg_over):
+    """`device` / `autocast`: as in gen_sd (edit_ppo/generate_ours.py:135-141 runs the fp32 policy on the GPU with bf16
+    latents and no autocast; the training rollout runs under accelerator.autocast, edit_ppo/train_ppo.py:289)."""
     ref = ref_shim.load_reference()
     cfg = dict(FM_PROD, **cfg_over)
     fkw = dict(hidden_dim=cfg.pop("hidden_dim", 256), num_actions=cfg.pop("num_actions", 11))
     with ref_shim.quiet():
         s = ref.FMPPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
     _seed_policy(s.factor_net, seed, last_std)
+    bf, d = [], {}
+    for k, v in s.factor_net.state_dict().items():
+        d[f"sd.{k}"] = v.numpy().copy()
+    s.factor_net.to(device)
     full = []
     _hook_probs(s.factor_net, full)
-    s.set_timesteps(n, sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+    s.set_timesteps(n, device=device, sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
     if use_begin_index:
         s.set_begin_index(0)
     g = torch.Generator().manual_seed(seed + 1)
-    x = torch.randn(B, *shape, generator=g).to(dtype)
-    bf, d = [], {}
+    x = torch.randn(B, *shape, generator=g).to(dtype).to(device)
     d["x_T"] = _np(x, bf, "x_T")
-    for k, v in s.factor_net.state_dict().items():
-        d[f"sd.{k}"] = v.numpy()
-    d["timesteps"] = s.timesteps.numpy()
-    d["sigmas"] = s.sigmas.numpy()
+    d["timesteps"] = s.timesteps.cpu().numpy()
+    d["sigmas"] = s.sigmas.cpu().numpy()
     A, K = s.factor_net.action_dims, s.factor_net.num_actions
     for i, t in enumerate(s.timesteps):
-        v = torch.randn(B, *shape, generator=g).to(dtype)
+        v = torch.randn(B, *shape, generator=g).to(dtype).to(device)
         torch.manual_seed(seed * 1000 + i)
-        with ref_shim.quiet():
+        with ref_shim.quiet(), _autocast(device, autocast):
             x, actions, probs, conds, masks = s.step(v, t, x, return_dict=False)
         torch.manual_seed(seed * 1000 + i)
-        q = torch.empty(B * A, K).exponential_(1)
+        q = torch.empty(B * A, K, device=device).exponential_(1)
         idx = torch.argmax(full[i].view(-1, K) / q, dim=-1).view(B, A)
-        assert torch.equal(s.factor_net.action_values[torch.arange(A), idx], actions), "q recovery failed"
+        assert torch.equal(s.factor_net.action_values[torch.arange(A, device=device), idx], actions), "q recovery failed"
         d[f"v_{i}"] = _np(v, bf, f"v_{i}")
-        d[f"q_{i}"] = q.numpy()
-        d[f"idx_{i}"] = idx.numpy()
-        d[f"actions_{i}"] = actions.detach().numpy()
-        d[f"probs_{i}"] = probs.detach().numpy()
-        d[f"probs_full_{i}"] = full[i].numpy()
-        d[f"masks_{i}"] = masks.numpy()
+        d[f"q_{i}"] = q.cpu().numpy()
+        d[f"idx_{i}"] = idx.cpu().numpy()
+        d[f"actions_{i}"] = _np(actions, bf, f"actions_{i}")
+        d[f"probs_{i}"] = _np(probs, bf, f"probs_{i}")
+        d[f"probs_full_{i}"] = _np(full[i], bf, f"probs_full_{i}")
+        d[f"masks_{i}"] = _np(masks, bf, f"masks_{i}")
         d[f"condx_{i}"] = _np(conds["x"], bf, f"condx_{i}")
         d[f"prev_{i}"] = _np(x, bf, f"prev_{i}")
     meta = dict(kind="fm", B=B, shape=list(shape), n=n, seed=seed, config=cfg, factor_net_kwargs=fkw,
                 dtype=str(dtype).split(".")[-1], mu=1.15, use_begin_index=use_begin_index,
-                torch=torch.__version__)
+                torch=torch.__version__, device=torch.device(device).type,
+                autocast=None if autocast is None else str(autocast).split(".")[-1],
+                gpu=torch.cuda.get_device_name(0) if torch.device(device).type == "cuda" else None)
     d["__meta__"] = np.array(json.dumps(meta))
     d["__bf16__"] = np.array(json.dumps(bf))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
@@ -312,8 +338,74 @@ def main_fm_general():
                    use_dynamic_shifting=False)
 
 
+def main_cuda():
+    """`python oracle/make_golden.py cuda` — run ON A GPU BOX (gpurun), where the reference is the byte-identical copy
+    under oracle/_ref (oracle/stage_ref.py).  The reference's schedulers execute on cuda:0 the way its drivers run them;
+    fixtures are prefixed `cuda_`.  They pin what a CPU run cannot:
+      * ATen's CUDA treatment of `0-d CPU scalar (op) 16-bit CUDA tensor` (the schedule scalars of
+        scheduler_ppo.py:309-330 stay on the host) — the sd16 flows,
+      * gen_ppo.py:193-195,:309 — policy cast to fp16 (bins included) and everything under torch.autocast("cuda", fp16),
+      * train_ppo.py:353 / edit_ppo/train_ppo.py:289 — fp32 policy evaluated under accelerator.autocast,
+      * cuBLAS instead of MKL in the policy MLP (the FM softmax at temperature 0.01 amplifies the difference),
+      * use_conv on 16-bit outputs, with the reference's own sampling.
+    Same seeds as the CPU fixtures of the same configuration, so CPU-vs-CUDA spreads of the reference itself can be
+    read off the pairs."""
+    assert torch.cuda.is_available(), "main_cuda needs a GPU"
+    dev = "cuda"
+    small, tok = (4, 8, 8), (16, 8)
+    f16, b16, f32 = torch.float16, torch.bfloat16, torch.float32
+    # fp32 production flows
+    gen_sd("cuda_sd_eps_s0_n8_B3", B=3, shape=small, n=8, guidance=3.0, seed=18, device=dev)
+    gen_sd("cuda_sd_v_s2_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=7.5, seed=24, device=dev,
+           prediction_type="v_prediction", scaler_dim=2)
+    gen_sd("cuda_sd_eps_conv_s0_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=29, use_conv=True,
+           device=dev)
+    # 16-bit model outputs, fp32 policy, no autocast (the CPU sd16_* configurations, now with CUDA scalar semantics)
+    gen_sd("cuda_sd16_f16_pipeline_eps_s0_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=90, dtype=f16,
+           device=dev)
+    gen_sd("cuda_sd16_bf16_pipeline_v_s0_n6_B2", hidden_dim=64, B=2, shape=small, n=6, guidance=3.0, seed=91, dtype=b16,
+           prediction_type="v_prediction", device=dev)
+    gen_sd("cuda_sd16_f16_autocastlayout_eps_s0_n8_B3", hidden_dim=64, B=3, shape=small, n=8, guidance=3.0, seed=92,
+           dtype=f16, latent_dtype=f32, device=dev)
+    gen_sd("cuda_sd16_bf16_autocastlayout_v_s0_n5_B2_ragged", hidden_dim=64, B=2, shape=(3, 5, 7), n=5, guidance=3.0,
+           seed=93, dtype=b16, latent_dtype=f32, prediction_type="v_prediction", device=dev)
+    gen_sd("cuda_sd16_f16_pipeline_eps_s2_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=94, dtype=f16,
+           scaler_dim=2, device=dev)
+    gen_sd("cuda_sd16_f16_pipeline_v_s1_n4_B2", hidden_dim=64, B=2, shape=small, n=4, guidance=3.0, seed=96, dtype=f16,
+           scaler_dim=1, prediction_type="v_prediction", device=dev)
+    gen_sd("cuda_sd16_bf16_autocastlayout_eps_s1_o3_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=95,
+           dtype=b16, latent_dtype=f32, scaler_dim=1, order_dim=3, device=dev)
+    # gen_ppo.py's shipped inference flow: fp16 pipeline, policy (bins included) cast to fp16, all under autocast
+    gen_sd("cuda_genppo_f16_eps_s0_n8_B3", B=3, shape=small, n=8, guidance=3.0, seed=101, dtype=f16, policy_dtype=f16,
+           autocast=f16, device=dev)
+    gen_sd("cuda_genppo_f16_eps_s0_n8_B2_full", B=2, shape=(4, 64, 64), n=8, guidance=7.5, seed=102, dtype=f16,
+           policy_dtype=f16, autocast=f16, device=dev)
+    gen_sd("cuda_genppo_f16_v_s2_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=103, dtype=f16,
+           policy_dtype=f16, autocast=f16, prediction_type="v_prediction", scaler_dim=2, device=dev)
+    gen_sd("cuda_genppo_bf16_eps_s1_n6_B2", hidden_dim=64, B=2, shape=small, n=6, guidance=3.0, seed=104, dtype=b16,
+           policy_dtype=b16, autocast=b16, scaler_dim=1, device=dev)
+    # train_ppo.py:353 rollout: fp32 policy and latents, 16-bit U-Net output, step() inside accelerator.autocast
+    gen_sd("cuda_rollout_f16_eps_s0_n8_B3", B=3, shape=small, n=8, guidance=3.0, seed=105, dtype=f16, latent_dtype=f32,
+           autocast=f16, device=dev)
+    gen_sd("cuda_rollout_bf16_v_s2_n5_B2", hidden_dim=64, B=2, shape=small, n=5, guidance=3.0, seed=106, dtype=b16,
+           latent_dtype=f32, autocast=b16, prediction_type="v_prediction", scaler_dim=2, device=dev)
+    # FM / FLUX flows on the GPU: same seeds as fm_* (CPU) for the reference-vs-reference spread
+    gen_fm("cuda_fm_o2_s0_m0_bf16_n8_B3", B=3, shape=tok, n=8, seed=31, dtype=b16, device=dev)
+    gen_fm("cuda_fm_o2_s0_m0_f32_n8_B3", hidden_dim=64, B=3, shape=tok, n=8, seed=32, dtype=f32, device=dev)
+    gen_fm("cuda_fm_o4_s2_m1_bf16_n8_B3", B=3, shape=tok, n=8, seed=33, dtype=b16, order_dim=4, scaler_dim=2, mu_dim=1,
+           device=dev)
+    gen_fm("cuda_fm_o4_s0_m0_f32_n5_B2", hidden_dim=64, B=2, shape=tok, n=5, seed=34, dtype=f32, order_dim=4, device=dev)
+    gen_fm("cuda_fm_o4_s1_m0_bf16_n6_B2", hidden_dim=64, B=2, shape=tok, n=6, seed=35, dtype=b16, order_dim=4,
+           scaler_dim=1, device=dev)
+    gen_fm("cuda_fm_conv_o4_s0_m0_bf16_n6_B2", hidden_dim=64, B=2, shape=tok, n=6, seed=38, dtype=b16, order_dim=4,
+           use_conv=True, device=dev)
+    gen_fm("cuda_fm_rollout_bf16_autocast_n8_B3", B=3, shape=tok, n=8, seed=39, dtype=b16, autocast=b16, device=dev)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["cuda"]:
+        return main_cuda()
     if sys.argv[1:] == ["fm_general"]:
         return main_fm_general()
     if sys.argv[1:] == ["amed"]:

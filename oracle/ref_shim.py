@@ -9,8 +9,9 @@ This file installs minimal stand-ins for the diffusers base classes (they contai
 `self.config` plumbing), a one-class stub for the missing module, and loads the SD / FM variants under
 distinct module names.  Nothing from the reference is copied; the reference source files are executed
 where they lie.  /root/reference exists only in the build container, so this module is used solely by
-`oracle/make_golden.py` (to write tests/golden/*.npz) and by the optional `-m "not gpu"` cross-check
-tests, which skip when the tree is missing.  It is never imported by the product package.
+`oracle/make_golden.py` (to write tests/golden/*.npz), by the optional `-m "not gpu"` cross-check tests (which skip
+when the tree is missing) and by bench.py's reference legs.  On the GPU box the same unmodified files are found under
+the git-ignored oracle/_ref/ (oracle/stage_ref.py).  It is never imported by the product package.
 """
 from __future__ import annotations
 
@@ -25,11 +26,29 @@ import sys
 import types
 from collections import OrderedDict
 
-REFERENCE_ROOT = os.environ.get("CONSOLVER_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve_root() -> str:
+    """CONSOLVER_REFERENCE_ROOT if set; else the live tree (build container); else the byte-identical copies that
+    oracle/stage_ref.py put under the git-ignored oracle/_ref/ (the GPU box, where /root/reference does not exist)."""
+    env = os.environ.get("CONSOLVER_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/scheduler_ppo.py"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "scheduler_ppo.py"))
+
+
+def reference_is_staged_copy() -> bool:
+    return os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_STAGED)
 
 
 class _FrozenDict(OrderedDict):
@@ -346,4 +365,12 @@ def load_reference():
 def quiet():
     """The reference prints on every step (scheduler_ppo.py:243,:289); silence it."""
     with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+@contextlib.contextmanager
+def devnull():
+    """stdout -> /dev/null for timed runs of the reference (its per-step prints still format their tensors:
+    that cost is the reference's own)."""
+    with open(os.devnull, "w") as f, contextlib.redirect_stdout(f):
         yield

@@ -61,6 +61,73 @@ def test_fm_oracle_matches_reference(name):
         assert torch.equal(x, g[f"prev_{i}"]), f"step {i} latent not bit-exact"
 
 
+# ---- fixtures made by the reference running ON A B200 (oracle/make_golden.py cuda): ATen's CUDA scalar rules, the
+# ---- shipped fp16-autocast inference flow (gen_ppo.py:193-195,:309), the autocast training rollouts ---------------------
+_DT = {None: None, "float16": torch.float16, "bfloat16": torch.bfloat16}
+# measured on the 23 fixtures (profiles/parity_spread_r02.md): the oracle's torch-CPU MLP vs the reference's cuBLAS MLP
+CUDA_PROB_ATOL, CUDA_PROB_RTOL = 4e-6, 1e-4
+
+
+def cuda_oracle(g):
+    """the oracle configured the way fixture `g` was produced (device / autocast / policy dtype from its meta)"""
+    import numpy as np
+    m = g.meta
+    sem = orc.TorchSemantics(m.get("device", "cpu"), _DT[m.get("autocast")])
+    if m["kind"] == "sd":
+        s = orc.OracleSDScheduler(g.state_dict, sem=sem, policy_dtype=_DT[m.get("policy_dtype")], **m["config"])
+        s.set_timesteps(m["n"])
+        return s
+    cfg = dict(m["config"])
+    for k in ("base_shift", "max_shift", "base_image_seq_len", "max_image_seq_len"):
+        cfg.pop(k, None)
+    s = orc.OracleFMScheduler(g.state_dict, sem=sem, **cfg)
+    s.set_timesteps(m["n"], sigmas=np.linspace(1.0, 1 / m["n"], m["n"]), mu=m["mu"])
+    if m["use_begin_index"]:
+        s.set_begin_index(0)
+    return s
+
+
+@pytest.mark.parametrize("name", names("cuda_"))
+def test_oracle_with_cuda_semantics_matches_the_reference_run_on_a_gpu(name):
+    """Every latent (value AND dtype), the CFG-combined outputs, actions, masks and condition rows bit-identical; the
+    oracle's own categorical draw (its MLP + the fixture's Exp(1) values) picks the reference's indices; softmax
+    tables within the measured MKL-vs-cuBLAS spread."""
+    g = Golden(name)
+    m = g.meta
+    assert m["device"] == "cuda"
+    s = cuda_oracle(g)
+    assert torch.equal(s.timesteps, g["timesteps"])
+    x = g["x_T"]
+    for i, t in enumerate(s.timesteps):
+        if m["kind"] == "sd":
+            u, c = g[f"pair_{i}"].chunk(2)
+            mo = orc.cfg_combine(u, c, m["guidance"])
+            assert torch.equal(mo, g[f"eps_{i}"])
+        else:
+            mo = g[f"v_{i}"]
+        x, actions, probs, conds, masks = s.step(mo, t, x, q=g[f"q_{i}"])
+        assert torch.equal(s.last_idx, g[f"idx_{i}"]), f"step {i} indices"
+        assert actions.dtype == g[f"actions_{i}"].dtype and torch.equal(actions, g[f"actions_{i}"])
+        assert torch.equal(masks, g[f"masks_{i}"])
+        assert torch.equal(conds["x"], g[f"condx_{i}"])
+        torch.testing.assert_close(s.last_probs_full, g[f"probs_full_{i}"], rtol=CUDA_PROB_RTOL, atol=CUDA_PROB_ATOL)
+        ref = g[f"prev_{i}"]
+        assert x.dtype == ref.dtype, f"step {i}: latent dtype {x.dtype} vs {ref.dtype}"
+        assert torch.equal(x, ref), f"step {i} latent not bit-exact"
+
+
+def test_host_and_cuda_semantics_differ_where_aten_differs():
+    """the two rule sets are not interchangeable: true division vs reciprocal multiply (fp32), scalar rounding (fp16)"""
+    torch.manual_seed(0)
+    x, e = torch.randn(4096), torch.randn(4096)
+    sc = orc.ddim_scalars(orc.sd_alphas_cumprod(orc.sd_betas(beta_schedule="scaled_linear", beta_start=0.00085,
+                                                             beta_end=0.012)), 624, 499)
+    a, b = orc.ddim_update(x, e, sc, sem=orc.HOST), orc.ddim_update(x, e, sc, sem=orc.CUDA)
+    assert not torch.equal(a, b) and (a - b).abs().max() <= 4e-6
+    a, b = orc.ddim_update(x.half(), e.half(), sc, sem=orc.HOST), orc.ddim_update(x.half(), e.half(), sc, sem=orc.CUDA)
+    assert a.dtype == b.dtype == torch.float16 and not torch.equal(a, b)
+
+
 def _fmgen_set_timesteps(s, m):
     import numpy as np
     if m["config"]["use_dynamic_shifting"]:
