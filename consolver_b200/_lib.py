@@ -14,6 +14,9 @@ LIB_PATH = os.path.join(_PKG, "libconsolver.so")
 F32, F16, BF16 = 0, 1, 2
 DPM_CONVERT_NONE, DPM_CONVERT_DIV, DPM_CONVERT_LIN = 0, 1, 2
 FLAG_VPRED, FLAG_EFF_SCALE, FLAG_X_SCALE, FLAG_PDL, FLAG_CHAIN, FLAG_LOWP_COMBINE, FLAG_X_F32, FLAG_X_WAS_LOWP = 1, 2, 4, 8, 16, 32, 64, 128
+FLAG_HOST_SCALARS, FLAG_LOWP_COEF = 256, 512
+POLICY_HOST_DIV, POLICY_ACT_F16, POLICY_ACT_BF16, POLICY_COEF_F16, POLICY_COEF_BF16 = 1, 2, 4, 8, 16
+ABI_VERSION = 3          # must equal CONSOLVER_ABI_VERSION of include/consolver.h (tests/test_abi_cpu.py checks)
 MAX_ORDER, MAX_HIDDEN, MAX_LOGITS, MAX_IN = 8, 1024, 4096, 16
 
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -21,17 +24,18 @@ _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 # name -> (restype, argtypes): must list every symbol declared in include/consolver.h
 SIGNATURES = {
     "consolver_abi_version": (_i, []),
+    "consolver_abi_hash": (C.c_uint64, []),
     "consolver_error_string": (C.c_char_p, [_i]),
-    "consolver_policy_f32": (_i, [_p] * 7 + [_f] * 4 + [_p, _i] + [_p, _p] + [_i] * 7 + [_p] * 7 + [_p]),
+    "consolver_policy_f32": (_i, [_p] * 7 + [_f] * 4 + [_p, _i] + [_p, _p] + [_i] * 8 + [_p] * 7 + [_p]),
     "consolver_step_sd": (_i, [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_step_fm": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
     "consolver_step_fm_strided": (_i, [_i, _i, _p, _i64, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _i, _f, _i, _i, _i64, _p]),
     "consolver_step_dpm": (_i, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _p, _i, _i64, _p]),
-    "consolver_policy_table_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i, _p, _p]),
-    "consolver_policy_sample_f32": (_i, [_p] * 4 + [_p, _p] + [_i] * 6 + [_p] * 6 + [_p]),
+    "consolver_policy_table_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i, _i, _p, _p]),
+    "consolver_policy_sample_f32": (_i, [_p] * 4 + [_p, _p] + [_i] * 7 + [_p] * 6 + [_p]),
     "consolver_rng_state_advance": (_i, [_p, C.c_uint64, _p]),
     "consolver_torch_philox_plan": (_i, [_i64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
-    "consolver_sd_policy_and_step": (_i, [_p] * 8 + [_f] * 4 + [_p, _p, _p] + [_i] * 4 + [_p] * 7 +
+    "consolver_sd_policy_and_step": (_i, [_p] * 8 + [_f] * 4 + [_p, _p, _p] + [_i] * 5 + [_p] * 7 +
                                      [_i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _i64, _i, _f, _f, _f, _f, _i, _i, _i64, _p]),
     "consolver_set_step_launch": (_i, [_i, _i]),
     "consolver_ppo_workspace": (C.c_size_t, [_i, _i, _i, _i]),
@@ -65,8 +69,38 @@ class ConsolverError(RuntimeError):
     pass
 
 
+def bind(path: str):
+    """dlopen `path`, check that it was built from THIS tree's include/consolver.h (ABI version + header hash) and
+    attach the ctypes signatures.  A library built from another header revision is rejected before any entry point
+    with a possibly different argument list can be called."""
+    lib = C.CDLL(path)
+    for name in ("consolver_abi_version", "consolver_abi_hash"):
+        if not hasattr(lib, name):
+            raise ConsolverError(f"{path} does not export {name}: it predates this header; rebuild it "
+                                 "(`python -m consolver_b200.build --force`)")
+    lib.consolver_abi_version.restype, lib.consolver_abi_version.argtypes = _i, []
+    lib.consolver_abi_hash.restype, lib.consolver_abi_hash.argtypes = C.c_uint64, []
+    if lib.consolver_abi_version() != ABI_VERSION:
+        raise ConsolverError(f"{path}: ABI version {lib.consolver_abi_version()} != {ABI_VERSION}; rebuild it")
+    from .build import HEADER, header_hash
+
+    if os.path.exists(HEADER) and lib.consolver_abi_hash() != header_hash():
+        raise ConsolverError(f"{path} was built from a different include/consolver.h "
+                             f"(hash {lib.consolver_abi_hash():#x} != {header_hash():#x}); rebuild it")
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ConsolverError(f"{path} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
 def load(autobuild: bool = True):
-    """Load (building first if the .so is missing or stale and nvcc is present).  Raises on failure."""
+    """Load libconsolver.so, rebuilding it first when its content stamp says it is not current.  A failed rebuild
+    raises: a stale library is never used in its place.  CONSOLVER_NO_AUTOBUILD=1 skips the rebuild (the header-hash
+    check in `bind` still applies)."""
     global _lib
     if _lib is not None:
         return _lib
@@ -74,28 +108,18 @@ def load(autobuild: bool = True):
         if _lib is not None:
             return _lib
         if autobuild and os.environ.get("CONSOLVER_NO_AUTOBUILD") != "1":
-            try:
-                from .build import build_library
+            from .build import build_library
 
+            try:
                 build_library()
             except Exception as e:  # noqa: BLE001
-                if not os.path.exists(LIB_PATH):
-                    raise ConsolverError(
-                        f"libconsolver.so is missing and could not be built ({e}). consolver_b200 has no "
-                        "CPU/PyTorch fallback: run `python -m consolver_b200.build` with nvcc available.") from e
+                raise ConsolverError(
+                    f"libconsolver.so is missing or out of date and could not be rebuilt ({e}). consolver_b200 has no "
+                    "CPU/PyTorch fallback and does not fall back to a stale library: run "
+                    "`python -m consolver_b200.build` with nvcc available.") from e
         if not os.path.exists(LIB_PATH):
             raise ConsolverError(f"{LIB_PATH} not found; run `python -m consolver_b200.build`")
-        lib = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            try:
-                fn = getattr(lib, name)
-            except AttributeError as e:
-                raise ConsolverError(f"libconsolver.so does not export {name}; rebuild it") from e
-            fn.restype = res
-            fn.argtypes = args
-        if lib.consolver_abi_version() != 1:
-            raise ConsolverError("libconsolver.so ABI version mismatch; rebuild it")
-        _lib = lib
+        _lib = bind(LIB_PATH)
     return _lib
 
 

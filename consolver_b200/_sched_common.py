@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -10,6 +11,10 @@ import torch
 from . import _lib
 from .config_utils import LazyConds
 from .factor_net import alloc_policy_outputs
+
+
+#: default of `scheduler.reference_device` for newly built schedulers ("cuda" unless CONSOLVER_REFERENCE_DEVICE=cpu)
+DEFAULT_REFERENCE_DEVICE = os.environ.get("CONSOLVER_REFERENCE_DEVICE", "cuda")
 
 
 class Trajectory:
@@ -166,6 +171,12 @@ class SolverOptions:
     """Optional knobs shared by both schedulers (none of them changes a number)."""
 
     def _init_solver_options(self):
+        #: Which execution of the reference the arithmetic reproduces bit for bit.  "cuda" (default): the reference run
+        #: on CUDA tensors, the way its drivers run it — ATen hands the host-resident schedule scalars to the kernels as
+        #: fp32 values and turns `t / scalar` into `t * (1/scalar)` (pinned by tests/golden/cuda_*).  "cpu": the
+        #: reference run on CPU tensors (true divisions, scalars rounded to a 16-bit tensor's dtype first; pinned by the
+        #: CPU-made fixtures).  The two differ by an ulp here and there, also in fp32.
+        self.reference_device = DEFAULT_REFERENCE_DEVICE
         #: True (default): a CUDA `timestep` tensor is NOT read back; the value is taken from the host copy of the grid
         #: at the current step count (pipelines step in grid order).  False: `.item()` it (one sync per step).
         self.sync_free = True
@@ -188,6 +199,38 @@ class SolverOptions:
         self.fixed_depth: Optional[int] = None
         self._hist: List[torch.Tensor] = []    # model outputs, NEWEST FIRST (references or ring slots)
         self._traj: Optional[Trajectory] = None
+
+    def _semantics(self, model_dtype: torch.dtype):
+        """-> (step flags, policy flags, dtype the policy MLP runs in or None) for this call, from `reference_device`,
+        the autocast state and the policy's own dtype.
+
+        * autocast (gen_ppo.py:309, train_ppo.py:353, edit_ppo/train_ppo.py:289): nn.Linear runs in the autocast dtype,
+          softmax and torch.sum in fp32.  A policy whose parameters are 16-bit only runs under autocast in the
+          reference (fp32 inputs into a 16-bit Linear raise otherwise) and is treated the same.
+        * a policy cast to the pipeline dtype, bin buffer included (gen_ppo.py:193-195): the per-sample coefficients
+          are 16-bit tensors (CONSOLVER_FLAG_LOWP_COEF / CONSOLVER_POLICY_COEF_*)."""
+        if self.reference_device not in ("cuda", "cpu"):
+            raise ValueError("reference_device must be 'cuda' or 'cpu'")
+        host = self.reference_device == "cpu"
+        sflags = _lib.FLAG_HOST_SCALARS if host else 0
+        pflags = _lib.POLICY_HOST_DIV if host else 0
+        fn = self.factor_net_module
+        act = None
+        wdt = fn._kparams_dtype()
+        if wdt in (torch.float16, torch.bfloat16):
+            act = wdt
+        elif torch.is_autocast_enabled("cuda"):
+            ad = torch.get_autocast_dtype("cuda")
+            if ad in (torch.float16, torch.bfloat16):
+                act = ad
+        if act is not None:
+            pflags |= _lib.POLICY_ACT_F16 if act == torch.float16 else _lib.POLICY_ACT_BF16
+        bdt = fn._buffers["action_values"].dtype
+        if bdt in (torch.float16, torch.bfloat16):
+            pflags |= _lib.POLICY_COEF_F16 if bdt == torch.float16 else _lib.POLICY_COEF_BF16
+            if bdt == model_dtype:
+                sflags |= _lib.FLAG_LOWP_COEF
+        return sflags, pflags, act
 
     @property
     def factor_net_module(self):

@@ -2,9 +2,13 @@
 // PPO update kernel (ppo.cu): warp reductions, L2 prefetch / cp.async helpers, the one-warp-per-row dense layer and
 // the MLP + softmax forward for one input row.  See policy.cu for the design notes.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+
+#include "../../include/consolver.h"
 
 namespace consolver {
 
@@ -12,7 +16,21 @@ struct MlpView {
   const float *w1, *b1, *w2, *b2, *w3, *b3;
   int H, A, K;
   float temp;
+  int flags;   // CONSOLVER_POLICY_*
 };
+
+// the value a 16-bit torch tensor would hold: mode = CONSOLVER_POLICY_ACT_F16 / _BF16 bits (0: fp32, unchanged)
+__device__ __forceinline__ float round_act(float v, int mode) {
+  if (mode & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_COEF_F16)) return __half2float(__float2half_rn(v));
+  if (mode & (CONSOLVER_POLICY_ACT_BF16 | CONSOLVER_POLICY_COEF_BF16)) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+// normalize_input (factor_net_ppo.py:104-106): x.float() / 999.0 — on CUDA tensors ATen multiplies by the fp32
+// reciprocal of the python scalar; under autocast the first Linear then rounds its input to the autocast dtype
+__device__ __forceinline__ float policy_input(float x, float x_div, int flags) {
+  const float v = (flags & CONSOLVER_POLICY_HOST_DIV) ? __fdiv_rn(x, x_div) : __fmul_rn(x, __fdiv_rn(1.f, x_div));
+  return round_act(v, flags & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_ACT_BF16));
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -43,7 +61,7 @@ __device__ __forceinline__ void prefetch_range_l2(const void* p, size_t bytes) {
 // y[r] = act(b[r] + W[r,:] . x) for r in [0,R): one warp per row, ROWS rows of loads in flight per warp.
 template <bool RELU>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias,
-                                            const float* x_s, float* y_s, int R, int C) {
+                                            const float* x_s, float* y_s, int R, int C, int act_mode = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const bool vec = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15u) == 0);
   constexpr int ROWS = 8;
@@ -79,7 +97,7 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
     for (int i = 0; i < ROWS; ++i) {
       const double s = warp_sum((double)acc[i]);
       if (lane == 0 && r0 + i < R) {
-        float v = (float)(s + (double)__ldg(bias + r0 + i));
+        float v = round_act((float)(s + (double)__ldg(bias + r0 + i)), act_mode);
         y_s[r0 + i] = RELU ? fmaxf(v, 0.f) : v;
       }
     }
@@ -90,24 +108,28 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
 __device__ __forceinline__ void mlp_softmax(const MlpView& p, int in_dim, const float* x_s, float* h1_s,
                                             float* h2_s, float* lg_s, float* p_s) {
   const int H = p.H, AK = p.A * p.K;
+  const int act = p.flags & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_ACT_BF16);
   // layer 0: in_dim is 2 (or 2 + order_dim - 1): one thread per hidden unit
   for (int j = threadIdx.x; j < H; j += blockDim.x) {
     double acc = 0.0;
     for (int i = 0; i < in_dim; ++i) acc = fma((double)__ldg(p.w1 + j * in_dim + i), (double)x_s[i], acc);
-    h1_s[j] = fmaxf((float)(acc + (double)__ldg(p.b1 + j)), 0.f);
+    h1_s[j] = fmaxf(round_act((float)(acc + (double)__ldg(p.b1 + j)), act), 0.f);
   }
   __syncthreads();
-  dense_layer<true>(p.w2, p.b2, h1_s, h2_s, H, H);
+  dense_layer<true>(p.w2, p.b2, h1_s, h2_s, H, H, act);
   __syncthreads();
-  dense_layer<false>(p.w3, p.b3, h2_s, lg_s, AK, H);
+  dense_layer<false>(p.w3, p.b3, h2_s, lg_s, AK, H, act);
   __syncthreads();
+  // logits / temp: a true division on CPU tensors, a multiplication by the fp32 reciprocal on CUDA tensors
+  const bool host_div = p.flags & CONSOLVER_POLICY_HOST_DIV;
+  const float inv_temp = __fdiv_rn(1.f, p.temp);
   // softmax(logits / temp) per action dim: one warp per dim
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int a = warp; a < p.A; a += nwarp) {
     float* l = lg_s + a * p.K;
     float m = -INFINITY;
     for (int k = lane; k < p.K; k += 32) {
-      const float v = __fdiv_rn(l[k], p.temp);
+      const float v = round_act(host_div ? __fdiv_rn(l[k], p.temp) : __fmul_rn(l[k], inv_temp), act);
       l[k] = v;
       m = fmaxf(m, v);
     }

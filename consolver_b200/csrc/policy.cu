@@ -40,6 +40,7 @@ struct PolicyParams {
   const float* q;
   const long long* idx_in;
   int B, H, A, K, order_dim, scaler_dim, n_hist;
+  int flags;                // CONSOLVER_POLICY_*
   float* probs_table;
   long long* idx;
   float *actions, *act_probs, *act_logp, *masks, *coef;
@@ -75,7 +76,7 @@ __device__ __forceinline__ float torch_exponential_at(unsigned long long seed, u
 }
 
 __device__ __forceinline__ MlpView mlp_view(const PolicyParams& p) {
-  return MlpView{p.w1, p.b1, p.w2, p.b2, p.w3, p.b3, p.H, p.A, p.K, p.temp};
+  return MlpView{p.w1, p.b1, p.w2, p.b2, p.w3, p.b3, p.H, p.A, p.K, p.temp, p.flags};
 }
 
 // Start the asynchronous copy of this CTA's contiguous Exp(1) slab q[b_begin*A*K ...] into shared memory.
@@ -161,12 +162,15 @@ __device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin,
     if (p.masks) p.masks[o] = (a >= p.n_hist - 1 && a < od - 1) ? 0.f : 1.f;   // scheduler_ppo.py:248-249
   }
   __syncthreads();
-  // set_default_coefficients (scheduler_ppo.py:165-175): c0 = a0 + 1, c_{n-1} = 1 - sum(c_0..c_{n-2})
+  // set_default_coefficients (scheduler_ppo.py:165-175): c0 = a0 + 1, c_{n-1} = 1 - sum(c_0..c_{n-2}).
+  // COEF_F16/_BF16: the bin values are 16-bit tensors, so a0 + 1 and s + 1 are rounded to that dtype; torch.sum
+  // returns fp32 under autocast, so the running sum and the closing coefficient are fp32 (exact sums of 16-bit values)
   const int n = p.n_hist;
+  const int cm = p.flags & (CONSOLVER_POLICY_COEF_F16 | CONSOLVER_POLICY_COEF_BF16);
   for (int bl = threadIdx.x; bl < nb; bl += blockDim.x) {
     const float* act = act_s + (size_t)bl * A;
     float* c = p.coef + (size_t)(b_begin + bl) * (od + 2);
-    const float c0 = __fadd_rn(act[0], 1.f);
+    const float c0 = round_act(__fadd_rn(act[0], 1.f), cm);
     float run = c0;
     for (int i = 0; i < od; ++i) {
       float v = 0.f;
@@ -182,8 +186,8 @@ __device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin,
       }
       c[i] = v;
     }
-    c[od] = p.scaler_dim >= 1 ? __fadd_rn(act[od - 1], 1.f) : 1.f;
-    c[od + 1] = p.scaler_dim >= 2 ? __fadd_rn(act[od], 1.f) : 1.f;
+    c[od] = p.scaler_dim >= 1 ? round_act(__fadd_rn(act[od - 1], 1.f), cm) : 1.f;
+    c[od + 1] = p.scaler_dim >= 2 ? round_act(__fadd_rn(act[od], 1.f), cm) : 1.f;
   }
 }
 
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(kPolicyThreads) policy_kernel(const PolicyPara
 
   if (p.feat == nullptr) {
     if (threadIdx.x == 0) {
-      s.x[0] = __fdiv_rn(p.x0, p.x_div);   // normalize_input: x.float() / 999.0 (identity for FM)
-      s.x[1] = __fdiv_rn(p.x1, p.x_div);
+      s.x[0] = policy_input(p.x0, p.x_div, p.flags);   // normalize_input: x.float() / 999.0 (identity for FM)
+      s.x[1] = policy_input(p.x1, p.x_div, p.flags);
     }
     __syncthreads();
     mlp_softmax(mlp_view(p), in_dim, s.x, s.h1, s.h2, s.lg, s.p);
@@ -235,10 +239,12 @@ __global__ void __launch_bounds__(kPolicyThreads) policy_kernel(const PolicyPara
     for (int bl = 0; bl < nb; ++bl) {
       const int b = b_begin + bl;
       if (threadIdx.x == 0) {
-        s.x[0] = __fdiv_rn(p.x0, p.x_div);
-        s.x[1] = __fdiv_rn(p.x1, p.x_div);
+        s.x[0] = policy_input(p.x0, p.x_div, p.flags);
+        s.x[1] = policy_input(p.x1, p.x_div, p.flags);
       }
-      if (threadIdx.x < p.n_feat) s.x[2 + threadIdx.x] = __ldg(p.feat + (size_t)b * p.n_feat + threadIdx.x);
+      if (threadIdx.x < p.n_feat)
+        s.x[2 + threadIdx.x] = round_act(__ldg(p.feat + (size_t)b * p.n_feat + threadIdx.x),
+                                         p.flags & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_ACT_BF16));
       __syncthreads();
       mlp_softmax(mlp_view(p), in_dim, s.x, s.h1, s.h2, s.lg, s.p);
       if (p.probs_table)   // per-sample tables [B,A,K]
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(kPolicyThreads) policy_table_kernel(const Poli
   const Smem s = carve(smem, p.H, AK, 0, p.A);
   prefetch_range_l2(p.w2, (size_t)p.H * p.H * sizeof(float));
   prefetch_range_l2(p.w3, (size_t)AK * p.H * sizeof(float));
-  if (threadIdx.x < 2) s.x[threadIdx.x] = __fdiv_rn(__ldg(p.x_rows + 2 * blockIdx.x + threadIdx.x), p.x_div);
+  if (threadIdx.x < 2) s.x[threadIdx.x] = policy_input(__ldg(p.x_rows + 2 * blockIdx.x + threadIdx.x), p.x_div, p.flags);
   __syncthreads();
   mlp_softmax(mlp_view(p), 2, s.x, s.h1, s.h2, s.lg, s.p);
   for (int i = threadIdx.x; i < AK; i += blockDim.x) p.probs_table[(size_t)blockIdx.x * AK + i] = s.p[i];
@@ -334,11 +340,14 @@ static int launch_policy(const PolicyParams& pp, int mode, int rows, cudaStream_
   const int grid = (p.B + spc - 1) / spc;
   const int H = mode == kLaunchSample ? 0 : p.H;
   const size_t smem = smem_floats(H, AK, spc, p.A, q_floats) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per DEVICE (the attribute lives in the device's context): one process may drive several GPUs
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(policy_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   if (mode == kLaunchSample)
     policy_sample_kernel<<<grid, kPolicyThreads, smem, stream>>>(p);
@@ -351,7 +360,9 @@ static int launch_policy(const PolicyParams& pp, int mode, int rows, cudaStream_
 
 using namespace consolver;
 
+#include "abi_hash.h"   // generated from include/consolver.h by consolver_b200/build.py
 extern "C" int consolver_abi_version(void) { return CONSOLVER_ABI_VERSION; }
+extern "C" uint64_t consolver_abi_hash(void) { return CONSOLVER_ABI_HEADER_HASH; }
 
 extern "C" const char* consolver_error_string(int err) {
   switch (err) {
@@ -370,9 +381,11 @@ extern "C" int consolver_policy_f32(const float* w1, const float* b1, const floa
                                     const float* feat, int n_feat,
                                     const float* q, const int64_t* idx_in,
                                     int B, int H, int A, int K, int order_dim, int scaler_dim, int n_hist,
+                                    int policy_flags,
                                     float* probs_table, int64_t* idx, float* actions, float* act_probs,
                                     float* act_logp, float* masks, float* coef, consolver_stream_t stream) {
   PolicyParams p = {};
+  p.flags = policy_flags;
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.action_values = action_values;
   p.x0 = x0; p.x1 = x1; p.x_div = x_div; p.temp = temp;
   p.feat = feat; p.n_feat = n_feat; p.q = q; p.idx_in = reinterpret_cast<const long long*>(idx_in);
@@ -384,9 +397,10 @@ extern "C" int consolver_policy_f32(const float* w1, const float* b1, const floa
 
 extern "C" int consolver_policy_table_f32(const float* w1, const float* b1, const float* w2, const float* b2,
                                           const float* w3, const float* b3, const float* x_rows, int rows,
-                                          float x_div, float temp, int H, int A, int K, float* probs_tables,
-                                          consolver_stream_t stream) {
+                                          float x_div, float temp, int H, int A, int K, int policy_flags,
+                                          float* probs_tables, consolver_stream_t stream) {
   PolicyParams p = {};
+  p.flags = policy_flags;
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
   p.x_rows = x_rows; p.x_div = x_div; p.temp = temp; p.H = H; p.A = A; p.K = K; p.probs_table = probs_tables;
   return launch_policy(p, kLaunchTable, rows, static_cast<cudaStream_t>(stream));
@@ -414,14 +428,12 @@ extern "C" int consolver_torch_philox_plan(int64_t numel, uint32_t* nthreads, ui
   // at::cuda::detail calc_execution_policy (ATen/native/cuda/DistributionTemplates.h): block 256, grid =
   // min(ceil(numel/256), SMs * maxThreadsPerSM/256), increment = ceil(numel / (256*grid*4)) * 4
   if (numel <= 0 || !nthreads || !offset_increment) return CONSOLVER_ERR_SIZE;
-  static int sms = 0, per_sm = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
-  }
+  int sms = 0, per_sm = 0, dev = 0;     // of the CURRENT device (two attribute reads; not on the per-step path)
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  if (sms <= 0 || per_sm <= 0) return CONSOLVER_ERR_UNSUPPORTED;
   const uint64_t n = (uint64_t)numel, block = 256;
   uint64_t grid = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)sms * (uint64_t)(per_sm / (int)block);
@@ -434,10 +446,11 @@ extern "C" int consolver_torch_philox_plan(int64_t numel, uint32_t* nthreads, ui
 extern "C" int consolver_policy_sample_f32(const float* probs_in, const float* action_values, const float* q,
                                            const int64_t* idx_in, const consolver_rng_t* rng, float* q_out,
                                            int B, int A, int K, int order_dim,
-                                           int scaler_dim, int n_hist, int64_t* idx, float* actions,
+                                           int scaler_dim, int n_hist, int policy_flags, int64_t* idx, float* actions,
                                            float* act_probs, float* act_logp, float* masks, float* coef,
                                            consolver_stream_t stream) {
   PolicyParams p = {};
+  p.flags = policy_flags;
   p.probs_in = probs_in; p.action_values = action_values; p.q = q;
   p.idx_in = reinterpret_cast<const long long*>(idx_in);
   p.B = B; p.A = A; p.K = K; p.order_dim = order_dim; p.scaler_dim = scaler_dim; p.n_hist = n_hist;
@@ -452,7 +465,7 @@ extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, co
                                             const float* probs_in,
                                             float x0, float x1, float x_div, float temp,
                                             const float* q, const int64_t* idx_in, const consolver_rng_t* rng,
-                                            int H, int A, int K, int scaler_dim,
+                                            int H, int A, int K, int scaler_dim, int policy_flags,
                                             float* probs_table, int64_t* idx, float* actions, float* act_probs,
                                             float* act_logp, float* masks, float* coef,
                                             int dtype, const void* e0, const void* cond, float guidance,
@@ -464,11 +477,12 @@ extern "C" int consolver_sd_policy_and_step(const float* w1, const float* b1, co
   int rc;
   if (probs_in) {
     rc = consolver_policy_sample_f32(probs_in, action_values, q, idx_in, rng, nullptr, B, A, K, order_dim,
-                                     scaler_dim, n_hist, idx, actions, act_probs, act_logp, masks, coef, stream);
+                                     scaler_dim, n_hist, policy_flags, idx, actions, act_probs, act_logp, masks, coef,
+                                     stream);
   } else {
     rc = consolver_policy_f32(w1, b1, w2, b2, w3, b3, action_values, x0, x1, x_div, temp, nullptr, 0, q, idx_in,
-                              B, H, A, K, order_dim, scaler_dim, n_hist, probs_table, idx, actions, act_probs,
-                              act_logp, masks, coef, stream);
+                              B, H, A, K, order_dim, scaler_dim, n_hist, policy_flags, probs_table, idx, actions,
+                              act_probs, act_logp, masks, coef, stream);
   }
   if (rc) return rc;
   int f = flags;

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kPpoThreads) ppo_row_kernel(const PpoParams p)
 
   prefetch_range_l2(p.m.w2, (size_t)H * H * sizeof(float));
   prefetch_range_l2(p.m.w3, (size_t)AK * H * sizeof(float));
-  if (tid < 2) x_s[tid] = __fdiv_rn(__ldg(p.x_rows + 2 * r + tid), p.x_div);
+  if (tid < 2) x_s[tid] = policy_input(__ldg(p.x_rows + 2 * r + tid), p.x_div, p.m.flags);
   __syncthreads();
   mlp_softmax(p.m, 2, x_s, h1_s, h2_s, lg_s, p_s);
 
@@ -244,7 +244,7 @@ extern "C" int consolver_ppo_loss_grad_f32(const float* w1, const float* b1, con
       (long long)A * K > CONSOLVER_MAX_LOGITS || !(temp > 0.f) || x_div == 0.f)
     return CONSOLVER_ERR_SIZE;
   PpoParams p = {};
-  p.m = MlpView{w1, b1, w2, b2, w3, b3, H, A, K, temp};
+  p.m = MlpView{w1, b1, w2, b2, w3, b3, H, A, K, temp, 0};   // the update runs on CUDA tensors in the reference
   p.x_rows = x_rows; p.x_div = x_div;
   p.idx = reinterpret_cast<const long long*>(idx); p.old_probs = old_probs; p.adv = advantages;
   p.R = rows; p.B = B; p.clip = clip_range; p.ent_coef = entropy_coef;
@@ -254,10 +254,12 @@ extern "C" int consolver_ppo_loss_grad_f32(const float* w1, const float* b1, con
   p.parts = 8192 / (A * K) >= 8 ? 8 : (8192 / (A * K) >= 1 ? 8192 / (A * K) : 1);
   const size_t smem = (size_t)(16 + 4 * r4(H) + 3 * r4(A * K) + 32 + kPpoChunk + A * K * p.parts) * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};     // per device: the attribute lives in the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaFuncSetAttribute(ppo_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   ppo_row_kernel<<<rows, kPpoThreads, smem, s>>>(p);
   cudaError_t e = cudaGetLastError();

@@ -23,7 +23,9 @@ enum : int { kModeSD = 0, kModeFM = 1, kModeFMStrided = 2 };
 // The next latent is written as T by the FM step (the reference casts back to the model dtype,
 // edit_ppo/scheduler_fmppo.py:436) and as TX by the SD step (torch promotion: fp32 latents with 16-bit model outputs
 // under accelerator.autocast stay fp32, train_ppo.py:353).
-template <typename T, typename TX, int NH, int MODE, int E, int U>
+// HOST : CONSOLVER_FLAG_HOST_SCALARS resolved at compile time (SD only), so that the default instantiations — the ones
+//        that run in production — carry no IEEE-division slow path; HOST = true exists only with U = 1.
+template <typename T, typename TX, int NH, int MODE, int E, int U, bool HOST = false>
 __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
   using TO = typename std::conditional<MODE == kModeSD, TX, T>::type;
   constexpr int kOlder = NH ? NH - 1 : kMaxOlder;
@@ -89,6 +91,24 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
   const bool vpred = p.flags & CONSOLVER_FLAG_VPRED;
   const bool lowp = p.flags & CONSOLVER_FLAG_LOWP_COMBINE;
   const float g = p.guidance;
+  // ---- which torch rules the reference's expressions were evaluated under (see consolver.h) ----------------------
+  constexpr bool k16 = Elem<T>::k16;
+  constexpr bool host = HOST;                                  // CPU-torch: true division, scalars rounded to 16 bit
+  const bool lowc = k16 && (p.flags & CONSOLVER_FLAG_LOWP_COEF);   // coefficients are 16-bit tensors (all but the last)
+  const float inv_k0 = __fdiv_rn(1.f, p.k0);                   // ATen CUDA: t / scalar == t * (1/scalar)
+  // Is the combined estimate / the sample still a 16-bit TENSOR in the reference when _get_prev_sample runs?  Uniform
+  // over the launch.  The estimate is promoted by the first fp32 per-sample multiplier it meets: any coefficient of an
+  // fp32 policy (n_hist > 1, or a scaler), the closing coefficient of a 16-bit policy (n_hist > 1).  The sample is a
+  // 16-bit tensor when the latent is stored as one, or was one before this step's promotion (X_WAS_LOWP), and stays
+  // one through a 16-bit (1+s1) scaling.
+  const bool e16_in = k16 && nh == 1 && (!eff_scale || lowc);
+  const bool x16_in = k16 && (Elem<TX>::k16 || (p.flags & CONSOLVER_FLAG_X_WAS_LOWP)) && (!x_scale || lowc);
+  // scalar (0-d host tensor) times tensor: a 16-bit product when the tensor is 16-bit
+  auto smul = [&](float k, float t, bool is16) -> float {
+    if (k16 && is16) return round_to<T>(__fmul_rn(host ? round_to<T>(k) : k, t));
+    return __fmul_rn(k, t);
+  };
+  auto r16 = [&](float v, bool is16) -> float { return (k16 && is16) ? round_to<T>(v) : v; };
 
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -113,50 +133,47 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
       float eff;
       if (nh == 1) {
         eff = eps;
+      } else if (MODE == kModeSD && lowc) {
+        // 16-bit coefficient tensors: 16-bit products and partial sums, until the closing coefficient — the fp32
+        // `1 - torch.sum(...)` of set_default_coefficients under autocast — promotes the sum
+        float acc = round_to<T>(__fadd_rn(0.f, round_to<T>(__fmul_rn(c[0], eps))));
+        eff = acc;
+#pragma unroll
+        for (int j = 0; j < kOlder; ++j) {
+          if (NH || j < nh - 1) {
+            if (j + 1 < nh - 1) {
+              acc = round_to<T>(__fadd_rn(acc, round_to<T>(__fmul_rn(c[j + 1], r_h[u][j].get(i)))));
+            } else {
+              eff = __fadd_rn(acc, __fmul_rn(c[j + 1], r_h[u][j].get(i)));
+            }
+          }
+        }
       } else {
         eff = __fadd_rn(0.f, __fmul_rn(c[0], eps));
 #pragma unroll
         for (int j = 0; j < kOlder; ++j)
           if (NH || j < nh - 1) eff = __fadd_rn(eff, __fmul_rn(c[j + 1], r_h[u][j].get(i)));
       }
-      if (eff_scale) eff = __fmul_rn(eff, cs0);                       // :274-277
       float xs = r_x[u].get(i);
-      if (x_scale) xs = __fmul_rn(xs, cs1);                           // :278
       float out;
-      if (MODE == kModeSD && Elem<T>::k16 && nh == 1 && !eff_scale && !x_scale) {
-        // First step of a 16-bit pipeline: `eff` is still the raw 16-bit model output (scheduler_ppo.py:263-265), so
-        // torch evaluates every `0-d fp32 scalar * eff` of :316-330 in the 16-bit dtype — scalar rounded to it, product
-        // rounded to it — while `tensor / 0-d scalar` keeps the scalar in fp32.  With a 16-bit latent every
-        // intermediate is rounded as well; with an fp32 latent (autocast) the rest promotes to fp32.
-        float e = eff;
-        if (Elem<TX>::k16) {
-          if (vpred)
-            e = round_to<T>(__fadd_rn(round_to<T>(__fmul_rn(round_to<T>(p.k0), e)),
-                                      round_to<T>(__fmul_rn(round_to<T>(p.k1), xs))));
-          const float t2 = round_to<T>(__fsub_rn(xs, round_to<T>(__fmul_rn(round_to<T>(p.k1), e))));
-          const float x0 = round_to<T>(__fdiv_rn(t2, p.k0));
-          out = round_to<T>(__fadd_rn(round_to<T>(__fmul_rn(round_to<T>(p.k2), x0)),
-                                      round_to<T>(__fmul_rn(round_to<T>(p.k3), e))));
-        } else if (vpred) {
-          e = __fadd_rn(round_to<T>(__fmul_rn(round_to<T>(p.k0), e)), __fmul_rn(p.k1, xs));     // fp32 from here on
-          const float x0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.k1, e)), p.k0);
-          out = __fadd_rn(__fmul_rn(p.k2, x0), __fmul_rn(p.k3, e));
-        } else {
-          const float x0 = __fdiv_rn(__fsub_rn(xs, round_to<T>(__fmul_rn(round_to<T>(p.k1), e))), p.k0);
-          out = __fadd_rn(__fmul_rn(p.k2, x0), round_to<T>(__fmul_rn(round_to<T>(p.k3), e)));
+      if (MODE == kModeSD) {
+        bool e16 = e16_in;
+        if (eff_scale) eff = r16(__fmul_rn(eff, cs0), e16);               // :274-277
+        if (x_scale) xs = r16(__fmul_rn(xs, cs1), x16_in);                // :278
+        // _get_prev_sample (scheduler_ppo.py:306-332): every `0-d scalar * tensor` is a product in the tensor's dtype,
+        // every tensor-tensor op is 16-bit only when both sides are
+        if (vpred) {                                                      // :316-317
+          const bool b16 = e16 && x16_in;
+          eff = r16(__fadd_rn(smul(p.k0, eff, e16), smul(p.k1, xs, x16_in)), b16);
+          e16 = b16;
         }
-      } else if (MODE == kModeSD) {
-        if (vpred) {                                                                     // :316-317
-          // X_WAS_LOWP: the sample is still a 16-bit tensor in the reference at this step, so its product with the
-          // 0-d scalar is a 16-bit product; everything else has been promoted to fp32 by the coefficients
-          const float sx = (Elem<T>::k16 && (p.flags & CONSOLVER_FLAG_X_WAS_LOWP) && !x_scale)
-                               ? round_to<T>(__fmul_rn(round_to<T>(p.k1), xs))
-                               : __fmul_rn(p.k1, xs);
-          eff = __fadd_rn(__fmul_rn(p.k0, eff), sx);
-        }
-        const float x0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.k1, eff)), p.k0);          // :323
-        out = __fadd_rn(__fmul_rn(p.k2, x0), __fmul_rn(p.k3, eff));                     // :329-330
+        const bool b16 = e16 && x16_in;
+        const float t2 = r16(__fsub_rn(xs, smul(p.k1, eff, e16)), b16);
+        const float x0 = r16(host ? __fdiv_rn(t2, p.k0) : __fmul_rn(t2, inv_k0), b16);           // :323
+        out = r16(__fadd_rn(smul(p.k2, x0, b16), smul(p.k3, eff, e16)), b16);                     // :329-330
       } else {
+        if (eff_scale) eff = __fmul_rn(eff, cs0);                         // edit_ppo/scheduler_fmppo.py:419-424
+        if (x_scale) xs = __fmul_rn(xs, cs1);
         // edit_ppo/scheduler_fmppo.py:429.  First step without scalers: `dt * model_output` is a 0-d fp32
         // tensor times a 16-bit tensor, which torch evaluates in the 16-bit dtype — dt is rounded to it, the
         // product is formed in fp32 and rounded to it — before the fp32 add with the upcast sample.
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
   }
 }
 
-template <typename T, typename TX, int NH, int MODE, int E, int U>
+template <typename T, typename TX, int NH, int MODE, int E, int U, bool HOST = false>
 static int launch_one(StepParams& p, int threads, cudaStream_t stream) {
   const long long per_cta = (long long)threads * U;
   p.chunks_per_sample = (int)((p.nvec_per_sample + per_cta - 1) / per_cta);
@@ -204,20 +221,19 @@ static int launch_one(StepParams& p, int threads, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, step_kernel<T, TX, NH, MODE, E, U>, (const StepParams)p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, step_kernel<T, TX, NH, MODE, E, U, HOST>, (const StepParams)p);
   return (int)e;
 }
 
 template <typename T, typename TX, int NH, int MODE>
-static int launch_nh(StepParams& p, bool vec_ok, cudaStream_t stream) {
+static int launch_nh(StepParams& p, cudaStream_t stream) {
   StepLaunchCfg lc = step_launch_cfg();
   int threads = lc.threads > 0 ? lc.threads : 256;
-  if (!vec_ok) {
-    p.nvec_per_sample = p.n_per_sample;
-    return launch_one<T, TX, NH, MODE, 1, 1>(p, threads, stream);
-  }
   constexpr int E = Elem<T>::kPerVec;
   p.nvec_per_sample = p.n_per_sample / E;
+  if constexpr (MODE == kModeSD) {
+    if (p.flags & CONSOLVER_FLAG_HOST_SCALARS) return launch_one<T, TX, NH, MODE, E, 1, true>(p, threads, stream);
+  }
   int unroll = lc.unroll;
   if (unroll <= 0) {
     // default: 2 vectors/thread once the grid is at least ~8 CTAs per SM, else 1 (small batches need CTAs)
@@ -228,14 +244,31 @@ static int launch_nh(StepParams& p, bool vec_ok, cudaStream_t stream) {
   return launch_one<T, TX, NH, MODE, E, 1>(p, threads, stream);
 }
 
+// Instantiation matrix (kept small: every entry is a separate SASS kernel in libconsolver.so):
+//   128-bit path   depths 1..4 fully unrolled (NH = n_hist), deeper histories through the guarded runtime-depth form
+//                  (NH = 0); the sample-strided FM form only as NH = 2 (the FLUX configuration) and NH = 0
+//   scalar path    ragged sizes / unaligned pointers: only the runtime-depth form
 template <typename T, typename TX, int MODE>
 static int launch_step(StepParams& p, bool vec_ok, cudaStream_t stream) {
-  switch (p.n_hist) {
-    case 1: return launch_nh<T, TX, 1, MODE>(p, vec_ok, stream);
-    case 2: return launch_nh<T, TX, 2, MODE>(p, vec_ok, stream);
-    case 3: return launch_nh<T, TX, 3, MODE>(p, vec_ok, stream);
-    case 4: return launch_nh<T, TX, 4, MODE>(p, vec_ok, stream);
-    default: return launch_nh<T, TX, 0, MODE>(p, vec_ok, stream);
+  if (!vec_ok) {
+    StepLaunchCfg lc = step_launch_cfg();
+    p.nvec_per_sample = p.n_per_sample;
+    const int threads = lc.threads > 0 ? lc.threads : 256;
+    if constexpr (MODE == kModeSD) {
+      if (p.flags & CONSOLVER_FLAG_HOST_SCALARS) return launch_one<T, TX, 0, MODE, 1, 1, true>(p, threads, stream);
+    }
+    return launch_one<T, TX, 0, MODE, 1, 1>(p, threads, stream);
+  }
+  if constexpr (MODE == kModeFMStrided) {
+    return p.n_hist == 2 ? launch_nh<T, TX, 2, MODE>(p, stream) : launch_nh<T, TX, 0, MODE>(p, stream);
+  } else {
+    switch (p.n_hist) {
+      case 1: return launch_nh<T, TX, 1, MODE>(p, stream);
+      case 2: return launch_nh<T, TX, 2, MODE>(p, stream);
+      case 3: return launch_nh<T, TX, 3, MODE>(p, stream);
+      case 4: return launch_nh<T, TX, 4, MODE>(p, stream);
+      default: return launch_nh<T, TX, 0, MODE>(p, stream);
+    }
   }
 }
 

@@ -78,20 +78,35 @@ class FactorNetPPO(nn.Module):
 
     # ---- fp32 weight pointers for the kernel (the reference may cast the module to fp16, gen_ppo.py:193-195;
     #      the kernel always computes in fp32) -----------------------------------------------------------------
-    def kernel_weights(self):
+    def _params(self):
         # nn.Module attribute lookups cost ~1 us each: hold the six Parameter objects (stable across .to() /
         # load_state_dict, which rewrite .data in place) and re-fetch only the buffer (a new tensor after .to())
         mlp = self._modules["mlp"]
         if self._kparams is None or self._kparams[0] is not mlp:
             self._kparams = (mlp, [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias])
-        ps = self._kparams[1] + [self._buffers["action_values"]]
-        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        return self._kparams[1]
+
+    def _kparams_dtype(self):
+        return self._params()[0].dtype
+
+    def kernel_weights(self, act_dtype: Optional[torch.dtype] = None):
+        """Seven device pointers (w1 b1 w2 b2 w3 b3 action_values) to fp32 copies of the parameters.  `act_dtype`
+        (fp16 / bf16): the MLP runs under autocast — the six Linear parameters are rounded to that dtype first, as
+        autocast's cast of the operands does; the kernel then rounds the activations (CONSOLVER_POLICY_ACT_*)."""
+        ps = self._params() + [self._buffers["action_values"]]
+        key = (act_dtype,) + tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
         c = self._w32_cache
         if c is None or c[0] != key:
             if not ps[0].is_cuda:
                 raise RuntimeError("consolver_b200 has no CPU path: move factor_net to a CUDA device")
-            ws = [p.detach() if (p.dtype == torch.float32 and p.is_contiguous())
-                  else p.detach().float().contiguous() for p in ps]
+
+            def f32(p, lowp):
+                t = p.detach()
+                if lowp is not None and t.dtype != lowp:
+                    t = t.to(lowp)
+                return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+            ws = [f32(p, act_dtype) for p in ps[:6]] + [f32(ps[6], None)]
             self._w32_cache = c = (key, ws, [w.data_ptr() for w in ws])
         return c[2]
 
@@ -119,11 +134,12 @@ class FactorNetPPO(nn.Module):
 
     def policy_launch(self, x0: float, x1: float, B: int, n_hist: int, *, q: Optional[torch.Tensor] = None,
                       idx_in: Optional[torch.Tensor] = None, out: Optional[dict] = None, stream=None,
-                      feat: Optional[torch.Tensor] = None):
+                      feat: Optional[torch.Tensor] = None, policy_flags: int = 0,
+                      act_dtype: Optional[torch.dtype] = None):
         """Launch the policy kernel.  `q` None => drawn here from the default CUDA generator with the shape
-        torch.multinomial consumes ([B*A, K] fp32)."""
+        torch.multinomial consumes ([B*A, K] fp32).  `policy_flags`: CONSOLVER_POLICY_* (see include/consolver.h)."""
         lib = _lib.load()
-        w = self.kernel_weights()
+        w = self.kernel_weights(act_dtype)
         dev = self.action_values.device
         A, K = self.action_dims, self.num_actions
         if q is None and idx_in is None:
@@ -136,22 +152,23 @@ class FactorNetPPO(nn.Module):
             *w, x0, x1, self.x_div, self.temperature,
             feat.data_ptr() if feat is not None else None, feat.shape[1] if feat is not None else 0,
             q.data_ptr() if q is not None else None, idx_in.data_ptr() if idx_in is not None else None,
-            B, self.hidden_dim, A, K, self.order_dim, self.scaler_dim, n_hist,
+            B, self.hidden_dim, A, K, self.order_dim, self.scaler_dim, n_hist, policy_flags,
             out["probs_table"].data_ptr(), out["idx"].data_ptr(), out["actions"].data_ptr(),
             out["probs"].data_ptr(), out["logp"].data_ptr(), out["masks"].data_ptr(), out["coef"].data_ptr(),
             stream)
         _lib.check(rc, "consolver_policy_f32")
         return out
 
-    def policy_tables(self, x_rows: torch.Tensor, out: torch.Tensor, stream=None):
+    def policy_tables(self, x_rows: torch.Tensor, out: torch.Tensor, stream=None, policy_flags: int = 0,
+                      act_dtype: Optional[torch.dtype] = None):
         """Probability tables for many input rows in one launch: x_rows [R,2] fp32 (device) -> out [R,A,K]."""
         lib = _lib.load()
-        w = self.kernel_weights()
+        w = self.kernel_weights(act_dtype)
         if stream is None:
             stream = torch.cuda.current_stream(x_rows.device).cuda_stream
         rc = lib.consolver_policy_table_f32(*w[:6], x_rows.data_ptr(), x_rows.shape[0], self.x_div, self.temperature,
-                                            self.hidden_dim, self.action_dims, self.num_actions, out.data_ptr(),
-                                            stream)
+                                            self.hidden_dim, self.action_dims, self.num_actions, policy_flags,
+                                            out.data_ptr(), stream)
         _lib.check(rc, "consolver_policy_table_f32")
         return out
 

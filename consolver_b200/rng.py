@@ -59,7 +59,7 @@ def draw_reference_check(device: torch.device, numel: int = 5 * 3 * 11) -> bool:
         coef = torch.empty(B, 4, device=device)
         rng = _lib.Rng(seed, off, None, nthreads)
         rc = lib.consolver_policy_sample_f32(table.data_ptr(), av.data_ptr(), None, None, C.byref(rng),
-                                             q_out.data_ptr(), B, 1, K, 2, 0, 1, *[o.data_ptr() for o in outs],
+                                             q_out.data_ptr(), B, 1, K, 2, 0, 1, 0, *[o.data_ptr() for o in outs],
                                              coef.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "consolver_policy_sample_f32")
         return bool(torch.equal(ref, q_out)) and consumed == inc

@@ -149,6 +149,10 @@ class FMPPOScheduler(FlowSigmaSchedule, SolverOptions, SchedulerMixin, ConfigMix
         outs = tuple(tr.p(k, i) for k in ("idx", "actions", "probs", "logp", "masks", "coef"))
         coef_ptr = outs[5]
         flags = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
+        # the FM update itself has no host-resident scalars (sigmas live on the device; dt is a CUDA 0-d tensor): only
+        # the policy's `logits / 0.01` and autocast depend on where / how the reference runs
+        _, pflags, act_dt = self._semantics(e0.dtype)
+        pflags &= ~(_lib.POLICY_COEF_F16 | _lib.POLICY_COEF_BF16)
         if fixed:
             coef_ptr = tr.fixed_rows(self.fixed_coefficients, n_hist).data_ptr()      # baseline solvers: no policy
         elif fn.use_conv:
@@ -158,15 +162,15 @@ class FMPPOScheduler(FlowSigmaSchedule, SolverOptions, SchedulerMixin, ConfigMix
             feat, ws, full = tr.conv_buffers(fn)
             cosine_features_cuda(e0, None, 0.0, older, od, feat, ws, stream)
             rc = lib.consolver_policy_f32(
-                *fn.kernel_weights(), x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
-                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
+                *fn.kernel_weights(act_dt), x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
+                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist, pflags,
                 full[i].data_ptr(), *outs, stream)
             _lib.check(rc, "consolver_policy_f32")
             flags |= _lib.FLAG_PDL if self.use_pdl else 0
         else:
             # all n (sigma, sigma_next) rows of the schedule go through the MLP in one launch per pass
             if tr.table_pass != tr.count // tr.n:
-                fn.policy_tables(tr.condx_f32, tr.out["probs_table"], stream)
+                fn.policy_tables(tr.condx_f32, tr.out["probs_table"], stream, policy_flags=pflags, act_dtype=act_dt)
                 tr.table_pass = tr.count // tr.n
                 tr.policy_forked = False
             ps = self.policy_stream if rng_arg is not None else None      # two-stream form: see PPOScheduler._step
@@ -176,8 +180,9 @@ class FMPPOScheduler(FlowSigmaSchedule, SolverOptions, SchedulerMixin, ConfigMix
                     ps.wait_stream(main)
                     tr.policy_forked = True
             rc = lib.consolver_policy_sample_f32(
-                tr.p("probs_table", si), fn.kernel_weights()[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
-                fn.num_actions, od, cfg.scaler_dim, n_hist, *outs, ps.cuda_stream if ps is not None else stream)
+                tr.p("probs_table", si), fn.kernel_weights(act_dt)[6], q_ptr, idx_ptr, rng_arg, None, B, fn.action_dims,
+                fn.num_actions, od, cfg.scaler_dim, n_hist, pflags, *outs,
+                ps.cuda_stream if ps is not None else stream)
             _lib.check(rc, "consolver_policy_sample_f32")
             if ps is not None:
                 ev = torch.cuda.Event()

@@ -217,9 +217,12 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         """Does the combined estimate keep the 16-bit model dtype at this step?  In the reference the per-sample
         coefficients and scalers are gathered from the policy's `action_values` buffer (factor_net_ppo.py:163) and
         carry ITS dtype: an fp32 policy promotes the estimate at every step that multiplies by one (all but a
-        scaler-free first step), a policy cast to the pipeline's own 16-bit dtype (gen_ppo.py:193-195) never does."""
+        scaler-free first step).  A policy cast to the pipeline's own 16-bit dtype (gen_ppo.py:193-195) keeps a depth-1
+        estimate 16-bit through its 16-bit scalers, but from depth 2 on the closing coefficient `1 - torch.sum(...)`
+        (scheduler_ppo.py:172) is fp32 — torch.sum returns fp32 under autocast (gen_ppo.py:309) — and promotes it
+        (tests/golden/cuda_genppo_*: fp16 latents only after the first step)."""
         if self.factor_net_module.action_values.dtype == model_dtype:
-            return True
+            return n_hist == 1
         return n_hist == 1 and self.config.scaler_dim == 0
 
     def _new_trajectory(self, B, shape, dtype, device) -> Trajectory:
@@ -294,7 +297,8 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         q_ptr, idx_ptr, rng_arg = draw_source(self, tr, e0.device, fused_ok=on_grid and not fn.use_conv)
         x_out = out if out is not None else torch.empty_like(sample)
         slot = tr.slot(tr.count) if cond is not None else None
-        vflag = (_lib.FLAG_VPRED if cfg.prediction_type == "v_prediction" else 0) | mixed
+        sem_flags, pflags, act_dt = self._semantics(e0.dtype)
+        vflag = (_lib.FLAG_VPRED if cfg.prediction_type == "v_prediction" else 0) | mixed | sem_flags
         sflag = (_lib.FLAG_EFF_SCALE if cfg.scaler_dim >= 1 else 0) | (_lib.FLAG_X_SCALE if cfg.scaler_dim >= 2 else 0)
         pdl = _lib.FLAG_PDL if self.use_pdl else 0
         lib = _lib.load()
@@ -321,18 +325,18 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             feat, ws, full = tr.conv_buffers(fn)
             cosine_features_cuda(e0, cond, guidance, older, od, feat, ws, stream)
             rc = lib.consolver_policy_f32(
-                *fn.kernel_weights(), x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
-                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist,
+                *fn.kernel_weights(act_dt), x0, x1, fn.x_div, fn.temperature, feat.data_ptr(), od - 1, q_ptr, idx_ptr,
+                B, fn.hidden_dim, fn.action_dims, fn.num_actions, od, cfg.scaler_dim, n_hist, pflags,
                 full[i].data_ptr(), *outs, stream)
             _lib.check(rc, "consolver_policy_f32")
             rc = lib.consolver_step_sd(*step_args, outs[5], od + 2, *tail, vflag | sflag | pdl, B, N, stream)
             _lib.check(rc, "consolver_step_sd")
         else:
-            w = fn.kernel_weights()
+            w = fn.kernel_weights(act_dt)
             # The policy input row depends only on the timestep grid: evaluate the MLP + softmax for ALL n rows in
             # one launch at the first step of a pass; every step then only samples from its row of the table.
             if on_grid and tr.table_pass != tr.count // tr.n:
-                fn.policy_tables(tr.condx_f32, tr.out["probs_table"])
+                fn.policy_tables(tr.condx_f32, tr.out["probs_table"], policy_flags=pflags, act_dtype=act_dt)
                 tr.table_pass = tr.count // tr.n
                 tr.policy_forked = False                          # the side stream must see the new tables
             probs_in = tr.p("probs_table", gi) if on_grid else None
@@ -347,7 +351,8 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
                     ps.wait_stream(main)                          # fork (also orders after the table launch above)
                     tr.policy_forked = True
                 rc = lib.consolver_policy_sample_f32(probs_in, w[6], None, None, rng_arg, None, B, fn.action_dims,
-                                                     fn.num_actions, od, cfg.scaler_dim, n_hist, *outs, ps.cuda_stream)
+                                                     fn.num_actions, od, cfg.scaler_dim, n_hist, pflags, *outs,
+                                                     ps.cuda_stream)
                 _lib.check(rc, "consolver_policy_sample_f32")
                 ev = torch.cuda.Event()
                 ev.record(ps)
@@ -359,7 +364,7 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             else:
                 rc = lib.consolver_sd_policy_and_step(
                     *w, probs_in, x0, x1, fn.x_div, fn.temperature, q_ptr, idx_ptr, rng_arg,
-                    fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim,
+                    fn.hidden_dim, fn.action_dims, fn.num_actions, cfg.scaler_dim, pflags,
                     tr.p("probs_table", gi if on_grid else tr.n), *outs, *step_args, *tail, vflag | pdl, B, N, stream)
                 _lib.check(rc, "consolver_sd_policy_and_step")
 
@@ -371,6 +376,8 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
 
         o = tr.out
         actions, probs, masks = (None, None, None) if fixed else (o["actions"][i], o["probs"][i], o["masks"][i])
+        if actions is not None and fn.action_values.dtype != torch.float32:
+            actions = actions.to(fn.action_values.dtype)      # exact: a policy cast to 16 bit returns 16-bit bin values
         conds = lazy_conds(conds_x, list(self._hist), od)
         if not return_dict:
             return (x_out, actions, probs, conds, masks)

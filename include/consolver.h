@@ -23,7 +23,9 @@
 extern "C" {
 #endif
 
-#define CONSOLVER_ABI_VERSION 1
+/* Bumped on EVERY change of a signature, struct layout or flag meaning in this header.  Loaders must also compare
+ * consolver_abi_hash() with the hash of the header they were written against (see consolver_abi_hash below). */
+#define CONSOLVER_ABI_VERSION 3
 
 /* element type of latents / model outputs */
 #define CONSOLVER_F32  0
@@ -75,6 +77,38 @@ extern "C" {
                                            sample by a scalar — v-prediction's sqrt(1-abar_t)*sample,
                                            scheduler_ppo.py:317 — is then a 16-bit product; ignored with X_SCALE     */
 
+/* WHERE THE REFERENCE RUNS.  The reference keeps its schedule scalars as 0-d fp32 tensors on the HOST
+ * (scheduler_ppo.py:110-114,:309-312) and ATen combines such a scalar with a tensor differently per device.  By default
+ * the kernels follow ATen's CUDA rules, i.e. the reference executed on a GPU the way its drivers run it (pinned by the
+ * tests/golden/cuda_* fixtures, produced by the unmodified reference on a B200):
+ *     scalar * t   the scalar enters as an fp32 value: one rounding, to t's dtype
+ *     t / scalar   t * (1/scalar), reciprocal taken once in fp32 — this moves fp32 results by an ulp here and there
+ * CONSOLVER_FLAG_HOST_SCALARS selects torch's CPU rules instead (the reference executed on CPU tensors; fixtures
+ * tests/golden/{sd,sd16,fm}_*): scalar rounded to a 16-bit t's dtype before the product, true division. */
+#define CONSOLVER_FLAG_HOST_SCALARS 256
+
+#define CONSOLVER_FLAG_LOWP_COEF    512  /* consolver_step_sd, 16-bit dtype: the per-sample coefficients are 16-bit TENSORS
+                                           in the reference — the policy, bin buffer included, was cast to the pipeline
+                                           dtype (gen_ppo.py:193-195) — so `c_i * e_i` and the partial sums are 16-bit
+                                           ops, EXCEPT the closing coefficient 1 - sum(...), which is fp32 because
+                                           torch.sum returns fp32 under autocast (gen_ppo.py:309) and promotes the sum
+                                           from there on; `(1+s0)` / `(1+s1)` are 16-bit too, so a depth-1 estimate and a
+                                           16-bit sample stay 16-bit through their scalings.  coef[] holds the values
+                                           consolver_policy_* wrote with CONSOLVER_POLICY_COEF_F16/_BF16 */
+
+/* policy_flags of the policy entry points */
+#define CONSOLVER_POLICY_HOST_DIV    1   /* x / x_div and logits / temp as true divisions (torch on CPU tensors); default:
+                                           multiplications by the fp32 reciprocals (ATen's CUDA division by a scalar)  */
+#define CONSOLVER_POLICY_ACT_F16     2   /* the MLP runs under torch.autocast(fp16) (gen_ppo.py:309, train_ppo.py:353) or
+                                           with parameters cast to fp16: the input row, every Linear output and
+                                           logits/temp are rounded to fp16 (fp32 accumulation, bias added before the
+                                           rounding); softmax in fp32.  The caller passes weights already rounded      */
+#define CONSOLVER_POLICY_ACT_BF16    4   /* same with bfloat16                                                         */
+#define CONSOLVER_POLICY_COEF_F16    8   /* the bin values are fp16 tensors (policy cast to the pipeline dtype): a0+1,
+                                           1+s0, 1+s1 are rounded to fp16, the closing coefficient is the fp32
+                                           1 - sum (see CONSOLVER_FLAG_LOWP_COEF)                                      */
+#define CONSOLVER_POLICY_COEF_BF16  16   /* same with bfloat16                                                         */
+
 #define CONSOLVER_ERR_NULL        (-1)
 #define CONSOLVER_ERR_SIZE        (-2)
 #define CONSOLVER_ERR_UNSUPPORTED (-3)
@@ -101,6 +135,10 @@ typedef struct consolver_rng {
 } consolver_rng_t;
 
 CONSOLVER_API int consolver_abi_version(void);
+/* FNV-1a 64-bit hash of this header's text as it was when the library was compiled (csrc/abi_hash.h is generated from
+ * include/consolver.h by the build).  A loader hashes the header it binds against the same way and refuses a library
+ * whose hash differs: a stale .so built from an older header cannot be called with the wrong argument list. */
+CONSOLVER_API uint64_t consolver_abi_hash(void);
 /* human-readable text for any return value of this library (static storage). */
 CONSOLVER_API const char* consolver_error_string(int err);
 
@@ -125,6 +163,7 @@ CONSOLVER_API const char* consolver_error_string(int err);
  *   q [B*A,K] or NULL        the Exp(1) draw; NULL => use idx_in
  *   idx_in [B,A] or NULL     forced bin indices (replay / PPO update); exactly one of q, idx_in is given
  *   n_hist                   number of model outputs in the history INCLUDING the current one (1..order_dim)
+ *   policy_flags             CONSOLVER_POLICY_* (0 = fp32 policy evaluated by the reference on CUDA tensors)
  * outputs (any may be NULL except coef):
  *   probs_table [A,K]        full softmax table of the shared row ([B,A,K], one table per sample, when feat != NULL)
  *   idx [B,A] int64          sampled bin indices
@@ -139,7 +178,7 @@ CONSOLVER_API int consolver_policy_f32(const float* w1, const float* b1, const f
                          float x0, float x1, float x_div, float temp,
                          const float* feat, int n_feat,
                          const float* q, const int64_t* idx_in,
-                         int B, int H, int A, int K, int order_dim, int scaler_dim, int n_hist,
+                         int B, int H, int A, int K, int order_dim, int scaler_dim, int n_hist, int policy_flags,
                          float* probs_table, int64_t* idx, float* actions, float* act_probs, float* act_logp,
                          float* masks, float* coef, consolver_stream_t stream);
 
@@ -149,11 +188,12 @@ CONSOLVER_API int consolver_policy_f32(const float* w1, const float* b1, const f
  *
  *   dtype            CONSOLVER_F32 / F16 / BF16: element type of the model outputs, history and ring slot, and of
  *                    x / x_out / x_out2 unless CONSOLVER_FLAG_X_F32 is set.  F32: bit-identical to the reference's
- *                    op-by-op fp32 arithmetic.  16-bit: the arithmetic torch performs on those dtypes —
+ *                    op-by-op fp32 arithmetic (on CUDA tensors; CONSOLVER_FLAG_HOST_SCALARS: on CPU tensors).
+ *                    16-bit: the arithmetic torch performs on those dtypes —
  *                      CFG combine: a rounding to `dtype` after each op, guidance kept in fp32;
  *                      n_hist == 1 without scaler flags (the estimate is the raw 16-bit output): every
- *                        `scalar * tensor` product of scheduler_ppo.py:316-330 is a 16-bit product (scalar and
- *                        product rounded), `tensor / scalar` keeps the fp32 scalar; with a 16-bit latent all
+ *                        `scalar * tensor` product of scheduler_ppo.py:316-330 is a 16-bit product (one rounding;
+ *                        with HOST_SCALARS the scalar is rounded first as well); with a 16-bit latent all
  *                        intermediates are rounded too, with CONSOLVER_FLAG_X_F32 the rest is fp32;
  *                      otherwise (n_hist > 1 or scalers): fp32 arithmetic on the upcast values — exactly torch's
  *                        promotion when the latent is fp32 (X_F32); with a 16-bit latent (a layout the reference
@@ -246,8 +286,8 @@ CONSOLVER_API int consolver_step_dpm(int dtype, int x_dtype, const void* e0, con
  */
 CONSOLVER_API int consolver_policy_table_f32(const float* w1, const float* b1, const float* w2, const float* b2,
                                              const float* w3, const float* b3, const float* x_rows, int rows,
-                                             float x_div, float temp, int H, int A, int K, float* probs_tables,
-                                             consolver_stream_t stream);
+                                             float x_div, float temp, int H, int A, int K, int policy_flags,
+                                             float* probs_tables, consolver_stream_t stream);
 
 /*
  * Sampling only, from a given probability table probs_in [A,K]: the draw, gathers, masks and coefficient assembly
@@ -262,7 +302,7 @@ CONSOLVER_API int consolver_rng_state_advance(uint64_t* state, uint64_t amount, 
 CONSOLVER_API int consolver_policy_sample_f32(const float* probs_in, const float* action_values, const float* q,
                                               const int64_t* idx_in, const consolver_rng_t* rng, float* q_out,
                                               int B, int A, int K, int order_dim,
-                                              int scaler_dim, int n_hist, int64_t* idx, float* actions,
+                                              int scaler_dim, int n_hist, int policy_flags, int64_t* idx, float* actions,
                                               float* act_probs, float* act_logp, float* masks, float* coef,
                                               consolver_stream_t stream);
 
@@ -277,7 +317,7 @@ CONSOLVER_API int consolver_sd_policy_and_step(const float* w1, const float* b1,
                                  const float* probs_in,
                                  float x0, float x1, float x_div, float temp,
                                  const float* q, const int64_t* idx_in, const consolver_rng_t* rng,
-                                 int H, int A, int K, int scaler_dim,
+                                 int H, int A, int K, int scaler_dim, int policy_flags,
                                  float* probs_table, int64_t* idx, float* actions, float* act_probs,
                                  float* act_logp, float* masks, float* coef,
                                  int dtype, const void* e0, const void* cond, float guidance, void* slot_out,

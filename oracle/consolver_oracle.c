@@ -20,7 +20,10 @@
 #include <stdint.h>
 
 /* history: hist[0] is the newest model output (already CFG-combined), hist[j] older; coef: [B, order_dim+2] with
- * the layout of include/consolver.h.  flags: 1 v-prediction, 2 eff scale, 4 x scale. */
+ * the layout of include/consolver.h.  flags: 1 v-prediction, 2 eff scale, 4 x scale, 256 (the value of
+ * CONSOLVER_FLAG_HOST_SCALARS) the reference executed on CPU tensors: `t / sqrt(abar_t)` is a true division.
+ * Without it the reference executed on CUDA tensors: ATen computes t * (1 / scalar), the reciprocal taken once in
+ * fp32 (pinned by tests/golden/cuda_sd_*). */
 void oracle_sd_step_f32(const float* const* hist, int n_hist, const float* x, float* x_out, const float* coef,
                         int order_dim, float sa_t, float sb_t, float sa_p, float sb_p, int flags, int B, int64_t N) {
   const int stride = order_dim + 2;
@@ -46,7 +49,9 @@ void oracle_sd_step_f32(const float* const* hist, int n_hist, const float* x, fl
         eff = a + bb;
       }
       float t0 = sb_t * eff;
-      float x0 = (xs - t0) / sa_t;
+      float t1 = xs - t0;
+      float inv = 1.0f / sa_t;
+      float x0 = (flags & 256) ? t1 / sa_t : t1 * inv;
       float p0 = sa_p * x0, p1 = sb_p * eff;
       x_out[o] = p0 + p1;
     }

@@ -16,8 +16,12 @@ def weights(sd):
                                       "mlp.4.bias", "action_values")]
 
 
-def policy(sd, x0, x1, x_div, temp, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None, feat=None):
+# `host=True` (default of these helpers): torch's CPU rules (CONSOLVER_POLICY_HOST_DIV / CONSOLVER_FLAG_HOST_SCALARS),
+# the rules the oracle's default functions follow; host=False: ATen's CUDA rules (oracle: sem=orc.CUDA).
+def policy(sd, x0, x1, x_div, temp, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None, feat=None, host=True,
+           policy_flags=0):
     lib = _lib.load()
+    policy_flags |= _lib.POLICY_HOST_DIV if host else 0
     A, K = sd["action_values"].shape
     H = sd["mlp.0.weight"].shape[0]
     dev = sd["action_values"].device
@@ -29,7 +33,7 @@ def policy(sd, x0, x1, x_div, temp, B, order_dim, scaler_dim, n_hist, q=None, id
         *weights(sd), float(x0), float(x1), float(x_div), float(temp),
         feat.data_ptr() if feat is not None else None, feat.shape[1] if feat is not None else 0,
         q.data_ptr() if q is not None else None, idx_in.data_ptr() if idx_in is not None else None,
-        B, H, A, K, order_dim, scaler_dim, n_hist,
+        B, H, A, K, order_dim, scaler_dim, n_hist, policy_flags,
         out["probs_table"].data_ptr(), out["idx"].data_ptr(), out["actions"].data_ptr(), out["probs"].data_ptr(),
         out["logp"].data_ptr(), out["masks"].data_ptr(), out["coef"].data_ptr(),
         torch.cuda.current_stream().cuda_stream)
@@ -37,8 +41,9 @@ def policy(sd, x0, x1, x_div, temp, B, order_dim, scaler_dim, n_hist, q=None, id
     return out
 
 
-def step_sd(e0, cond, guidance, hist, x, coef, order_dim, scalars, flags=0, slot=False, out2=None):
+def step_sd(e0, cond, guidance, hist, x, coef, order_dim, scalars, flags=0, slot=False, out2=None, host=True):
     lib = _lib.load()
+    flags |= _lib.FLAG_HOST_SCALARS if host else 0
     B = x.shape[0]
     N = x.numel() // B
     x_out = torch.empty_like(x)
@@ -70,19 +75,21 @@ def step_fm(e0, hist, x, coef, order_dim, dt, flags=0, out2=None):
     return x_out
 
 
-def policy_table(sd, x_rows, x_div, temp):
+def policy_table(sd, x_rows, x_div, temp, host=True, policy_flags=0):
     lib = _lib.load()
+    policy_flags |= _lib.POLICY_HOST_DIV if host else 0
     A, K = sd["action_values"].shape
     H = sd["mlp.0.weight"].shape[0]
     x_rows = x_rows.to(device=sd["action_values"].device, dtype=torch.float32).contiguous()
     out = torch.full((x_rows.shape[0], A, K), -1.0, device=x_rows.device)
     rc = lib.consolver_policy_table_f32(*weights(sd)[:6], x_rows.data_ptr(), x_rows.shape[0], float(x_div), float(temp),
-                                        H, A, K, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                                        H, A, K, policy_flags, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "consolver_policy_table_f32")
     return out
 
 
-def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None, rng=None, q_out=None):
+def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=None, rng=None, q_out=None,
+                  policy_flags=0):
     lib = _lib.load()
     A, K = sd["action_values"].shape
     dev = table.device
@@ -94,7 +101,7 @@ def policy_sample(sd, table, B, order_dim, scaler_dim, n_hist, q=None, idx_in=No
         table.data_ptr(), sd["action_values"].data_ptr(), q.data_ptr() if q is not None else None,
         idx_in.data_ptr() if idx_in is not None else None,
         ctypes.byref(rng) if rng is not None else None, q_out.data_ptr() if q_out is not None else None,
-        B, A, K, order_dim, scaler_dim, n_hist,
+        B, A, K, order_dim, scaler_dim, n_hist, policy_flags,
         out["idx"].data_ptr(), out["actions"].data_ptr(), out["probs"].data_ptr(), out["logp"].data_ptr(),
         out["masks"].data_ptr(), out["coef"].data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "consolver_policy_sample_f32")

@@ -69,16 +69,19 @@ int main(void) {
     /* GPU: the pair goes in raw; eps is written into ring slot s % OD; older slots are read by pointer */
     const void* hist[OD];
     for (int j = 1; j < n_hist; ++j) hist[j - 1] = d_ring + (size_t)((s - j) % OD) * n;
+    /* odd steps with CONSOLVER_FLAG_HOST_SCALARS (the reference on CPU tensors), even steps with the default rules
+     * (the reference on CUDA tensors): the oracle gets the same flag */
+    const int sem = (s & 1) ? CONSOLVER_FLAG_HOST_SCALARS : 0;
     int rc = consolver_step_sd(CONSOLVER_F32, d_pair[s], d_pair[s] + n, guidance, d_ring + (size_t)(s % OD) * n, hist,
                                n_hist, d_x, d_xn, NULL, 0, d_coef, CONSOLVER_COEF_STRIDE(OD), OD, sc[s][0], sc[s][1],
-                               sc[s][2], sc[s][3], 0, B, N, stream);
+                               sc[s][2], sc[s][3], sem, B, N, stream);
     if (rc != 0) { fprintf(stderr, "consolver_step_sd: %s\n", consolver_error_string(rc)); return 3; }
     { float* t = d_x; d_x = d_xn; d_xn = t; }
     /* CPU oracle: the reference's sequence — CFG combine, then the step on the newest-first history */
     oracle_cfg_f32(h_pair[s], h_pair[s] + n, guidance, h_eps[s], (int64_t)n);
     const float* ohist[OD];
     for (int j = 0; j < n_hist; ++j) ohist[j] = h_eps[s - j];
-    oracle_sd_step_f32(ohist, n_hist, h_ref, h_got, h_coef, OD, sc[s][0], sc[s][1], sc[s][2], sc[s][3], 0, B, N);
+    oracle_sd_step_f32(ohist, n_hist, h_ref, h_got, h_coef, OD, sc[s][0], sc[s][1], sc[s][2], sc[s][3], sem, B, N);
     memcpy(h_ref, h_got, bytes);
     CK(cudaStreamSynchronize(stream));
     CK(cudaMemcpy(h_got, d_x, bytes, cudaMemcpyDeviceToHost));

@@ -27,3 +27,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def cpu_reference(monkeypatch):
+    """Schedulers built inside the test reproduce the reference as executed on CPU tensors (true divisions, 16-bit
+    scalar rounding) — the rules the CPU-made fixtures (tests/golden/{sd,sd16,fm}_*) and the oracle's default
+    functions follow.  Without it the product default applies: the reference as executed on CUDA tensors (cuda_*)."""
+    from consolver_b200 import _sched_common
+
+    monkeypatch.setattr(_sched_common, "DEFAULT_REFERENCE_DEVICE", "cpu")

@@ -31,7 +31,55 @@ def test_library_exports_every_declared_symbol():
         assert n in exported, f"{n} declared in consolver.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
         assert hasattr(lib, n)
-    assert lib.consolver_abi_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "consolver.h")).read()
+    assert lib.consolver_abi_version() == int(re.search(r"#define CONSOLVER_ABI_VERSION (\d+)", hdr).group(1))
+    assert lib.consolver_abi_version() == _lib.ABI_VERSION
+
+
+def test_library_carries_the_hash_of_the_header_it_was_built_from():
+    from consolver_b200 import build
+
+    lib = _lib.load()
+    assert lib.consolver_abi_hash() == build.header_hash()
+    assert build.is_current(), "libconsolver.so.stamp does not match the sources"
+    # the hash the loader computes is FNV-1a 64 of the header bytes
+    assert build.fnv1a64(b"") == 0xCBF29CE484222325 and build.fnv1a64(b"a") == 0xAF63DC4C8601EC8C
+
+
+def test_a_library_built_from_an_older_header_is_rejected(tmp_path):
+    """ABI hygiene: a stale .so must not be bound.  Three stand-ins for 'older': (1) a library whose embedded header hash
+    differs, (2) one that predates consolver_abi_hash altogether, (3) one with another ABI version."""
+    def make(name, body):
+        src = tmp_path / (name + ".c")
+        src.write_text(body)
+        so = tmp_path / (name + ".so")
+        subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+        return str(so)
+
+    v = _lib.ABI_VERSION
+    other_hash = make("other_hash", f"int consolver_abi_version(void){{return {v};}}\n"
+                                    "unsigned long long consolver_abi_hash(void){return 0x1234ull;}\n")
+    with pytest.raises(_lib.ConsolverError, match="different include/consolver.h"):
+        _lib.bind(other_hash)
+    no_hash = make("no_hash", "int consolver_abi_version(void){return 1;}\n")
+    with pytest.raises(_lib.ConsolverError, match="predates"):
+        _lib.bind(no_hash)
+    old_version = make("old_version", f"int consolver_abi_version(void){{return {v - 1};}}\n"
+                                      "unsigned long long consolver_abi_hash(void){return 0;}\n")
+    with pytest.raises(_lib.ConsolverError, match="ABI version"):
+        _lib.bind(old_version)
+
+
+def test_a_failed_rebuild_never_falls_back_to_the_existing_library(monkeypatch):
+    """_lib.load() with a stale stamp and no working compiler raises instead of binding the old .so"""
+    from consolver_b200 import build
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(build, "is_current", lambda: False)
+    monkeypatch.setattr(build, "_nvcc", lambda: (_ for _ in ()).throw(RuntimeError("nvcc not found")))
+    monkeypatch.delenv("CONSOLVER_NO_AUTOBUILD", raising=False)
+    with pytest.raises(_lib.ConsolverError, match="does not fall back to a stale library"):
+        _lib.load()
 
 
 def test_header_compiles_as_plain_c():
@@ -50,7 +98,7 @@ def test_library_is_built_for_sm_100a():
 def test_argument_validation_returns_error_codes_without_a_gpu():
     lib = _lib.load()
     # null weights
-    rc = lib.consolver_policy_f32(*([None] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, None, None, 1, 256, 3, 11, 4, 0, 1,
+    rc = lib.consolver_policy_f32(*([None] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, None, None, 1, 256, 3, 11, 4, 0, 1, 0,
                                   *([None] * 7), None)
     assert rc == -1
     rc = lib.consolver_step_sd(0, None, None, 0.0, None, None, 1, None, None, None, 0, None, 6, 4, 1.0, 0.0, 1.0, 0.0,
@@ -68,10 +116,10 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     assert rc == -4  # dtype
     rc = lib.consolver_step_fm(2, 1, one, None, None, 1, one, one, None, 0, one, 6, 4, -0.1, 0, 1, 16, None)
     assert rc == -4  # x_dtype must be dtype or f32
-    rc = lib.consolver_policy_f32(*([one] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, one, one, 1, 256, 3, 11, 4, 0, 1,
+    rc = lib.consolver_policy_f32(*([one] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, one, one, 1, 256, 3, 11, 4, 0, 1, 0,
                                   *([one] * 7), None)
     assert rc == -1  # both q and idx_in
-    rc = lib.consolver_policy_f32(*([one] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, one, None, 1, 2048, 3, 11, 4, 0, 1,
+    rc = lib.consolver_policy_f32(*([one] * 7), 0.0, 0.0, 999.0, 1.0, None, 0, one, None, 1, 2048, 3, 11, 4, 0, 1, 0,
                                   *([one] * 7), None)
     assert rc == -2  # hidden too large
     assert lib.consolver_set_step_launch(100, 1) == -2

@@ -6,7 +6,9 @@ import torch
 import consolver_oracle as orc
 from golden_io import Golden, names as golden_names
 
-pytestmark = pytest.mark.gpu
+# cpu_reference: these tests check against CPU-made fixtures / the oracle's default (CPU-torch) rules; the product
+# default — the reference as executed on CUDA tensors — is covered by tests/test_gpu_cuda_reference.py
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cpu_reference")]
 
 SD = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, steps_offset=1, timestep_spacing="trailing")
 

@@ -9,7 +9,9 @@ import torch
 import abi_helpers as ah
 import consolver_oracle as orc
 
-pytestmark = pytest.mark.gpu
+# cpu_reference: these tests check against CPU-made fixtures / the oracle's default (CPU-torch) rules; the product
+# default — the reference as executed on CUDA tensors — is covered by tests/test_gpu_cuda_reference.py
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cpu_reference")]
 
 SCAL = (0.8378, 0.5460, 0.9151, 0.4033)
 

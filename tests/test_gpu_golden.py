@@ -8,7 +8,9 @@ import torch
 
 from golden_io import Golden, names
 
-pytestmark = pytest.mark.gpu
+# cpu_reference: these tests check against CPU-made fixtures / the oracle's default (CPU-torch) rules; the product
+# default — the reference as executed on CUDA tensors — is covered by tests/test_gpu_cuda_reference.py
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cpu_reference")]
 
 PROB_ATOL = 1e-6
 # FM softmax runs at temperature 0.01 (edit_ppo/factor_net_ppo.py:168): a 1-ulp change of a logit moves a

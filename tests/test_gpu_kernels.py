@@ -9,7 +9,9 @@ import torch
 import abi_helpers as ah
 import consolver_oracle as orc
 
-pytestmark = pytest.mark.gpu
+# cpu_reference: these tests check against CPU-made fixtures / the oracle's default (CPU-torch) rules; the product
+# default — the reference as executed on CUDA tensors — is covered by tests/test_gpu_cuda_reference.py
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cpu_reference")]
 
 
 def make_sd(variant, H, K, order_dim, scaler_dim, mu_dim, seed, last_std):

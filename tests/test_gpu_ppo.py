@@ -2,7 +2,9 @@
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# cpu_reference: these tests check against CPU-made fixtures / the oracle's default (CPU-torch) rules; the product
+# default — the reference as executed on CUDA tensors — is covered by tests/test_gpu_cuda_reference.py
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cpu_reference")]
 
 PROD = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, num_train_timesteps=1000,
             steps_offset=1, timestep_spacing="trailing", order_dim=4, scaler_dim=0, use_conv=False,

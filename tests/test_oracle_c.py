@@ -32,7 +32,7 @@ def _ptrs(ts):
     return arr
 
 
-@pytest.mark.parametrize("name", [n for n in names("sd_")])
+@pytest.mark.parametrize("name", [n for n in names("sd_")] + [n for n in names("cuda_sd_")])
 def test_c_oracle_sd_trajectory_matches_reference(lib, name):
     g = Golden(name)
     m = g.meta
@@ -47,6 +47,8 @@ def test_c_oracle_sd_trajectory_matches_reference(lib, name):
     x = g["x_T"].contiguous()
     hist = []
     flags = (1 if cfg.get("prediction_type", "epsilon") == "v_prediction" else 0) | (2 if sdim >= 1 else 0) | (4 if sdim >= 2 else 0)
+    on_gpu = m.get("device") == "cuda"          # fixture made by the reference running on a B200: ATen's CUDA rules
+    flags |= 0 if on_gpu else 256               # 256 = CONSOLVER_FLAG_HOST_SCALARS: true division
     for i, t in enumerate(s.timesteps):
         pair = g[f"pair_{i}"].contiguous()
         eps = torch.empty_like(x)
