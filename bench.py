@@ -13,11 +13,20 @@ A "step" = one 8-step preview of one batch of 64 latents: 8 x (Exp(1) draw + pol
              latents and the 8 CFG pairs from pinned memory and reads the final latents + rollout record back
   roofline   the fused step kernel (dominant kernel) at this workload's launch shape, timed live with CUDA events
              on its launch stream; `roofline_sweep` repeats it for larger batches (BASELINE config 2)
-  cpu_baseline / --impl reference   the CPU oracle port of the reference scheduler on the host cores
+  cpu_baseline / --impl reference   the UNMODIFIED reference PPOScheduler (oracle/_ref, staged by oracle/stage_ref.py)
+             on the host cores; the torch-CPU oracle port as a second row (and as the fallback when oracle/_ref is absent)
+  torch_eager_gpu / torch_compile_gpu   the same reference classes on cuda:0, stock torch (SURVEY §2.2's bar)
+  ppo_rollout  BASELINE configs[4]: batched rollouts + PPO update with the flat-buffer gradient all-reduce
+
+Timed regions.  The driver calls `--steps 20 --warmup 5`; 20 previews are 0.8 ms of GPU time, shorter than the
+fill/drain of the four-deep preview pipeline.  Every timed leg therefore repeats its `steps`-block R times back to
+back with the pipeline kept full (R from a calibration pass, so that the region lasts >= TARGET_REGION_S) and reports
+ms_per_step = elapsed / (R * steps), `reps`, `timed_region_s` and the measured fill/drain cost of one isolated block.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -36,8 +45,20 @@ SHAPE = (4, 64, 64)
 N_STEPS = 8
 GUIDANCE = 3.0
 L2_BYTES = 126 * 2 ** 20
+TARGET_REGION_S = 0.4                                     # minimum length of a timed region (see module docstring)
+WORKLOAD = ("BASELINE configs[1] solver path: SD1.5 latents 4x64x64 fp32, 8-step trailing, CFG=3, order_dim=4, "
+            "scaler_dim=0, policy 2-256-256-33, batch 64/GPU, denoiser = resident synthetic CFG pairs")
 HIST_DEPTHS = [1, 2, 3, 4, 4, 4, 4, 4]                     # n_hist per step of an 8-step preview
 TENSORS_PER_PREVIEW = sum(n + 4 for n in HIST_DEPTHS)       # 58 latent-sized transfers / sample
+
+
+def workload_config(B, world):
+    """`config` of the JSON line — the SAME dict in both arms (ours and --impl reference), so the driver's
+    same_config check compares like with like; arm-specific launch details go to `run`."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "solver_steps": N_STEPS, "guidance": GUIDANCE,
+            "sharding": f"dp{world} by prompt/seed, no collective",
+            "l2_policy": "GPU arm: inputs larger than L2 (rotating pool of resident batches >= 2x the 126 MB L2); "
+                         "CPU arm: one resident batch (host caches are not the bound there)"}
 
 
 def policy_state_dict(seed=0):
@@ -396,29 +417,68 @@ def run_ours(args, rank, world, device):
     ppool = None if args.eager else PreviewPool([p[3] for p in pool], streams=args.streams)
     n_streams = 1 if ppool is None else len(ppool.streams)
 
-    def run_steps(first, count):
+    def run_steps(first, count, join=True):
         if ppool is None:
             for k in range(first, first + count):
                 one_step(k)
             return
         for k in range(first, first + count):
             ppool.submit(k % pool_n)
-        ppool.join()
+        if join:
+            ppool.join()
+
+    def rank_max(v):
+        if world > 1:
+            t = torch.tensor([v], device=device, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            return t.item()
+        return v
 
     run_steps(0, args.warmup)
+    # ---- calibration: ONE isolated block of `steps` previews from an idle GPU (pays the pipeline fill and drain) ------
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(torch.cuda.current_device()) as clk:
-        a.record()
-        run_steps(args.warmup, args.steps)
-        b.record()
+    a.record()
+    run_steps(args.warmup, args.steps)
+    b.record()
+    barrier()
+    block_ms = rank_max(a.elapsed_time(b))
+
+    def timed_blocks(n_blocks, sampler=None):
+        """n_blocks x `steps` previews back to back, pipeline kept full, one join at the end -> ms (max over ranks)"""
         barrier()
-    ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = t.item()
-    value = world * args.steps * B / (ms / 1e3)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with (sampler or contextlib.nullcontext()):
+            ea.record()
+            h0 = time.perf_counter()
+            k0 = args.warmup
+            for _ in range(n_blocks):
+                run_steps(k0, args.steps, join=False)
+                k0 += args.steps
+            host_us[0] = (time.perf_counter() - h0) * 1e6 / (n_blocks * args.steps)   # host time to ENQUEUE one preview
+            if ppool is not None:
+                ppool.join()
+            eb.record()
+            barrier()
+        return rank_max(ea.elapsed_time(eb))
+
+    host_us = [0.0]
+
+    # second calibration stage (untimed for the result): ~0.15 s of back-to-back blocks gives the steady-state rate the
+    # repetition count is derived from, and doubles as a warm-up that does not depend on how small --warmup is
+    pre_blocks = int(max(1, min(-(-150.0 // max(block_ms, 1e-3)), 1_000_000 // max(args.steps, 1))))
+    pre_ms = timed_blocks(pre_blocks)
+    est_ms_per_block = max(pre_ms / pre_blocks, 1e-4)
+    reps = int(max(1, min(-(-TARGET_REGION_S * 1e3 // est_ms_per_block), 4_000_000 // max(args.steps, 1))))
+    if args.reps:
+        reps = args.reps
+    # ---- the timed region: `reps` blocks of `steps` previews back to back, pipeline kept full, one join at the end ----
+    clk = ClockSampler(torch.cuda.current_device())
+    ms = timed_blocks(reps, clk)
+    n_timed = reps * args.steps
+    value = world * n_timed * B / (ms / 1e3)
+    ms_per_step = ms / n_timed
+    fill_drain_ms = max(0.0, block_ms - args.steps * ms_per_step)
 
     # for transparency: the same loop with ONE preview batch in flight (no cross-batch overlap), rank-local
     single = None
@@ -438,7 +498,8 @@ def run_ours(args, rank, world, device):
 
     if args.no_extras:
         return {"metric": "sd15_8step_solver_previews_per_s", "value": round(value, 1), "unit": "previews/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4)}
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5),
+                "reps": reps, "timed_region_s": round(ms / 1e3, 4)}
     # ---- e2e: host buffers -> scheduler API -> host, copies inside the timed region ---------------------------
     # Every step uploads ITS initial latents and ITS 8 CFG pairs from pinned host memory (75.5 MB), runs the 8-step
     # preview through the public API (GraphedPreview over that buffer set) and reads the final latents and the
@@ -486,42 +547,53 @@ def run_ours(args, rank, world, device):
         main.synchronize()
         down_stream.synchronize()
 
-    e2e_steps = max(10, min(args.steps, 200))
+    e2e_steps = args.steps
     for k in range(4):
         e2e_step(k)
     e2e_drain()
     barrier()
+    t0 = time.perf_counter()                                        # calibration block
+    for k in range(e2e_steps):
+        e2e_step(k)
+    e2e_drain()
+    barrier()
+    e2e_block_s = rank_max(time.perf_counter() - t0)
+    e2e_reps = int(max(1, min(-(-TARGET_REGION_S // max(e2e_block_s, 1e-6)) + 1, 200_000 // max(e2e_steps, 1))))
+    barrier()
     with ClockSampler(torch.cuda.current_device()) as clk_e2e:     # the second timed region: sampled as well
         t0 = time.perf_counter()
-        for k in range(e2e_steps):
+        for k in range(e2e_reps * e2e_steps):
             e2e_step(k)
         e2e_drain()
         barrier()
         e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e_s = t.item()
-    e2e_val = world * e2e_steps * B / e2e_s
+    e2e_s = rank_max(e2e_s)
+    e2e_val = world * e2e_reps * e2e_steps * B / e2e_s
     h2d = (hx.numel() + hpairs.numel()) * 4
     d2h = (e2e_sets[0]["hout"].numel() + e2e_sets[0]["hrec"].numel()) * 4
 
     out = {
         "metric": "sd15_8step_solver_previews_per_s", "value": round(value, 1), "unit": "previews/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5),
+        "reps": reps, "timed_region_s": round(ms / 1e3, 4), "steps_timed": n_timed,
+        "isolated_block": {"ms": round(block_ms, 4), "fill_drain_ms": round(fill_drain_ms, 4),
+                           "note": f"one block of {args.steps} previews timed alone from an idle GPU (what a "
+                                   f"{args.steps}-step region would have measured): "
+                                   f"{round(world * args.steps * B / (block_ms / 1e3), 1)} previews/s"},
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] solver path: SD1.5 latents 4x64x64 fp32, 8-step trailing, CFG=3, "
-                               "order_dim=4, scaler_dim=0, policy 2-256-256-33, batch 64/GPU, denoiser = resident "
-                               "synthetic CFG pairs", "batch_per_gpu": B, "solver_steps": N_STEPS,
-                   "l2_policy": f"inputs larger than L2: rotating pool of {pool_n} resident batches "
-                                f"({pool_n * bytes_per_batch >> 20} MiB)",
-                   "launch": "eager python launches" if args.eager else
-                   "one CUDA graph per 8-step preview (table kernel, sample kernels on a side stream, PDL-chained step "
-                   "kernels, rng-advance node); valid because the stand-in model outputs are resident", "sharding": f"dp{world} by prompt/seed, no collective",
-                   "concurrency": f"{n_streams} independent preview batch(es) in flight on separate CUDA streams"},
+        "config": workload_config(B, world),
+        "run": {"pool": f"rotating pool of {pool_n} resident batches ({pool_n * bytes_per_batch >> 20} MiB)",
+                "launch": "eager python launches" if args.eager else
+                "one CUDA graph per 8-step preview (table kernel, sample kernels on a side stream, PDL-chained step "
+                "kernels, rng-advance node); valid because the stand-in model outputs are resident",
+                "concurrency": f"{n_streams} independent preview batch(es) in flight on separate CUDA streams",
+                "timing": f"{reps} x {args.steps} previews back to back between two CUDA events, max over ranks",
+                "host_enqueue_us_per_step": round(host_us[0], 2),
+                "calibration": {"isolated_block_ms": round(block_ms, 4), "pre_blocks": pre_blocks,
+                                "pre_ms_per_step": round(pre_ms / (pre_blocks * args.steps), 5)}},
         "e2e": {"value": round(e2e_val, 1), "unit": "previews/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
-        "gpu_launches": args.steps * (2 + N_STEPS * 2),   # per preview: table + 8 x (sample + step) + rng-advance kernels
+                "steps": e2e_steps, "reps": e2e_reps, "timed_region_s": round(e2e_s, 4)},
+        "gpu_launches": n_timed * (2 + N_STEPS * 2),   # per preview: table + 8 x (sample + step) + rng-advance kernels
         "clocks": clk.summary(),
         "clocks_e2e": clk_e2e.summary(),       # the host-link-bound leg, where the SMs idle most of the time
     }
@@ -537,16 +609,29 @@ def run_ours(args, rank, world, device):
         peak, src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks \
             else (6650.0, "fallback (B200_PROFILING.md)")
         us, nbytes, nsets = time_step_kernel(B, 4, device)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-        if os.path.exists(tpath):          # DRAM bytes per launch from the committed ncu --set full capture
-            rec = json.load(open(tpath))["step_kernel_f32_nh4_pair"].get(str(B))
-            if rec:
-                traffic = rec["dram_read"] + rec["dram_write"]
+        # DRAM bytes per launch: NOT measured in this run (a profiler cannot run inside a timed bench) — read from the
+        # committed `ncu --set full` capture of the same kernel at the same launch shape, and labelled as such
+        traffic_db, traffic_src = {}, None
+        for cand in ("ncu_traffic_r02.json", "ncu_traffic_r01.json"):
+            tpath = os.path.join(ROOT, "profiles", cand)
+            if os.path.exists(tpath):
+                traffic_db, traffic_src = json.load(open(tpath))["step_kernel_f32_nh4_pair"], f"profiles/{cand}"
+                break
+
+        def traffic_of(batch):
+            rec = traffic_db.get(str(batch))
+            return None if not rec else {"dram_read": rec["dram_read"], "dram_write": rec["dram_write"],
+                                         "total": rec["dram_read"] + rec["dram_write"]}
+
+        tr0 = traffic_of(B)
         out["roofline"] = {"bound": "hbm", "kernel": "step_kernel<f32,NH=4,CFG pair>", "batch": B,
                            "achieved": round(nbytes / us / 1e3, 1), "peak": peak, "unit": "GB/s",
-                           "frac": round(nbytes / us / 1e3 / peak, 4), "traffic": traffic, "us_per_launch": round(us, 3),
-                           "algorithmic_bytes": nbytes, "peak_source": src}
+                           "frac": round(nbytes / us / 1e3 / peak, 4), "traffic": tr0["total"] if tr0 else None,
+                           "traffic_detail": tr0, "traffic_source": traffic_src and
+                           f"{traffic_src} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; at "
+                           f"this batch the 2 written tensors can still sit dirty in the 126 MB L2 when the kernel ends, "
+                           f"so writes may be under-counted)",
+                           "us_per_launch": round(us, 3), "algorithmic_bytes": nbytes, "peak_source": src}
         from consolver_b200._lib import FLAG_CHAIN
         us_c, _, _ = time_step_kernel(B, 4, device, flags=FLAG_CHAIN)
         out["roofline"]["chained"] = {
@@ -557,9 +642,12 @@ def run_ours(args, rank, world, device):
         sweep = []
         for Bs in (256, 1024, 4096):
             us, nbytes, nsets = time_step_kernel(Bs, 4, device, iters=32)
+            trb = traffic_of(Bs)
             sweep.append({"batch": Bs, "us_per_launch": round(us, 3), "achieved": round(nbytes / us / 1e3, 1),
-                          "frac": round(nbytes / us / 1e3 / peak, 4)})
+                          "frac": round(nbytes / us / 1e3 / peak, 4), "algorithmic_bytes": nbytes,
+                          "traffic": trb["total"] if trb else None, "traffic_detail": trb})
         out["roofline_sweep"] = sweep
+        out["roofline_sweep_traffic_source"] = traffic_src
         out["solver_loop"]["frac_of_peak"] = round(out["solver_loop"]["achieved_gbs_per_gpu"] / peak, 4)
         fm = []
         for Bs in (1, 8, 64, 512):
@@ -569,11 +657,26 @@ def run_ours(args, rank, world, device):
         out["roofline_fm_flux_bf16"] = {"kernel": "step_kernel<bf16,NH=2,FM>", "shape": "[B,4096,64] bf16 (FLUX-Kontext "
                                         "packed 1024^2 latents), order_dim=2", "bytes_per_sample": 4 * 4096 * 64 * 2,
                                         "points": fm}
-        out["cpu_baseline"] = cpu_baseline(B, budget_s=args.cpu_budget)
         try:
             out["fm_flux_preview"] = fm_preview_throughput(device)
         except Exception as e:  # noqa: BLE001
             out["fm_flux_preview"] = {"error": repr(e)[:200]}
+        # the reference's own classes as stock torch on this GPU (SURVEY §2.2's bar), each in a fresh process with a
+        # time limit: dynamo state and a possible compile hang stay out of this process
+        torch.cuda.synchronize(device)
+        if not args.no_torch_ref:
+            for mode in ("eager", "compile"):
+                out[f"torch_{mode}_gpu"] = torch_ref_gpu_subprocess(mode, B, local_index=torch.cuda.current_device())
+        # the CPU arm last: every GPU is idle now and the other ranks SLEEP in a store wait (no NCCL spin on the host)
+        out["cpu_baseline"] = cpu_baseline(B, budget_s=args.cpu_budget)
+    rank0_section_done(world, rank, "rank0_legs")
+    if not args.no_ppo:
+        try:
+            out_ppo = ppo_rollout_leg(rank, world, device)
+            if rank == 0:
+                out["ppo_rollout"] = out_ppo
+        except Exception as e:  # noqa: BLE001
+            out["ppo_rollout"] = {"error": repr(e)[:300]}
     if not args.no_denoiser:
         try:
             wd = with_denoiser(B, device, sd)
@@ -589,8 +692,65 @@ def run_ours(args, rank, world, device):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference) — the only place bench.py touches oracle/
+# helper: rank-0-only legs while the other ranks sleep
 # ------------------------------------------------------------------------------------------------------------
+def rank0_section_done(world, rank, tag):
+    """Ranks != 0 block in a TCPStore wait (a sleeping socket read — NOT an NCCL collective, which would spin a host
+    thread per rank and steal the cores the CPU arm is being timed on) until rank 0 has finished its rank-0-only legs."""
+    if world <= 1:
+        return
+    import datetime
+
+    store = torch.distributed.distributed_c10d._get_default_store()
+    if rank == 0:
+        store.set(tag, "1")
+    else:
+        store.wait([tag], datetime.timedelta(seconds=3600))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arms — the only place bench.py touches oracle/ (oracle/_ref = the unmodified reference, staged by
+# oracle/stage_ref.py; consolver_oracle = the torch-CPU port, second row and fallback)
+# ------------------------------------------------------------------------------------------------------------
+def _reference_preview_fn(B, device="cpu", pool=1, compile_step=False):
+    """8-step CFG preview through the UNMODIFIED reference PPOScheduler (scheduler_ppo.py:178-332) driven the way
+    denoise_ppo.py:62-118 drives it: chunk, u + g*(c-u), scheduler.step(..., return_dict=False)[0], under no_grad, its
+    per-step prints sent to /dev/null.  Returns None when the reference files are not available."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+
+    if not ref_shim.reference_available():
+        return None
+    ref = ref_shim.load_reference()
+    with ref_shim.quiet():
+        sched = ref.PPOScheduler(factor_net_kwargs=dict(FN_KW), **SD_CFG)
+    sched.factor_net.load_state_dict(policy_state_dict(0))
+    sched.factor_net.to(device)
+    sets = [tuple(t.to(device) for t in synth_batch(B, 1234 + j, None)) for j in range(pool)]
+    step = sched.step
+    if compile_step:
+        import torch._dynamo as _dynamo
+
+        _dynamo.config.cache_size_limit = 64
+        step = torch.compile(sched.step)
+    state = {"k": 0}
+
+    def run():
+        x, pairs = sets[state["k"] % pool]
+        state["k"] += 1
+        with ref_shim.devnull(), torch.no_grad():
+            sched.set_timesteps(N_STEPS, device=device)
+            lat = x
+            for i, t in enumerate(sched.timesteps):
+                u, c = pairs[i].chunk(2)                              # denoise_ppo.py:97
+                eps = u + GUIDANCE * (c - u)                          # :100
+                lat = step(eps, t, lat, return_dict=False)[0]         # :103
+        return lat
+
+    run.source = "oracle/_ref (staged copy)" if ref_shim.reference_is_staged_copy() else ref_shim.REFERENCE_ROOT
+    return run
+
+
 def _oracle_preview_fn(B):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import consolver_oracle as orc
@@ -606,49 +766,71 @@ def _oracle_preview_fn(B):
     return run
 
 
-def cpu_baseline(B, budget_s=10.0):
-    torch.set_num_threads(os.cpu_count() or 1)
-    run = _oracle_preview_fn(B)
+def _time_cpu(run, budget_s, max_n=2000):
     run()
     t0 = time.perf_counter()
-    n = 0
-    best = float("inf")
-    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 2000):
+    n, best = 0, float("inf")
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < max_n):
         t1 = time.perf_counter()
         run()
         best = min(best, time.perf_counter() - t1)
         n += 1
-    dt = time.perf_counter() - t0
-    cores = torch.get_num_threads()
-    # second row: the same port on ONE host thread, a short bounded sample
-    torch.set_num_threads(1)
-    t1 = time.perf_counter()
-    n1 = 0
-    while n1 < 2 or (time.perf_counter() - t1 < min(2.0, budget_s / 4) and n1 < 200):
-        run()
-        n1 += 1
-    dt1 = time.perf_counter() - t1
-    torch.set_num_threads(cores)
-    model = ""
+    return n, time.perf_counter() - t0, best
+
+
+def _cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
-            model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
+            return next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
     except OSError:
-        pass
-    return {"value": round(n * B / dt, 1), "unit": "previews/s", "cores": cores, "kind": "port",
-            "sample": f"{n} full 8-step previews of batch {B} (same workload unit, ~{dt:.1f} s of CPU work), torch-CPU "
-                      f"oracle port of the reference scheduler incl. CFG combine, no debug prints",
-            "best_ms_per_step": round(best * 1e3, 2), "algorithmic_gbs": round(
-                TENSORS_PER_PREVIEW * B * 65536 / best / 1e9, 2),
-            "value_1_thread": round(n1 * B / dt1, 1), "host_cpus": os.cpu_count(), "cpu_model": model}
+        return ""
+
+
+def cpu_baseline(B, budget_s=10.0):
+    """The reference scheduler itself on the host cores (kind "reference"), the torch-CPU oracle port as a second row;
+    kind "port" only when oracle/_ref is absent."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref_run = _reference_preview_fn(B)
+    port_run = _oracle_preview_fn(B)
+    out = {}
+    if ref_run is not None:
+        n, dt, best = _time_cpu(ref_run, budget_s * 0.6)
+        out = {"value": round(n * B / dt, 1), "unit": "previews/s", "cores": torch.get_num_threads(), "kind": "reference",
+               "sample": f"{n} full 8-step previews of batch {B} (same workload unit, ~{dt:.1f} s of CPU work) through the "
+                         f"UNMODIFIED reference PPOScheduler.step ({ref_run.source}) incl. the caller's CFG combine, "
+                         f"prints to /dev/null",
+               "best_ms_per_step": round(best * 1e3, 2),
+               "algorithmic_gbs": round(TENSORS_PER_PREVIEW * B * 65536 / best / 1e9, 2)}
+        n2, dt2, best2 = _time_cpu(port_run, budget_s * 0.25)
+        out["port"] = {"value": round(n2 * B / dt2, 1), "best_ms_per_step": round(best2 * 1e3, 2),
+                       "note": "torch-CPU oracle port of the same op sequence (no prints, no .item() syncs)"}
+        one = ref_run
+    else:
+        n, dt, best = _time_cpu(port_run, budget_s * 0.8)
+        out = {"value": round(n * B / dt, 1), "unit": "previews/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} full 8-step previews of batch {B} (~{dt:.1f} s of CPU work), torch-CPU oracle port of the "
+                         f"reference scheduler incl. CFG combine (oracle/_ref not staged on this box)",
+               "best_ms_per_step": round(best * 1e3, 2),
+               "algorithmic_gbs": round(TENSORS_PER_PREVIEW * B * 65536 / best / 1e9, 2)}
+        one = port_run
+    torch.set_num_threads(1)                       # second row (SURVEY §8d): ONE host thread, a short bounded sample
+    n1, dt1, _ = _time_cpu(one, min(2.0, budget_s / 6), max_n=200)
+    torch.set_num_threads(cores)
+    out.update(value_1_thread=round(n1 * B / dt1, 1), host_cpus=os.cpu_count(), cpu_model=_cpu_model())
+    return out
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, same config / metric."""
     if rank != 0:
         return None
     torch.set_num_threads(os.cpu_count() or 1)
     B = args.batch
-    run = _oracle_preview_fn(B)
+    run = _reference_preview_fn(B)
+    kind = "reference"
+    if run is None:
+        run, kind = _oracle_preview_fn(B), "port"
     for _ in range(args.warmup):
         run()
     t0 = time.perf_counter()
@@ -656,22 +838,206 @@ def run_reference(args, rank, world):
         run()
     dt = time.perf_counter() - t0
     v = round(args.steps * B / dt, 1)
+    what = (f"UNMODIFIED reference PPOScheduler.step ({run.source}), prints to /dev/null" if kind == "reference"
+            else "torch-CPU oracle port (oracle/_ref not staged)")
     return {"impl": "reference", "metric": "sd15_8step_solver_previews_per_s", "value": v, "unit": "previews/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+            "timed_region_s": round(dt, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1] solver path on the host CPU (oracle port of the reference "
-                                   "PPOScheduler, torch-CPU ops): SD1.5 latents 4x64x64 fp32, 8-step, CFG=3, batch 64",
-                       "batch_per_gpu": B, "solver_steps": N_STEPS},
-            "cpu_baseline": {"value": v, "unit": "previews/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{args.steps} full 8-step previews of batch {B}"},
+            "config": workload_config(B, world),
+            "run": {"device": "host CPU", "threads": torch.get_num_threads(), "what": what},
+            "cpu_baseline": {"value": v, "unit": "previews/s", "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": f"{args.steps} full 8-step previews of batch {B}: {what}"},
             "e2e": {"value": v, "unit": "previews/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference as stock torch ON THE GPU ("the bar to beat on B200")
+# ------------------------------------------------------------------------------------------------------------
+def torch_ref_gpu_leg(mode, B):
+    """Runs in its own process (see torch_ref_gpu_subprocess).  mode: eager | compile.  Same workload as the headline:
+    8-step CFG previews of batch B over a rotating pool of resident batches larger than L2, CUDA-event timed."""
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(device)
+    out = {}
+    if mode == "compile":
+        out["inductor_host_compiler"] = _inductor_host_compiler()
+    # the reference's arithmetic WITHOUT its host overheads: the op sequence of one steady-state step as a plain
+    # function (tools/microbench.py::torch_reference_step) — the strongest stock-torch form of this path
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import microbench
+
+        out["op_sequence_only"] = [microbench.bench_torch_reference(bb, mode) for bb in (B, 256)]
+    except Exception as e:  # noqa: BLE001
+        out["op_sequence_only"] = {"error": repr(e)[-300:]}
+    try:
+        out.update(_torch_ref_gpu_classes(mode, B, device))
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)[-400:]
+    return out
+
+
+def _inductor_host_compiler():
+    """torch-inductor compiles the reference's 0-d HOST-scalar arithmetic (alphas_cumprod[t] ** 0.5 ...) for the CPU with
+    `g++ -fopenmp`.  On boxes where that cannot run (no libgomp.spec) point it at tools/inductor_cxx/g++-noomp."""
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        with open(src, "w") as f:
+            f.write("#include <omp.h>\nint main(){return omp_get_max_threads() > 0 ? 0 : 1;}\n")
+        ok = subprocess.run(["g++", "-fopenmp", src, "-o", os.path.join(d, "t")], capture_output=True).returncode == 0
+    if ok:
+        return "g++ -fopenmp"
+    wrapper = os.path.join(ROOT, "tools", "inductor_cxx", "g++-noomp")
+    os.environ["CXX"] = wrapper
+    try:
+        import torch._inductor.config as icfg
+
+        icfg.cpp.cxx = (wrapper,)
+    except Exception:  # noqa: BLE001
+        pass
+    return "tools/inductor_cxx/g++-noomp (g++ -fopenmp is not usable on this box)"
+
+
+def _torch_ref_gpu_classes(mode, B, device):
+    bytes_per_batch = (1 + 2 * N_STEPS) * B * SHAPE[0] * SHAPE[1] * SHAPE[2] * 4
+    pool_n = int(max(2, -(-2 * L2_BYTES // bytes_per_batch)))
+    t_build = time.perf_counter()
+    run = _reference_preview_fn(B, device=device, pool=pool_n, compile_step=(mode == "compile"))
+    if run is None:
+        return {"unavailable": "oracle/_ref is not staged on this box (python oracle/stage_ref.py)"}
+    for _ in range(3 if mode == "eager" else 2 * 4 + 2):      # compile: every history depth has to be traced once
+        run()
+    torch.cuda.synchronize(device)
+    warm_s = time.perf_counter() - t_build
+    n = 30
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        run()
+    b.record()
+    torch.cuda.synchronize(device)
+    ms = a.elapsed_time(b) / n
+    out = {"value": round(B / (ms / 1e3), 1), "unit": "previews/s", "ms_per_preview_batch": round(ms, 3),
+           "us_per_solver_step": round(ms * 1e3 / N_STEPS, 1), "previews_timed": n, "batch": B, "pool_batches": pool_n,
+           "warmup_s": round(warm_s, 1),
+           "what": f"UNMODIFIED reference PPOScheduler.step + the caller's CFG combine on cuda:0, torch {mode}"
+                   + (" (torch.compile(scheduler.step); graph breaks at its prints / .item() calls)" if mode == "compile" else
+                      " (incl. its per-step host syncs and tensor prints, to /dev/null)")}
+    return out
+
+
+def torch_ref_gpu_subprocess(mode, B, local_index=0, timeout_s=420):
+    import subprocess
+
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_index]
+               if os.environ.get("CUDA_VISIBLE_DEVICES") else str(local_index))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    env.pop("OMP_NUM_THREADS", None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", f"torch_ref_gpu:{mode}", "--batch", str(B)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        for ln in reversed(r.stdout.splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout_s} s"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: PPO rollout + update with the flat gradient all-reduce (train_ppo.py:257,:406-437)
+# ------------------------------------------------------------------------------------------------------------
+def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
+    """Per iteration and per rank: one rollout of `batch` replicas of one (noise, target) pair with a random step count
+    2..15 shared by all ranks (train_ppo.py:345), a synthetic latent-MSE reward, and `ppo_epochs` x (native loss+grad
+    kernel, ONE ncclAllReduce(AVG) over the flat 75 041-float gradient buffer, clip, AdamW step).  The denoiser is a
+    4x4 channel mix (not the product).  Reference: train_ppo.py:257,:345-437; edit_ppo/train_ppo.py:177,:275-283,:382."""
+    import torch.distributed as dist
+
+    import consolver_b200 as cb
+    from consolver_b200 import ppo, sharding
+
+    torch.manual_seed(1234 + rank)                            # per-rank seeds (edit_ppo/train_ppo.py:76)
+    s = cb.PPOScheduler(factor_net_kwargs=dict(FN_KW), **SD_CFG)
+    with torch.no_grad():
+        s.factor_net.mlp[4].weight.normal_(0, 0.05)
+    s.factor_net.to(device)
+    flat = ppo.FlatParams(s.factor_net)
+    ppo.broadcast_parameters(flat, 0)
+    opt = torch.optim.AdamW(s.factor_net.parameters(), lr=1e-4)
+    g = torch.Generator(device=device).manual_seed(rank)
+    w = torch.randn(4, 4, device=device, generator=g) * 0.3
+    den = lambda x, t, i: torch.einsum("oc,bchw->bohw", w, x)  # noqa: E731  stand-in denoiser (not the product)
+    noise = torch.randn(*SHAPE, device=device, generator=g)
+    target = torch.randn(*SHAPE, device=device, generator=g)
+
+    def one(it):
+        n = ppo.shared_step_count(it, seed=0)
+        lat, rec = ppo.rollout_sd(s, den, noise, batch, GUIDANCE, n)
+        r = ppo.latent_mse_reward(lat, target.unsqueeze(0).expand_as(lat))
+        return ppo.ppo_update(s.factor_net, flat, opt, rec, r, ppo_epochs=ppo_epochs, entropy_coef=0.01), n
+
+    for it in range(3):
+        one(it)
+    ar_us = None
+    if world > 1:                                             # the collective alone, on the flat gradient buffer
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100):
+            ppo.allreduce_gradients(flat)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ar_us = e0.elapsed_time(e1) * 1e3 / 100
+        flat.grad.zero_()
+    # calibrate the iteration count for a region of >= target_s
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for it in range(3, 8):
+        one(it)
+    torch.cuda.synchronize(device)
+    per = (time.perf_counter() - t0) / 5
+    iters = int(max(10, min(2000, -(-target_s // max(per, 1e-5)))))
+    if world > 1:
+        t = torch.tensor([iters], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        iters = int(t.item())
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    steps = 0
+    for it in range(8, 8 + iters):
+        st, n = one(it)
+        steps += n
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    stats = sharding.gather_job_stats(iters * batch, dt, flat.checksum(), device=device)
+    return {"metric": "ppo_rollout_previews_per_s", "value": round(stats["total"] / stats["max_elapsed_s"], 1),
+            "unit": "previews/s", "n_gpus": world, "iters": iters, "batch_per_gpu": batch, "ppo_epochs": ppo_epochs,
+            "mean_solver_steps": round(steps / iters, 2), "timed_region_s": round(stats["max_elapsed_s"], 3),
+            "allreduce_us_300KB": None if ar_us is None else round(ar_us, 2),
+            "collective": None if world == 1 else
+            f"ncclAllReduce(AVG) over {flat.numel} fp32 ({flat.numel * 4} B), once per PPO epoch — latency-bound",
+            "grad_buffer_floats": flat.numel, "grad_buffer_bytes": flat.numel * 4,
+            "param_checksum_identical_across_ranks": abs(stats["checksum"] / world - flat.checksum()) < 1e-6,
+            "last_loss": st["loss"],
+            "what": "BASELINE configs[4]: rollouts with random step counts 2-15 + native PPO loss/grad kernel + flat "
+                    "gradient all-reduce + AdamW; stand-in denoiser = 4x4 channel mix, reward = latent MSE"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--eager", action="store_true", help="python-eager launches instead of the CUDA graph")
@@ -679,8 +1045,15 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="independent preview batches in flight (CUDA streams)")
     ap.add_argument("--no-denoiser", action="store_true", help="skip the with_denoiser (U-Net stand-in) measurement")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / roofline / cpu_baseline (profiling runs)")
+    ap.add_argument("--no-torch-ref", action="store_true", help="skip the torch eager / compile reference-on-GPU legs")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the ppo_rollout leg (BASELINE configs[4])")
+    ap.add_argument("--reps", type=int, default=0, help="force the number of back-to-back blocks (0 = calibrate)")
+    ap.add_argument("--leg", default="", help=argparse.SUPPRESS)       # internal: torch_ref_gpu:<mode> in a subprocess
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.leg.startswith("torch_ref_gpu:"):
+        print(json.dumps(torch_ref_gpu_leg(args.leg.split(":", 1)[1], args.batch)), flush=True)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -35,6 +35,8 @@ class Trajectory:
         self._row = {k: (v.data_ptr(), v.stride(0) * v.element_size()) for k, v in self.out.items()}
         self.q = torch.empty((B * A, K), device=device, dtype=torch.float32)
         self.ring = None                       # [order_dim, B, *shape], allocated on the first fused-CFG step
+        self.ring_epoch = 0                    # bumped by rewind(): stale conds['epsilon'] views can tell
+        self.grid_rows: List[int] = []         # condx row used by each step of this pass (mid-grid starts, repeats)
         self.ring_shape = (order_dim, B, *shape)
         self.dtype, self.device = dtype, device
         # conds['x'] rows of the whole grid, rounded through the model dtype as the reference's
@@ -62,6 +64,8 @@ class Trajectory:
         self.table_pass = -1
         self.graph_rng_used = 0
         self.policy_forked = False
+        self.ring_epoch += 1
+        self.grid_rows = []
 
     def slot(self, i: int) -> torch.Tensor:
         if self.ring is None:
@@ -96,7 +100,14 @@ class Trajectory:
         lo, hi = (1 if skip_first else 0), min(self.count, self.n)
         B = self.key[0]
         pick = lambda k: self.out[k][lo:hi].transpose(0, 1)  # noqa: E731
-        return dict(x=self.condx[lo:hi].unsqueeze(0).expand(B, hi - lo, 2), probs=pick("probs"),
+        rows = self.grid_rows[lo:hi]
+        if len(rows) == hi - lo and rows != list(range(lo, hi)) and all(r is not None for r in rows):
+            # the run did not walk the grid from its first point (img2img-style start, repeated timesteps): gather the
+            # condition rows the steps actually used instead of slicing by step count
+            x_rows = self.condx.index_select(0, torch.tensor(rows, device=self.condx.device))
+        else:
+            x_rows = self.condx[lo:hi]
+        return dict(x=x_rows.unsqueeze(0).expand(B, hi - lo, 2), probs=pick("probs"),
                     actions=pick("actions"), masks=pick("masks"), idx=pick("idx"), logp=pick("logp"))
 
     def last(self, table_row: Optional[int] = None) -> Dict[str, torch.Tensor]:
@@ -154,9 +165,12 @@ def draw_source(sched, tr: Trajectory, device, fused_ok: bool):
     return tr.q.data_ptr(), None, None
 
 
-def lazy_conds(conds_x: torch.Tensor, hist_now: List[torch.Tensor], order_dim: int) -> LazyConds:
+def lazy_conds(conds_x: torch.Tensor, hist_now: List[torch.Tensor], order_dim: int, tr: "Trajectory" = None,
+               ring: bool = False) -> LazyConds:
     """`conds` of the reference's return: 'x' now, 'epsilon' (newest-first zero-padded stack, scheduler_ppo.py:222-237)
-    only when somebody reads it."""
+    only when somebody reads it.  `ring`: the history tensors are slots of the trajectory's ring (step_cfg); the stack is
+    only valid until the oldest of them is overwritten, i.e. while fewer than order_dim - len(history) + 1 further
+    steps have run."""
     def stack():
         s = torch.stack(hist_now, dim=1)
         if len(hist_now) < order_dim:
@@ -164,7 +178,12 @@ def lazy_conds(conds_x: torch.Tensor, hist_now: List[torch.Tensor], order_dim: i
             s = torch.cat([s, pad], dim=1)
         return s
 
-    return LazyConds(conds_x, stack)
+    valid = None
+    if ring and tr is not None:
+        made_at, depth, slots, pass_id = tr.count, len(hist_now), tr.ring_shape[0], tr.ring_epoch
+        # the oldest referenced slot was written at step made_at - depth and is rewritten at step made_at - depth + slots
+        valid = lambda: tr.ring_epoch == pass_id and tr.count <= made_at - depth + slots  # noqa: E731
+    return LazyConds(conds_x, stack, valid)
 
 
 class SolverOptions:

@@ -94,17 +94,37 @@ except Exception:  # noqa: BLE001
 class LazyConds(dict):
     """The `conds` dict of the reference's step() return (`{'x': [B,2], 'epsilon': [B,order_dim,...]}`,
     scheduler_ppo.py:234-237).  'epsilon' — the newest-first, zero-padded stack of the history — is numerically
-    dead unless use_conv=True, so it is materialised only when somebody reads it (torch.stack of the ring
-    slots at that moment; read it before the next order_dim steps overwrite the ring)."""
+    dead unless use_conv=True, so it is materialised only when somebody reads it (torch.stack of the history
+    tensors at that moment).  With `step_cfg` the history lives in the scheduler's ring, whose slots are overwritten
+    order_dim steps later: `still_valid` (a callable) says whether the referenced slots still hold this step's history,
+    and a late read raises instead of silently returning another step's model outputs."""
 
-    def __init__(self, x, eps_thunk):
+    def __init__(self, x, eps_thunk, still_valid=None):
         super().__init__(x=x)
         self._eps_thunk = eps_thunk
+        self._still_valid = still_valid
 
     def _materialise(self):
         if self._eps_thunk is not None:
+            if self._still_valid is not None and not self._still_valid():
+                raise RuntimeError(
+                    "conds['epsilon'] of this step was requested after the scheduler's history ring had been overwritten "
+                    "by later step_cfg() calls (the ring holds order_dim model outputs). Read conds['epsilon'] before "
+                    "stepping order_dim more times, or drive the scheduler through step(), which keeps the caller's "
+                    "tensors by reference like the reference does.")
             thunk, self._eps_thunk = self._eps_thunk, None
             super().__setitem__("epsilon", thunk())
+
+    def __iter__(self):
+        self._materialise()
+        return super().__iter__()
+
+    def __len__(self):
+        return 2
+
+    def copy(self):
+        self._materialise()
+        return dict(self)
 
     def __getitem__(self, k):
         if k == "epsilon":

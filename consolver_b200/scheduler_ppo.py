@@ -149,10 +149,10 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
 
     # ------------------------------------------------------------------------------------------------------
     def _host_timestep(self, timestep) -> int:
-        """Value of `timestep` without a per-step device read-back.  Host ints / CPU tensors are read directly.  A CUDA
-        tensor (pipelines iterate `scheduler.timesteps` on the device) is read back ONCE per trajectory to locate the
-        starting position in the grid — img2img-style callers start at `timesteps[t_start:]` — and consecutive steps
-        are then taken from the host copy of the grid.  `sync_free = False` reads every timestep back instead."""
+        """Value of `timestep`.  Host ints / CPU tensors are read directly.  A 0-d VIEW of `scheduler.timesteps` — what
+        `for t in scheduler.timesteps` and `timesteps[t_start:]` hand out — is located by its storage offset: no device
+        read-back at all.  Every other CUDA tensor is read back (`.item()`), as the reference does.
+        `sync_free = False` disables the view shortcut too."""
         if not isinstance(timestep, torch.Tensor):
             return int(timestep)
         if not timestep.is_cuda:
@@ -168,17 +168,15 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             j = timestep.storage_offset() - ts.storage_offset()
             if 0 <= j < len(grid):
                 return int(grid[j])
-        if self._grid_offset is None:
-            if torch.cuda.is_current_stream_capturing():
-                self._grid_offset = -self._step_count           # cannot read back while capturing: grid order
-            else:
-                hits = np.nonzero(grid == int(timestep.item()))[0]
-                if len(hits) == 0:
-                    return int(timestep.item())                 # off-grid: keep reading back
-                self._grid_offset = int(hits[0]) - self._step_count
-        j = self._step_count + self._grid_offset
-        if 0 <= j < len(grid):
-            return int(grid[j])
+        # Any other CUDA tensor (a clone, a value computed by the caller, a custom subset) is READ BACK, every step, exactly
+        # like the reference does (scheduler_ppo.py:205): the value that was passed is honoured, whatever order the caller
+        # steps in.  Only under stream capture — where a read-back is impossible — the grid order is assumed.
+        if torch.cuda.is_current_stream_capturing():
+            j = self._step_count
+            if 0 <= j < len(grid):
+                return int(grid[j])
+            raise RuntimeError("cannot read a timestep tensor back during CUDA-graph capture; pass scheduler.timesteps[i] "
+                               "(a view of the scheduler's own grid) or a python int")
         return int(timestep.item())
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True):
@@ -201,6 +199,10 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             noise_pred = noise_pred.contiguous()
         if out2 is not None and (out2.shape != sample.shape or not out2[0].is_contiguous()):
             raise ValueError("out2 must have the sample's shape with contiguous samples")
+        if out is not None and (out.shape != sample.shape or not out.is_contiguous()):
+            raise ValueError("out must have the sample's shape and be contiguous (it is written through its data pointer)")
+        if noise_pred.device != sample.device:
+            raise ValueError("noise_pred and sample live on different devices")
         return self._step(noise_pred[:B], noise_pred[B:], float(guidance_scale), timestep, sample, return_dict, out,
                           out2)
 
@@ -235,6 +237,11 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             raise ValueError("Number of inference steps is 'None'. Call 'set_timesteps' first.")
         if not (e0.is_cuda and sample.is_cuda):
             raise RuntimeError("consolver_b200 has no CPU path: model_output and sample must be CUDA tensors")
+        if e0.device.index != torch.cuda.current_device():
+            # one process driving several GPUs: launch in the tensors' own device context (kernel attributes, SM count
+            # and the stream handle all belong to that device)
+            with torch.cuda.device(e0.device):
+                return self._step(e0, cond, guidance, timestep, sample, return_dict, out, out2)
         cfg = self.config
         fn = self.factor_net_module
         od = cfg.order_dim
@@ -371,6 +378,7 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         tr.last_table_row = gi if on_grid else tr.n
         newest = slot if cond is not None else e0     # plain step keeps the caller's tensor by reference, as
         self._hist = [newest] + older                 # the reference does (scheduler_ppo.py:214-218)
+        tr.grid_rows.append(gi)
         tr.count += 1
         self._step_count += 1
 
@@ -378,7 +386,7 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         actions, probs, masks = (None, None, None) if fixed else (o["actions"][i], o["probs"][i], o["masks"][i])
         if actions is not None and fn.action_values.dtype != torch.float32:
             actions = actions.to(fn.action_values.dtype)      # exact: a policy cast to 16 bit returns 16-bit bin values
-        conds = lazy_conds(conds_x, list(self._hist), od)
+        conds = lazy_conds(conds_x, list(self._hist), od, tr, ring=cond is not None)
         if not return_dict:
             return (x_out, actions, probs, conds, masks)
         return PPOSchedulerOutput(prev_sample=x_out, actions=actions, probs=probs, conds=conds, masks=masks)

@@ -27,9 +27,12 @@ _DT = {None: None, "float16": torch.float16, "bfloat16": torch.bfloat16}
 # (rtol, atol) on the softmax tables, = 2x the worst spread MEASURED on the B200 over all fixtures of the class
 # (profiles/parity_spread_r02.md, tools/parity_spread.py), never a round guess:
 PROB_TOL = {
-    "sd_f32": (0.0, 1e-6),          # SD fp32 policy: north-star bar (1e-6)
-    "fm_f32": (2e-5, 1e-7),         # FM fp32 policy, softmax temperature 0.01
-    "autocast": (4e-3, 1e-6),       # 16-bit Linear layers: one 16-bit ulp of a logit
+    "sd_f32": (0.0, 1e-6),          # SD fp32 policy: the north-star bar; measured worst |dp| 2.1e-7
+    "fm_f32": (8e-6, 1e-6),         # FM fp32 policy, softmax temperature 0.01: measured worst rel 3.8e-6, abs 4.8e-7
+                                    #   (the reference's own CPU-vs-CUDA spread on the same weights is 7.7e-6 rel)
+    "autocast": (1.2e-4, 6e-6),     # 16-bit Linear layers (cuBLAS vs the kernel's fp64 butterfly): measured worst rel
+                                    #   5.8e-5, abs 3.0e-6 (cuda_rollout_f16_*); every other autocast fixture <= 6e-8 abs
+    "conv16": (3.4e-3, 5e-4),       # use_conv on bf16 outputs: features agree to bf16 precision; measured 1.7e-3 / 2.3e-4
 }
 
 
@@ -130,29 +133,18 @@ def test_fm_scheduler_matches_the_reference_run_on_a_gpu(name):
 def test_fm_use_conv_on_bf16_outputs_samples_its_own_actions(name):
     """use_conv with 16-bit model outputs.  The reference computes the cosine features in bf16 arithmetic (every op of
     F.cosine_similarity rounded to 8 bits); the feature kernel reduces in fp32/fp64, so the features agree to bf16
-    precision only and, at softmax temperature 0.01, the tables differ visibly.  This test lets the scheduler draw its
-    OWN actions from the fixture's Exp(1) values and reports how often they differ from the reference's; the latents are
-    then checked bit for bit on the steps whose actions agree (the step arithmetic itself is exact)."""
+    precision only and the tables to ~2e-3 relative (softmax temperature 0.01).  The scheduler draws its OWN actions from
+    the fixture's Exp(1) values — nothing is replayed from the reference.  Measured on the B200
+    (profiles/parity_spread_r02.md): 0 of 36 sampled indices differ, so the whole trajectory is bit-identical."""
     g = Golden(name)
     m = g.meta
     s = _scheduler(g)
     s.replay = {"q": [g[f"q_{i}"].cuda() for i in range(m["n"])]}
     x = g["x_T"].cuda()
-    mism = tot = 0
     for i, t in enumerate(s.timesteps):
-        x_in = g[f"prev_{i - 1}"].cuda() if i else x          # re-anchor on the reference trajectory every step
-        out = s.step(g[f"v_{i}"].cuda(), t, x_in, return_dict=False)
-        idx = s.last_policy()["idx"].cpu()
-        used = g[f"masks_{i}"].bool()                          # only the action dims the step consumes
-        same_rows = ((idx == g[f"idx_{i}"]) | ~used).all(dim=1)
-        mism += int(((idx != g[f"idx_{i}"]) & used).sum())
-        tot += int(used.sum())
-        ref, got = g[f"prev_{i}"], out[0].cpu()
-        assert got.dtype == ref.dtype
-        assert torch.equal(got[same_rows], ref[same_rows]), f"step {i}: latents of samples with equal actions differ"
-    rate = mism / max(tot, 1)
-    print(f"\n{name}: own-draw index mismatch rate vs the reference (used action dims): {mism}/{tot} = {rate:.3f}")
-    assert rate <= 0.5
+        out = s.step(g[f"v_{i}"].cuda(), t, x, return_dict=False)
+        _check(g, i, s, out, *PROB_TOL["conv16"])
+        x = out[0]
 
 
 # ---- kernel level, default (CUDA-tensor) rules against the oracle with sem=CUDA ----------------------------------------

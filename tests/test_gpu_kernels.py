@@ -46,8 +46,8 @@ def test_policy_kernel_vs_oracle(variant, H, K, od, sdim, mu, B):
         out = ah.policy(dsd, x[0, 0], x[0, 1], 999.0 if variant == "sd" else 1.0, 1.0 if variant == "sd" else 0.01,
                         B, od, sdim, n_hist, q=q.cuda())
         probs = orc.policy_probs(sd, x, variant)                       # [1, A, K]
-        rtol = 0 if variant == "sd" else 2e-4
-        torch.testing.assert_close(out["probs_table"].cpu(), probs[0], rtol=rtol, atol=1e-6 if variant == "sd" else 1e-7)
+        rtol = 0 if variant == "sd" else 2e-5      # FM (temperature 0.01): see the measured spreads in test_gpu_golden.py
+        torch.testing.assert_close(out["probs_table"].cpu(), probs[0], rtol=rtol, atol=1e-6)
         # the draw itself is checked against the kernel's own table (bit-exact argmax of p/q) ...
         tab = out["probs_table"].cpu().unsqueeze(0).expand(B, A, K)
         idx = orc.sample_indices(tab, q)
@@ -217,8 +217,7 @@ def test_table_and_sample_kernels_match_the_fused_policy_kernel(variant, H, K, o
     x_div, temp = (999.0, 1.0) if variant == "sd" else (1.0, 0.01)
     tables = ah.policy_table(dsd, rows, x_div, temp)
     ref = orc.policy_probs(sd, rows, variant)
-    torch.testing.assert_close(tables.cpu(), ref, rtol=0 if variant == "sd" else 2e-4,
-                               atol=1e-6 if variant == "sd" else 1e-7)
+    torch.testing.assert_close(tables.cpu(), ref, rtol=0 if variant == "sd" else 2e-5, atol=1e-6)
     g = torch.Generator().manual_seed(B + 1)
     q = torch.empty(B * A, K).exponential_(1, generator=g).cuda()
     for r, n_hist in ((1, od), (2, 1)):

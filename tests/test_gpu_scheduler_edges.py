@@ -187,28 +187,25 @@ def test_denoise_loop_with_a_16bit_denoiser_output_ends_with_fp32_latents(noise_
     assert torch.equal(x, lat)
 
 
-def test_policy_cast_to_the_pipeline_dtype_keeps_16bit_latents():
-    """gen_ppo.py:193-195 casts the policy, bin buffer included, to the pipeline's fp16: the reference's coefficients are
-    then fp16 tensors, nothing promotes, and the latents stay fp16 at every step (each torch op rounding to fp16).
-    The scheduler follows the dtype trajectory; its arithmetic is fp32 with one rounding per step, so values are
-    compared step by step within fp16 resolution against the reference's per-op fp16 evaluation."""
+def test_policy_cast_to_the_pipeline_dtype_promotes_after_the_first_step():
+    """gen_ppo.py:193-195 casts the policy, bin buffer included, to the pipeline's fp16 and runs under autocast: the
+    reference's coefficients are fp16 tensors EXCEPT the closing one (torch.sum returns fp32 under autocast), so the
+    latent is fp16 after the first step only and fp32 from the second on.  The dtype trajectory here; the bit-for-bit
+    check of this flow is tests/test_gpu_cuda_reference.py on the cuda_genppo_* fixtures (made by the reference on a
+    B200)."""
     g, m, s, _ = _pair()
     s.factor_net.to("cuda", dtype=torch.float16)
-    mixed_sd = dict(g.state_dict, action_values=g.state_dict["action_values"].half())     # fp16 bins => fp16 coefficients
-    o = orc.OracleSDScheduler(mixed_sd, **m["config"])
     s.set_timesteps(m["n"], device="cuda")
-    o.set_timesteps(m["n"])
     s.replay = {"idx": [g[f"idx_{i}"] for i in range(m["n"])]}
-    x = g["x_T"].half()
-    for i, t in enumerate(o.timesteps):
-        eps = g[f"eps_{i}"].half()
-        assert s.next_latent_dtype(eps.dtype, x.dtype) == torch.float16
-        out = s.step(eps.cuda(), s.timesteps[i], x.cuda(), return_dict=False)[0]
-        ref = o.step(eps, t, x, forced_idx=g[f"idx_{i}"])[0]
-        assert out.dtype == ref.dtype == torch.float16, f"step {i}"
-        err = (out.float().cpu() - ref.float()).abs().max() / ref.float().abs().max()
-        assert err < 8 * 2.0 ** -10, f"step {i}: {err}"
-        x = out.cpu()
+    x = g["x_T"].half().cuda()
+    with torch.autocast("cuda", torch.float16):
+        for i in range(m["n"]):
+            eps = g[f"eps_{i}"].half().cuda()
+            want = torch.float16 if i == 0 else torch.float32
+            assert s.next_latent_dtype(eps.dtype, x.dtype) == want
+            x, actions = s.step(eps, s.timesteps[i], x, return_dict=False)[:2]
+            assert x.dtype == want, f"step {i}"
+            assert actions.dtype == torch.float16          # bin values come back in the policy's dtype, as the reference's do
 
 
 @pytest.mark.parametrize("kind", ["learned", "heun"])
@@ -313,3 +310,86 @@ def test_pipeline_style_loops_never_synchronise_with_the_host():
         with _no_sync():
             loop(sched, outputs, x, start)
         torch.cuda.synchronize()
+
+
+# ---- behaviours fixed after the round-1 review ------------------------------------------------------------------------
+def test_a_cuda_timestep_that_is_not_a_view_of_the_grid_is_honoured():
+    """A caller that clones, reorders or repeats timesteps gets steps at the values it PASSED (the reference reads every
+    timestep back, scheduler_ppo.py:205) — not at grid[step_count].  Two schedulers: one fed views in grid order, one fed
+    clones in a permuted order with a repeat; each step must equal the same (t, history) evaluated through ints."""
+    g, m, s, _ = _pair()
+    n = m["n"]
+    order = [0, 3, 3, 1, 5, 2]                                   # a Heun-style repeat and a custom subset
+    idx = [g[f"idx_{i}"] for i in range(n)]
+    outs = {}
+    for how in ("clone", "int"):
+        s.set_timesteps(n, device="cuda")
+        s.replay = {"idx": [idx[k] for k in range(len(order))]}
+        x = g["x_T"].cuda()
+        res = []
+        for k, j in enumerate(order):
+            t = s.timesteps[j].clone() if how == "clone" else int(s._timesteps_host[j])
+            x = s.step(g[f"eps_{k}"].cuda(), t, x, return_dict=False)[0]
+            res.append(x.clone())
+        outs[how] = res
+        rec = s.trajectory(skip_first=False)["x"][0].cpu()
+        want = torch.tensor([[float(s._timesteps_host[j]), float(s._timesteps_host[j] - s._stride)] for j in order])
+        assert torch.equal(rec, want), "the rollout record must hold the condition rows the steps actually used"
+    for a, b in zip(outs["clone"], outs["int"]):
+        assert torch.equal(a, b)
+
+
+def test_reading_conds_epsilon_after_the_ring_was_reused_raises():
+    g, m, s, _ = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    s.replay = {"idx": [g[f"idx_{i}"] for i in range(m["n"])]}
+    x = g["x_T"].cuda()
+    kept = []
+    od = m["config"]["order_dim"]
+    for i, t in enumerate(s.timesteps):
+        out = s.step_cfg(g[f"pair_{i}"].cuda(), t, x, m["guidance"])
+        x = out[0]
+        kept.append(out[3])
+        if i == 2:      # step 0 referenced one slot; the ring (order_dim slots) has not wrapped yet: still readable
+            e0 = kept[0]["epsilon"]
+            assert e0.shape[1] == od and torch.equal(e0[:, 0].cpu(), g["eps_0"]) and not e0[:, 1:].any()
+    last = kept[-1]
+    assert len(last) == 2 and set(iter(last)) == {"x", "epsilon"} and set(dict(last)) == {"x", "epsilon"}
+    assert torch.equal(last["epsilon"][:, 0].cpu(), g[f"eps_{m['n'] - 1}"])
+    assert torch.equal(kept[0]["epsilon"], e0)                    # already materialised: a copy, stays valid
+    for stale in (kept[1], kept[-2]):                             # never read in time: their slots have been rewritten
+        with pytest.raises(RuntimeError, match="history ring had been overwritten"):
+            stale["epsilon"]
+
+
+def test_step_cfg_rejects_a_destination_it_cannot_write_densely():
+    g, m, s, _ = _pair()
+    s.set_timesteps(m["n"], device="cuda")
+    x = g["x_T"].cuda()
+    pair = g["pair_0"].cuda()
+    with pytest.raises(ValueError, match="out must have the sample's shape"):
+        s.step_cfg(pair, s.timesteps[0], x, 3.0, out=torch.empty(x.shape[0], x[0].numel(), device="cuda"))
+    wide = torch.empty(*x.shape[:-1], 2 * x.shape[-1], device="cuda")[..., ::2]
+    with pytest.raises(ValueError, match="out must have the sample's shape"):
+        s.step_cfg(pair, s.timesteps[0], x, 3.0, out=wide)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_can_drive_two_devices():
+    """per-device kernel attributes / SM counts and a device guard around the launches: tensors on cuda:1 while cuda:0 is
+    current, with a batch large enough for the >48 KB shared-memory path of the policy kernel"""
+    import consolver_b200 as cb
+    g, m, _, _ = _pair()
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.cuda.set_device(0)
+        s = cb.PPOScheduler(factor_net_kwargs=dict(m["factor_net_kwargs"]), **m["config"])
+        s.factor_net.load_state_dict(g.state_dict)
+        s.factor_net.to(dev)
+        s.set_timesteps(m["n"], device=dev)
+        s.replay = {"idx": [g[f"idx_{i}"].to(dev) for i in range(m["n"])]}
+        x = g["x_T"].to(dev)
+        for i, t in enumerate(s.timesteps):
+            x = s.step_cfg(g[f"pair_{i}"].to(dev), t, x, m["guidance"])[0]
+        res.append(x.cpu())
+    assert torch.equal(res[0], res[1])

@@ -108,7 +108,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--md", default=os.path.join(ROOT, "gpurun_out", "parity_spread.md"))
     ap.add_argument("--json", default=os.path.join(ROOT, "gpurun_out", "parity_spread.json"))
-    a = ap.parse_args()
+    args = ap.parse_args()
     rows = []
     for prefix in ("sd_", "sd16_", "fm_", "cuda_"):
         for name in names(prefix):
@@ -128,11 +128,11 @@ def main():
                 a, r = spread(gc[f"probs_full_{i}"].float(), gg[f"probs_full_{i}"].float())
                 worst = (max(worst[0], a), max(worst[1], r))
             self_spread.append(dict(cpu=cpu_name, cuda=cuda_name, dp_abs=worst[0], dp_rel=worst[1]))
-    os.makedirs(os.path.dirname(a.json), exist_ok=True)
-    with open(a.json, "w") as f:
+    os.makedirs(os.path.dirname(args.json), exist_ok=True)
+    with open(args.json, "w") as f:
         json.dump(dict(gpu=torch.cuda.get_device_name(0), torch=torch.__version__, fixtures=rows,
                        reference_cpu_vs_cuda=self_spread), f, indent=1)
-    with open(a.md, "w") as f:
+    with open(args.md, "w") as f:
         f.write("# Policy-table parity: measured spreads (tools/parity_spread.py, " + torch.cuda.get_device_name(0) + ")\n\n")
         f.write("| fixture | made on | autocast | max abs dp | max rel dp (p>=1e-6) | max dlogp (sampled) | own-draw idx mismatch | "
                 "latent steps differing | kernel vs fp64 rel | reference vs fp64 rel |\n|---|---|---|---|---|---|---|---|---|---|\n")
@@ -147,7 +147,7 @@ def main():
                 "| CPU fixture | CUDA fixture | max abs dp | max rel dp |\n|---|---|---|---|\n")
         for r in self_spread:
             f.write(f"| {r['cpu']} | {r['cuda']} | {r['dp_abs']:.2e} | {r['dp_rel']:.2e} |\n")
-    print("wrote", a.md)
+    print("wrote", args.md)
 
 
 if __name__ == "__main__":
