@@ -880,26 +880,39 @@ def torch_ref_gpu_leg(mode, B):
 
 def _inductor_host_compiler():
     """torch-inductor compiles the reference's 0-d HOST-scalar arithmetic (alphas_cumprod[t] ** 0.5 ...) for the CPU with
-    `g++ -fopenmp`.  On boxes where that cannot run (no libgomp.spec) point it at tools/inductor_cxx/g++-noomp."""
+    `$CXX -fopenmp`.  This image exports CXX=/opt/gcc/bin/g++, a trimmed gcc without libgomp.spec, while /usr/bin/g++
+    has OpenMP: pick the first candidate that can build an OpenMP program; if none can, fall back to
+    tools/inductor_cxx/g++-noomp (g++ minus -fopenmp, with a two-function omp.h stub)."""
+    import shutil
     import subprocess
     import tempfile
 
-    with tempfile.TemporaryDirectory() as d:
-        src = os.path.join(d, "t.cpp")
-        with open(src, "w") as f:
-            f.write("#include <omp.h>\nint main(){return omp_get_max_threads() > 0 ? 0 : 1;}\n")
-        ok = subprocess.run(["g++", "-fopenmp", src, "-o", os.path.join(d, "t")], capture_output=True).returncode == 0
-    if ok:
-        return "g++ -fopenmp"
-    wrapper = os.path.join(ROOT, "tools", "inductor_cxx", "g++-noomp")
-    os.environ["CXX"] = wrapper
+    def works(cxx):
+        with tempfile.TemporaryDirectory() as d:
+            src = os.path.join(d, "t.cpp")
+            with open(src, "w") as f:
+                f.write("#include <omp.h>\nint main(){return omp_get_max_threads() > 0 ? 0 : 1;}\n")
+            try:
+                return subprocess.run([cxx, "-fopenmp", "-shared", "-fPIC", src, "-o", os.path.join(d, "t.so")],
+                                      capture_output=True, timeout=60).returncode == 0
+            except Exception:  # noqa: BLE001
+                return False
+
+    cands = [c for c in (os.environ.get("CXX"), shutil.which("g++"), "/usr/bin/g++") if c]
+    chosen = next((c for c in dict.fromkeys(cands) if works(c)), None)
+    label = f"{chosen} -fopenmp" if chosen else "tools/inductor_cxx/g++-noomp (no candidate can build with -fopenmp)"
+    if chosen is None:
+        chosen = os.path.join(ROOT, "tools", "inductor_cxx", "g++-noomp")
+    if chosen != os.environ.get("CXX"):
+        label += f" (instead of CXX={os.environ.get('CXX')})"
+    os.environ["CXX"] = chosen
     try:
         import torch._inductor.config as icfg
 
-        icfg.cpp.cxx = (wrapper,)
+        icfg.cpp.cxx = (None, chosen)
     except Exception:  # noqa: BLE001
         pass
-    return "tools/inductor_cxx/g++-noomp (g++ -fopenmp is not usable on this box)"
+    return label
 
 
 def _torch_ref_gpu_classes(mode, B, device):

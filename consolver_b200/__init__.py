@@ -7,12 +7,12 @@ G-U-N/consolver, behind the reference's own scheduler plugin API.
 
 Host side: Python/PyTorch (device memory, streams, RNG, torch.distributed); hot path: hand-written CUDA behind
 the C ABI in include/consolver.h (libconsolver.so, built in-tree by consolver_b200.build).  No CPU fallback."""
-from .factor_net import FactorNetPPO, FactorNetPPOFM
+from .factor_net import FactorNetPPO, FactorNetPPOContinous, FactorNetPPOFM
 from .scheduler_dpm import DPMSolverMultistepScheduler
 from .scheduler_fm import FlowMatchGeneralDiscreteScheduler
 from .scheduler_fmppo import FMPPOScheduler, FMPPOSchedulerOutput
 from .scheduler_ppo import PPOScheduler, PPOSchedulerOutput
 
 __all__ = ["PPOScheduler", "PPOSchedulerOutput", "FMPPOScheduler", "FMPPOSchedulerOutput", "FactorNetPPO",
-           "FactorNetPPOFM", "FlowMatchGeneralDiscreteScheduler", "DPMSolverMultistepScheduler"]
-__version__ = "0.1.0"
+           "FactorNetPPOFM", "FactorNetPPOContinous", "FlowMatchGeneralDiscreteScheduler", "DPMSolverMultistepScheduler"]
+__version__ = "0.2.0"

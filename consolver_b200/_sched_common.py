@@ -244,7 +244,7 @@ class SolverOptions:
                 act = ad
         if act is not None:
             pflags |= _lib.POLICY_ACT_F16 if act == torch.float16 else _lib.POLICY_ACT_BF16
-        bdt = fn._buffers["action_values"].dtype
+        bdt = fn.action_values.dtype
         if bdt in (torch.float16, torch.bfloat16):
             pflags |= _lib.POLICY_COEF_F16 if bdt == torch.float16 else _lib.POLICY_COEF_BF16
             if bdt == model_dtype:

@@ -32,6 +32,31 @@ __device__ __forceinline__ float policy_input(float x, float x_div, int flags) {
   return round_act(v, flags & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_ACT_BF16));
 }
 
+// set_default_coefficients (scheduler_ppo.py:165-175) for one sample: act[0..A) are the sampled action values, c the
+// coefficient record of include/consolver.h: c0 = a0 + 1, c_{n-1} = 1 - sum(c_0..c_{n-2}), then (1+s0), (1+s1).
+// cm = CONSOLVER_POLICY_COEF_F16/_BF16: the action values are 16-bit tensors, so a0 + 1 and s + 1 are rounded to that
+// dtype; torch.sum returns fp32 under autocast, so the running sum and the closing coefficient are fp32.
+__device__ __forceinline__ void write_coef_record(const float* act, float* c, int n, int od, int scaler_dim, int cm) {
+  const float c0 = round_act(__fadd_rn(act[0], 1.f), cm);
+  float run = c0;
+  for (int i = 0; i < od; ++i) {
+    float v = 0.f;
+    if (n == 1) {
+      v = (i == 0) ? 1.f : 0.f;               // the step kernel bypasses the coefficient when n_hist == 1
+    } else if (i == 0) {
+      v = c0;
+    } else if (i < n - 1) {
+      v = act[i];
+      run = __fadd_rn(run, v);
+    } else if (i == n - 1) {
+      v = __fsub_rn(1.f, run);
+    }
+    c[i] = v;
+  }
+  c[od] = scaler_dim >= 1 ? round_act(__fadd_rn(act[od - 1], 1.f), cm) : 1.f;
+  c[od + 1] = scaler_dim >= 2 ? round_act(__fadd_rn(act[od], 1.f), cm) : 1.f;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -104,13 +129,12 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
   }
 }
 
-// MLP + softmax for one input row held in x_s[0..in_dim); leaves probs in p_s[0..A*K).
-__device__ __forceinline__ void mlp_softmax(const MlpView& p, int in_dim, const float* x_s, float* h1_s,
-                                            float* h2_s, float* lg_s, float* p_s) {
+// The three Linear layers for one input row held in x_s[0..in_dim); leaves the A*K raw outputs in lg_s.
+__device__ __forceinline__ void mlp_logits(const MlpView& p, int in_dim, const float* x_s, float* h1_s, float* h2_s,
+                                           float* lg_s) {
   const int H = p.H, AK = p.A * p.K;
   const int act = p.flags & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_ACT_BF16);
-  // layer 0: in_dim is 2 (or 2 + order_dim - 1): one thread per hidden unit
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {     // layer 0: in_dim is 2 (or 2 + order_dim - 1)
     double acc = 0.0;
     for (int i = 0; i < in_dim; ++i) acc = fma((double)__ldg(p.w1 + j * in_dim + i), (double)x_s[i], acc);
     h1_s[j] = fmaxf(round_act((float)(acc + (double)__ldg(p.b1 + j)), act), 0.f);
@@ -120,6 +144,13 @@ __device__ __forceinline__ void mlp_softmax(const MlpView& p, int in_dim, const 
   __syncthreads();
   dense_layer<false>(p.w3, p.b3, h2_s, lg_s, AK, H, act);
   __syncthreads();
+}
+
+// MLP + softmax for one input row held in x_s[0..in_dim); leaves probs in p_s[0..A*K).
+__device__ __forceinline__ void mlp_softmax(const MlpView& p, int in_dim, const float* x_s, float* h1_s,
+                                            float* h2_s, float* lg_s, float* p_s) {
+  const int act = p.flags & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_ACT_BF16);
+  mlp_logits(p, in_dim, x_s, h1_s, h2_s, lg_s);
   // logits / temp: a true division on CPU tensors, a multiplication by the fp32 reciprocal on CUDA tensors
   const bool host_div = p.flags & CONSOLVER_POLICY_HOST_DIV;
   const float inv_temp = __fdiv_rn(1.f, p.temp);

@@ -162,33 +162,9 @@ __device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin,
     if (p.masks) p.masks[o] = (a >= p.n_hist - 1 && a < od - 1) ? 0.f : 1.f;   // scheduler_ppo.py:248-249
   }
   __syncthreads();
-  // set_default_coefficients (scheduler_ppo.py:165-175): c0 = a0 + 1, c_{n-1} = 1 - sum(c_0..c_{n-2}).
-  // COEF_F16/_BF16: the bin values are 16-bit tensors, so a0 + 1 and s + 1 are rounded to that dtype; torch.sum
-  // returns fp32 under autocast, so the running sum and the closing coefficient are fp32 (exact sums of 16-bit values)
-  const int n = p.n_hist;
-  const int cm = p.flags & (CONSOLVER_POLICY_COEF_F16 | CONSOLVER_POLICY_COEF_BF16);
-  for (int bl = threadIdx.x; bl < nb; bl += blockDim.x) {
-    const float* act = act_s + (size_t)bl * A;
-    float* c = p.coef + (size_t)(b_begin + bl) * (od + 2);
-    const float c0 = round_act(__fadd_rn(act[0], 1.f), cm);
-    float run = c0;
-    for (int i = 0; i < od; ++i) {
-      float v = 0.f;
-      if (n == 1) {
-        v = (i == 0) ? 1.f : 0.f;               // the step kernel bypasses the coefficient when n_hist == 1
-      } else if (i == 0) {
-        v = c0;
-      } else if (i < n - 1) {
-        v = act[i];
-        run = __fadd_rn(run, v);
-      } else if (i == n - 1) {
-        v = __fsub_rn(1.f, run);
-      }
-      c[i] = v;
-    }
-    c[od] = p.scaler_dim >= 1 ? round_act(__fadd_rn(act[od - 1], 1.f), cm) : 1.f;
-    c[od + 1] = p.scaler_dim >= 2 ? round_act(__fadd_rn(act[od], 1.f), cm) : 1.f;
-  }
+  for (int bl = threadIdx.x; bl < nb; bl += blockDim.x)
+    write_coef_record(act_s + (size_t)bl * A, p.coef + (size_t)(b_begin + bl) * (od + 2), p.n_hist, od, p.scaler_dim,
+                      p.flags & (CONSOLVER_POLICY_COEF_F16 | CONSOLVER_POLICY_COEF_BF16));
 }
 
 struct Smem {

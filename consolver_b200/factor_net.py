@@ -206,6 +206,118 @@ class FactorNetPPOFM(FactorNetPPO):
                          input_channels, conv_out_channels, mu_dim=mu_dim)
 
 
+class FactorNetPPOContinous(nn.Module):
+    """CONTINUOUS (Gaussian) policy — `ppo_type != "discrete"`.  EXTENSION, PARITY UNPINNED.
+
+    The reference imports and instantiates a class of this name (scheduler_ppo.py:23,:139 — the spelling is the
+    reference's) but ships no source for it, so there is nothing to restate or to pin against: the semantics are this
+    repo's own, documented in csrc/policy_gauss.cu and tested against closed forms (torch.distributions.Normal).  What IS
+    the reference's — the (actions, probs) return convention of `sample_action`, the masks and the coefficient assembly
+    of the scheduler — is shared with the discrete policy.
+
+      trunk   Linear(2,H) ReLU Linear(H,H) ReLU Linear(H, 2A): raw mean / raw log-std per action dim
+      mean_a  = mid_a + half_a * tanh(raw_mean_a);   std_a = half_a * exp(clamp(raw_logstd_a, -7, 1))
+              [lo_a, hi_a] (buffer `action_range`) = the value range of the discrete policy's bins for that dim
+      draw    actions = mean + std * z, z = ONE torch.randn([B, A]) per step from the default CUDA generator
+      probs   exp(log N(action; mean, std)) — a density; the PPO loss takes log(probs + 1e-9) like train_ppo.py:410-411
+    The last layer starts at zero with raw log-std `log_std_init` (mean = centre of the range)."""
+
+    variant = "sd"
+    x_div = 999.0
+    temperature = 1.0
+    num_actions = 2                  # the head has two outputs per action dim (sizes the shared trajectory buffers)
+    continuous = True
+
+    def __init__(self, embedding_dim=1024, hidden_dim=256, num_actions=None, order_dim=4, scaler_dim=2, use_conv=False,
+                 input_channels=4, conv_out_channels=8, log_std_init=-1.0):
+        super().__init__()
+        if use_conv:
+            raise NotImplementedError("use_conv is not defined for the continuous policy extension")
+        if order_dim < 2 or order_dim > _lib.MAX_ORDER:
+            raise ValueError(f"order_dim must be in [2, {_lib.MAX_ORDER}]")
+        self.order_dim, self.scaler_dim, self.hidden_dim, self.use_conv = order_dim, scaler_dim, hidden_dim, False
+        self.action_dims = A = order_dim + scaler_dim - 1
+        self.mlp = nn.Sequential(nn.Linear(2, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, hidden_dim), nn.ReLU(),
+                                 nn.Linear(hidden_dim, 2 * A))
+        nn.init.zeros_(self.mlp[-1].weight)
+        with torch.no_grad():
+            self.mlp[-1].bias[:A].zero_()
+            self.mlp[-1].bias[A:].fill_(float(log_std_init))
+        bins = _action_values("sd", 3, order_dim, scaler_dim, 0)                      # rows: [lo, mid, hi] of each dim
+        self.register_buffer("action_range", torch.stack([bins[:, 0], bins[:, -1]], dim=1).contiguous())   # [A,2]
+        self._w32_cache = None
+
+    # the schedulers read these two like the discrete policy's
+    @property
+    def action_values(self):
+        return self.action_range
+
+    def _kparams_dtype(self):
+        return self.mlp[0].weight.dtype
+
+    def kernel_weights(self, act_dtype=None):
+        ps = [self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight, self.mlp[2].bias, self.mlp[4].weight,
+              self.mlp[4].bias, self.action_range]
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        c = self._w32_cache
+        if c is None or c[0] != key:
+            if not ps[0].is_cuda:
+                raise RuntimeError("consolver_b200 has no CPU path: move factor_net to a CUDA device")
+            ws = [p.detach().float().contiguous() for p in ps]
+            self._w32_cache = c = (key, ws, [w.data_ptr() for w in ws])
+        return c[2]
+
+    def mean_std(self, x):
+        """torch (autograd) evaluation of the head: x [R,2] -> (mean [R,A], std [R,A])"""
+        A = self.action_dims
+        raw = self.mlp(x.float() / 999.0)
+        lo, hi = self.action_range[:, 0], self.action_range[:, 1]
+        mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+        return mid + half * torch.tanh(raw[:, :A]), half * torch.exp(raw[:, A:].clamp(-7.0, 1.0))
+
+    def forward(self, x_dict, actions=None):
+        if actions is None:
+            return self.sample_action(x_dict)
+        return self.get_action_probs(x_dict, actions)
+
+    def policy_launch(self, x0, x1, B, n_hist, *, z=None, actions_in=None, rng=None, out=None, stream=None):
+        import ctypes
+
+        lib = _lib.load()
+        w = self.kernel_weights()
+        dev = self.action_range.device
+        A = self.action_dims
+        if z is None and actions_in is None and rng is None:
+            z = torch.randn(B, A, device=dev)
+        if out is None:
+            out = alloc_policy_outputs(B, A, 2, self.order_dim, dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.consolver_policy_gauss_f32(
+            *w, float(x0), float(x1), self.x_div, z.data_ptr() if z is not None else None,
+            actions_in.data_ptr() if actions_in is not None else None, ctypes.byref(rng) if rng is not None else None,
+            B, self.hidden_dim, A, self.order_dim, self.scaler_dim, n_hist, 0, out["probs_table"].data_ptr(), None,
+            out["actions"].data_ptr(), out["probs"].data_ptr(), out["logp"].data_ptr(), out["masks"].data_ptr(),
+            out["coef"].data_ptr(), stream)
+        _lib.check(rc, "consolver_policy_gauss_f32")
+        return out
+
+    def sample_action(self, x_dict):
+        """(actions [B,A], probs [B,A]) — the reference's return convention (factor_net_ppo.py:159-168)."""
+        x = x_dict["x"]
+        if not x.is_cuda:
+            raise RuntimeError("consolver_b200 has no CPU path: x_dict['x'] must be a CUDA tensor")
+        row = x[0].float().tolist()
+        out = self.policy_launch(row[0], row[1], x.shape[0], n_hist=self.order_dim)
+        return out["actions"], out["probs"]
+
+    def get_action_probs(self, x_dict, actions):
+        """PPO-update side (autograd): (density of `actions` under the current policy [R,A], normalised entropy [R,A])."""
+        mean, std = self.mean_std(x_dict["x"])
+        dist = torch.distributions.Normal(mean, std)
+        return dist.log_prob(actions.to(mean.device)).exp(), dist.entropy()
+
+
 def alloc_policy_outputs(B, A, K, order_dim, device, lead=()):
     """Buffers the policy kernel writes; `lead` prepends dims (the schedulers allocate [n_steps, ...] once per
     trajectory so the per-step results ARE the trajectory record — no unsqueeze/cat at the end)."""

@@ -31,7 +31,7 @@ import torch
 from . import _lib
 from ._sched_common import SolverOptions, Trajectory, draw_source, lazy_conds, next_rng  # noqa: F401 (next_rng re-export)
 from .config_utils import KARRAS_COMPATIBLES, BaseOutput, ConfigMixin, SchedulerMixin, register_to_config
-from .factor_net import FactorNetPPO
+from .factor_net import FactorNetPPO, FactorNetPPOContinous
 
 
 @dataclasses.dataclass
@@ -109,10 +109,12 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         kw.setdefault("embedding_dim", 32)
         kw.setdefault("hidden_dim", 256)
         if ppo_type != "discrete":
-            # scheduler_ppo.py:139 instantiates FactorNetPPOContinous, whose source is not part of the reference
-            raise NotImplementedError("ppo_type != 'discrete': the continuous policy does not exist in the reference")
-        kw.setdefault("num_actions", 161)
-        self.factor_net = FactorNetPPO(**kw)
+            # scheduler_ppo.py:139 instantiates FactorNetPPOContinous, whose source is not part of the reference: this
+            # is an EXTENSION with self-defined semantics (factor_net.FactorNetPPOContinous), parity unpinned
+            self.factor_net = FactorNetPPOContinous(**kw)
+        else:
+            kw.setdefault("num_actions", 161)
+            self.factor_net = FactorNetPPO(**kw)
 
         self._init_solver_options()
         self._step_count = 0
@@ -301,7 +303,10 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
         pi = prev_t if prev_t >= 0 else 0            # final step uses alphas_cumprod[0] (scheduler_ppo.py:114,:310)
         sa_p, sb_p = float(self._sqrt_abar[pi]), float(self._sqrt_1m_abar[pi])
 
-        q_ptr, idx_ptr, rng_arg = draw_source(self, tr, e0.device, fused_ok=on_grid and not fn.use_conv)
+        if getattr(fn, "continuous", False):
+            q_ptr = idx_ptr = rng_arg = None              # the Gaussian policy draws torch.randn, see _gauss_draw
+        else:
+            q_ptr, idx_ptr, rng_arg = draw_source(self, tr, e0.device, fused_ok=on_grid and not fn.use_conv)
         x_out = out if out is not None else torch.empty_like(sample)
         slot = tr.slot(tr.count) if cond is not None else None
         sem_flags, pflags, act_dt = self._semantics(e0.dtype)
@@ -322,6 +327,17 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             # policy — DDIM is depth 1, Adams-Bashforth / iPNDM style multistep are depths 2..4
             rc = lib.consolver_step_sd(*step_args, tr.fixed_rows(self.fixed_coefficients, n_hist).data_ptr(), od + 2,
                                        *tail, vflag, B, N, stream)
+            _lib.check(rc, "consolver_step_sd")
+        elif getattr(fn, "continuous", False):
+            # Gaussian policy (extension, parity unpinned): one fused kernel — MLP head, the torch.randn draw regenerated
+            # in the kernel, log-prob, masks, coefficient assembly — then the ordinary fused step as its PDL dependent
+            z_ptr, act_ptr, g_rng = self._gauss_draw(tr, e0.device, B, fn.action_dims)
+            rc = lib.consolver_policy_gauss_f32(
+                *fn.kernel_weights(), x0, x1, fn.x_div, z_ptr, act_ptr, g_rng, B, fn.hidden_dim, fn.action_dims, od,
+                cfg.scaler_dim, n_hist, pflags & _lib.POLICY_HOST_DIV, tr.p("probs_table", gi if on_grid else tr.n),
+                None, *outs[1:], stream)
+            _lib.check(rc, "consolver_policy_gauss_f32")
+            rc = lib.consolver_step_sd(*step_args, outs[5], od + 2, *tail, vflag | sflag | pdl, B, N, stream)
             _lib.check(rc, "consolver_step_sd")
         elif fn.use_conv:
             # use_conv=True (factor_net_ppo.py:146-149): two passes.  Pass 1 reduces the cosine features of the
@@ -391,11 +407,43 @@ class PPOScheduler(SolverOptions, SchedulerMixin, ConfigMixin):
             return (x_out, actions, probs, conds, masks)
         return PPOSchedulerOutput(prev_sample=x_out, actions=actions, probs=probs, conds=conds, masks=masks)
 
+    def _gauss_draw(self, tr, device, B, A):
+        """draw source of the continuous policy -> (z_ptr, actions_ptr, rng_arg), exactly one non-null: replay['z'] /
+        replay['actions'] per step, else the in-kernel regeneration of torch.randn([B,A]) (or that launch itself)"""
+        import ctypes
+
+        from . import rng as _rng
+
+        rp = self.replay
+        if rp is not None and rp.get("actions") is not None:
+            forced = rp["actions"][tr.count].to(device=device, dtype=torch.float32).contiguous()
+            tr._forced_keepalive = forced
+            return None, forced.data_ptr(), None
+        if rp is not None and rp.get("z") is not None:
+            z = rp["z"][tr.count].to(device=device, dtype=torch.float32).contiguous()
+            tr._forced_keepalive = z
+            return z.data_ptr(), None, None
+        if self.use_fused_rng and not torch.cuda.is_current_stream_capturing() and _rng.fused_rng_available(device):
+            nthreads, inc = _lib.philox_plan(B * A)
+            seed, off = _rng.take(device, inc)
+            r = _lib.Rng(seed, off, None, nthreads)
+            tr._rng_keepalive = r
+            return None, None, ctypes.byref(r)
+        z = torch.randn(B, A, device=device)
+        tr._forced_keepalive = z
+        return z.data_ptr(), None, None
+
     # ------------------------------------------------------------------------------------------------------
     def last_policy(self):
         """Full softmax table [A,K] ([B,A,K] with use_conv), sampled indices [B,A], coefficient records
         [B,order_dim+2] and log-probs of the most recent step (views)."""
-        return self._traj.last()
+        lp = self._traj.last()
+        fn = self.factor_net_module
+        if getattr(fn, "continuous", False):       # the table row holds {mean[A], std[A]} for the Gaussian policy
+            ms = lp.pop("probs_table").reshape(2, fn.action_dims)
+            lp.update(mean=ms[0], std=ms[1])
+            lp.pop("idx", None)
+        return lp
 
     def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         """DDPM forward noising (scheduler_ppo.py:336-358); not on the hot path, plain torch."""

@@ -25,7 +25,7 @@ extern "C" {
 
 /* Bumped on EVERY change of a signature, struct layout or flag meaning in this header.  Loaders must also compare
  * consolver_abi_hash() with the hash of the header they were written against (see consolver_abi_hash below). */
-#define CONSOLVER_ABI_VERSION 3
+#define CONSOLVER_ABI_VERSION 4
 
 /* element type of latents / model outputs */
 #define CONSOLVER_F32  0
@@ -305,6 +305,27 @@ CONSOLVER_API int consolver_policy_sample_f32(const float* probs_in, const float
                                               int scaler_dim, int n_hist, int policy_flags, int64_t* idx, float* actions,
                                               float* act_probs, float* act_logp, float* masks, float* coef,
                                               consolver_stream_t stream);
+
+/*
+ * CONTINUOUS (Gaussian) policy — ppo_type != "discrete".  EXTENSION, PARITY UNPINNED: the reference instantiates
+ * `FactorNetPPOContinous` (scheduler_ppo.py:23,:139) but ships no source for it, so these semantics are this library's
+ * own (csrc/policy_gauss.cu states them); masks and coefficient assembly are the discrete policy's
+ * (scheduler_ppo.py:248-259,:165-175).  Same trunk, last layer w3 [2A,H] -> raw mean / raw log-std per action dim;
+ *   mean = mid + half*tanh(raw_mean), std = half*exp(clamp(raw_logstd,-7,1)), [lo,hi] = action_range[a] (host-chosen,
+ *   by default the discrete bins' ranges); action = mean + std*z; logp = -z^2/2 - log std - log(2 pi)/2.
+ * Exactly one draw source: z [B*A] (given N(0,1) values), actions_in [B*A] (forced actions: z is recovered), or rng (the
+ * kernel regenerates what torch.randn([B,A]) on the CUDA default generator would draw; plan =
+ * consolver_torch_philox_plan(B*A)).  Outputs: mean_std [2,A] (nullable), z_out [B*A] (nullable), actions / act_probs
+ * (= exp(logp), a density) / act_logp / masks [B,A], coef [B,order_dim+2].
+ */
+CONSOLVER_API int consolver_policy_gauss_f32(const float* w1, const float* b1, const float* w2, const float* b2,
+                                             const float* w3, const float* b3, const float* action_range,
+                                             float x0, float x1, float x_div,
+                                             const float* z, const float* actions_in, const consolver_rng_t* rng,
+                                             int B, int H, int A, int order_dim, int scaler_dim, int n_hist,
+                                             int policy_flags, float* mean_std, float* z_out, float* actions,
+                                             float* act_probs, float* act_logp, float* masks, float* coef,
+                                             consolver_stream_t stream);
 
 /*
  * One call per scheduler step for the SD path: the policy (consolver_policy_sample_f32 when probs_in != NULL,

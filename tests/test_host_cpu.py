@@ -88,8 +88,10 @@ def test_error_behaviour_matches_reference():
         cb.PPOScheduler(beta_schedule="bogus")
     with pytest.raises(ValueError):
         cb.PPOScheduler(prediction_type="sample")
+    cont = cb.PPOScheduler(ppo_type="continuous")        # extension (parity unpinned): builds FactorNetPPOContinous
+    assert isinstance(cont.factor_net, cb.FactorNetPPOContinous) and cont.factor_net.action_dims == 5
     with pytest.raises(NotImplementedError):
-        cb.PPOScheduler(ppo_type="continuous")
+        cb.FMPPOScheduler(ppo_type="continuous")          # edit_ppo/scheduler_fmppo.py:169-170 is `assert 0`
     s.set_timesteps(4)
     with pytest.raises(RuntimeError, match="no CPU path"):     # the product never falls back to the CPU
         s.step(x, 999, x)

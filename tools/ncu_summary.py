@@ -44,6 +44,26 @@ def main():
                 else:
                     cells.append("-")
             lines.append(f"| {rep.split('/')[-1]} | `{name[:70]}` | " + " | ".join(cells) + " |")
+    # warp-state (stall) breakdown: every `..issue_stalled_<reason>_per_issue_active.ratio` column of --set full,
+    # top reasons per kernel (average warps stalled on <reason> per issue slot)
+    lines += ["", "## Stall breakdown (warps stalled per issue-active cycle, top reasons)", "",
+              "| report | kernel | waves/SM | " + "top stall reasons |", "|---|---|---|---|"]
+    for rep in reps:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr = rows[0]
+        cols = [(i, h) for i, h in enumerate(hdr) if "issue_stalled" in h and h.endswith("per_issue_active.ratio")]
+        for r in rows[2:]:
+            vals = []
+            for i, h in cols:
+                try:
+                    vals.append((float(r[i].replace(",", "")), h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")))
+                except ValueError:
+                    pass
+            vals.sort(reverse=True)
+            waves = r[hdr.index("launch__waves_per_multiprocessor")] if "launch__waves_per_multiprocessor" in hdr else "-"
+            top = ", ".join(f"{n} {v:.2f}" for v, n in vals[:5])
+            lines.append(f"| {rep.split('/')[-1]} | `{r[hdr.index('Kernel Name')][:60]}` | {waves} | {top} |")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
 
