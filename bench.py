@@ -991,15 +991,53 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
     noise = torch.randn(*SHAPE, device=device, generator=g)
     target = torch.randn(*SHAPE, device=device, generator=g)
 
-    def one(it):
+    exchange, exchange_err = None, None
+    if world > 1:
+        try:                                                  # fused one-shot exchange over NVLink peer memory
+            exchange = ppo.PeerGradExchange(flat)
+        except Exception as e:  # noqa: BLE001  (no P2P / symmetric memory on this box: NCCL path)
+            exchange_err = repr(e)[:200]
+        ok = torch.tensor([1 if exchange is not None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            exchange = None
+
+    def one(it, ex=None):
         n = ppo.shared_step_count(it, seed=0)
         lat, rec = ppo.rollout_sd(s, den, noise, batch, GUIDANCE, n)
         r = ppo.latent_mse_reward(lat, target.unsqueeze(0).expand_as(lat))
-        return ppo.ppo_update(s.factor_net, flat, opt, rec, r, ppo_epochs=ppo_epochs, entropy_coef=0.01), n
+        return ppo.ppo_update(s.factor_net, flat, opt, rec, r, ppo_epochs=ppo_epochs, entropy_coef=0.01,
+                              exchange=ex), n
 
     for it in range(3):
-        one(it)
-    ar_us = None
+        one(it, exchange)
+    ar_us = fused_us = plain_us = None
+    if world > 1:
+        # the update kernels alone: (loss+grad, reduce) + ncclAllReduce  vs  (loss+grad, reduce FUSED with the exchange)
+        R_, A_ = 7, s.factor_net.action_dims
+        xr = torch.tensor([[999.0 - 125 * r, 874.0 - 125 * r] for r in range(R_)], device=device)
+        ix = torch.randint(0, FN_KW["num_actions"], (R_, batch, A_), device=device)
+        ol = torch.rand(R_, batch, A_, device=device) * 0.5 + 0.05
+        ad = torch.randn(R_, batch, A_, device=device)
+
+        def time_updates(ex, nccl):
+            dist.barrier()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(100):
+                ppo.ppo_loss_grad_cuda(s.factor_net, flat, xr, ix, ol, ad, 0.2, 0.01, exchange=ex)
+                if nccl:
+                    ppo.allreduce_gradients(flat)
+            e1.record()
+            torch.cuda.synchronize(device)
+            return e0.elapsed_time(e1) * 1e3 / 100
+
+        plain_us = time_updates(None, False)
+        nccl_us = time_updates(None, True)
+        if exchange is not None:
+            fused_us = time_updates(exchange, False)
+        flat.grad.zero_()
     if world > 1:                                             # the collective alone, on the flat gradient buffer
         dist.barrier()
         torch.cuda.synchronize(device)
@@ -1015,7 +1053,7 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     for it in range(3, 8):
-        one(it)
+        one(it, exchange)
     torch.cuda.synchronize(device)
     per = (time.perf_counter() - t0) / 5
     iters = int(max(10, min(2000, -(-target_s // max(per, 1e-5)))))
@@ -1028,7 +1066,7 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
     t0 = time.perf_counter()
     steps = 0
     for it in range(8, 8 + iters):
-        st, n = one(it)
+        st, n = one(it, exchange)
         steps += n
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
@@ -1037,8 +1075,17 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
             "unit": "previews/s", "n_gpus": world, "iters": iters, "batch_per_gpu": batch, "ppo_epochs": ppo_epochs,
             "mean_solver_steps": round(steps / iters, 2), "timed_region_s": round(stats["max_elapsed_s"], 3),
             "allreduce_us_300KB": None if ar_us is None else round(ar_us, 2),
-            "collective": None if world == 1 else
-            f"ncclAllReduce(AVG) over {flat.numel} fp32 ({flat.numel * 4} B), once per PPO epoch — latency-bound",
+            "collective": None if world == 1 else (
+                f"one-shot all-reduce(AVG) over NVLink peer memory FUSED into ppo_reduce_allreduce_kernel "
+                f"({flat.numel} fp32 = {flat.numel * 4} B per rank, once per PPO epoch)" if exchange is not None else
+                f"ncclAllReduce(AVG) over {flat.numel} fp32 ({flat.numel * 4} B), once per PPO epoch — latency-bound"),
+            "exchange": None if world == 1 else {
+                "used_in_timed_region": "fused peer-memory exchange" if exchange is not None else "ncclAllReduce",
+                "update_kernels_us": None if plain_us is None else round(plain_us, 2),
+                "update_kernels_plus_nccl_allreduce_us": None if plain_us is None else round(nccl_us, 2),
+                "update_kernels_with_fused_exchange_us": None if fused_us is None else round(fused_us, 2),
+                "nccl_allreduce_alone_us": None if ar_us is None else round(ar_us, 2),
+                "fused_exchange_error": exchange_err},
             "grad_buffer_floats": flat.numel, "grad_buffer_bytes": flat.numel * 4,
             "param_checksum_identical_across_ranks": abs(stats["checksum"] / world - flat.checksum()) < 1e-6,
             "last_loss": st["loss"],

@@ -221,6 +221,95 @@ __global__ void ppo_reduce_kernel(const float* __restrict__ partial, int R, long
   }
 }
 
+// ---- fused reduce + data-parallel exchange over NVLink peer memory ------------------------------------------------------
+// The reference averages the policy gradient over ranks with one DDP all-reduce per PPO epoch (train_ppo.py:257,:430;
+// edit_ppo/train_ppo.py:382): 75 041 floats = 300 KB, far below the size where a ring/tree pays off — NCCL's cost there is
+// its launch + protocol latency (measured 23-35 us at 2-8 GPUs).  Here the exchange is folded into the kernel that
+// produces the gradient, as a ONE-SHOT all-reduce over peer-mapped ("symmetric") buffers:
+//   phase 1  every thread sums its element over the per-row partials (fixed order) and stores it into THIS rank's
+//            symmetric buffer (local HBM, peer-readable);
+//   phase 2  the last CTA to finish publishes `epoch` into slot [rank] of every peer's signal pad with a system-scope
+//            release store (through NVLink); thread 0 of each CTA then spins, with system-scope acquire loads on the LOCAL
+//            pad, until all `world` slots carry the epoch;
+//   phase 3  every thread loads its element from all `world` buffers (peer loads over NVLink/NVSwitch, issued together:
+//            one round trip), adds them IN RANK ORDER — so every rank forms the bit-identical sum — and writes
+//            sum * (1/world) into the flat gradient.
+// Buffers are double-buffered by epoch parity: a rank can only overwrite parity p two epochs later, which requires every
+// peer to have signalled the epoch in between, i.e. to have finished reading.  All CTAs must be co-resident (grid of
+// ~300 CTAs of 256 threads on 148 SMs): they are.
+struct PeerView {
+  float* const* bufs;          // device array [world]: peer-mapped base pointers; each buffer = [2][P_pad] floats + pad
+  unsigned int* const* sig;    // device array [world]: peer-mapped signal pads, `world` words each
+  int rank, world;
+  unsigned int epoch;
+  long long parity_offset;     // floats: (epoch & 1) * P_pad
+  unsigned int* ticket;        // device word, zero between launches
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) ppo_reduce_allreduce_kernel(const float* __restrict__ partial, int R, long long P,
+                                                                  int B, float ent_coef, float* __restrict__ grad,
+                                                                  float* __restrict__ stats, const PeerView pv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = P + kPpoStats;
+  float* mine = pv.bufs[pv.rank] + pv.parity_offset;
+  if (i < P) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += partial[(size_t)r * stride + i];
+    mine[i] = s;
+  } else if (i == P) {
+    float pl = 0.f, ent = 0.f, ratio = 0.f;
+    for (int r = 0; r < R; ++r) {
+      pl += partial[(size_t)r * stride + P];
+      ent += partial[(size_t)r * stride + P + 1];
+      ratio += partial[(size_t)r * stride + P + 2];
+    }
+    ent /= (float)R;
+    stats[0] = pl - ent_coef * ent;      // this rank's loss statistics (the reference logs them per rank as well)
+    stats[1] = pl;
+    stats[2] = ent;
+    stats[3] = ratio / ((float)R * (float)B);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                   // this CTA's stores are visible system-wide
+    const unsigned int t = atomicAdd(pv.ticket, 1u);
+    if (t == gridDim.x - 1) {                                  // the whole local buffer is written: tell every peer
+      *pv.ticket = 0u;
+      __threadfence_system();
+      for (int r = 0; r < pv.world; ++r) st_release_sys(pv.sig[r] + pv.rank, pv.epoch);
+    }
+    const unsigned int* my_pad = pv.sig[pv.rank];
+    for (int r = 0; r < pv.world; ++r)
+      while ((int)(ld_acquire_sys(my_pad + r) - pv.epoch) < 0) {}
+  }
+  __syncthreads();
+  if (i < P) {
+    float v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < pv.world) v[r] = ld_relaxed_sys(pv.bufs[r] + pv.parity_offset + i);
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < pv.world) acc += v[r];
+    grad[i] = acc * (1.f / (float)pv.world);
+  }
+}
+
 }  // namespace consolver
 
 using namespace consolver;
@@ -237,6 +326,18 @@ extern "C" int consolver_ppo_loss_grad_f32(const float* w1, const float* b1, con
                                            int B, float clip_range, float entropy_coef,
                                            void* workspace, float* grad_flat, float* stats,
                                            consolver_stream_t stream) {
+  return consolver_ppo_loss_grad_allreduce_f32(w1, b1, w2, b2, w3, b3, x_rows, rows, x_div, temp, H, A, K, idx, old_probs,
+                                               advantages, B, clip_range, entropy_coef, workspace, grad_flat, stats,
+                                               nullptr, stream);
+}
+
+extern "C" int consolver_ppo_loss_grad_allreduce_f32(const float* w1, const float* b1, const float* w2, const float* b2,
+                                                     const float* w3, const float* b3, const float* x_rows, int rows,
+                                                     float x_div, float temp, int H, int A, int K,
+                                                     const int64_t* idx, const float* old_probs,
+                                                     const float* advantages, int B, float clip_range,
+                                                     float entropy_coef, void* workspace, float* grad_flat, float* stats,
+                                                     const consolver_peers_t* peers, consolver_stream_t stream) {
   if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !x_rows || !idx || !old_probs || !advantages || !workspace ||
       !grad_flat || !stats)
     return CONSOLVER_ERR_NULL;
@@ -265,6 +366,20 @@ extern "C" int consolver_ppo_loss_grad_f32(const float* w1, const float* b1, con
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const long long n = p.P + 1;
-  ppo_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p.partial, rows, p.P, B, entropy_coef, grad_flat, stats);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (peers && peers->world > 1) {
+    if (!peers->buffer_ptrs_dev || !peers->signal_ptrs_dev || !peers->ticket) return CONSOLVER_ERR_NULL;
+    if (peers->world > 16 || peers->rank < 0 || peers->rank >= peers->world || peers->stride_floats < p.P)
+      return CONSOLVER_ERR_SIZE;
+    PeerView pv;
+    pv.bufs = reinterpret_cast<float* const*>(peers->buffer_ptrs_dev);
+    pv.sig = reinterpret_cast<unsigned int* const*>(peers->signal_ptrs_dev);
+    pv.rank = peers->rank; pv.world = peers->world; pv.epoch = peers->epoch;
+    pv.parity_offset = (long long)(peers->epoch & 1u) * peers->stride_floats;
+    pv.ticket = peers->ticket;
+    ppo_reduce_allreduce_kernel<<<grid, 256, 0, s>>>(p.partial, rows, p.P, B, entropy_coef, grad_flat, stats, pv);
+    return (int)cudaGetLastError();
+  }
+  ppo_reduce_kernel<<<grid, 256, 0, s>>>(p.partial, rows, p.P, B, entropy_coef, grad_flat, stats);
   return (int)cudaGetLastError();
 }

@@ -81,6 +81,56 @@ def allreduce_gradients(flat: FlatParams):
         flat.grad.div_(dist.get_world_size())
 
 
+class PeerGradExchange:
+    """One-shot all-reduce (AVG) of the flat policy gradient over NVLink peer memory, FUSED into the PPO reduction kernel
+    (csrc/ppo.cu::ppo_reduce_allreduce_kernel) — the B200-native replacement for the DDP gradient all-reduce of
+    train_ppo.py:257,:430 / edit_ppo/train_ppo.py:382.  300 KB is latency-bound: NCCL costs 23-35 us at 2-8 GPUs; here
+    every rank stores its gradient into a peer-mapped buffer, signals, and sums all ranks' buffers in rank order (every
+    rank gets the bit-identical average), inside the kernel that produced the gradient.
+
+    Buffers come from torch's symmetric-memory allocator (cudaMalloc'd / fabric memory mapped into every peer over
+    NVLink/NVSwitch); the kernel only sees raw pointers (consolver_peers_t).  Collective: construct on all ranks."""
+
+    def __init__(self, flat: FlatParams, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerGradExchange needs an initialised process group")
+        group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise ValueError("one-shot exchange supports up to 16 ranks of one NVLink domain")
+        dev = flat.grad.device
+        self.stride = (flat.numel + 63) // 64 * 64                     # floats per parity, 256-byte granules
+        pad_words = 64                                                  # signal pad: one word per rank
+        enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+        if enable is not None:                                          # older torch: explicit opt-in per group
+            try:
+                enable(group.group_name)
+            except Exception:  # noqa: BLE001
+                pass
+        self.buf = symm_mem.empty(2 * self.stride + pad_words, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        torch.cuda.synchronize(dev)
+        self.hdl.barrier()                                              # everybody's pad is zero before anyone signals
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._buf_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self._sig_ptrs = torch.tensor([p + 2 * self.stride * 4 for p in ptrs], dtype=torch.int64, device=dev)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch = 0
+
+    def next_peers(self):
+        """consolver_peers_t for the next fused update (every rank must make the same sequence of calls)"""
+        from . import _lib
+
+        self.epoch += 1
+        p = _lib.Peers(self._buf_ptrs.data_ptr(), self._sig_ptrs.data_ptr(), self.rank, self.world,
+                       self.epoch & 0xFFFFFFFF, self.stride, self._ticket.data_ptr())
+        self._keepalive = p
+        return p
+
+
 def shared_step_count(step: int, seed: int, lo: int = 2, hi: int = 15) -> int:
     """Number of inference steps of rollout `step`, identical on every rank without a collective
     (train_ppo.py:345 draws random.choice(range(2,16)) under identical seeds; the FLUX driver broadcasts it)."""
@@ -127,7 +177,8 @@ def ppo_loss(factor_net, x_rows: torch.Tensor, idx: torch.Tensor, old_probs: tor
 
 def ppo_loss_grad_cuda(factor_net, flat: FlatParams, x_rows: torch.Tensor, idx_rba: torch.Tensor,
                        old_rba: torch.Tensor, adv_rba: torch.Tensor, clip_range: float, entropy_coef: float,
-                       workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       workspace: Optional[torch.Tensor] = None,
+                       exchange: Optional["PeerGradExchange"] = None) -> torch.Tensor:
     """Hand-written CUDA forward + loss + backward (csrc/ppo.cu): writes d loss / d params into `flat.grad` and
     returns stats [4] = {loss, policy_loss, mean entropy, mean ratio} (device tensor, no sync).
     Inputs in the trajectory buffers' native layout: idx / old probs / advantages as [R, B, A]."""
@@ -147,21 +198,27 @@ def ppo_loss_grad_cuda(factor_net, flat: FlatParams, x_rows: torch.Tensor, idx_r
     expected = sum(p.numel() for p in fn.parameters())
     if flat.grad.numel() != expected or flat.grad.dtype != torch.float32:
         raise ValueError("flat gradient buffer does not match the policy's parameters")
-    rc = lib.consolver_ppo_loss_grad_f32(
+    import ctypes
+
+    peers = ctypes.byref(exchange.next_peers()) if exchange is not None and exchange.world > 1 else None
+    rc = lib.consolver_ppo_loss_grad_allreduce_f32(
         *w[:6], x_rows.data_ptr(), R, fn.x_div, fn.temperature, fn.hidden_dim, fn.action_dims, fn.num_actions,
         idx_rba.data_ptr(), old_rba.data_ptr(), adv_rba.data_ptr(), B, float(clip_range), float(entropy_coef),
-        workspace.data_ptr(), flat.grad.data_ptr(), stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(rc, "consolver_ppo_loss_grad_f32")
+        workspace.data_ptr(), flat.grad.data_ptr(), stats.data_ptr(), peers,
+        torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "consolver_ppo_loss_grad_allreduce_f32")
     return stats
 
 
 def ppo_update(factor_net, flat: FlatParams, optimizer, record: Dict[str, torch.Tensor], rewards: torch.Tensor,
                ppo_epochs: int = 1, clip_range: float = 0.2, entropy_coef: float = 0.0,
-               max_grad_norm: Optional[float] = 1.0, native: Optional[bool] = None) -> Dict[str, float]:
+               max_grad_norm: Optional[float] = 1.0, native: Optional[bool] = None,
+               exchange: Optional["PeerGradExchange"] = None) -> Dict[str, float]:
     """ppo_epochs x (loss, backward, flat all-reduce, clip, optimizer step) — train_ppo.py:406-437.
     `record` is `scheduler.trajectory()` (views); it is detached/cloned here because the next rollout reuses the
     buffers.  `native` (default: on for CUDA tensors with the shared-row policy) runs forward + loss + backward as the
-    hand-written kernels of csrc/ppo.cu; otherwise torch autograd on the distinct rows."""
+    hand-written kernels of csrc/ppo.cu; otherwise torch autograd on the distinct rows.  `exchange` (PeerGradExchange, native
+    path only): the gradient all-reduce is fused into the reduction kernel over NVLink peer memory instead of a NCCL call."""
     x_rows = record["x"][0].detach().float().clone()
     idx = record["idx"].detach().clone()
     old_probs = record["probs"].detach().clone()
@@ -178,8 +235,9 @@ def ppo_update(factor_net, flat: FlatParams, optimizer, record: Dict[str, torch.
             for p, (o, k) in zip(flat.params, flat._spans()):       # keep p.grad aliased to the flat buffer
                 if p.grad is None or p.grad.data_ptr() != flat.grad[o:o + k].data_ptr():
                     p.grad = flat.grad[o:o + k].view_as(p)
-            st = ppo_loss_grad_cuda(fn, flat, x_rows, idx_r, old_r, adv_r, clip_range, entropy_coef, ws)
-            allreduce_gradients(flat)
+            st = ppo_loss_grad_cuda(fn, flat, x_rows, idx_r, old_r, adv_r, clip_range, entropy_coef, ws, exchange)
+            if exchange is None:
+                allreduce_gradients(flat)      # NCCL; with `exchange` the all-reduce already happened inside the kernel
             if max_grad_norm is not None:
                 norm = flat.grad.norm()
                 flat.grad.mul_(torch.clamp(max_grad_norm / (norm + 1e-6), max=1.0))

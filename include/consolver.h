@@ -25,7 +25,7 @@ extern "C" {
 
 /* Bumped on EVERY change of a signature, struct layout or flag meaning in this header.  Loaders must also compare
  * consolver_abi_hash() with the hash of the header they were written against (see consolver_abi_hash below). */
-#define CONSOLVER_ABI_VERSION 4
+#define CONSOLVER_ABI_VERSION 5
 
 /* element type of latents / model outputs */
 #define CONSOLVER_F32  0
@@ -380,6 +380,36 @@ CONSOLVER_API int consolver_ppo_loss_grad_f32(const float* w1, const float* b1, 
                                               int B, float clip_range, float entropy_coef,
                                               void* workspace, float* grad_flat, float* stats,
                                               consolver_stream_t stream);
+
+/*
+ * The same update with the data-parallel gradient exchange FUSED into the reduction kernel: a one-shot all-reduce (AVG)
+ * over NVLink peer memory instead of a separate NCCL call — replaces DDP's gradient all-reduce of train_ppo.py:257,:430
+ * and edit_ppo/train_ppo.py:382 (300 KB per PPO epoch, latency-bound).  `peers` == NULL or world == 1: identical to
+ * consolver_ppo_loss_grad_f32.  Otherwise every rank must call this with the same `epoch`; on return (in stream order)
+ * grad_flat holds (sum over ranks, added in rank order — bit-identical on every rank) / world.
+ *   buffer_ptrs_dev   device array [world] of peer-mapped base pointers of the ranks' exchange buffers, each
+ *                     2 * stride_floats floats (two epoch parities); entry [rank] is this rank's own buffer
+ *   signal_ptrs_dev   device array [world] of peer-mapped signal pads, `world` uint32 each, zero before the first call
+ *   epoch             1, 2, 3, ... incremented by one per call, identical on all ranks
+ *   ticket            device uint32 private to this rank, zero before the first call
+ * The buffers are obtained by the caller from any symmetric-memory allocator (the Python host uses
+ * torch.distributed._symmetric_memory); the library only needs the pointers.
+ */
+typedef struct consolver_peers {
+  void* const* buffer_ptrs_dev;
+  void* const* signal_ptrs_dev;
+  int rank, world;
+  uint32_t epoch;
+  int64_t stride_floats;
+  uint32_t* ticket;
+} consolver_peers_t;
+CONSOLVER_API int consolver_ppo_loss_grad_allreduce_f32(const float* w1, const float* b1, const float* w2, const float* b2,
+                                              const float* w3, const float* b3, const float* x_rows, int rows,
+                                              float x_div, float temp, int H, int A, int K,
+                                              const int64_t* idx, const float* old_probs, const float* advantages,
+                                              int B, float clip_range, float entropy_coef,
+                                              void* workspace, float* grad_flat, float* stats,
+                                              const consolver_peers_t* peers, consolver_stream_t stream);
 
 /* Tuning knobs for benchmarking (process-global; not part of the numerical contract).
  *   threads: CTA size of the step kernels (32..512, multiple of 32; 0 = default)

@@ -69,3 +69,61 @@ def test_two_gpu_nccl_rollouts_and_update_keep_replicas_identical():
         assert p.exitcode == 0
     assert res[0][1] == res[1][1], "parameter checksums differ across ranks"
     assert res[0][2] == 80 and res[0][3] == [40, 40]
+
+
+def _exchange_worker(rank, world, port, q):
+    """the fused one-shot exchange (csrc/ppo.cu::ppo_reduce_allreduce_kernel) against NCCL's all-reduce(AVG) on the same
+    per-rank gradients, several epochs in a row (both buffer parities, monotonic signals)"""
+    import torch.distributed as dist
+
+    import consolver_b200 as cb
+    from consolver_b200 import ppo, sharding
+
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    sharding.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(7)                                # same policy on every rank ...
+    s = cb.PPOScheduler(**PROD)
+    with torch.no_grad():
+        s.factor_net.mlp[4].weight.normal_(0, 0.05)
+    s.factor_net.to(dev)
+    flat = ppo.FlatParams(s.factor_net)
+    ex = ppo.PeerGradExchange(flat)
+    R, B, A = 7, 24, 3
+    worst, same = 0.0, True
+    for it in range(5):
+        g = torch.Generator(device=dev).manual_seed(1000 * it + rank)          # ... different rollouts per rank
+        x_rows = torch.tensor([[999.0 - 125 * r, 874.0 - 125 * r] for r in range(R)], device=dev)
+        idx = torch.randint(0, 11, (R, B, A), device=dev, generator=g)
+        old = torch.rand(R, B, A, device=dev, generator=g) * 0.5 + 0.05
+        adv = torch.randn(R, B, A, device=dev, generator=g)
+        ppo.ppo_loss_grad_cuda(s.factor_net, flat, x_rows, idx, old, adv, 0.2, 0.01)             # local gradient
+        want = flat.grad.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.AVG)
+        ppo.ppo_loss_grad_cuda(s.factor_net, flat, x_rows, idx, old, adv, 0.2, 0.01, exchange=ex)  # fused exchange
+        got = flat.grad.clone()
+        worst = max(worst, float((got - want).abs().max() / want.abs().max()))
+        both = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(both, got)
+        same = same and all(torch.equal(both[0], b) for b in both[1:])
+    q.put((rank, worst, same))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_fused_peer_memory_gradient_exchange_matches_nccl_average():
+    world, port = min(torch.cuda.device_count(), 8), _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, worst, same in res:
+        assert worst <= 2e-6, f"rank {rank}: fused exchange vs ncclAllReduce(AVG): {worst}"     # summation order only
+        assert same, "ranks hold different averages (the rank-ordered sum must be bit-identical everywhere)"
