@@ -91,8 +91,7 @@ __global__ void __launch_bounds__(kGaussThreads) policy_gauss_kernel(const Gauss
     const float mean = fmaf(half, tanhf(raw_s[a]), mid);
     const float ls = fminf(fmaxf(raw_s[A + a], -7.f), 1.f) + logf(half);
     lstd_s[a] = ls;
-    __syncwarp();
-    raw_s[a] = mean;
+    raw_s[a] = mean;                 // each thread overwrites only the two raw entries it has just read
     raw_s[A + a] = expf(ls);
     if (blockIdx.x == 0 && p.mean_std) {
       p.mean_std[a] = mean;

@@ -128,9 +128,38 @@ class FactorNetPPO(nn.Module):
         if self.use_conv:
             raise NotImplementedError("use_conv=True sampling goes through the scheduler (cosine features)")
         B = x.shape[0]
-        row = x[0].float().tolist()  # host read; the schedulers call policy_launch directly and never sync
-        out = self.policy_launch(row[0], row[1], B, n_hist=self.order_dim, stream=None)
-        return out["actions"], out["probs"]
+        A, K = self.action_dims, self.num_actions
+        lib = _lib.load()
+        dev = x.device
+        # no host read-back of the row: the table kernel takes it from device memory, the sample kernel draws from the
+        # table (two launches; the schedulers use the same pair with the tables of the whole grid evaluated once)
+        act = None
+        pflags = 0
+        wdt = self._kparams_dtype()
+        if wdt in (torch.float16, torch.bfloat16):
+            act = wdt
+        elif torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") in (torch.float16, torch.bfloat16):
+            act = torch.get_autocast_dtype("cuda")
+        if act is not None:
+            pflags |= _lib.POLICY_ACT_F16 if act == torch.float16 else _lib.POLICY_ACT_BF16
+        bdt = self.action_values.dtype
+        if bdt in (torch.float16, torch.bfloat16):
+            pflags |= _lib.POLICY_COEF_F16 if bdt == torch.float16 else _lib.POLICY_COEF_BF16
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            out = alloc_policy_outputs(B, A, K, self.order_dim, dev)
+            table = out["probs_table"].view(1, A, K)
+            self.policy_tables(x[:1].float().contiguous(), table, stream, policy_flags=pflags, act_dtype=act)
+            q = torch.empty((B * A, K), device=dev, dtype=torch.float32).exponential_(1)   # torch.multinomial's own draw
+            w = self.kernel_weights(act)
+            rc = lib.consolver_policy_sample_f32(
+                table.data_ptr(), w[6], q.data_ptr(), None, None, None, B, A, K, self.order_dim, self.scaler_dim,
+                self.order_dim, pflags, out["idx"].data_ptr(), out["actions"].data_ptr(), out["probs"].data_ptr(),
+                out["logp"].data_ptr(), out["masks"].data_ptr(), out["coef"].data_ptr(), stream)
+            _lib.check(rc, "consolver_policy_sample_f32")
+        self._last_sample = out
+        actions = out["actions"] if bdt == torch.float32 else out["actions"].to(bdt)
+        return actions, out["probs"]
 
     def policy_launch(self, x0: float, x1: float, B: int, n_hist: int, *, q: Optional[torch.Tensor] = None,
                       idx_in: Optional[torch.Tensor] = None, out: Optional[dict] = None, stream=None,

@@ -219,6 +219,16 @@ def ppo_update(factor_net, flat: FlatParams, optimizer, record: Dict[str, torch.
     buffers.  `native` (default: on for CUDA tensors with the shared-row policy) runs forward + loss + backward as the
     hand-written kernels of csrc/ppo.cu; otherwise torch autograd on the distinct rows.  `exchange` (PeerGradExchange, native
     path only): the gradient all-reduce is fused into the reduction kernel over NVLink peer memory instead of a NCCL call."""
+    fn0 = factor_net.module if hasattr(factor_net, "module") else factor_net
+    if getattr(fn0, "use_conv", False):
+        # use_conv makes the policy input per-sample (cosine features of the model-output history), which the rollout
+        # record does not keep — the scheduler's ring is overwritten as the trajectory advances (the reference keeps
+        # hundreds of MiB of conds['epsilon'] for this, denoise_ppo.py:105-118; no shipped config trains with use_conv)
+        raise NotImplementedError("ppo_update: training a use_conv=True policy is not supported (the rollout record holds "
+                                  "no per-step model-output history); sample with it, or train with use_conv=False")
+    if getattr(fn0, "continuous", False):
+        raise NotImplementedError("ppo_update covers the discrete policy; for the continuous extension build the loss from "
+                                  "factor_net(conds, actions) (density, entropy) with autograd")
     x_rows = record["x"][0].detach().float().clone()
     idx = record["idx"].detach().clone()
     old_probs = record["probs"].detach().clone()
