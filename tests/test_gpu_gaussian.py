@@ -50,11 +50,11 @@ def test_in_kernel_normal_draw_is_torch_randn(B):
     x = torch.randn(B, 4, 8, 8, device="cuda")
     s.set_timesteps(4, device="cuda")
     for i, t in enumerate(s.timesteps):
+        e = torch.randn_like(x)                          # model output: drawn BEFORE the seed is set
         torch.manual_seed(100 + i)
         z_ref = torch.randn(B, A, device="cuda")
-        state_after = torch.cuda.get_rng_state()
         torch.manual_seed(100 + i)
-        x, actions, probs, conds, masks = s.step(torch.randn_like(x), t, x, return_dict=False)
+        x, actions, probs, conds, masks = s.step(e, t, x, return_dict=False)
         lp = s.last_policy()
         z = (actions - lp["mean"]) / lp["std"]
         torch.testing.assert_close(z, z_ref, rtol=1e-5, atol=1e-5)          # recovered through mean + std*z
@@ -64,12 +64,11 @@ def test_in_kernel_normal_draw_is_torch_randn(B):
     torch.manual_seed(7)
     torch.randn(B, A, device="cuda")
     want = torch.cuda.get_rng_state()
+    e = torch.randn(B, 4, 8, 8, device="cuda")
     torch.manual_seed(7)
     s.set_timesteps(4, device="cuda")
-    s.step(torch.randn(B, 4, 8, 8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)), s.timesteps[0],
-           torch.zeros(B, 4, 8, 8, device="cuda"), return_dict=False)
+    s.step(e, s.timesteps[0], torch.zeros(B, 4, 8, 8, device="cuda"), return_dict=False)
     assert torch.equal(torch.cuda.get_rng_state(), want)
-    del state_after
 
 
 @pytest.mark.parametrize("order_dim,scaler_dim", [(4, 2), (4, 0), (2, 0), (3, 1)])
