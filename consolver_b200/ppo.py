@@ -103,15 +103,17 @@ class PeerGradExchange:
         dev = flat.grad.device
         self.stride = (flat.numel + 63) // 64 * 64                     # floats per parity, 256-byte granules
         pad_words = 64                                                  # signal pad: one word per rank
-        enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
-        if enable is not None:                                          # older torch: explicit opt-in per group
-            try:
-                enable(group.group_name)
-            except Exception:  # noqa: BLE001
-                pass
         self.buf = symm_mem.empty(2 * self.stride + pad_words, dtype=torch.float32, device=dev)
         self.buf.zero_()
-        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        try:
+            self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        except Exception:  # noqa: BLE001  (older torch: the group has to be enabled explicitly first)
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
         torch.cuda.synchronize(dev)
         self.hdl.barrier()                                              # everybody's pad is zero before anyone signals
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
