@@ -1020,18 +1020,45 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
         ol = torch.rand(R_, batch, A_, device=device) * 0.5 + 0.05
         ad = torch.randn(R_, batch, A_, device=device)
 
-        def time_updates(ex, nccl):
+        import ctypes
+
+        from consolver_b200 import _lib
+
+        lib = _lib.load()
+        fnm = s.factor_net
+        wk = fnm.kernel_weights()
+        need = int(lib.consolver_ppo_workspace(R_, fnm.hidden_dim, A_, fnm.num_actions))
+        wsp = torch.empty((need + 3) // 4, device=device)
+        stt = torch.empty(4, device=device)
+        strm = torch.cuda.current_stream(device).cuda_stream
+
+        def time_updates(ex, nccl, n=200):
+            """DEVICE time per update, timed with CUDA events over `n` back-to-back direct C-ABI calls (~5 us of host time
+            each, below the ~55 us the two kernels take, so the GPU — not Python — sets the pace)"""
+            def call(peers):
+                rc = lib.consolver_ppo_loss_grad_allreduce_f32(
+                    *wk[:6], xr.data_ptr(), R_, fnm.x_div, fnm.temperature, fnm.hidden_dim, A_, fnm.num_actions,
+                    ix.data_ptr(), ol.data_ptr(), ad.data_ptr(), batch, 0.2, 0.01, wsp.data_ptr(), flat.grad.data_ptr(),
+                    stt.data_ptr(), peers, strm)
+                assert rc == 0, rc
+
+            for _ in range(5):
+                call(ctypes.byref(ex.next_peers()) if ex is not None else None)
+                if nccl:
+                    ppo.allreduce_gradients(flat)
             dist.barrier()
             torch.cuda.synchronize(device)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(100):
-                ppo.ppo_loss_grad_cuda(s.factor_net, flat, xr, ix, ol, ad, 0.2, 0.01, exchange=ex)
+            for _ in range(n):
+                call(ctypes.byref(ex.next_peers()) if ex is not None else None)
                 if nccl:
                     ppo.allreduce_gradients(flat)
             e1.record()
             torch.cuda.synchronize(device)
-            return e0.elapsed_time(e1) * 1e3 / 100
+            t = torch.tensor([e0.elapsed_time(e1) * 1e3 / n], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
 
         plain_us = time_updates(None, False)
         nccl_us = time_updates(None, True)
@@ -1081,6 +1108,7 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
                 f"ncclAllReduce(AVG) over {flat.numel} fp32 ({flat.numel * 4} B), once per PPO epoch — latency-bound"),
             "exchange": None if world == 1 else {
                 "used_in_timed_region": "fused peer-memory exchange" if exchange is not None else "ncclAllReduce",
+                "timing": "CUDA events over 200 back-to-back direct C-ABI calls (device-bound), max over ranks",
                 "update_kernels_us": None if plain_us is None else round(plain_us, 2),
                 "update_kernels_plus_nccl_allreduce_us": None if plain_us is None else round(nccl_us, 2),
                 "update_kernels_with_fused_exchange_us": None if fused_us is None else round(fused_us, 2),

@@ -259,6 +259,12 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)
+               : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(256) ppo_reduce_allreduce_kernel(const float* __restrict__ partial, int R, long long P,
                                                                   int B, float ent_coef, float* __restrict__ grad,
@@ -297,16 +303,33 @@ __global__ void __launch_bounds__(256) ppo_reduce_allreduce_kernel(const float* 
       while ((int)(ld_acquire_sys(my_pad + r) - pv.epoch) < 0) {}
   }
   __syncthreads();
-  if (i < P) {
-    float v[16];
+  // phase 3: 128-bit peer loads (one NVLink request of 512 B per warp and peer), all `world` of them in flight before
+  // the first add; the buffers are 256-byte aligned per parity.  The first quarter of the threads covers the vector
+  // part, the tail (P % 4 elements) goes through scalar loads.
+  const float inv_world = 1.f / (float)pv.world;
+  const long long e = 4 * i;
+  const bool grad_vec = (reinterpret_cast<uintptr_t>(grad) & 15u) == 0;
+  if (e + 3 < P) {
+    float4 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r)
-      if (r < pv.world) v[r] = ld_relaxed_sys(pv.bufs[r] + pv.parity_offset + i);
-    float acc = 0.f;
+      if (r < pv.world) v[r] = ld_relaxed_sys_v4(pv.bufs[r] + pv.parity_offset + e);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < 16; ++r)
-      if (r < pv.world) acc += v[r];
-    grad[i] = acc * (1.f / (float)pv.world);
+      if (r < pv.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+    acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
+    if (grad_vec) {
+      *reinterpret_cast<float4*>(grad + e) = acc;
+    } else {
+      grad[e] = acc.x; grad[e + 1] = acc.y; grad[e + 2] = acc.z; grad[e + 3] = acc.w;
+    }
+  } else if (e < P) {
+    for (long long j = e; j < P; ++j) {
+      float acc = 0.f;
+      for (int r = 0; r < pv.world; ++r) acc += ld_relaxed_sys(pv.bufs[r] + pv.parity_offset + j);
+      grad[j] = acc * inv_world;
+    }
   }
 }
 
