@@ -16,7 +16,7 @@ DPM_CONVERT_NONE, DPM_CONVERT_DIV, DPM_CONVERT_LIN = 0, 1, 2
 FLAG_VPRED, FLAG_EFF_SCALE, FLAG_X_SCALE, FLAG_PDL, FLAG_CHAIN, FLAG_LOWP_COMBINE, FLAG_X_F32, FLAG_X_WAS_LOWP = 1, 2, 4, 8, 16, 32, 64, 128
 FLAG_HOST_SCALARS, FLAG_LOWP_COEF = 256, 512
 POLICY_HOST_DIV, POLICY_ACT_F16, POLICY_ACT_BF16, POLICY_COEF_F16, POLICY_COEF_BF16 = 1, 2, 4, 8, 16
-ABI_VERSION = 5          # must equal CONSOLVER_ABI_VERSION of include/consolver.h (tests/test_abi_cpu.py checks)
+ABI_VERSION = 6          # must equal CONSOLVER_ABI_VERSION of include/consolver.h (tests/test_abi_cpu.py checks)
 MAX_ORDER, MAX_HIDDEN, MAX_LOGITS, MAX_IN = 8, 1024, 4096, 16
 
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -43,6 +43,7 @@ SIGNATURES = {
     "consolver_ppo_loss_grad_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i] + [_p] * 3 + [_i, _f, _f] + [_p] * 3 + [_p]),
     "consolver_ppo_loss_grad_allreduce_f32": (_i, [_p] * 7 + [_i, _f, _f, _i, _i, _i] + [_p] * 3 + [_i, _f, _f] + [_p] * 3 +
                                               [_p, _p]),
+    "consolver_ppo_exchange_pad_words": (C.c_int64, [_i, _i, _i, _i]),
     "consolver_cosine_features_workspace": (C.c_size_t, [_i, _i]),
     "consolver_cosine_features": (_i, [_i, _p, _p, _f, _p, _i, _i, _i, _i64, _p, _p, _p]),
 }
@@ -55,7 +56,7 @@ class Rng(C.Structure):
 class Peers(C.Structure):
     """consolver_peers_t"""
     _fields_ = [("buffer_ptrs_dev", C.c_void_p), ("signal_ptrs_dev", C.c_void_p), ("rank", C.c_int), ("world", C.c_int),
-                ("epoch", C.c_uint32), ("stride_floats", C.c_int64), ("ticket", C.c_void_p)]
+                ("epoch", C.c_uint32), ("stride_floats", C.c_int64), ("pad_words", C.c_int64)]
 
 
 class DpmUpdate(C.Structure):

@@ -224,26 +224,25 @@ __global__ void ppo_reduce_kernel(const float* __restrict__ partial, int R, long
 // ---- fused reduce + data-parallel exchange over NVLink peer memory ------------------------------------------------------
 // The reference averages the policy gradient over ranks with one DDP all-reduce per PPO epoch (train_ppo.py:257,:430;
 // edit_ppo/train_ppo.py:382): 75 041 floats = 300 KB, far below the size where a ring/tree pays off — NCCL's cost there is
-// its launch + protocol latency (measured 23-35 us at 2-8 GPUs).  Here the exchange is folded into the kernel that
-// produces the gradient, as a ONE-SHOT all-reduce over peer-mapped ("symmetric") buffers:
-//   phase 1  every thread sums its element over the per-row partials (fixed order) and stores it into THIS rank's
+// launch + protocol latency.  Here the exchange is folded into the kernel that produces the gradient, as a ONE-SHOT
+// all-reduce over peer-mapped ("symmetric") buffers with PER-CTA flags (no grid-wide step anywhere):
+//   phase 1  CTA c sums its 1024 elements over the per-row partials (fixed order) and stores them into THIS rank's
 //            symmetric buffer (local HBM, peer-readable);
-//   phase 2  the last CTA to finish publishes `epoch` into slot [rank] of every peer's signal pad with a system-scope
-//            release store (through NVLink); thread 0 of each CTA then spins, with system-scope acquire loads on the LOCAL
-//            pad, until all `world` slots carry the epoch;
-//   phase 3  every thread loads its element from all `world` buffers (peer loads over NVLink/NVSwitch, issued together:
-//            one round trip), adds them IN RANK ORDER — so every rank forms the bit-identical sum — and writes
-//            sum * (1/world) into the flat gradient.
-// Buffers are double-buffered by epoch parity: a rank can only overwrite parity p two epochs later, which requires every
-// peer to have signalled the epoch in between, i.e. to have finished reading.  All CTAs must be co-resident (grid of
-// ~300 CTAs of 256 threads on 148 SMs): they are.
+//   phase 2  `world` threads of the CTA publish `epoch` into flag [rank][c] of every peer's pad (system-scope release
+//            store through NVLink, cumulative over the CTA barrier before it), then spin with system-scope acquire loads
+//            on the LOCAL pad until flags [0..world)[c] carry the epoch: CTA c only ever waits for CTA c of the peers;
+//   phase 3  every thread loads its 4 elements from all `world` buffers (128-bit peer loads over NVLink/NVSwitch, all
+//            in flight together: one round trip), adds them IN RANK ORDER — every rank forms the bit-identical sum — and
+//            writes sum * (1/world) into the flat gradient.
+// Buffers are double-buffered by epoch parity: a rank overwrites parity p again two epochs later, which requires every
+// peer to have published the epoch in between for the same chunk, i.e. to have finished reading it.  Flags are monotonic
+// (compared with >=), one word per (rank, CTA).
 struct PeerView {
-  float* const* bufs;          // device array [world]: peer-mapped base pointers; each buffer = [2][P_pad] floats + pad
-  unsigned int* const* sig;    // device array [world]: peer-mapped signal pads, `world` words each
+  float* const* bufs;          // device array [world]: peer-mapped base pointers; each buffer = [2][stride] floats
+  unsigned int* const* sig;    // device array [world]: peer-mapped flag pads, [world][gridDim.x] words each
   int rank, world;
   unsigned int epoch;
-  long long parity_offset;     // floats: (epoch & 1) * P_pad
-  unsigned int* ticket;        // device word, zero between launches
+  long long parity_offset;     // floats: (epoch & 1) * stride
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -266,17 +265,32 @@ __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) ppo_reduce_allreduce_kernel(const float* __restrict__ partial, int R, long long P,
-                                                                  int B, float ent_coef, float* __restrict__ grad,
-                                                                  float* __restrict__ stats, const PeerView pv) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kExThreads = 256;
+constexpr int kExPerCta = kExThreads * 4;     // elements per CTA
+
+// grid = ceil((P + 1) / 1024): thread t of CTA c owns elements [1024c + 4t, +4); element index P is the statistics slot
+__global__ void __launch_bounds__(kExThreads) ppo_reduce_allreduce_kernel(const float* __restrict__ partial, int R,
+                                                                         long long P, int B, float ent_coef,
+                                                                         float* __restrict__ grad,
+                                                                         float* __restrict__ stats, const PeerView pv) {
+  const long long e = (long long)blockIdx.x * kExPerCta + 4 * threadIdx.x;
   const long long stride = P + kPpoStats;
   float* mine = pv.bufs[pv.rank] + pv.parity_offset;
-  if (i < P) {
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s += partial[(size_t)r * stride + i];
-    mine[i] = s;
-  } else if (i == P) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < R; ++r) {
+    const float* row = partial + (size_t)r * stride;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e + k < P) s[k] += row[e + k];
+  }
+  if (e + 3 < P) {
+    *reinterpret_cast<float4*>(mine + e) = make_float4(s[0], s[1], s[2], s[3]);      // stride is a multiple of 64 floats
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e + k < P) mine[e + k] = s[k];
+  }
+  if (e <= P && P < e + 4) {          // the thread whose 4-element span contains index P also reduces the statistics
     float pl = 0.f, ent = 0.f, ratio = 0.f;
     for (int r = 0; r < R; ++r) {
       pl += partial[(size_t)r * stride + P];
@@ -290,25 +304,14 @@ __global__ void __launch_bounds__(256) ppo_reduce_allreduce_kernel(const float* 
     stats[3] = ratio / ((float)R * (float)B);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();                                   // this CTA's stores are visible system-wide
-    const unsigned int t = atomicAdd(pv.ticket, 1u);
-    if (t == gridDim.x - 1) {                                  // the whole local buffer is written: tell every peer
-      *pv.ticket = 0u;
-      __threadfence_system();
-      for (int r = 0; r < pv.world; ++r) st_release_sys(pv.sig[r] + pv.rank, pv.epoch);
-    }
-    const unsigned int* my_pad = pv.sig[pv.rank];
-    for (int r = 0; r < pv.world; ++r)
-      while ((int)(ld_acquire_sys(my_pad + r) - pv.epoch) < 0) {}
+  if (threadIdx.x < pv.world) {
+    const int r = threadIdx.x;
+    st_release_sys(pv.sig[r] + (size_t)pv.rank * gridDim.x + blockIdx.x, pv.epoch);     // "chunk c of rank `rank` is ready"
+    const unsigned int* flag = pv.sig[pv.rank] + (size_t)r * gridDim.x + blockIdx.x;
+    while ((int)(ld_acquire_sys(flag) - pv.epoch) < 0) {}                               // chunk c of rank r is ready
   }
   __syncthreads();
-  // phase 3: 128-bit peer loads (one NVLink request of 512 B per warp and peer), all `world` of them in flight before
-  // the first add; the buffers are 256-byte aligned per parity.  The first quarter of the threads covers the vector
-  // part, the tail (P % 4 elements) goes through scalar loads.
   const float inv_world = 1.f / (float)pv.world;
-  const long long e = 4 * i;
-  const bool grad_vec = (reinterpret_cast<uintptr_t>(grad) & 15u) == 0;
   if (e + 3 < P) {
     float4 v[16];
 #pragma unroll
@@ -319,13 +322,13 @@ __global__ void __launch_bounds__(256) ppo_reduce_allreduce_kernel(const float* 
     for (int r = 0; r < 16; ++r)
       if (r < pv.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
     acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
-    if (grad_vec) {
+    if ((reinterpret_cast<uintptr_t>(grad) & 15u) == 0) {
       *reinterpret_cast<float4*>(grad + e) = acc;
     } else {
       grad[e] = acc.x; grad[e + 1] = acc.y; grad[e + 2] = acc.z; grad[e + 3] = acc.w;
     }
-  } else if (e < P) {
-    for (long long j = e; j < P; ++j) {
+  } else {
+    for (long long j = e; j < P && j < e + 4; ++j) {
       float acc = 0.f;
       for (int r = 0; r < pv.world; ++r) acc += ld_relaxed_sys(pv.bufs[r] + pv.parity_offset + j);
       grad[j] = acc * inv_world;
@@ -336,6 +339,11 @@ __global__ void __launch_bounds__(256) ppo_reduce_allreduce_kernel(const float* 
 }  // namespace consolver
 
 using namespace consolver;
+
+extern "C" int64_t consolver_ppo_exchange_pad_words(int H, int A, int K, int world) {
+  const long long P = 4LL * H + (long long)H * H + (long long)A * K * H + (long long)A * K;
+  return (int64_t)world * ((P + 1 + kExPerCta - 1) / kExPerCta);
+}
 
 extern "C" size_t consolver_ppo_workspace(int rows, int H, int A, int K) {
   const long long P = 4LL * H + (long long)H * H + (long long)A * K * H + (long long)A * K;
@@ -391,16 +399,17 @@ extern "C" int consolver_ppo_loss_grad_allreduce_f32(const float* w1, const floa
   const long long n = p.P + 1;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (peers && peers->world > 1) {
-    if (!peers->buffer_ptrs_dev || !peers->signal_ptrs_dev || !peers->ticket) return CONSOLVER_ERR_NULL;
-    if (peers->world > 16 || peers->rank < 0 || peers->rank >= peers->world || peers->stride_floats < p.P)
+    if (!peers->buffer_ptrs_dev || !peers->signal_ptrs_dev) return CONSOLVER_ERR_NULL;
+    const unsigned xgrid = (unsigned)((n + kExPerCta - 1) / kExPerCta);
+    if (peers->world > 16 || peers->rank < 0 || peers->rank >= peers->world || peers->stride_floats < p.P ||
+        peers->stride_floats % 4 != 0 || peers->pad_words < (int64_t)peers->world * xgrid)
       return CONSOLVER_ERR_SIZE;
     PeerView pv;
     pv.bufs = reinterpret_cast<float* const*>(peers->buffer_ptrs_dev);
     pv.sig = reinterpret_cast<unsigned int* const*>(peers->signal_ptrs_dev);
     pv.rank = peers->rank; pv.world = peers->world; pv.epoch = peers->epoch;
     pv.parity_offset = (long long)(peers->epoch & 1u) * peers->stride_floats;
-    pv.ticket = peers->ticket;
-    ppo_reduce_allreduce_kernel<<<grid, 256, 0, s>>>(p.partial, rows, p.P, B, entropy_coef, grad_flat, stats, pv);
+    ppo_reduce_allreduce_kernel<<<xgrid, kExThreads, 0, s>>>(p.partial, rows, p.P, B, entropy_coef, grad_flat, stats, pv);
     return (int)cudaGetLastError();
   }
   ppo_reduce_kernel<<<grid, 256, 0, s>>>(p.partial, rows, p.P, B, entropy_coef, grad_flat, stats);

@@ -91,8 +91,10 @@ class PeerGradExchange:
     Buffers come from torch's symmetric-memory allocator (cudaMalloc'd / fabric memory mapped into every peer over
     NVLink/NVSwitch); the kernel only sees raw pointers (consolver_peers_t).  Collective: construct on all ranks."""
 
-    def __init__(self, flat: FlatParams, group=None):
+    def __init__(self, flat: FlatParams, group=None, policy=None):
         import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
 
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerGradExchange needs an initialised process group")
@@ -102,7 +104,9 @@ class PeerGradExchange:
             raise ValueError("one-shot exchange supports up to 16 ranks of one NVLink domain")
         dev = flat.grad.device
         self.stride = (flat.numel + 63) // 64 * 64                     # floats per parity, 256-byte granules
-        pad_words = 64                                                  # signal pad: one word per rank
+        # one flag per (rank, CTA of the exchange kernel): 1024 gradient elements per CTA (+ the statistics slot)
+        self.pad_words = pad_words = (self.world * ((flat.numel + 1 + 1023) // 1024) + 63) // 64 * 64
+        _lib.load()
         self.buf = symm_mem.empty(2 * self.stride + pad_words, dtype=torch.float32, device=dev)
         self.buf.zero_()
         try:
@@ -119,7 +123,6 @@ class PeerGradExchange:
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self._buf_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
         self._sig_ptrs = torch.tensor([p + 2 * self.stride * 4 for p in ptrs], dtype=torch.int64, device=dev)
-        self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.epoch = 0
 
     def next_peers(self):
@@ -128,7 +131,7 @@ class PeerGradExchange:
 
         self.epoch += 1
         p = _lib.Peers(self._buf_ptrs.data_ptr(), self._sig_ptrs.data_ptr(), self.rank, self.world,
-                       self.epoch & 0xFFFFFFFF, self.stride, self._ticket.data_ptr())
+                       self.epoch & 0xFFFFFFFF, self.stride, self.pad_words)
         self._keepalive = p
         return p
 

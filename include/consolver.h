@@ -25,7 +25,7 @@ extern "C" {
 
 /* Bumped on EVERY change of a signature, struct layout or flag meaning in this header.  Loaders must also compare
  * consolver_abi_hash() with the hash of the header they were written against (see consolver_abi_hash below). */
-#define CONSOLVER_ABI_VERSION 5
+#define CONSOLVER_ABI_VERSION 6
 
 /* element type of latents / model outputs */
 #define CONSOLVER_F32  0
@@ -389,9 +389,10 @@ CONSOLVER_API int consolver_ppo_loss_grad_f32(const float* w1, const float* b1, 
  * grad_flat holds (sum over ranks, added in rank order — bit-identical on every rank) / world.
  *   buffer_ptrs_dev   device array [world] of peer-mapped base pointers of the ranks' exchange buffers, each
  *                     2 * stride_floats floats (two epoch parities); entry [rank] is this rank's own buffer
- *   signal_ptrs_dev   device array [world] of peer-mapped signal pads, `world` uint32 each, zero before the first call
+ *                     (stride_floats >= P, a multiple of 64)
+ *   signal_ptrs_dev   device array [world] of peer-mapped flag pads, pad_words uint32 each, zero before the first call;
+ *                     pad_words >= consolver_ppo_exchange_pad_words(H, A, K, world) (one flag per rank and CTA)
  *   epoch             1, 2, 3, ... incremented by one per call, identical on all ranks
- *   ticket            device uint32 private to this rank, zero before the first call
  * The buffers are obtained by the caller from any symmetric-memory allocator (the Python host uses
  * torch.distributed._symmetric_memory); the library only needs the pointers.
  */
@@ -401,8 +402,9 @@ typedef struct consolver_peers {
   int rank, world;
   uint32_t epoch;
   int64_t stride_floats;
-  uint32_t* ticket;
+  int64_t pad_words;
 } consolver_peers_t;
+CONSOLVER_API int64_t consolver_ppo_exchange_pad_words(int H, int A, int K, int world);
 CONSOLVER_API int consolver_ppo_loss_grad_allreduce_f32(const float* w1, const float* b1, const float* w2, const float* b2,
                                               const float* w3, const float* b3, const float* x_rows, int rows,
                                               float x_div, float temp, int H, int A, int K,
