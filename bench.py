@@ -416,15 +416,40 @@ def run_ours(args, rank, world, device):
 
     ppool = None if args.eager else PreviewPool([p[3] for p in pool], streams=args.streams)
     n_streams = 1 if ppool is None else len(ppool.streams)
+    # Groups of `streams` previews captured as ONE graph each (denoise.PreviewGroup: one branch per preview, one shared
+    # device-resident generator state): one host launch and one generator update per g previews instead of per preview.
+    # Without it the host needs ~30 us per preview, as much as the GPU does, and eight ranks sharing one host's cores
+    # become host-bound.  Previews are still taken round-robin from the pool; a stretch that is not aligned to a
+    # group (warm-up of 5, say) goes through the per-preview graphs.
+    groups, g = [], 0
+    if ppool is not None and n_streams > 1 and not args.no_groups:
+        from consolver_b200.denoise import PreviewGroup
+
+        g = n_streams
+        groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)]) for i in range(0, pool_n - pool_n % g, g)]
+    counts = {"group_replays": 0, "single_replays": 0}
 
     def run_steps(first, count, join=True):
         if ppool is None:
             for k in range(first, first + count):
                 one_step(k)
             return
-        for k in range(first, first + count):
-            ppool.submit(k % pool_n)
-        if join:
+        k, end, pending = first, first + count, False
+        while k < end:
+            slot = k % pool_n
+            if groups and slot % g == 0 and slot + g <= len(groups) * g and k + g <= end:
+                if pending:                       # per-preview replays on the side streams touch the same buffers
+                    ppool.join()
+                    pending = False
+                groups[slot // g].replay()
+                counts["group_replays"] += 1
+                k += g
+            else:
+                ppool.submit(slot)
+                counts["single_replays"] += 1
+                pending = True
+                k += 1
+        if join or pending:
             ppool.join()
 
     def rank_max(v):
@@ -474,7 +499,9 @@ def run_ours(args, rank, world, device):
         reps = args.reps
     # ---- the timed region: `reps` blocks of `steps` previews back to back, pipeline kept full, one join at the end ----
     clk = ClockSampler(torch.cuda.current_device())
+    counts.update(group_replays=0, single_replays=0)
     ms = timed_blocks(reps, clk)
+    timed_counts = dict(counts)
     n_timed = reps * args.steps
     value = world * n_timed * B / (ms / 1e3)
     ms_per_step = ms / n_timed
@@ -586,14 +613,18 @@ def run_ours(args, rank, world, device):
                 "launch": "eager python launches" if args.eager else
                 "one CUDA graph per 8-step preview (table kernel, sample kernels on a side stream, PDL-chained step "
                 "kernels, rng-advance node); valid because the stand-in model outputs are resident",
-                "concurrency": f"{n_streams} independent preview batch(es) in flight on separate CUDA streams",
+                "concurrency": f"{n_streams} independent preview batch(es) in flight" + (
+                    f": groups of {g} previews captured as one CUDA graph with {g} parallel branches "
+                    f"({timed_counts['group_replays']} group + {timed_counts['single_replays']} single replays timed)"
+                    if groups else " on separate CUDA streams"),
                 "timing": f"{reps} x {args.steps} previews back to back between two CUDA events, max over ranks",
                 "host_enqueue_us_per_step": round(host_us[0], 2),
                 "calibration": {"isolated_block_ms": round(block_ms, 4), "pre_blocks": pre_blocks,
                                 "pre_ms_per_step": round(pre_ms / (pre_blocks * args.steps), 5)}},
         "e2e": {"value": round(e2e_val, 1), "unit": "previews/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "reps": e2e_reps, "timed_region_s": round(e2e_s, 4)},
-        "gpu_launches": n_timed * (2 + N_STEPS * 2),   # per preview: table + 8 x (sample + step) + rng-advance kernels
+        # per preview: table + 8 x (sample + step) kernels; one rng-advance node per graph replay (group or single)
+        "gpu_launches": n_timed * (1 + N_STEPS * 2) + timed_counts["group_replays"] + timed_counts["single_replays"],
         "clocks": clk.summary(),
         "clocks_e2e": clk_e2e.summary(),       # the host-link-bound leg, where the SMs idle most of the time
     }
@@ -1135,6 +1166,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / roofline / cpu_baseline (profiling runs)")
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the torch eager / compile reference-on-GPU legs")
     ap.add_argument("--no-ppo", action="store_true", help="skip the ppo_rollout leg (BASELINE configs[4])")
+    ap.add_argument("--no-groups", action="store_true", help="replay previews one graph at a time (PreviewPool only)")
     ap.add_argument("--reps", type=int, default=0, help="force the number of back-to-back blocks (0 = calibrate)")
     ap.add_argument("--leg", default="", help=argparse.SUPPRESS)       # internal: torch_ref_gpu:<mode> in a subprocess
     args = ap.parse_args()

@@ -272,6 +272,69 @@ def test_preview_pool_concurrent_replays_match_serial_execution():
             k += 1
 
 
+@pytest.mark.parametrize("kind", ["sd", "fm"])
+def test_preview_group_one_graph_for_several_previews_matches_serial_execution(kind):
+    """PreviewGroup: g independent previews as ONE CUDA graph (one branch each, a shared device-resident generator
+    state).  Replays — back to back, and interleaved with other users of the generator — give the bits of running the g
+    previews eagerly one after the other, and leave the default generator where eager execution leaves it."""
+    import numpy as np
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedPreview, PreviewGroup, preview_from_outputs, preview_from_pairs
+
+    g_ = torch.Generator(device="cuda").manual_seed(19)
+    n, G = 6, 3
+    previews, eager, batches = [], [], []
+    for j in range(G):
+        if kind == "sd":
+            B, shape = 16, (4, 32, 32)
+            s, e = cb.PPOScheduler(**PROD), cb.PPOScheduler(**PROD)
+            tk = None
+        else:
+            B, shape = 4, (256, 64)
+            kw = dict(shift=3.0, use_dynamic_shifting=True, order_dim=2, scaler_dim=0, mu_dim=0,
+                      factor_net_kwargs=dict(hidden_dim=64, num_actions=11))
+            s, e = cb.FMPPOScheduler(**kw), cb.FMPPOScheduler(**kw)
+            tk = dict(sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+        with torch.no_grad():
+            torch.manual_seed(70 + j)
+            s.factor_net.mlp[4].weight.normal_(0, 0.05)
+        e.factor_net.load_state_dict(s.factor_net.state_dict())
+        s.factor_net.cuda(), e.factor_net.cuda()
+        dt = torch.float32 if kind == "sd" else torch.bfloat16
+        x = torch.randn(B, *shape, device="cuda", generator=g_).to(dt)
+        outs_in = [torch.randn((2 * B if kind == "sd" else B), *shape, device="cuda", generator=g_).to(dt) for _ in range(n)]
+        previews.append(GraphedPreview(s, x, outs_in, 3.0 if kind == "sd" else None, n, set_timesteps_kwargs=tk))
+        eager.append((e, tk))
+        batches.append((x, outs_in))
+    group = PreviewGroup(previews)
+    assert len(group) == G
+
+    def run_eager(j):
+        e, tk = eager[j]
+        e.set_timesteps(n, device="cuda", **(tk or {}))
+        if kind == "sd":
+            return preview_from_pairs(e, *batches[j], 3.0)
+        e.set_begin_index(0)
+        return preview_from_outputs(e, *batches[j])
+
+    torch.manual_seed(77)
+    got = []
+    for rnd in range(3):
+        got.append([o.clone() for o in group.replay()])
+        if rnd == 1:
+            torch.rand(5, device="cuda")                 # somebody else draws: the group must notice and re-seed its state
+    single = previews[1].replay().clone()                # the member previews stay usable on their own
+    end_state = torch.cuda.get_rng_state()
+    torch.manual_seed(77)
+    for rnd in range(3):
+        for j in range(G):
+            assert torch.equal(run_eager(j), got[rnd][j]), f"round {rnd} preview {j}"
+        if rnd == 1:
+            torch.rand(5, device="cuda")
+    assert torch.equal(run_eager(1), single)
+    assert torch.equal(torch.cuda.get_rng_state(), end_state)
+
+
 def test_graphed_denoise_loop_with_a_denoiser_matches_eager():
     """Whole CFG loop (denoiser included) in one CUDA graph == eager denoise_loop, bit for bit, seeds included."""
     import consolver_b200 as cb
