@@ -476,7 +476,7 @@ def run_ours(args, rank, world, device):
         with (sampler or contextlib.nullcontext()):
             ea.record()
             h0 = time.perf_counter()
-            k0 = args.warmup
+            k0 = 0                      # aligned to the preview groups (a block of `steps` = steps/g group replays)
             for _ in range(n_blocks):
                 run_steps(k0, args.steps, join=False)
                 k0 += args.steps
