@@ -117,6 +117,17 @@ def preview_from_outputs(scheduler, x_T: torch.Tensor, outputs: Sequence[torch.T
     return x
 
 
+def _quiesce_before_capture(dev):
+    """A stream capture in CUDA's default ("global") error mode is invalidated by ANY thread of the process making a
+    capture-unsafe call — an NVML/clock sampler thread, or Python's cyclic GC freeing tensors of an earlier trajectory
+    (the allocator then queries their stream events).  Collect garbage and drain the device first, and capture in
+    "thread_local" mode (see the torch.cuda.graph calls below): other threads can no longer break a capture."""
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize(dev)
+
+
 class GraphedPreview:
     """One CUDA graph for a whole n-step solver-only preview over fixed device buffers.
 
@@ -171,8 +182,9 @@ class GraphedPreview:
             self._pin_events = [None] * 64
             self._k = 0
         self._rewind()
+        _quiesce_before_capture(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             res = run()
             if self.out is None:
                 self.out = res          # lives in the graph's private pool: valid after every replay
@@ -311,15 +323,18 @@ class PreviewGroup:
             if p.used_policy_stream:
                 sch.policy_stream = torch.cuda.Stream(device=dev)
             sch.chain_steps = p.used_chain
+        _quiesce_before_capture(dev)
         self.graph = torch.cuda.CUDAGraph()
         self.outs = []
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             main = torch.cuda.current_stream(dev)
             for p, st in zip(self.previews, branches):
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
                     res = p._run()
-                self.outs.append(p.out if p.out is not None else res)
+                # with CFG pairs the result is written into the preview's own `out` buffer; through plain step() it
+                # is the last tensor the loop allocated — from THIS graph's pool — so that is what holds the result
+                self.outs.append(p.out if p.guidance is not None else res)
             for st in branches:
                 main.wait_stream(st)
             _lib.check(_lib.load().consolver_rng_state_advance(self.shared.data_ptr(), self._inc, main.cuda_stream),
@@ -401,8 +416,9 @@ class GraphedDenoiseLoop:
             tr.rng_plan = _lib.philox_plan(tr.q.numel())
             tr.graph_rng = torch.zeros(2, dtype=torch.int64, device=dev)
         self._rewind()
+        _quiesce_before_capture(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"), torch.no_grad():
             self.latents = run()
             if tr.graph_rng is not None and tr.graph_rng_used:
                 self._rng_inc = tr.graph_rng_used * tr.rng_plan[1]
