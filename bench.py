@@ -426,7 +426,11 @@ def run_ours(args, rank, world, device):
         from consolver_b200.denoise import PreviewGroup
 
         g = n_streams
-        groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)]) for i in range(0, pool_n - pool_n % g, g)]
+        n_groups = (pool_n - pool_n % g) // g
+        groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)], rotation=n_groups)
+                  for i in range(0, n_groups * g, g)]
+    # one stream per group: consecutive group replays overlap (a group's join would otherwise drain the GPU)
+    gpool = PreviewPool(groups, streams=len(groups)) if groups else None
     counts = {"group_replays": 0, "single_replays": 0}
 
     def run_steps(first, count, join=True):
@@ -434,23 +438,35 @@ def run_ours(args, rank, world, device):
             for k in range(first, first + count):
                 one_step(k)
             return
-        k, end, pending = first, first + count, False
+        k, end, pending, gpending = first, first + count, False, False
         while k < end:
             slot = k % pool_n
             if groups and slot % g == 0 and slot + g <= len(groups) * g and k + g <= end:
                 if pending:                       # per-preview replays on the side streams touch the same buffers
                     ppool.join()
                     pending = False
-                groups[slot // g].replay()
+                gpool.submit(slot // g)
                 counts["group_replays"] += 1
+                gpending = True
                 k += g
             else:
+                if gpending:
+                    gpool.join()
+                    gpending = False
                 ppool.submit(slot)
                 counts["single_replays"] += 1
                 pending = True
                 k += 1
         if join or pending:
             ppool.join()
+        if gpool is not None and (join or (gpending and pending)):
+            gpool.join()
+
+    def join_all():
+        if ppool is not None:
+            ppool.join()
+        if gpool is not None:
+            gpool.join()
 
     def rank_max(v):
         if world > 1:
@@ -481,8 +497,7 @@ def run_ours(args, rank, world, device):
                 run_steps(k0, args.steps, join=False)
                 k0 += args.steps
             host_us[0] = (time.perf_counter() - h0) * 1e6 / (n_blocks * args.steps)   # host time to ENQUEUE one preview
-            if ppool is not None:
-                ppool.join()
+            join_all()
             eb.record()
             barrier()
         return rank_max(ea.elapsed_time(eb))

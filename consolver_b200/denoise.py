@@ -294,7 +294,11 @@ class PreviewGroup:
 
     Built from existing GraphedPreview objects (their buffers, schedulers and eager closures); those stay usable."""
 
-    def __init__(self, previews: Sequence[GraphedPreview]):
+    def __init__(self, previews: Sequence[GraphedPreview], rotation: int = 1):
+        """`rotation`: how many groups of this size are replayed round-robin (A, B, A, B, ... with rotation 2).  The
+        device-resident generator state then advances by the WHOLE rotation's consumption per replay, so that in steady
+        round-robin order it already holds the right offset at the next replay and the host never has to refresh it;
+        any other order is detected (replay() compares with the default generator) and costs one small refresh."""
         from . import _lib, rng as _rng
 
         self.previews = list(previews)
@@ -306,6 +310,7 @@ class PreviewGroup:
             raise ValueError("PreviewGroup needs previews that use the fused RNG and consume the same amount per replay")
         self._inc_one = incs.pop()
         self._inc = self._inc_one * len(self.previews)
+        self._advance = self._inc * max(1, int(rotation))
         self.shared = torch.zeros(2, dtype=torch.int64, device=dev)
         self._pinned = torch.zeros(16, 2, dtype=torch.int64).pin_memory()
         self._pin_events = [None] * 16
@@ -337,7 +342,7 @@ class PreviewGroup:
                 self.outs.append(p.out if p.guidance is not None else res)
             for st in branches:
                 main.wait_stream(st)
-            _lib.check(_lib.load().consolver_rng_state_advance(self.shared.data_ptr(), self._inc, main.cuda_stream),
+            _lib.check(_lib.load().consolver_rng_state_advance(self.shared.data_ptr(), self._advance, main.cuda_stream),
                        "rng advance")
         for p, (own_rng, ps, chain) in zip(self.previews, saved):
             sch, tr = p.scheduler, p.scheduler._traj
@@ -348,8 +353,14 @@ class PreviewGroup:
     def __len__(self):
         return len(self.previews)
 
+    @property
+    def x_T(self):                      # lets a PreviewPool of groups find the device
+        return self.previews[0].x_T
+
     def replay(self):
-        """enqueue one replay of all previews of the group on the current stream; returns their output buffers"""
+        """enqueue one replay of all previews of the group on the current stream; returns their output buffers.
+        Replays on ONE stream serialise (each waits for the previous group's join): to keep the GPU full across group
+        boundaries put two or more groups into a PreviewPool, one stream each."""
         from . import rng as _rng
 
         seed, off = _rng.take(self._dev, self._inc)          # torch's generator advances as g eager previews would
@@ -365,7 +376,7 @@ class PreviewGroup:
             ev = torch.cuda.Event()
             ev.record()
             self._pin_events[j] = ev
-        self._expected = (seed, off + self._inc)
+        self._expected = (seed, off + self._advance)     # what the device state holds after this replay
         self.graph.replay()
         return self.outs
 

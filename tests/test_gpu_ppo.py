@@ -335,6 +335,55 @@ def test_preview_group_one_graph_for_several_previews_matches_serial_execution(k
     assert torch.equal(torch.cuda.get_rng_state(), end_state)
 
 
+def test_two_preview_groups_in_rotation_on_two_streams_match_serial_execution():
+    """the bench's launch form: groups replayed round-robin, one stream each (PreviewPool of PreviewGroups), device
+    generator states advancing by the whole rotation — same bits and same generator consumption as serial eager runs"""
+    import consolver_b200 as cb
+    from consolver_b200.denoise import GraphedPreview, PreviewGroup, PreviewPool, preview_from_pairs
+
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    n, B = 8, 16
+    previews, eager, batches = [], [], []
+    for j in range(4):
+        s, e = cb.PPOScheduler(**PROD), cb.PPOScheduler(**PROD)
+        with torch.no_grad():
+            torch.manual_seed(90 + j)
+            s.factor_net.mlp[4].weight.normal_(0, 0.05)
+        e.factor_net.load_state_dict(s.factor_net.state_dict())
+        s.factor_net.cuda(), e.factor_net.cuda()
+        x = torch.randn(B, 4, 32, 32, device="cuda", generator=gen)
+        pairs = [torch.randn(2 * B, 4, 32, 32, device="cuda", generator=gen) for _ in range(n)]
+        previews.append(GraphedPreview(s, x, pairs, 3.0, n))
+        eager.append(e)
+        batches.append((x, pairs))
+    groups = [PreviewGroup(previews[:2], rotation=2), PreviewGroup(previews[2:], rotation=2)]
+    pool = PreviewPool(groups, streams=2)
+    assert len(pool.streams) == 2
+    torch.manual_seed(11)
+    got = []
+    for rnd in range(3):
+        for gi in range(2):
+            outs = pool.submit(gi)
+            pool.join() if rnd == 2 else None
+            got.append(outs)
+        if rnd < 2:
+            pool.join()
+        got = got[:-2] + [[o.clone() for o in outs] for outs in got[-2:]]
+    torch.cuda.synchronize()
+    end_state = torch.cuda.get_rng_state()
+    torch.manual_seed(11)
+    k = 0
+    for rnd in range(3):
+        for gi in range(2):
+            for m in range(2):
+                j = 2 * gi + m
+                eager[j].set_timesteps(n, device="cuda")
+                assert torch.equal(preview_from_pairs(eager[j], *batches[j], 3.0), got[k][m]), f"round {rnd} preview {j}"
+            k += 1
+    assert torch.equal(torch.cuda.get_rng_state(), end_state)
+    assert groups[0]._k <= 1 and groups[1]._k <= 1      # steady rotation: one initial state refresh per group, then none
+
+
 def test_graphed_denoise_loop_with_a_denoiser_matches_eager():
     """Whole CFG loop (denoiser included) in one CUDA graph == eager denoise_loop, bit for bit, seeds included."""
     import consolver_b200 as cb
