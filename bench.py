@@ -389,6 +389,11 @@ def run_ours(args, rank, world, device):
     pool_n = int(max(2, -(-2 * L2_BYTES // bytes_per_batch)))
     if not args.eager:
         pool_n = max(pool_n, 2 * max(1, args.streams))     # two resident batches per stream
+        if not args.no_groups and args.streams > 1:
+            # preview groups (see below): `group_rotation` groups of `streams` previews replayed round-robin, one stream
+            # each, so that one group's join never leaves the GPU short of work
+            pool_n = max(pool_n, args.group_rotation * args.streams)
+            pool_n -= pool_n % args.streams
     pool = []
     for j in range(pool_n):
         s = make_scheduler(device, sd)
@@ -1182,6 +1187,7 @@ def main():
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the torch eager / compile reference-on-GPU legs")
     ap.add_argument("--no-ppo", action="store_true", help="skip the ppo_rollout leg (BASELINE configs[4])")
     ap.add_argument("--no-groups", action="store_true", help="replay previews one graph at a time (PreviewPool only)")
+    ap.add_argument("--group-rotation", type=int, default=4, help="preview groups replayed round-robin (one stream each)")
     ap.add_argument("--reps", type=int, default=0, help="force the number of back-to-back blocks (0 = calibrate)")
     ap.add_argument("--leg", default="", help=argparse.SUPPRESS)       # internal: torch_ref_gpu:<mode> in a subprocess
     args = ap.parse_args()
