@@ -432,7 +432,9 @@ def run_ours(args, rank, world, device):
 
         g = n_streams
         n_groups = (pool_n - pool_n % g) // g
-        groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)], rotation=n_groups)
+        # each group = g previews chained on ONE branch (parallel=False); the parallelism comes from replaying the
+        # n_groups groups on n_groups streams, every stream a gap-free chain of previews
+        groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)], rotation=n_groups, parallel=not args.serial_groups)
                   for i in range(0, n_groups * g, g)]
     # one stream per group: consecutive group replays overlap (a group's join would otherwise drain the GPU)
     gpool = PreviewPool(groups, streams=len(groups)) if groups else None
@@ -634,7 +636,9 @@ def run_ours(args, rank, world, device):
                 "one CUDA graph per 8-step preview (table kernel, sample kernels on a side stream, PDL-chained step "
                 "kernels, rng-advance node); valid because the stand-in model outputs are resident",
                 "concurrency": f"{n_streams} independent preview batch(es) in flight" + (
-                    f": groups of {g} previews captured as one CUDA graph with {g} parallel branches "
+                    f": groups of {g} previews captured as one CUDA graph ("
+                    + ("a serial chain per group" if args.serial_groups else f"{g} parallel branches") +
+                    f"), {len(groups)} groups replayed round-robin on {len(groups)} streams "
                     f"({timed_counts['group_replays']} group + {timed_counts['single_replays']} single replays timed)"
                     if groups else " on separate CUDA streams"),
                 "timing": f"{reps} x {args.steps} previews back to back between two CUDA events, max over ranks",
@@ -1187,6 +1191,8 @@ def main():
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the torch eager / compile reference-on-GPU legs")
     ap.add_argument("--no-ppo", action="store_true", help="skip the ppo_rollout leg (BASELINE configs[4])")
     ap.add_argument("--no-groups", action="store_true", help="replay previews one graph at a time (PreviewPool only)")
+    ap.add_argument("--parallel-groups", dest="serial_groups", action="store_false",
+                    help="one graph branch per preview inside a group instead of a serial chain")
     ap.add_argument("--group-rotation", type=int, default=4, help="preview groups replayed round-robin (one stream each)")
     ap.add_argument("--reps", type=int, default=0, help="force the number of back-to-back blocks (0 = calibrate)")
     ap.add_argument("--leg", default="", help=argparse.SUPPRESS)       # internal: torch_ref_gpu:<mode> in a subprocess

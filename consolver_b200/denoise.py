@@ -294,8 +294,12 @@ class PreviewGroup:
 
     Built from existing GraphedPreview objects (their buffers, schedulers and eager closures); those stay usable."""
 
-    def __init__(self, previews: Sequence[GraphedPreview], rotation: int = 1):
-        """`rotation`: how many groups of this size are replayed round-robin (A, B, A, B, ... with rotation 2).  The
+    def __init__(self, previews: Sequence[GraphedPreview], rotation: int = 1, parallel: bool = True):
+        """`parallel`: True — one graph branch per preview (the previews of ONE replay overlap; the graph's implicit join
+        at its end drains the GPU once per replay).  False — the previews are captured one after the other on a single
+        branch: a replay is then a plain chain, and several such groups replayed on separate streams (PreviewPool) keep
+        every stream busy back to back with no join anywhere — the form with the highest steady-state throughput.
+        `rotation`: how many groups of this size are replayed round-robin (A, B, A, B, ... with rotation 2).  The
         device-resident generator state then advances by the WHOLE rotation's consumption per replay, so that in steady
         round-robin order it already holds the right offset at the next replay and the host never has to refresh it;
         any other order is detected (replay() compares with the default generator) and costs one small refresh."""
@@ -334,14 +338,18 @@ class PreviewGroup:
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             main = torch.cuda.current_stream(dev)
             for p, st in zip(self.previews, branches):
-                st.wait_stream(main)
-                with torch.cuda.stream(st):
+                if parallel:
+                    st.wait_stream(main)
+                    with torch.cuda.stream(st):
+                        res = p._run()
+                else:
                     res = p._run()
                 # with CFG pairs the result is written into the preview's own `out` buffer; through plain step() it
                 # is the last tensor the loop allocated — from THIS graph's pool — so that is what holds the result
                 self.outs.append(p.out if p.guidance is not None else res)
-            for st in branches:
-                main.wait_stream(st)
+            if parallel:
+                for st in branches:
+                    main.wait_stream(st)
             _lib.check(_lib.load().consolver_rng_state_advance(self.shared.data_ptr(), self._advance, main.cuda_stream),
                        "rng advance")
         for p, (own_rng, ps, chain) in zip(self.previews, saved):

@@ -272,8 +272,9 @@ def test_preview_pool_concurrent_replays_match_serial_execution():
             k += 1
 
 
+@pytest.mark.parametrize("parallel", [True, False])
 @pytest.mark.parametrize("kind", ["sd", "fm"])
-def test_preview_group_one_graph_for_several_previews_matches_serial_execution(kind):
+def test_preview_group_one_graph_for_several_previews_matches_serial_execution(kind, parallel):
     """PreviewGroup: g independent previews as ONE CUDA graph (one branch each, a shared device-resident generator
     state).  Replays — back to back, and interleaved with other users of the generator — give the bits of running the g
     previews eagerly one after the other, and leave the default generator where eager execution leaves it."""
@@ -306,7 +307,7 @@ def test_preview_group_one_graph_for_several_previews_matches_serial_execution(k
         previews.append(GraphedPreview(s, x, outs_in, 3.0 if kind == "sd" else None, n, set_timesteps_kwargs=tk))
         eager.append((e, tk))
         batches.append((x, outs_in))
-    group = PreviewGroup(previews)
+    group = PreviewGroup(previews, parallel=parallel)
     assert len(group) == G
 
     def run_eager(j):
@@ -356,7 +357,7 @@ def test_two_preview_groups_in_rotation_on_two_streams_match_serial_execution():
         previews.append(GraphedPreview(s, x, pairs, 3.0, n))
         eager.append(e)
         batches.append((x, pairs))
-    groups = [PreviewGroup(previews[:2], rotation=2), PreviewGroup(previews[2:], rotation=2)]
+    groups = [PreviewGroup(previews[:2], rotation=2, parallel=False), PreviewGroup(previews[2:], rotation=2, parallel=False)]
     pool = PreviewPool(groups, streams=2)
     assert len(pool.streams) == 2
     torch.manual_seed(11)
