@@ -437,7 +437,7 @@ def run_ours(args, rank, world, device):
         groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)], rotation=n_groups, parallel=not args.serial_groups)
                   for i in range(0, n_groups * g, g)]
     # one stream per group: consecutive group replays overlap (a group's join would otherwise drain the GPU)
-    gpool = PreviewPool(groups, streams=len(groups)) if groups else None
+    gpool = PreviewPool(groups, streams=len(groups), stagger_us=args.stagger_us) if groups else None
     counts = {"group_replays": 0, "single_replays": 0}
 
     def run_steps(first, count, join=True):
@@ -1193,6 +1193,8 @@ def main():
     ap.add_argument("--no-groups", action="store_true", help="replay previews one graph at a time (PreviewPool only)")
     ap.add_argument("--parallel-groups", dest="serial_groups", action="store_false",
                     help="one graph branch per preview inside a group instead of a serial chain")
+    ap.add_argument("--stagger-us", type=float, default=9.0,
+                    help="phase shift between the group streams when the pipeline opens (a quarter of a preview)")
     ap.add_argument("--group-rotation", type=int, default=4, help="preview groups replayed round-robin (one stream each)")
     ap.add_argument("--reps", type=int, default=0, help="force the number of back-to-back blocks (0 = calibrate)")
     ap.add_argument("--leg", default="", help=argparse.SUPPRESS)       # internal: torch_ref_gpu:<mode> in a subprocess

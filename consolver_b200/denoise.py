@@ -249,7 +249,12 @@ class PreviewPool:
     (≈0.97 of the HBM copy peak for the whole loop).  Preview j always runs on stream j % n_streams, so two replays
     of the same preview never overlap; the default generator is consumed in submission order."""
 
-    def __init__(self, previews: Sequence[GraphedPreview], streams: int = 4):
+    def __init__(self, previews: Sequence[GraphedPreview], streams: int = 4, stagger_us: float = 0.0):
+        """`stagger_us`: when the pool opens (first submit after a join) stream j is delayed by j * stagger_us.  Equal
+        graphs replayed round-robin by a fast host run in LOCKSTEP — all streams in their latency-bound phases (first
+        steps, policy->step hand-offs) at the same moment, then all in their streaming phases — which wastes the overlap
+        several streams are there to provide; a one-off phase shift of a fraction of a preview keeps them interleaved."""
+        self.stagger_us = float(stagger_us)
         self.previews = list(previews)
         n = max(1, min(streams, len(self.previews)))
         while len(self.previews) % n:
@@ -262,8 +267,11 @@ class PreviewPool:
     def submit(self, j: int) -> torch.Tensor:
         """enqueue one replay of preview j; returns its output buffer (valid after join() / stream order)"""
         if not self._open and len(self.streams) > 1:
-            for st in self.streams:
+            for i, st in enumerate(self.streams):
                 st.wait_stream(self.main)
+                if self.stagger_us > 0 and i:
+                    with torch.cuda.stream(st):
+                        torch.cuda._sleep(int(i * self.stagger_us * 1.9e3))      # ~1.9 cycles per ns at B200 clocks
             self._open = True
         st = self.streams[j % len(self.streams)]
         if st is self.main:
