@@ -392,8 +392,9 @@ def run_ours(args, rank, world, device):
         if not args.no_groups and args.streams > 1:
             # preview groups (see below): `group_rotation` groups of `streams` previews replayed round-robin, one stream
             # each, so that one group's join never leaves the GPU short of work
-            pool_n = max(pool_n, args.group_rotation * args.streams)
-            pool_n -= pool_n % args.streams
+            gsz = args.group_size or args.streams
+            pool_n = max(pool_n, args.group_rotation * gsz)
+            pool_n -= pool_n % gsz
     pool = []
     for j in range(pool_n):
         s = make_scheduler(device, sd)
@@ -430,7 +431,7 @@ def run_ours(args, rank, world, device):
     if ppool is not None and n_streams > 1 and not args.no_groups:
         from consolver_b200.denoise import PreviewGroup
 
-        g = n_streams
+        g = args.group_size or n_streams
         n_groups = (pool_n - pool_n % g) // g
         # each group = g previews chained on ONE branch (parallel=False); the parallelism comes from replaying the
         # n_groups groups on n_groups streams, every stream a gap-free chain of previews
@@ -1193,7 +1194,8 @@ def main():
     ap.add_argument("--no-groups", action="store_true", help="replay previews one graph at a time (PreviewPool only)")
     ap.add_argument("--parallel-groups", dest="serial_groups", action="store_false",
                     help="one graph branch per preview inside a group instead of a serial chain")
-    ap.add_argument("--stagger-us", type=float, default=9.0,
+    ap.add_argument("--group-size", type=int, default=0, help="previews per group graph (0 = --streams)")
+    ap.add_argument("--stagger-us", type=float, default=0.0,
                     help="phase shift between the group streams when the pipeline opens (a quarter of a preview)")
     ap.add_argument("--group-rotation", type=int, default=4, help="preview groups replayed round-robin (one stream each)")
     ap.add_argument("--reps", type=int, default=0, help="force the number of back-to-back blocks (0 = calibrate)")
