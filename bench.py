@@ -393,7 +393,7 @@ def run_ours(args, rank, world, device):
             # preview groups (see below): `group_rotation` groups of `streams` previews replayed round-robin, one stream
             # each, so that one group's join never leaves the GPU short of work
             gsz = args.group_size or args.streams
-            pool_n = max(pool_n, args.group_rotation * gsz)
+            pool_n = max(pool_n, args.group_rotation * gsz, args.pool)
             pool_n -= pool_n % gsz
     pool = []
     for j in range(pool_n):
@@ -438,7 +438,8 @@ def run_ours(args, rank, world, device):
         groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)], rotation=n_groups, parallel=not args.serial_groups)
                   for i in range(0, n_groups * g, g)]
     # one stream per group: consecutive group replays overlap (a group's join would otherwise drain the GPU)
-    gpool = PreviewPool(groups, streams=len(groups), stagger_us=args.stagger_us) if groups else None
+    gpool = PreviewPool(groups, streams=min(len(groups), args.group_rotation), stagger_us=args.stagger_us) \
+        if groups else None
     counts = {"group_replays": 0, "single_replays": 0}
 
     def run_steps(first, count, join=True):
@@ -639,7 +640,7 @@ def run_ours(args, rank, world, device):
                 "concurrency": f"{n_streams} independent preview batch(es) in flight" + (
                     f": groups of {g} previews captured as one CUDA graph ("
                     + ("a serial chain per group" if args.serial_groups else f"{g} parallel branches") +
-                    f"), {len(groups)} groups replayed round-robin on {len(groups)} streams "
+                    f"), {len(groups)} groups replayed round-robin on {len(gpool.streams)} streams "
                     f"({timed_counts['group_replays']} group + {timed_counts['single_replays']} single replays timed)"
                     if groups else " on separate CUDA streams"),
                 "timing": f"{reps} x {args.steps} previews back to back between two CUDA events, max over ranks",
@@ -1194,6 +1195,7 @@ def main():
     ap.add_argument("--no-groups", action="store_true", help="replay previews one graph at a time (PreviewPool only)")
     ap.add_argument("--parallel-groups", dest="serial_groups", action="store_false",
                     help="one graph branch per preview inside a group instead of a serial chain")
+    ap.add_argument("--pool", type=int, default=0, help="minimum number of resident preview batches in the rotating pool")
     ap.add_argument("--group-size", type=int, default=0, help="previews per group graph (0 = --streams)")
     ap.add_argument("--stagger-us", type=float, default=0.0,
                     help="phase shift between the group streams when the pipeline opens (a quarter of a preview)")
