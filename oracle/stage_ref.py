@@ -25,7 +25,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")
 SOURCE = os.environ.get("CONSOLVER_REFERENCE_SRC", "/root/reference")
 
-# the files ref_shim.load_reference() executes: the two schedulers, their policies, and the baseline solvers
+# the files ref_shim.load_reference() executes: the two schedulers, their policies, the baseline solvers — and the
+# SD caller loop, which tests/test_gpu_live_reference.py runs unmodified over BOTH schedulers
 FILES = [
     "scheduler_ppo.py",                    # PPOScheduler                     
     "factor_net_ppo.py",                   # FactorNetPPO, SD                 (F1-F4, T1)
@@ -35,6 +36,7 @@ FILES = [
     "edit_ppo/conv_net.py",
     "edit_ppo/scheduler_fm.py",            # FlowMatchGeneralDiscreteScheduler (N4 baselines)
     "diffusers_amed_plugin_dpmpp.py",      # AMED plugin                      (N4)
+    "denoise_ppo.py",                      # the caller loop (D1, D2): drives the scheduler in the live drop-in test
 ]
 
 

@@ -1,0 +1,183 @@
+"""LIVE differential tests on the GPU: the unmodified reference (byte-identical copies staged under oracle/_ref by
+oracle/stage_ref.py — they travel with the working tree) and the drop-in run SIDE BY SIDE on the same device, same seeds,
+same inputs.  Beyond the committed fixtures this covers (a) the reference's own caller loop `denoise_ppo.denoise_diffusion`
+driving either scheduler — the drop-in claim at the call site — and (b) randomly drawn configurations.
+Skipped when oracle/_ref is absent (nothing here reads /root/reference)."""
+import importlib.util
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import ref_shim
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_shim.reference_available(),
+                                                  reason="oracle/_ref not staged (python oracle/stage_ref.py)")]
+
+SD_PROD = dict(beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, num_train_timesteps=1000,
+               steps_offset=1, timestep_spacing="trailing", use_conv=False)
+
+
+def _seed_policy(fn, seed, last_std):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in fn.named_parameters():
+            if name.startswith("mlp.4"):
+                p.copy_(torch.randn(p.shape, generator=g) * (last_std if name.endswith("weight") else 0.1))
+            else:
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * 0.3)
+
+
+def _pair(kind, seed, last_std=0.5, **cfg):
+    """(reference scheduler, drop-in scheduler) with identical weights, both on cuda"""
+    import consolver_b200 as cb
+
+    ref = ref_shim.load_reference()
+    fkw = dict(hidden_dim=64, num_actions=11)
+    with ref_shim.quiet():
+        if kind == "sd":
+            r = ref.PPOScheduler(factor_net_kwargs=dict(embedding_dim=64, **fkw), **cfg)
+            o = cb.PPOScheduler(factor_net_kwargs=dict(embedding_dim=64, **fkw), **cfg)
+        else:
+            r = ref.FMPPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
+            o = cb.FMPPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
+    _seed_policy(r.factor_net, seed, last_std)
+    o.factor_net.load_state_dict(r.factor_net.state_dict())
+    r.factor_net.cuda(), o.factor_net.cuda()
+    return r, o
+
+
+def _load_caller():
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "denoise_ppo.py")
+    if not os.path.isfile(path):
+        pytest.skip("denoise_ppo.py not staged")
+    spec = importlib.util.spec_from_file_location("_ref_denoise_ppo", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _Tok:
+    model_max_length = 8
+
+    def __call__(self, text, **kw):
+        ids = torch.tensor([[(len(t) * 7 + j) % 50 for j in range(self.model_max_length)] for t in text])
+        return types.SimpleNamespace(input_ids=ids)
+
+
+def _text_encoder(ids):
+    return (torch.sin(ids.float().unsqueeze(-1) * torch.arange(1, 5, device=ids.device)),)
+
+
+def _unet(x, t, encoder_hidden_states=None, return_dict=False):
+    """deterministic element-wise stand-in for the U-Net (not the product): depends on the latent, the timestep and the
+    text embedding, so the two CFG halves differ"""
+    c = encoder_hidden_states.mean(dim=(1, 2)).view(-1, 1, 1, 1)
+    return (0.55 * x + 0.25 * torch.roll(x, 1, dims=3) - 0.15 * torch.roll(x, 1, dims=1) + 0.1 * c +
+            0.0003 * t.float(),)
+
+
+@pytest.mark.parametrize("pred,scaler_dim,n", [("epsilon", 0, 8), ("v_prediction", 2, 6), ("epsilon", 1, 15)])
+def test_the_references_own_caller_loop_gives_the_same_rollout_with_either_scheduler(pred, scaler_dim, n):
+    """denoise_ppo.denoise_diffusion (UNMODIFIED) with the reference's PPOScheduler and with the drop-in: final latents,
+    the whole rollout record (conds x / epsilon, actions, masks) bit-identical, probabilities within the measured
+    cuBLAS-vs-kernel spread."""
+    caller = _load_caller()
+    r, o = _pair("sd", seed=n, order_dim=4, scaler_dim=scaler_dim, prediction_type=pred, **SD_PROD)
+    noise = torch.randn(5, 4, 16, 16, generator=torch.Generator().manual_seed(1)).cuda()
+    text = [f"prompt {i}" * (i + 1) for i in range(5)]
+    outs = []
+    for sched in (r, o):
+        torch.manual_seed(1234)
+        with ref_shim.quiet(), torch.no_grad():
+            outs.append(caller.denoise_diffusion(_text_encoder, sched, _unet, noise, text, _Tok(), cfg=3.0,
+                                                 num_inference_steps=n))
+    (lat_r, conds_r, probs_r, act_r, masks_r, _), (lat_o, conds_o, probs_o, act_o, masks_o, _) = outs
+    assert torch.equal(act_r, act_o), "sampled actions differ"
+    assert torch.equal(masks_r, masks_o) and torch.equal(conds_r["x"], conds_o["x"])
+    assert torch.equal(conds_r["epsilon"], conds_o["epsilon"])
+    torch.testing.assert_close(probs_o, probs_r, rtol=0, atol=1e-6)
+    assert lat_o.dtype == lat_r.dtype and torch.equal(lat_r, lat_o), "final latents differ"
+
+
+def _random_sd_case(rng):
+    od = rng.choice([2, 3, 4, 4])
+    return dict(order_dim=od, scaler_dim=rng.choice([0, 0, 1, 2]),
+                prediction_type=rng.choice(["epsilon", "epsilon", "v_prediction"]),
+                timestep_spacing=rng.choice(["trailing", "leading", "linspace"]),
+                beta_schedule=rng.choice(["scaled_linear", "linear", "squaredcos_cap_v2"]),
+                beta_start=0.00085, beta_end=0.012, steps_offset=rng.choice([0, 1]), use_conv=False)
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_random_sd_configurations_step_for_step(case):
+    """randomly drawn scheduler configs, step counts, batch / latent shapes and dtype flows (fp32; fp16 / bf16 outputs
+    with fp32 or 16-bit latents; the autocast rollout; gen_ppo.py's fp16 policy under autocast): every step bit-identical
+    to the reference stepping next to it on the same GPU with the same seed"""
+    rng = random.Random(1000 + case)
+    cfg = _random_sd_case(rng)
+    n = rng.choice([2, 3, 5, 8, 13])
+    B = rng.choice([1, 2, 3, 7])
+    shape = rng.choice([(4, 8, 8), (3, 5, 7), (4, 16, 16), (1, 33)])
+    flow = rng.choice(["f32", "f32", "f16_out", "bf16_out", "f16_pipeline", "autocast_f16", "genppo_f16", "genppo_bf16"])
+    r, o = _pair("sd", seed=case, **cfg)
+    mdt = {"f32": torch.float32, "f16_out": torch.float16, "bf16_out": torch.bfloat16, "f16_pipeline": torch.float16,
+           "autocast_f16": torch.float16, "genppo_f16": torch.float16, "genppo_bf16": torch.bfloat16}[flow]
+    xdt = mdt if flow in ("f16_pipeline", "genppo_f16", "genppo_bf16") else torch.float32
+    ac = {"autocast_f16": torch.float16, "genppo_f16": torch.float16, "genppo_bf16": torch.bfloat16}.get(flow)
+    if flow.startswith("genppo"):
+        r.factor_net.to("cuda", dtype=mdt), o.factor_net.to("cuda", dtype=mdt)
+    r.set_timesteps(n, device="cuda"), o.set_timesteps(n, device="cuda")
+    g = torch.Generator().manual_seed(case)
+    xr = xo = torch.randn(B, *shape, generator=g).to(xdt).cuda()
+    ctx = (lambda: torch.autocast("cuda", ac)) if ac is not None else __import__("contextlib").nullcontext
+    for i in range(n):
+        e = torch.randn(B, *shape, generator=g).to(mdt).cuda()
+        torch.manual_seed(77 + i)
+        with ref_shim.quiet(), ctx(), torch.no_grad():
+            xr, ar, pr, cr, mr = r.step(e, r.timesteps[i], xr, return_dict=False)
+        rng_after_ref = torch.cuda.get_rng_state()
+        torch.manual_seed(77 + i)
+        with ctx(), torch.no_grad():
+            xo, ao, po, co, mo = o.step(e, o.timesteps[i], xo, return_dict=False)
+        tag = f"case {case} ({flow}, {cfg}) step {i}"
+        assert ao.dtype == ar.dtype and torch.equal(ao, ar), tag + ": actions"
+        assert torch.equal(mo, mr) and torch.equal(co["x"], cr["x"]), tag
+        torch.testing.assert_close(po, pr, rtol=1.2e-4 if ac is not None else 0, atol=6e-6 if ac is not None else 1e-6)
+        assert xo.dtype == xr.dtype, tag + f": latent dtype {xo.dtype} vs {xr.dtype}"
+        assert torch.equal(xo, xr), tag + ": latent"
+        assert torch.equal(torch.cuda.get_rng_state(), rng_after_ref), tag + ": default generator consumed differently"
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_random_fm_configurations_step_for_step(case):
+    rng = random.Random(2000 + case)
+    od = rng.choice([2, 2, 3, 4])
+    cfg = dict(shift=3.0, use_dynamic_shifting=True, order_dim=od, scaler_dim=rng.choice([0, 0, 1, 2]),
+               mu_dim=rng.choice([0, 0, 1]))
+    n = rng.choice([3, 5, 8])
+    B = rng.choice([1, 2, 4])
+    shape = rng.choice([(16, 8), (5, 7), (64, 16)])
+    dt = rng.choice([torch.bfloat16, torch.bfloat16, torch.float32, torch.float16])
+    r, o = _pair("fm", seed=50 + case, last_std=0.02, **cfg)
+    for s in (r, o):
+        s.set_timesteps(n, device="cuda", sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+        s.set_begin_index(0)
+    g = torch.Generator().manual_seed(case)
+    xr = xo = torch.randn(B, *shape, generator=g).to(dt).cuda()
+    for i in range(n):
+        v = torch.randn(B, *shape, generator=g).to(dt).cuda()
+        torch.manual_seed(5 + i)
+        with ref_shim.quiet(), torch.no_grad():
+            xr, ar, pr, cr, mr = r.step(v, r.timesteps[i], xr, return_dict=False)
+        torch.manual_seed(5 + i)
+        with torch.no_grad():
+            xo, ao, po, co, mo = o.step(v, o.timesteps[i], xo, return_dict=False)
+        tag = f"case {case} ({cfg}, {dt}) step {i}"
+        assert torch.equal(ao, ar), tag + ": actions"
+        assert torch.equal(mo, mr) and torch.equal(co["x"], cr["x"]), tag
+        torch.testing.assert_close(po, pr, rtol=8e-6, atol=1e-6)
+        assert xo.dtype == xr.dtype and torch.equal(xo, xr), tag + ": latent"
