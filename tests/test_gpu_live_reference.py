@@ -121,8 +121,9 @@ def test_random_sd_configurations_step_for_step(case):
     cfg = _random_sd_case(rng)
     n = rng.choice([2, 3, 5, 8, 13])
     B = rng.choice([1, 2, 3, 7])
-    shape = rng.choice([(4, 8, 8), (3, 5, 7), (4, 16, 16), (1, 1, 33)])     # 4-D latents: the reference's coefficient
-    flow = rng.choice(                                                       # tensors are [B,1,1,1] (scheduler_ppo.py:253)["f32", "f32", "f16_out", "bf16_out", "f16_pipeline", "autocast_f16", "genppo_f16", "genppo_bf16"])
+    # 4-D latents only: the reference's coefficient tensors are [B,1,1,1] (scheduler_ppo.py:253)
+    shape = rng.choice([(4, 8, 8), (3, 5, 7), (4, 16, 16), (1, 1, 33)])
+    flow = rng.choice(["f32", "f32", "f16_out", "bf16_out", "f16_pipeline", "autocast_f16", "genppo_f16", "genppo_bf16"])
     r, o = _pair("sd", seed=case, **cfg)
     mdt = {"f32": torch.float32, "f16_out": torch.float16, "bf16_out": torch.bfloat16, "f16_pipeline": torch.float16,
            "autocast_f16": torch.float16, "genppo_f16": torch.float16, "genppo_bf16": torch.bfloat16}[flow]
