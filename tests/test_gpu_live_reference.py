@@ -112,7 +112,7 @@ def _random_sd_case(rng):
                 beta_start=0.00085, beta_end=0.012, steps_offset=rng.choice([0, 1]), use_conv=False)
 
 
-@pytest.mark.parametrize("case", range(12))
+@pytest.mark.parametrize("case", range(32))
 def test_random_sd_configurations_step_for_step(case):
     """randomly drawn scheduler configs, step counts, batch / latent shapes and dtype flows (fp32; fp16 / bf16 outputs
     with fp32 or 16-bit latents; the autocast rollout; gen_ppo.py's fp16 policy under autocast): every step bit-identical
@@ -153,7 +153,7 @@ def test_random_sd_configurations_step_for_step(case):
         assert torch.equal(torch.cuda.get_rng_state(), rng_after_ref), tag + ": default generator consumed differently"
 
 
-@pytest.mark.parametrize("case", range(6))
+@pytest.mark.parametrize("case", range(12))
 def test_random_fm_configurations_step_for_step(case):
     rng = random.Random(2000 + case)
     od = rng.choice([2, 2, 3, 4])
