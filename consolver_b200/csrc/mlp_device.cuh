@@ -32,24 +32,58 @@ __device__ __forceinline__ float policy_input(float x, float x_div, int flags) {
   return round_act(v, flags & (CONSOLVER_POLICY_ACT_F16 | CONSOLVER_POLICY_ACT_BF16));
 }
 
+// `torch.sum(torch.stack(terms), dim=0)` of set_default_coefficients (scheduler_ppo.py:172) in the order ATen adds.
+// fp32 addition is not associative, and which order the reference gets depends on where it runs (ATen/native/cuda/
+// Reduce.cuh of the pinned torch, restated here; m = n_hist - 1 <= 7 terms):
+//   kSumSequential  ((s0 + s1) + s2) + ...                        the reference on CPU tensors
+//   kSumCudaBatch   B >= 2: the batch is the fastest dimension, every thread reduces its own sample with vt0 = 4
+//                   accumulators: acc[i % 4] += s_i, result ((acc0 + acc1) + acc2) + acc3 (== sequential up to 4 terms)
+//   kSumCudaSingle  B == 1: the reduced dimension is the fastest one, so block.x = last_pow2(m) threads share ONE sum:
+//                   thread x accumulates s_x, s_{x+W}, ... (4 accumulators, combined in order), then a shuffle tree
+//                   with DECREASING offsets — three terms give (s0 + s2) + s1
+enum : int { kSumSequential = 0, kSumCudaBatch = 1, kSumCudaSingle = 2 };
+__device__ __forceinline__ float sum_terms(const float* s, int m, int mode) {
+  if (m <= 0) return 0.f;
+  if (mode == kSumSequential) {
+    float run = s[0];
+    for (int i = 1; i < m; ++i) run = __fadd_rn(run, s[i]);
+    return run;
+  }
+  if (mode == kSumCudaBatch) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < m; ++i) acc[i & 3] = __fadd_rn(acc[i & 3], s[i]);
+    return __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
+  }
+  int W = 1;
+  while (W * 2 <= m) W *= 2;                       // last_pow2(m): 1, 2 or 4 for m <= 7
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int x = 0; x < W; ++x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 4 && x + k * W < m; ++k) acc[k] = __fadd_rn(acc[k], s[x + k * W]);
+    t[x] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
+  }
+  for (int off = W >> 1; off > 0; off >>= 1)
+    for (int x = 0; x < off; ++x) t[x] = __fadd_rn(t[x], t[x + off]);
+  return t[0];
+}
+
 // set_default_coefficients (scheduler_ppo.py:165-175) for one sample: act[0..A) are the sampled action values, c the
 // coefficient record of include/consolver.h: c0 = a0 + 1, c_{n-1} = 1 - sum(c_0..c_{n-2}), then (1+s0), (1+s1).
 // cm = CONSOLVER_POLICY_COEF_F16/_BF16: the action values are 16-bit tensors, so a0 + 1 and s + 1 are rounded to that
-// dtype; torch.sum returns fp32 under autocast, so the running sum and the closing coefficient are fp32.
-__device__ __forceinline__ void write_coef_record(const float* act, float* c, int n, int od, int scaler_dim, int cm) {
-  const float c0 = round_act(__fadd_rn(act[0], 1.f), cm);
-  float run = c0;
+// dtype; torch.sum returns fp32 under autocast, so the sum and the closing coefficient are fp32.
+__device__ __forceinline__ void write_coef_record(const float* act, float* c, int n, int od, int scaler_dim, int cm,
+                                                  int sum_mode) {
+  float terms[CONSOLVER_MAX_ORDER];
+  terms[0] = round_act(__fadd_rn(act[0], 1.f), cm);
+  for (int i = 1; i < n - 1; ++i) terms[i] = act[i];
   for (int i = 0; i < od; ++i) {
     float v = 0.f;
     if (n == 1) {
       v = (i == 0) ? 1.f : 0.f;               // the step kernel bypasses the coefficient when n_hist == 1
-    } else if (i == 0) {
-      v = c0;
     } else if (i < n - 1) {
-      v = act[i];
-      run = __fadd_rn(run, v);
+      v = terms[i];
     } else if (i == n - 1) {
-      v = __fsub_rn(1.f, run);
+      v = __fsub_rn(1.f, sum_terms(terms, n - 1, sum_mode));
     }
     c[i] = v;
   }

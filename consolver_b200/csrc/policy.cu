@@ -164,7 +164,8 @@ __device__ __forceinline__ void sample_phase(const PolicyParams& p, int b_begin,
   __syncthreads();
   for (int bl = threadIdx.x; bl < nb; bl += blockDim.x)
     write_coef_record(act_s + (size_t)bl * A, p.coef + (size_t)(b_begin + bl) * (od + 2), p.n_hist, od, p.scaler_dim,
-                      p.flags & (CONSOLVER_POLICY_COEF_F16 | CONSOLVER_POLICY_COEF_BF16));
+                      p.flags & (CONSOLVER_POLICY_COEF_F16 | CONSOLVER_POLICY_COEF_BF16),
+                      (p.flags & CONSOLVER_POLICY_HOST_DIV) ? kSumSequential : (p.B == 1 ? kSumCudaSingle : kSumCudaBatch));
 }
 
 struct Smem {

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(kGaussThreads) policy_gauss_kernel(const Gauss
   __syncthreads();
   for (int bl = threadIdx.x; bl < nb; bl += blockDim.x)
     write_coef_record(act_s + (size_t)bl * A, p.coef + (size_t)(b_begin + bl) * (p.order_dim + 2), p.n_hist, p.order_dim,
-                      p.scaler_dim, 0);
+                      p.scaler_dim, 0,
+                      (p.flags & CONSOLVER_POLICY_HOST_DIV) ? kSumSequential : (p.B == 1 ? kSumCudaSingle : kSumCudaBatch));
 }
 
 }  // namespace consolver

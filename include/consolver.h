@@ -25,7 +25,7 @@ extern "C" {
 
 /* Bumped on EVERY change of a signature, struct layout or flag meaning in this header.  Loaders must also compare
  * consolver_abi_hash() with the hash of the header they were written against (see consolver_abi_hash below). */
-#define CONSOLVER_ABI_VERSION 6
+#define CONSOLVER_ABI_VERSION 7
 
 /* element type of latents / model outputs */
 #define CONSOLVER_F32  0
@@ -98,7 +98,12 @@ extern "C" {
 
 /* policy_flags of the policy entry points */
 #define CONSOLVER_POLICY_HOST_DIV    1   /* x / x_div and logits / temp as true divisions (torch on CPU tensors); default:
-                                           multiplications by the fp32 reciprocals (ATen's CUDA division by a scalar)  */
+                                           multiplications by the fp32 reciprocals (ATen's CUDA division by a scalar).
+                                           Also selects the ORDER in which the closing coefficient's
+                                           torch.sum(torch.stack(...), dim=0) adds its terms (scheduler_ppo.py:172):
+                                           left to right on CPU tensors; on CUDA tensors ATen's reduce kernel order —
+                                           per-sample 4-accumulator form for B >= 2, a two-level tree when B == 1
+                                           (three terms: (c0 + a2) + a1), see csrc/mlp_device.cuh::sum_terms            */
 #define CONSOLVER_POLICY_ACT_F16     2   /* the MLP runs under torch.autocast(fp16) (gen_ppo.py:309, train_ppo.py:353) or
                                            with parameters cast to fp16: the input row, every Linear output and
                                            logits/temp are rounded to fp16 (fp32 accumulation, bias added before the

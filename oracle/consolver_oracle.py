@@ -73,10 +73,40 @@ class TorchSemantics:
         return (t.float() * inv).to(t.dtype)
 
     def sum0(self, stacked: torch.Tensor) -> torch.Tensor:
-        """torch.sum(stacked, dim=0) — fp32 in, fp32 out under autocast"""
+        """torch.sum(stacked, dim=0) of set_default_coefficients (scheduler_ppo.py:172) — fp32 in, fp32 out under
+        autocast.  fp32 addition is not associative and ATen's CUDA reduce kernel (ATen/native/cuda/Reduce.cuh) does not
+        add left to right:
+          * B >= 2 per-sample values (the batch is the fastest dimension): each thread reduces its own sample with
+            vt0 = 4 accumulators, acc[i % 4] += s_i, then ((acc0 + acc1) + acc2) + acc3 — left to right up to 4 terms;
+          * B == 1 (the reduced dimension is the fastest one): block.x = last_pow2(m) threads share the sum: thread x
+            takes s_x, s_{x+W}, ... into its accumulators, then a shuffle tree with decreasing offsets —
+            three terms give (s0 + s2) + s1.
+        Pinned by the B = 1 / order_dim 6 and 8 fixtures made on the B200 and by the live differential tests."""
         if self.autocast is not None and stacked.dtype in (torch.float16, torch.bfloat16):
             stacked = stacked.float()
-        return torch.sum(stacked, dim=0)
+        if not self.cuda or stacked.dtype != F32:
+            return torch.sum(stacked, dim=0)
+        m = stacked.shape[0]
+        zero = torch.zeros_like(stacked[0])
+
+        def four(vals):
+            acc = [zero, zero, zero, zero]
+            for k, v in enumerate(vals):
+                acc[k % 4] = acc[k % 4] + v
+            return ((acc[0] + acc[1]) + acc[2]) + acc[3]
+
+        if stacked[0].numel() != 1:
+            return four([stacked[i] for i in range(m)])
+        W = 1
+        while W * 2 <= m:
+            W *= 2
+        t = [four([stacked[i] for i in range(x, m, W)]) for x in range(W)]
+        off = W // 2
+        while off > 0:
+            for x in range(off):
+                t[x] = t[x] + t[x + off]
+            off //= 2
+        return t[0]
 
 
 HOST = TorchSemantics("cpu")

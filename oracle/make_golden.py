@@ -402,10 +402,31 @@ def main_cuda():
     gen_fm("cuda_fm_rollout_bf16_autocast_n8_B3", B=3, shape=tok, n=8, seed=39, dtype=b16, autocast=b16, device=dev)
 
 
+def main_cuda2():
+    """`python oracle/make_golden.py cuda2` (GPU box): fixtures that pin the ORDER in which ATen's CUDA reduce kernel
+    adds the terms of `1 - torch.sum(torch.stack(...), dim=0)` (scheduler_ppo.py:172): batch size 1 (the reduced
+    dimension is the fastest one: a shuffle tree) and more than four terms (order_dim 6 / 8: four accumulators)."""
+    assert torch.cuda.is_available(), "main_cuda2 needs a GPU"
+    dev, small, tok = "cuda", (4, 8, 8), (16, 8)
+    gen_sd("cuda_sd_eps_s0_n8_B1", hidden_dim=64, B=1, shape=small, n=8, guidance=3.0, seed=111, device=dev)
+    gen_sd("cuda_sd_v_o8_s1_n12_B2", hidden_dim=64, B=2, shape=small, n=12, guidance=3.0, seed=112, device=dev,
+           order_dim=8, scaler_dim=1, prediction_type="v_prediction")
+    gen_sd("cuda_sd_eps_o6_s0_n10_B1", hidden_dim=64, B=1, shape=small, n=10, guidance=3.0, seed=113, device=dev,
+           order_dim=6)
+    gen_sd("cuda_sd_eps_o8_s2_n12_B1", hidden_dim=64, B=1, shape=small, n=12, guidance=3.0, seed=114, device=dev,
+           order_dim=8, scaler_dim=2)
+    gen_fm("cuda_fm_o4_s0_m0_f32_n6_B1", hidden_dim=64, B=1, shape=tok, n=6, seed=115, dtype=torch.float32, order_dim=4,
+           device=dev)
+    gen_fm("cuda_fm_o6_s1_m0_bf16_n8_B2", hidden_dim=64, B=2, shape=tok, n=8, seed=116, dtype=torch.bfloat16, order_dim=6,
+           scaler_dim=1, device=dev)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1:] == ["cuda"]:
         return main_cuda()
+    if sys.argv[1:] == ["cuda2"]:
+        return main_cuda2()
     if sys.argv[1:] == ["fm_general"]:
         return main_fm_general()
     if sys.argv[1:] == ["amed"]:

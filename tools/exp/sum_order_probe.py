@@ -33,3 +33,20 @@ for dev in ("cpu", "cuda"):
         want = float(one - ((np.float32(a0[i].item()) + one) + np.float32(a1[j].item()) + np.float32(a2[k].item())))
         mism += r != want
     print(dev, "B=1 mismatches vs left-to-right:", mism)
+
+
+# ---- the restated ATen order (oracle TorchSemantics.sum0) against torch.sum on this device, m = 2..7 terms ---------------
+sys.path.insert(0, "oracle")
+import consolver_oracle as orc  # noqa: E402
+
+if torch.cuda.is_available():
+    g = torch.Generator().manual_seed(0)
+    for m in range(2, 8):
+        for B in (1, 2, 5, 64):
+            bad = 0
+            for trial in range(200):
+                vals = (torch.randn(m, B, 1, 1, 1, generator=g) * 1.3).float()
+                ref = torch.sum(vals.cuda(), dim=0).cpu()
+                got = orc.CUDA.sum0(vals)
+                bad += int(not torch.equal(ref, got))
+            print(f"m={m} B={B}: restated order differs from torch.sum on cuda in {bad}/200 trials")
