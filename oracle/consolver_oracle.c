@@ -93,10 +93,43 @@ void oracle_fm_step_f32(const float* const* hist, int n_hist, const float* x, fl
   }
 }
 
-/* draw + gather + masks + coefficients from a probability table probs [A,K] and q [B*A,K] */
+/* torch.sum(torch.stack(terms), dim=0) of set_default_coefficients (scheduler_ppo.py:172) in the order ATen adds:
+ * sum_mode 0: left to right (CPU tensors); 1: CUDA tensors, B >= 2 — four accumulators acc[i%4] += s_i, then
+ * ((acc0+acc1)+acc2)+acc3; 2: CUDA tensors, B == 1 — last_pow2(m) threads, each with four accumulators over its strided
+ * terms, then a shuffle tree with decreasing offsets (ATen/native/cuda/Reduce.cuh; three terms: (s0+s2)+s1). */
+static float oracle_sum_terms(const float* s, int m, int sum_mode) {
+  if (m <= 0) return 0.0f;
+  if (sum_mode == 0) {
+    float run = s[0];
+    for (int i = 1; i < m; ++i) run = run + s[i];
+    return run;
+  }
+  if (sum_mode == 1) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int i = 0; i < m; ++i) acc[i & 3] = acc[i & 3] + s[i];
+    float r = acc[0] + acc[1];
+    r = r + acc[2];
+    return r + acc[3];
+  }
+  int W = 1;
+  while (W * 2 <= m) W *= 2;
+  float t[8] = {0};
+  for (int x = 0; x < W; ++x) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < 4 && x + k * W < m; ++k) acc[k] = acc[k] + s[x + k * W];
+    float r = acc[0] + acc[1];
+    r = r + acc[2];
+    t[x] = r + acc[3];
+  }
+  for (int off = W / 2; off > 0; off /= 2)
+    for (int x = 0; x < off; ++x) t[x] = t[x] + t[x + off];
+  return t[0];
+}
+
+/* draw + gather + masks + coefficients from a probability table probs [A,K] and q [B*A,K]; sum_mode: see above */
 void oracle_policy_sample(const float* probs, const float* action_values, const float* q, int B, int A, int K,
-                          int order_dim, int scaler_dim, int n_hist, int64_t* idx, float* actions, float* act_probs,
-                          float* masks, float* coef) {
+                          int order_dim, int scaler_dim, int n_hist, int sum_mode, int64_t* idx, float* actions,
+                          float* act_probs, float* masks, float* coef) {
   for (int b = 0; b < B; ++b) {
     float act[64];
     for (int a = 0; a < A; ++a) {
@@ -115,13 +148,14 @@ void oracle_policy_sample(const float* probs, const float* action_values, const 
       if (a < 64) act[a] = actions[o];
     }
     float* c = coef + (size_t)b * (order_dim + 2);
-    float c0 = act[0] + 1.0f, run = c0;
+    float terms[64];
+    terms[0] = act[0] + 1.0f;
+    for (int i = 1; i < n_hist - 1; ++i) terms[i] = act[i];
     for (int i = 0; i < order_dim; ++i) {
       float v = 0.0f;
       if (n_hist == 1) v = (i == 0) ? 1.0f : 0.0f;
-      else if (i == 0) v = c0;
-      else if (i < n_hist - 1) { v = act[i]; run = run + v; }
-      else if (i == n_hist - 1) v = 1.0f - run;
+      else if (i < n_hist - 1) v = terms[i];
+      else if (i == n_hist - 1) v = 1.0f - oracle_sum_terms(terms, n_hist - 1, sum_mode);
       c[i] = v;
     }
     c[order_dim] = scaler_dim >= 1 ? act[order_dim - 1] + 1.0f : 1.0f;

@@ -331,3 +331,38 @@ def test_default_and_cpu_reference_devices_differ_only_by_ulps():
     assert torch.equal(outs["cuda"], ref)
     assert not torch.equal(outs["cpu"], ref)
     assert (outs["cpu"] - ref).abs().max() <= 1e-4 * ref.abs().max()      # north-star bar on the final latent
+
+
+@pytest.mark.parametrize("B", [1, 2, 37])
+@pytest.mark.parametrize("od", [3, 4, 6, 8])
+@pytest.mark.parametrize("host", [False, True])
+def test_closing_coefficient_is_summed_in_atens_order(B, od, host):
+    """`1 - torch.sum(torch.stack(terms), dim=0)` (scheduler_ppo.py:172): left to right on CPU tensors; on CUDA tensors
+    ATen's reduce order — four accumulators per sample for B >= 2, a two-level tree when B == 1 (where the reduced
+    dimension is the fastest one).  The restated order is checked against torch.sum ON THIS DEVICE and against the
+    kernel's coefficient records, for every history depth up to order_dim."""
+    from consolver_b200 import _lib
+
+    K, sdim = 11, 1
+    A = od + sdim - 1
+    g = torch.Generator().manual_seed(B * 10 + od)
+    av = (torch.randn(A, K, generator=g) * 0.9)                       # generic values: rounding differences are common
+    table = torch.softmax(torch.randn(A, K, generator=g), -1)
+    dsd = {"action_values": av.cuda()}
+    sem = orc.HOST if host else orc.CUDA
+    for n_hist in range(1, od + 1):
+        q = torch.empty(B * A, K).exponential_(1, generator=g)
+        out = ah.policy_sample(dsd, table.cuda(), B, od, sdim, n_hist, q=q.cuda(),
+                               policy_flags=_lib.POLICY_HOST_DIV if host else 0)
+        idx = orc.sample_indices(table.unsqueeze(0).expand(B, A, K), q)
+        actions = av[torch.arange(A), idx]
+        coef, scale = orc.coefficients(actions, n_hist, od, sdim, sem=sem)
+        c = out["coef"].cpu()
+        for j, cj in enumerate(coef or []):
+            assert torch.equal(c[:, j], cj), f"n_hist {n_hist} coef {j}"
+        if coef is not None and not host:
+            # ... and the restated order IS what torch.sum does on this GPU with the reference's [B,1,1,1] tensors
+            terms = [(actions[:, 0] + 1)] + [actions[:, i] for i in range(1, n_hist - 1)]
+            stacked = torch.stack([t.view(B, 1, 1, 1) for t in terms]).cuda()
+            ref_last = (1 - torch.sum(stacked, dim=0)).flatten().cpu()
+            assert torch.equal(coef[-1], ref_last), f"n_hist {n_hist}: oracle order != torch.sum on cuda"

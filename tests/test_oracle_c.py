@@ -49,6 +49,7 @@ def test_c_oracle_sd_trajectory_matches_reference(lib, name):
     flags = (1 if cfg.get("prediction_type", "epsilon") == "v_prediction" else 0) | (2 if sdim >= 1 else 0) | (4 if sdim >= 2 else 0)
     on_gpu = m.get("device") == "cuda"          # fixture made by the reference running on a B200: ATen's CUDA rules
     flags |= 0 if on_gpu else 256               # 256 = CONSOLVER_FLAG_HOST_SCALARS: true division
+    sum_mode = 0 if not on_gpu else (2 if B == 1 else 1)      # the order ATen adds the closing coefficient's terms in
     for i, t in enumerate(s.timesteps):
         pair = g[f"pair_{i}"].contiguous()
         eps = torch.empty_like(x)
@@ -62,13 +63,13 @@ def test_c_oracle_sd_trajectory_matches_reference(lib, name):
         coef = torch.empty(B, od + 2)
         if not cfg.get("use_conv"):
             table = g[f"probs_full_{i}"][0].contiguous()     # the reference's own softmax table (rows identical)
-            lib.oracle_policy_sample(_p(table), _p(av), _p(q), B, A, K, od, sdim, n_hist, _p(idx), _p(actions),
+            lib.oracle_policy_sample(_p(table), _p(av), _p(q), B, A, K, od, sdim, n_hist, sum_mode, _p(idx), _p(actions),
                                      _p(probs), _p(masks), _p(coef))
         else:                                                # use_conv: one table per sample
             for b in range(B):
                 table = g[f"probs_full_{i}"][b].contiguous()
                 lib.oracle_policy_sample(_p(table), _p(av), _p(q[b * A:(b + 1) * A]), 1, A, K, od, sdim, n_hist,
-                                         _p(idx[b]), _p(actions[b]), _p(probs[b]), _p(masks[b]), _p(coef[b]))
+                                         sum_mode, _p(idx[b]), _p(actions[b]), _p(probs[b]), _p(masks[b]), _p(coef[b]))
         assert torch.equal(idx, g[f"idx_{i}"])
         assert torch.equal(actions, g[f"actions_{i}"]) and torch.equal(probs, g[f"probs_{i}"])
         assert torch.equal(masks, g[f"masks_{i}"])
@@ -81,7 +82,7 @@ def test_c_oracle_sd_trajectory_matches_reference(lib, name):
         x = out
 
 
-@pytest.mark.parametrize("name", [n for n in names("fm_") if "f32" in n])
+@pytest.mark.parametrize("name", [n for n in names("fm_") + names("cuda_fm_") if "f32" in n and "conv" not in n])
 def test_c_oracle_fm_trajectory_matches_reference(lib, name):
     g = Golden(name)
     m = g.meta
@@ -100,8 +101,9 @@ def test_c_oracle_fm_trajectory_matches_reference(lib, name):
         idx = torch.empty(B, A, dtype=torch.int64)
         actions, probs, masks = torch.empty(B, A), torch.empty(B, A), torch.empty(B, A)
         coef = torch.empty(B, od + 2)
+        sum_mode = 0 if m.get("device") != "cuda" else (2 if B == 1 else 1)
         lib.oracle_policy_sample(_p(g[f"probs_full_{i}"][0].contiguous()), _p(av), _p(g[f"q_{i}"].contiguous()), B, A, K,
-                                 od, sdim, n_hist, _p(idx), _p(actions), _p(probs), _p(masks), _p(coef))
+                                 od, sdim, n_hist, sum_mode, _p(idx), _p(actions), _p(probs), _p(masks), _p(coef))
         assert torch.equal(idx, g[f"idx_{i}"]) and torch.equal(masks, g[f"masks_{i}"])
         dt = float(sig[i + 1] - sig[i])
         out = torch.empty_like(x)
