@@ -101,7 +101,9 @@ extern "C" {
                                            multiplications by the fp32 reciprocals (ATen's CUDA division by a scalar).
                                            Also selects the ORDER in which the closing coefficient's
                                            torch.sum(torch.stack(...), dim=0) adds its terms (scheduler_ppo.py:172):
-                                           left to right on CPU tensors; on CUDA tensors ATen's reduce kernel order —
+                                           left to right on CPU tensors (exact for up to 4 terms, order_dim <= 5; torch's
+                                           CPU reduction of more terms is not restated); on CUDA tensors ATen's reduce
+                                           kernel order —
                                            per-sample 4-accumulator form for B >= 2, a two-level tree when B == 1
                                            (three terms: (c0 + a2) + a1), see csrc/mlp_device.cuh::sum_terms            */
 #define CONSOLVER_POLICY_ACT_F16     2   /* the MLP runs under torch.autocast(fp16) (gen_ppo.py:309, train_ppo.py:353) or

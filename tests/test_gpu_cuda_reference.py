@@ -343,6 +343,9 @@ def test_closing_coefficient_is_summed_in_atens_order(B, od, host):
     kernel's coefficient records, for every history depth up to order_dim."""
     from consolver_b200 import _lib
 
+    if host and od > 5:
+        pytest.skip("CPU-tensor rules are restated (left to right) for up to 4 terms, i.e. order_dim <= 5: torch's CPU "
+                    "reduction of more terms uses several accumulators and no CPU-made fixture has order_dim > 4")
     K, sdim = 11, 1
     A = od + sdim - 1
     g = torch.Generator().manual_seed(B * 10 + od)
