@@ -12,11 +12,11 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libconsolver.so")
 
 F32, F16, BF16 = 0, 1, 2
-DPM_CONVERT_NONE, DPM_CONVERT_DIV, DPM_CONVERT_LIN = 0, 1, 2
+DPM_CONVERT_NONE, DPM_CONVERT_DIV, DPM_CONVERT_LIN, DPM_CONVERT_DIV_RECIP = 0, 1, 2, 3
 FLAG_VPRED, FLAG_EFF_SCALE, FLAG_X_SCALE, FLAG_PDL, FLAG_CHAIN, FLAG_LOWP_COMBINE, FLAG_X_F32, FLAG_X_WAS_LOWP = 1, 2, 4, 8, 16, 32, 64, 128
 FLAG_HOST_SCALARS, FLAG_LOWP_COEF = 256, 512
 POLICY_HOST_DIV, POLICY_ACT_F16, POLICY_ACT_BF16, POLICY_COEF_F16, POLICY_COEF_BF16 = 1, 2, 4, 8, 16
-ABI_VERSION = 7          # must equal CONSOLVER_ABI_VERSION of include/consolver.h (tests/test_abi_cpu.py checks)
+ABI_VERSION = 8          # must equal CONSOLVER_ABI_VERSION of include/consolver.h (tests/test_abi_cpu.py checks)
 MAX_ORDER, MAX_HIDDEN, MAX_LOGITS, MAX_IN = 8, 1024, 4096, 16
 
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64

@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(512) dpm_step_kernel(const DpmParams p) {
       float m0;
       if (p.convert == CONSOLVER_DPM_CONVERT_DIV) {
         m0 = __fdiv_rn(__fsub_rn(xs, __fmul_rn(p.ck0, eps)), p.ck1);
+      } else if (p.convert == CONSOLVER_DPM_CONVERT_DIV_RECIP) {
+        m0 = __fmul_rn(__fsub_rn(xs, __fmul_rn(p.ck0, eps)), __fdiv_rn(1.f, p.ck1));   // ATen CUDA: t / scalar
       } else if (p.convert == CONSOLVER_DPM_CONVERT_LIN) {
         m0 = __fadd_rn(__fmul_rn(p.ck1, xs), __fmul_rn(p.ck0, eps));
       } else {
@@ -140,7 +142,7 @@ extern "C" int consolver_step_dpm(int dtype, int x_dtype, const void* e0, const 
   if (!e0 || !x || !x_out || !upd) return CONSOLVER_ERR_NULL;
   if (m2 && !m1) return CONSOLVER_ERR_NULL;
   if (B <= 0 || n_per_sample <= 0) return CONSOLVER_ERR_SIZE;
-  if (convert < CONSOLVER_DPM_CONVERT_NONE || convert > CONSOLVER_DPM_CONVERT_LIN) return CONSOLVER_ERR_UNSUPPORTED;
+  if (convert < CONSOLVER_DPM_CONVERT_NONE || convert > CONSOLVER_DPM_CONVERT_DIV_RECIP) return CONSOLVER_ERR_UNSUPPORTED;
   if (x_dtype != dtype && x_dtype != CONSOLVER_F32) return CONSOLVER_ERR_DTYPE;
   DpmParams p{};
   p.e0 = e0; p.cond = cond; p.slot_out = slot_out; p.m1 = m1; p.m2 = m2; p.x = x; p.x_out = x_out; p.x_out2 = x_out2;

@@ -114,6 +114,12 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
         self._plans = None
         self._ring = None
         self._n_prev = 0
+        #: "cuda" (default): `(sample - sigma*e) / alpha` of convert_model_output as ATen evaluates it on CUDA tensors (a
+        #: multiplication by the fp32 reciprocal of the host-resident scalar); "cpu": the true division of a run on CPU
+        #: tensors (what the amed_* fixtures were made under).  See _sched_common.SolverOptions.reference_device.
+        from . import _sched_common
+
+        self.reference_device = _sched_common.DEFAULT_REFERENCE_DEVICE
 
     # ---- reference / diffusers surface -------------------------------------------------------------------------
     @property
@@ -347,7 +353,8 @@ class DPMSolverMultistepScheduler(SchedulerMixin, ConfigMixin):
             cond.data_ptr() if cond is not None else None, guidance, slot.data_ptr(), m1, m2,
             sample.data_ptr(), x_out.data_ptr(),
             out2.data_ptr() if out2 is not None else None, out2.stride(0) if out2 is not None else 0,
-            p.convert, p.ck0, p.ck1, ctypes.byref(upd), B, N, stream)
+            (_lib.DPM_CONVERT_DIV_RECIP if p.convert == _lib.DPM_CONVERT_DIV and self.reference_device == "cuda"
+             else p.convert), p.ck0, p.ck1, ctypes.byref(upd), B, N, stream)
         _lib.check(rc, "consolver_step_dpm")
         self._n_prev = min(self._n_prev + 1, 2)
         self._advance()

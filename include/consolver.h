@@ -25,7 +25,7 @@ extern "C" {
 
 /* Bumped on EVERY change of a signature, struct layout or flag meaning in this header.  Loaders must also compare
  * consolver_abi_hash() with the hash of the header they were written against (see consolver_abi_hash below). */
-#define CONSOLVER_ABI_VERSION 7
+#define CONSOLVER_ABI_VERSION 8
 
 /* element type of latents / model outputs */
 #define CONSOLVER_F32  0
@@ -260,7 +260,7 @@ CONSOLVER_API int consolver_step_fm_strided(int dtype, int x_dtype, const void* 
  * (diffusers_amed_plugin_dpmpp.py:70-138, :140-262, :264-348) with one pass over HBM.  Scalars are computed by the host the way
  * the plugin computes them (0-d fp32 tensors) and handed in:
  *   m0 = e                            convert == CONSOLVER_DPM_CONVERT_NONE
- *      = (x - ck0*e) / ck1                        CONSOLVER_DPM_CONVERT_DIV   (dpmsolver++ / epsilon: ck0 = sigma_s, ck1 = alpha_s)
+ *      = (x - ck0*e) / ck1                        CONSOLVER_DPM_CONVERT_DIV / _DIV_RECIP   (dpmsolver++ / epsilon: ck0 = sigma_s, ck1 = alpha_s)
  *      = ck1*x + ck0*e                            CONSOLVER_DPM_CONVERT_LIN   (v-prediction forms)
  *   x'  = cx*x - a0*m0                                          m1 == NULL            (first order,  :121/:123)
  *       = (cx*x - a0*m0) - a1*D                                 m1 != NULL, m2 == NULL (second order, :201-208)
@@ -274,6 +274,9 @@ CONSOLVER_API int consolver_step_fm_strided(int dtype, int x_dtype, const void* 
 #define CONSOLVER_DPM_CONVERT_NONE 0
 #define CONSOLVER_DPM_CONVERT_DIV  1
 #define CONSOLVER_DPM_CONVERT_LIN  2
+#define CONSOLVER_DPM_CONVERT_DIV_RECIP 3   /* DIV as ATen evaluates it on CUDA tensors: (x - ck0*e) * (1/ck1), the
+                                              reciprocal of the host-resident scalar taken once in fp32 (DIV itself is
+                                              the true division of a run on CPU tensors)                              */
 typedef struct consolver_dpm_update {   /* host struct, fp32 values of the plugin's 0-d tensors */
   float cx, a0;              /* all orders                                                                 */
   float a1, rinv;            /* second and third order: rinv = 1/r0                                        */

@@ -214,30 +214,25 @@ AMED8 = ([999, 831, 749, 623, 500, 394, 250, 88, 0], [1.0, 0.9976, 1.0, 0.991, 1
 
 @pytest.mark.parametrize("over", [dict(), dict(algorithm_type="dpmsolver"), dict(prediction_type="v_prediction"),
                                   dict(solver_order=3), dict(solver_type="heun")])
-def test_amed_plugin_next_to_the_reference_reports_its_cuda_gap(over):
-    """AMED plugin (diffusers_amed_plugin_dpmpp.py) over the restated stand-in of its absent diffusers base class, run on
-    the GPU next to the drop-in.  The drop-in's DPM kernel follows the CPU-tensor rules its fixtures were made under
-    (true division in convert_model_output), so on CUDA tensors — where ATen turns `/ alpha_t` into a reciprocal
-    multiply — a gap of an ulp per step is expected for the epsilon / v forms: it is MEASURED and bounded here (1e-5
-    relative per step, the north-star bar), not hidden.  This baseline is only partially pinned anyway."""
+def test_amed_plugin_next_to_the_reference(over):
+    """AMED plugin (diffusers_amed_plugin_dpmpp.py, unmodified) over the restated stand-in of its absent diffusers base
+    class, run on the GPU next to the drop-in: every step bit-identical (the division by the host-resident alpha_t in
+    convert_model_output is a reciprocal multiply on CUDA tensors — CONSOLVER_DPM_CONVERT_DIV_RECIP).  The inherited half
+    of this baseline stays pinned only to the restatement of the published algorithm."""
     import consolver_b200 as cb
 
     ref = ref_shim.load_reference()
     cfg = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1, **over)
     ts, dirs, times = AMED8
     r, o = ref.AMEDDPMSolverMultistepScheduler(**cfg), cb.DPMSolverMultistepScheduler(**cfg)
+    assert o.reference_device == "cuda"
     for s in (r, o):
         s.scale_dirs, s.scale_times = dirs, times
         s.set_timesteps(8, device="cuda", timesteps=ts)
     g = torch.Generator().manual_seed(8)
     xr = xo = torch.randn(2, 4, 16, 16, generator=g).cuda()
-    worst = 0.0
     for i in range(8):
         e = torch.randn(2, 4, 16, 16, generator=g).cuda()
         xr = r.step(e, r.timesteps[i], xr, return_dict=False)[0]
-        xo = o.step(e, o.timesteps[i], xr, return_dict=False)[0] if False else o.step(e, o.timesteps[i], xo, return_dict=False)[0]
-        rel = float((xo - xr).abs().max() / xr.abs().max())
-        worst = max(worst, rel)
-        assert rel <= 1e-5, f"{over} step {i}: {rel}"
-        xo = xr.clone()                      # re-anchor: per-step bound
-    print(f"\\nAMED {over}: worst per-step relative gap vs the plugin on CUDA tensors: {worst:.2e}")
+        xo = o.step(e, o.timesteps[i], xo, return_dict=False)[0]
+        assert torch.equal(xo, xr), f"{over} step {i}: {float((xo - xr).abs().max() / xr.abs().max()):.2e}"
