@@ -236,3 +236,42 @@ def test_amed_plugin_next_to_the_reference(over):
         xr = r.step(e, r.timesteps[i], xr, return_dict=False)[0]
         xo = o.step(e, o.timesteps[i], xo, return_dict=False)[0]
         assert torch.equal(xo, xr), f"{over} step {i}: {float((xo - xr).abs().max() / xr.abs().max()):.2e}"
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_use_conv_policies_step_for_step(case):
+    """use_conv=True (factor_net_ppo.py:108-130,:146-149): per-sample cosine features of the history feed the MLP.  fp32
+    model outputs, SD and FM: own sampling, latents bit-identical; tables within the reduction-order spread of the
+    feature kernel vs torch's cosine_similarity."""
+    rng = random.Random(3000 + case)
+    kind = "sd" if case % 2 == 0 else "fm"
+    od = rng.choice([3, 4])
+    n, B = rng.choice([5, 8]), rng.choice([2, 3])
+    if kind == "sd":
+        cfg = dict(order_dim=od, scaler_dim=rng.choice([0, 2]), prediction_type=rng.choice(["epsilon", "v_prediction"]),
+                   **dict(SD_PROD, use_conv=True))
+        shape = (4, 16, 16)
+    else:
+        cfg = dict(shift=3.0, use_dynamic_shifting=True, order_dim=od, scaler_dim=0, mu_dim=0, use_conv=True)
+        shape = (64, 16)
+    r, o = _pair(kind, seed=300 + case, last_std=0.5 if kind == "sd" else 0.02, **cfg)
+    for s in (r, o):
+        if kind == "sd":
+            s.set_timesteps(n, device="cuda")
+        else:
+            s.set_timesteps(n, device="cuda", sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+            s.set_begin_index(0)
+    g = torch.Generator().manual_seed(case)
+    xr = xo = torch.randn(B, *shape, generator=g).cuda()
+    for i in range(n):
+        e = torch.randn(B, *shape, generator=g).cuda()
+        torch.manual_seed(9 + i)
+        with ref_shim.quiet(), torch.no_grad():
+            xr, ar, pr, cr, mr = r.step(e, r.timesteps[i], xr, return_dict=False)
+        torch.manual_seed(9 + i)
+        with torch.no_grad():
+            xo, ao, po, co, mo = o.step(e, o.timesteps[i], xo, return_dict=False)
+        tag = f"case {case} ({kind}, {cfg}) step {i}"
+        assert torch.equal(ao, ar), tag + ": actions"
+        torch.testing.assert_close(po, pr, rtol=2e-4, atol=2e-6)
+        assert torch.equal(xo, xr), tag + ": latent"
