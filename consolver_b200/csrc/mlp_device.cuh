@@ -42,29 +42,42 @@ __device__ __forceinline__ float policy_input(float x, float x_div, int flags) {
 //                   thread x accumulates s_x, s_{x+W}, ... (4 accumulators, combined in order), then a shuffle tree
 //                   with DECREASING offsets — three terms give (s0 + s2) + s1
 enum : int { kSumSequential = 0, kSumCudaBatch = 1, kSumCudaSingle = 2 };
-__device__ __forceinline__ float sum_terms(const float* s, int m, int mode) {
-  if (m <= 0) return 0.f;
+static_assert(CONSOLVER_MAX_ORDER == 8, "sum_terms is unrolled for at most 7 terms");
+
+// one thread's share of the B == 1 form: terms x, x+W, x+2W, x+3W into four accumulators, combined in order
+template <int W>
+__device__ __forceinline__ float sum_single_lane(const float (&s)[8], int m, int x) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (x + k * W < 8 && x + k * W < m) acc[k] = __fadd_rn(acc[k], s[(x + k * W) & 7]);
+  return __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
+}
+
+// every loop has a constant trip count and every array index is a compile-time constant after unrolling, so s[] and the
+// accumulators stay in registers (a version with run-time indices put a 96-byte stack frame into the sample kernel)
+__device__ __forceinline__ float sum_terms(const float (&s)[8], int m, int mode) {
   if (mode == kSumSequential) {
     float run = s[0];
-    for (int i = 1; i < m; ++i) run = __fadd_rn(run, s[i]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+      if (i < m) run = __fadd_rn(run, s[i]);
     return run;
   }
   if (mode == kSumCudaBatch) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < m; ++i) acc[i & 3] = __fadd_rn(acc[i & 3], s[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < m) acc[i & 3] = __fadd_rn(acc[i & 3], s[i]);
     return __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
   }
-  int W = 1;
-  while (W * 2 <= m) W *= 2;                       // last_pow2(m): 1, 2 or 4 for m <= 7
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int x = 0; x < W; ++x) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < 4 && x + k * W < m; ++k) acc[k] = __fadd_rn(acc[k], s[x + k * W]);
-    t[x] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
+  if (m >= 4) {                                    // W = last_pow2(m) = 4: lanes 0..3, tree offsets 2 then 1
+    const float t0 = sum_single_lane<4>(s, m, 0), t1 = sum_single_lane<4>(s, m, 1);
+    const float t2 = sum_single_lane<4>(s, m, 2), t3 = sum_single_lane<4>(s, m, 3);
+    return __fadd_rn(__fadd_rn(t0, t2), __fadd_rn(t1, t3));
   }
-  for (int off = W >> 1; off > 0; off >>= 1)
-    for (int x = 0; x < off; ++x) t[x] = __fadd_rn(t[x], t[x + off]);
-  return t[0];
+  if (m >= 2) return __fadd_rn(sum_single_lane<2>(s, m, 0), sum_single_lane<2>(s, m, 1));      // W = 2
+  return sum_single_lane<1>(s, m, 0);                                                            // W = 1
 }
 
 // set_default_coefficients (scheduler_ppo.py:165-175) for one sample: act[0..A) are the sampled action values, c the
@@ -73,19 +86,24 @@ __device__ __forceinline__ float sum_terms(const float* s, int m, int mode) {
 // dtype; torch.sum returns fp32 under autocast, so the sum and the closing coefficient are fp32.
 __device__ __forceinline__ void write_coef_record(const float* act, float* c, int n, int od, int scaler_dim, int cm,
                                                   int sum_mode) {
-  float terms[CONSOLVER_MAX_ORDER];
-  terms[0] = round_act(__fadd_rn(act[0], 1.f), cm);
-  for (int i = 1; i < n - 1; ++i) terms[i] = act[i];
-  for (int i = 0; i < od; ++i) {
-    float v = 0.f;
-    if (n == 1) {
-      v = (i == 0) ? 1.f : 0.f;               // the step kernel bypasses the coefficient when n_hist == 1
-    } else if (i < n - 1) {
-      v = terms[i];
-    } else if (i == n - 1) {
-      v = __fsub_rn(1.f, sum_terms(terms, n - 1, sum_mode));
+  float terms[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    terms[i] = (i < n - 1) ? (i == 0 ? round_act(__fadd_rn(act[0], 1.f), cm) : act[i]) : 0.f;
+  const float last = (n > 1) ? __fsub_rn(1.f, sum_terms(terms, n - 1, sum_mode)) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < od) {
+      float v = 0.f;
+      if (n == 1) {
+        v = (i == 0) ? 1.f : 0.f;             // the step kernel bypasses the coefficient when n_hist == 1
+      } else if (i < n - 1) {
+        v = terms[i];
+      } else if (i == n - 1) {
+        v = last;
+      }
+      c[i] = v;
     }
-    c[i] = v;
   }
   c[od] = scaler_dim >= 1 ? round_act(__fadd_rn(act[od - 1], 1.f), cm) : 1.f;
   c[od + 1] = scaler_dim >= 2 ? round_act(__fadd_rn(act[od], 1.f), cm) : 1.f;
