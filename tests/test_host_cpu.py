@@ -1,5 +1,7 @@
 """Host-side logic of the drop-in schedulers (no GPU): constructor/config surface, schedules against the golden
 vectors, state_dict interchange, error behaviour, lazy conds."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -295,3 +297,78 @@ def test_amed_scheduler_surface_and_errors():
     s2.set_timesteps(4, timesteps=[999, 694, 500, 110, 0])
     assert s2.timesteps.tolist()[0] == 999 and s2.timesteps.tolist()[2] == 500 and len(s2.timesteps) == 4
     assert s2.num_inference_steps == 5                        # plugin :60 counts the trailing 0
+
+
+# ---- round-2 host logic --------------------------------------------------------------------------------------------------
+def test_lazy_conds_is_a_complete_mapping_and_guards_stale_ring_reads():
+    from consolver_b200.config_utils import LazyConds
+
+    calls = []
+    x = torch.zeros(2, 2)
+
+    def thunk():
+        calls.append(1)
+        return torch.ones(2, 4, 3)
+
+    c = LazyConds(x, thunk)
+    assert len(c) == 2 and "epsilon" in c and not calls            # nothing materialised by len / contains
+    assert set(iter(c)) == {"x", "epsilon"} and len(calls) == 1     # iteration materialises (dict(conds), {**conds})
+    assert dict(c)["epsilon"].shape == (2, 4, 3) and len(calls) == 1
+    c2 = LazyConds(x, thunk)
+    assert set({**c2}) == {"x", "epsilon"} and c2.copy()["epsilon"].sum() == 24
+    alive = [True]
+    stale = LazyConds(x, thunk, still_valid=lambda: alive[0])
+    alive[0] = False
+    with pytest.raises(RuntimeError, match="history ring had been overwritten"):
+        stale["epsilon"]
+    with pytest.raises(RuntimeError, match="history ring had been overwritten"):
+        dict(stale)
+    ok = LazyConds(x, thunk, still_valid=lambda: True)
+    assert ok.get("epsilon").shape == (2, 4, 3)
+
+
+def test_reference_semantics_flags_follow_the_policy_dtype_and_the_device_setting(monkeypatch):
+    from consolver_b200 import _lib, _sched_common
+
+    s = cb.PPOScheduler(**PROD)
+    assert s.reference_device == "cuda"                                               # product default
+    assert s._semantics(torch.float32) == (0, 0, None)
+    s.reference_device = "cpu"
+    assert s._semantics(torch.float32) == (_lib.FLAG_HOST_SCALARS, _lib.POLICY_HOST_DIV, None)
+    s.reference_device = "tpu"
+    with pytest.raises(ValueError):
+        s._semantics(torch.float32)
+    s.reference_device = "cuda"
+    s.factor_net.to(torch.float16)                                                    # gen_ppo.py:194-195: bins too
+    sf, pf, act = s._semantics(torch.float16)
+    assert sf == _lib.FLAG_LOWP_COEF and pf == _lib.POLICY_ACT_F16 | _lib.POLICY_COEF_F16 and act == torch.float16
+    assert s._semantics(torch.float32)[0] == 0                 # fp32 model outputs: the 16-bit coefficients just promote
+    assert s._estimate_stays_lowp(torch.float16, 1) and not s._estimate_stays_lowp(torch.float16, 2)
+    monkeypatch.setattr(_sched_common, "DEFAULT_REFERENCE_DEVICE", "cpu")
+    assert cb.PPOScheduler(**PROD).reference_device == "cpu"
+    assert cb.DPMSolverMultistepScheduler().reference_device == "cpu"
+    f = cb.FMPPOScheduler(order_dim=2, scaler_dim=0, mu_dim=0)
+    assert f._semantics(torch.bfloat16)[1] == _lib.POLICY_HOST_DIV
+
+
+def test_stage_ref_copies_byte_identical_files_with_a_manifest(tmp_path):
+    import stage_ref
+
+    if not os.path.isdir(stage_ref.SOURCE):
+        pytest.skip("reference tree not present")
+    dest = tmp_path / "_ref"
+    assert stage_ref.stage(dest=str(dest), quiet=True)
+    assert stage_ref.verify(str(dest))
+    for rel in stage_ref.FILES:
+        assert open(os.path.join(stage_ref.SOURCE, rel), "rb").read() == open(dest / rel, "rb").read()
+    (dest / "scheduler_ppo.py").write_text("# edited\n")
+    assert not stage_ref.verify(str(dest))                     # an edited copy no longer matches its recorded hash
+    assert not stage_ref.stage(source=str(tmp_path / "nowhere"), dest=str(dest), quiet=True)
+
+
+def test_bench_arms_print_the_same_config():
+    import importlib
+
+    bench = importlib.import_module("bench")
+    a, b = bench.workload_config(64, 8), bench.workload_config(64, 8)
+    assert a == b and a["workload"] == bench.WORKLOAD and "l2_policy" in a and a["batch_per_gpu"] == 64
