@@ -395,8 +395,8 @@ def run_ours(args, rank, world, device):
     if not args.eager:
         pool_n = max(pool_n, 2 * max(1, args.streams))     # two resident batches per stream
         if not args.no_groups and args.streams > 1:
-            # preview groups (see below): `group_rotation` groups of `streams` previews replayed round-robin, one stream
-            # each, so that one group's join never leaves the GPU short of work
+            # preview groups (see below) of `group_size` previews each, replayed round-robin over a pool of at least
+            # `pool` resident batches
             gsz = args.group_size or args.streams
             pool_n = max(pool_n, args.group_rotation * gsz, args.pool)
             pool_n -= pool_n % gsz
@@ -427,11 +427,11 @@ def run_ours(args, rank, world, device):
 
     ppool = None if args.eager else PreviewPool([p[3] for p in pool], streams=args.streams)
     n_streams = 1 if ppool is None else len(ppool.streams)
-    # Groups of `streams` previews captured as ONE graph each (denoise.PreviewGroup: one branch per preview, one shared
-    # device-resident generator state): one host launch and one generator update per g previews instead of per preview.
-    # Without it the host needs ~30 us per preview, as much as the GPU does, and eight ranks sharing one host's cores
-    # become host-bound.  Previews are still taken round-robin from the pool; a stretch that is not aligned to a
-    # group (warm-up of 5, say) goes through the per-preview graphs.
+    # Groups of `group_size` previews captured as ONE graph each (denoise.PreviewGroup: a serial chain of previews, one
+    # shared device-resident generator state): one host launch and one generator update per g previews instead of per
+    # preview.  Without it the host needs ~30 us per preview, as much as the GPU does, and eight ranks sharing one host's
+    # cores become host-bound.  Previews are still taken round-robin from the pool; a stretch that is not aligned to a
+    # group goes through the per-preview graphs.
     groups, g = [], 0
     if ppool is not None and n_streams > 1 and not args.no_groups:
         from consolver_b200.denoise import PreviewGroup
@@ -442,7 +442,7 @@ def run_ours(args, rank, world, device):
         # n_groups groups on n_groups streams, every stream a gap-free chain of previews
         groups = [PreviewGroup([pool[j][3] for j in range(i, i + g)], rotation=n_groups, parallel=not args.serial_groups)
                   for i in range(0, n_groups * g, g)]
-    # one stream per group: consecutive group replays overlap (a group's join would otherwise drain the GPU)
+    # the groups are replayed round-robin on `group_rotation` streams: every stream is a gap-free chain of previews
     gpool = PreviewPool(groups, streams=min(len(groups), args.group_rotation), stagger_us=args.stagger_us) \
         if groups else None
     counts = {"group_replays": 0, "single_replays": 0}
@@ -640,8 +640,9 @@ def run_ours(args, rank, world, device):
         "config": workload_config(B, world),
         "run": {"pool": f"rotating pool of {pool_n} resident batches ({pool_n * bytes_per_batch >> 20} MiB)",
                 "launch": "eager python launches" if args.eager else
-                "one CUDA graph per 8-step preview (table kernel, sample kernels on a side stream, PDL-chained step "
-                "kernels, rng-advance node); valid because the stand-in model outputs are resident",
+                "CUDA graphs of whole 8-step previews (per preview: table kernel, sample kernels as a parallel branch, "
+                "PDL-chained step kernels; one rng-advance node per graph); valid because the stand-in model outputs are "
+                "resident",
                 "concurrency": f"{n_streams} independent preview batch(es) in flight" + (
                     f": groups of {g} previews captured as one CUDA graph ("
                     + ("a serial chain per group" if args.serial_groups else f"{g} parallel branches") +
