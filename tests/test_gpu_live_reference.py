@@ -275,3 +275,132 @@ def test_use_conv_policies_step_for_step(case):
         assert torch.equal(ao, ar), tag + ": actions"
         torch.testing.assert_close(po, pr, rtol=2e-4, atol=2e-6)
         assert torch.equal(xo, xr), tag + ": latent"
+
+
+# ---- wider random space (order_dim up to 8, K = 3..161, batch up to 64, full-size latents, every way a caller hands over the
+# timestep, step() and step_cfg()).  CONSOLVER_FUZZ_CASES scales the number of drawn cases for one-off deep runs
+# (profiles/live_fuzz_r02.md records one with several hundred); the default keeps the GPU suite short. ----------------------
+WIDE_CASES = int(os.environ.get("CONSOLVER_FUZZ_CASES", "24"))
+
+
+def _wide_pair(kind, seed, hidden, K, last_std, **cfg):
+    import consolver_b200 as cb
+
+    ref = ref_shim.load_reference()
+    fkw = dict(hidden_dim=hidden, num_actions=K)
+    with ref_shim.quiet():
+        if kind == "sd":
+            r = ref.PPOScheduler(factor_net_kwargs=dict(embedding_dim=64, **fkw), **cfg)
+            o = cb.PPOScheduler(factor_net_kwargs=dict(embedding_dim=64, **fkw), **cfg)
+        else:
+            r = ref.FMPPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
+            o = cb.FMPPOScheduler(factor_net_kwargs=dict(fkw), **cfg)
+    _seed_policy(r.factor_net, seed, last_std)
+    o.factor_net.load_state_dict(r.factor_net.state_dict())
+    r.factor_net.cuda(), o.factor_net.cuda()
+    return r, o
+
+
+def _hand_over(style, sched, i):
+    """the ways callers pass the timestep: a 0-d view of scheduler.timesteps (`for t in scheduler.timesteps`), a python
+    int, a clone on the device, a CPU tensor"""
+    t = sched.timesteps[i]
+    return {"view": lambda: t, "int": lambda: int(t), "clone": lambda: t.clone(), "cpu": lambda: t.cpu()}[style]()
+
+
+@pytest.mark.parametrize("case", range(WIDE_CASES))
+def test_wide_random_sd_configurations_step_for_step(case):
+    rng = random.Random(7000 + case)
+    od = rng.choice([2, 3, 4, 4, 5, 6, 8])
+    cfg = dict(order_dim=od, scaler_dim=rng.choice([0, 0, 1, 2]),
+               prediction_type=rng.choice(["epsilon", "epsilon", "v_prediction"]),
+               timestep_spacing=rng.choice(["trailing", "leading", "linspace"]),
+               beta_schedule=rng.choice(["scaled_linear", "linear", "squaredcos_cap_v2"]),
+               beta_start=0.00085, beta_end=0.012, steps_offset=rng.choice([0, 1]), use_conv=False)
+    K = rng.choice([3, 11, 11, 161])
+    hidden = rng.choice([16, 64, 256])
+    n = rng.choice([1, 2, 4, 8, 15, 21])
+    B = rng.choice([1, 2, 5, 33, 64])
+    shape = rng.choice([(4, 8, 8), (3, 5, 7), (1, 1, 33), (4, 32, 32)] + ([(4, 64, 64)] if B <= 5 else []))
+    flow = rng.choice(["f32", "f32", "f32", "f16_out", "bf16_out", "f16_pipeline", "bf16_pipeline", "autocast_f16",
+                       "autocast_bf16", "genppo_f16", "genppo_bf16"])
+    style = rng.choice(["view", "view", "int", "clone", "cpu"])
+    fused_cfg = rng.choice([False, True])
+    guidance = rng.choice([3.0, 7.5, 1.0])
+    r, o = _wide_pair("sd", case, hidden, K, rng.choice([0.5, 0.05, 2.0]), **cfg)
+    mdt = torch.float32 if flow == "f32" else (torch.float16 if "f16" in flow and "bf16" not in flow else torch.bfloat16)
+    xdt = mdt if flow.endswith("_pipeline") or flow.startswith("genppo") else torch.float32
+    ac = mdt if flow.startswith(("autocast", "genppo")) else None
+    if flow.startswith("genppo"):
+        r.factor_net.to("cuda", dtype=mdt), o.factor_net.to("cuda", dtype=mdt)
+    r.set_timesteps(n, device="cuda"), o.set_timesteps(n, device="cuda")
+    g = torch.Generator().manual_seed(case)
+    xr = xo = torch.randn(B, *shape, generator=g).to(xdt).cuda()
+    ctx = (lambda: torch.autocast("cuda", ac)) if ac is not None else __import__("contextlib").nullcontext
+    tag0 = f"wide case {case} ({flow}, K={K}, H={hidden}, n={n}, B={B}, {shape}, t as {style}, cfg={fused_cfg}, {cfg})"
+    for i in range(n):
+        pair = torch.randn(2 * B, *shape, generator=g).to(mdt).cuda()
+        u, c = pair.chunk(2)
+        e = u + guidance * (c - u)                       # the caller's combine, denoise_ppo.py:96-100
+        torch.manual_seed(77 + i)
+        with ref_shim.quiet(), ctx(), torch.no_grad():
+            xr, ar, pr, cr, mr = r.step(e, _hand_over(style, r, i), xr, return_dict=False)
+        rng_after_ref = torch.cuda.get_rng_state()
+        torch.manual_seed(77 + i)
+        with ctx(), torch.no_grad():
+            if fused_cfg:
+                xo, ao, po, co, mo = o.step_cfg(pair, _hand_over(style, o, i), xo, guidance)
+                assert torch.equal(o.ets[-1], e), tag0 + f" step {i}: ring slot != caller-side combine"
+            else:
+                xo, ao, po, co, mo = o.step(e, _hand_over(style, o, i), xo, return_dict=False)
+        tag = tag0 + f" step {i}"
+        assert ao.dtype == ar.dtype and torch.equal(ao, ar), tag + ": actions"
+        assert torch.equal(mo, mr) and torch.equal(co["x"], cr["x"]), tag
+        torch.testing.assert_close(po, pr, rtol=1.2e-4 if ac is not None else 0, atol=6e-6 if ac is not None else 1e-6)
+        assert xo.dtype == xr.dtype, tag + f": latent dtype {xo.dtype} vs {xr.dtype}"
+        assert torch.equal(xo, xr), tag + ": latent"
+        assert torch.equal(torch.cuda.get_rng_state(), rng_after_ref), tag + ": default generator consumed differently"
+
+
+@pytest.mark.parametrize("case", range(max(WIDE_CASES // 2, 1)))
+def test_wide_random_fm_configurations_step_for_step(case):
+    rng = random.Random(8000 + case)
+    od = rng.choice([2, 2, 3, 4, 6])
+    cfg = dict(shift=rng.choice([3.0, 1.0]), use_dynamic_shifting=rng.choice([True, True, False]), order_dim=od,
+               scaler_dim=rng.choice([0, 0, 1, 2]), mu_dim=rng.choice([0, 0, 1]))
+    K = rng.choice([3, 11, 11, 161])
+    hidden = rng.choice([16, 64, 256])
+    n = rng.choice([1, 2, 5, 8, 15])
+    B = rng.choice([1, 2, 4, 16])
+    shape = rng.choice([(16, 8), (5, 7), (64, 16), (256, 64)] + ([(4096, 64)] if B <= 2 else []))
+    dt = rng.choice([torch.bfloat16, torch.bfloat16, torch.float32, torch.float16])
+    style = rng.choice(["view", "view", "clone", "float"])
+    last_std = rng.choice([0.02, 0.002, 0.1])
+    r, o = _wide_pair("fm", 50 + case, hidden, K, last_std, **cfg)
+    # softmax(logits / 0.01): a rounding difference of the logits is multiplied by 100, and the logits grow with the last
+    # layer's scale — the measured 8e-6 (DESIGN §4) belongs to last_std 0.02
+    p_rtol = 8e-6 * max(1.0, last_std / 0.02)
+    for s in (r, o):
+        if cfg["use_dynamic_shifting"]:
+            s.set_timesteps(n, device="cuda", sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+        else:
+            s.set_timesteps(n, device="cuda")
+        s.set_begin_index(0)
+    g = torch.Generator().manual_seed(case)
+    xr = xo = torch.randn(B, *shape, generator=g).to(dt).cuda()
+    hand = lambda s, i: float(s.timesteps[i]) if style == "float" else _hand_over(style, s, i)  # noqa: E731
+    for i in range(n):
+        v = torch.randn(B, *shape, generator=g).to(dt).cuda()
+        torch.manual_seed(5 + i)
+        with ref_shim.quiet(), torch.no_grad():
+            xr, ar, pr, cr, mr = r.step(v, hand(r, i), xr, return_dict=False)
+        rng_after_ref = torch.cuda.get_rng_state()
+        torch.manual_seed(5 + i)
+        with torch.no_grad():
+            xo, ao, po, co, mo = o.step(v, hand(o, i), xo, return_dict=False)
+        tag = f"wide fm case {case} (K={K}, H={hidden}, n={n}, B={B}, {shape}, {dt}, t as {style}, {cfg}) step {i}"
+        assert torch.equal(ao, ar), tag + ": actions"
+        assert torch.equal(mo, mr) and torch.equal(co["x"], cr["x"]), tag
+        torch.testing.assert_close(po, pr, rtol=p_rtol, atol=1e-6)
+        assert xo.dtype == xr.dtype and torch.equal(xo, xr), tag + ": latent"
+        assert torch.equal(torch.cuda.get_rng_state(), rng_after_ref), tag + ": default generator consumed differently"
