@@ -80,6 +80,25 @@ __device__ __forceinline__ void st16(void* p, const uint4& v) {
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- loads of data the PDL PRIMARY produces (the coefficient record; under CHAIN the latent and the newest slot) ----
+// They sit after griddepcontrol.wait and must stay there.  `__ldg` / ld.global.nc declare the memory read-only for the
+// kernel's lifetime, which (a) is not true of such data — the primary is still writing it when this grid starts — and
+// (b) lets nvcc treat the load as invariant and HOIST IT ABOVE THE WAIT: seen in SASS as LDG.E.CONSTANT of the
+// coefficient record before ACQBULK in 12 instantiations (16-bit depth-1 and the runtime-depth forms), where the live
+// differential fuzzing caught stale coefficients (profiles/live_fuzz_r02.md).  These are volatile asm statements, which
+// the compiler keeps in order with the wait, on the L2-coherent path (.cg): no L1 line of an earlier grid can serve them.
+__device__ __forceinline__ float ld_produced_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_produced16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
 // A thread-vector of E elements of type T held as raw 16-byte words (E*sizeof(T) is 16 or 32 bytes).
 template <typename T, int E> struct Raw {
   static constexpr int kWords = (E * (int)sizeof(T)) / 16;
@@ -87,6 +106,11 @@ template <typename T, int E> struct Raw {
   __device__ __forceinline__ void load(const T* p) {
 #pragma unroll
     for (int i = 0; i < kWords; ++i) w[i] = ld_stream16(reinterpret_cast<const char*>(p) + 16 * i);
+  }
+  // data written by the PDL primary (see ld_produced16)
+  __device__ __forceinline__ void load_produced(const T* p) {
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) w[i] = ld_produced16(reinterpret_cast<const char*>(p) + 16 * i);
   }
   __device__ __forceinline__ void store(T* p) const {
 #pragma unroll
@@ -99,6 +123,17 @@ template <typename T, int E> struct Raw {
 template <typename T> struct Raw<T, 1> {
   T v;
   __device__ __forceinline__ void load(const T* p) { v = __ldg(p); }
+  __device__ __forceinline__ void load_produced(const T* p) {
+    if constexpr (sizeof(T) == 4) {
+      unsigned r;
+      asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+      v = *reinterpret_cast<const T*>(&r);
+    } else {
+      unsigned short r;
+      asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+      v = *reinterpret_cast<const T*>(&r);
+    }
+  }
   __device__ __forceinline__ void store(T* p) const { *p = v; }
   __device__ __forceinline__ float get(int) const { return Elem<T>::to_f(v); }
   __device__ __forceinline__ void set(int, float f) { v = Elem<T>::from_f(f); }

@@ -75,19 +75,20 @@ __global__ void __launch_bounds__(512) step_kernel(const StepParams p) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (live[u]) {
-        r_x[u].load(static_cast<const TX*>(p.x) + off[u]);
-        if (kOlder > 0 && (NH || 0 < nh - 1)) r_h[u][0].load(static_cast<const T*>(p.hist[0]) + off[u] + edelta);
+        r_x[u].load_produced(static_cast<const TX*>(p.x) + off[u]);
+        if (kOlder > 0 && (NH || 0 < nh - 1))
+          r_h[u][0].load_produced(static_cast<const T*>(p.hist[0]) + off[u] + edelta);
       }
     }
   }
   const float* cf = p.coef + (long long)b * p.coef_stride;
   float c[kOlder + 1];
 #pragma unroll
-  for (int j = 0; j < kOlder + 1; ++j) c[j] = (j < nh && nh > 1) ? __ldg(cf + j) : 0.f;
+  for (int j = 0; j < kOlder + 1; ++j) c[j] = (j < nh && nh > 1) ? ld_produced_f32(cf + j) : 0.f;
   const bool eff_scale = p.flags & CONSOLVER_FLAG_EFF_SCALE;
   const bool x_scale = p.flags & CONSOLVER_FLAG_X_SCALE;
-  const float cs0 = eff_scale ? __ldg(cf + p.order_dim) : 1.f;
-  const float cs1 = x_scale ? __ldg(cf + p.order_dim + 1) : 1.f;
+  const float cs0 = eff_scale ? ld_produced_f32(cf + p.order_dim) : 1.f;
+  const float cs1 = x_scale ? ld_produced_f32(cf + p.order_dim + 1) : 1.f;
   const bool vpred = p.flags & CONSOLVER_FLAG_VPRED;
   const bool lowp = p.flags & CONSOLVER_FLAG_LOWP_COMBINE;
   const float g = p.guidance;

@@ -128,3 +128,44 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
         assert lib.consolver_error_string(code)
     with pytest.raises(_lib.ConsolverError):
         _lib.check(-2, "x")
+
+
+def _cuobjdump():
+    import shutil
+
+    return shutil.which("cuobjdump") or ("/usr/local/cuda/bin/cuobjdump"
+                                         if os.path.exists("/usr/local/cuda/bin/cuobjdump") else None)
+
+
+@pytest.mark.skipif(_cuobjdump() is None, reason="cuobjdump not installed")
+@pytest.mark.parametrize("obj", ["step_sd.o", "step_fm.o"])
+def test_no_load_of_pdl_produced_data_is_hoisted_above_the_wait(obj):
+    """The step kernel starts while the policy kernel that writes its coefficient record is still running (programmatic
+    dependent launch) and reads the record after griddepcontrol.wait (SASS: ACQBULK).  `__ldg` loads are invariant to
+    nvcc, which hoisted two of them above the wait in 12 instantiations (stale coefficients, found by the live
+    differential fuzzing).  The loads are now volatile ld.global.cg: in every 128-bit instantiation, each load before the
+    wait must be one of the 128-bit streaming loads of the model outputs / latent, and each load after it L2-coherent."""
+    from consolver_b200 import build
+
+    path = os.path.join(build.PKG, "build", obj)
+    if not os.path.exists(path):
+        build.build_library(force=True)
+    sass = subprocess.run([_cuobjdump(), "-sass", path], capture_output=True, text=True, check=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    checked = 0
+    for fn in funcs:
+        name = fn.split("\n", 1)[0].strip()
+        if "step_kernel" not in name or "ACQBULK" not in fn:
+            continue
+        pre, post = fn.split("ACQBULK", 1)
+        elems = int(re.search(r"Li(\d+)ELi\d+ELb[01]EEE", name).group(1))      # E: elements per thread-vector
+        if elems > 1:
+            hoisted = [l for l in re.findall(r"LDG\S*", pre) if ".128" not in l]
+            assert not hoisted, f"{name}: {hoisted} before griddepcontrol.wait"
+        stale_path = [l for l in re.findall(r"LDG\S*", post) if "CONSTANT" in l]
+        assert not stale_path, f"{name}: non-coherent loads after griddepcontrol.wait: {stale_path}"
+        checked += 1
+    assert checked >= 60
+    for src in ("step_kernel.cuh",):
+        with open(os.path.join(build.CSRC, src)) as f:
+            assert "__ldg(" not in f.read(), f"{src}: __ldg in a kernel that waits on a PDL primary"

@@ -399,3 +399,67 @@ def test_one_process_can_drive_two_devices():
             x = s.step_cfg(g[f"pair_{i}"].to(dev), t, x, m["guidance"])[0]
         res.append(x.cpu())
     assert torch.equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("flow", ["genppo_bf16_scalers", "genppo_f16_scalers", "bf16_out_depth6", "f16_pipeline_depth8",
+                                  "f32_depth5_ragged", "fm_bf16_depth6"])
+def test_pdl_linked_step_reads_the_coefficient_record_the_policy_kernel_wrote(flow):
+    """The step kernel is a programmatic dependent launch of the policy kernel and starts while that one is still
+    running; its coefficient loads belong after griddepcontrol.wait.  nvcc had hoisted `__ldg` coefficient loads above
+    the wait in the 16-bit depth-1 and the runtime-depth instantiations (stale records, non-deterministic; found by the
+    live differential fuzzing).  Trajectories with the two kernels linked (use_pdl, the default) must equal the same
+    trajectories with ordinary stream order, every time."""
+    import numpy as np
+
+    import consolver_b200 as cb
+
+    fm = flow.startswith("fm")
+    od = {"genppo_bf16_scalers": 3, "genppo_f16_scalers": 4, "bf16_out_depth6": 6, "f16_pipeline_depth8": 8,
+          "f32_depth5_ragged": 5, "fm_bf16_depth6": 6}[flow]
+    mdt = torch.bfloat16 if "bf16" in flow else torch.float16 if "f16" in flow else torch.float32
+    xdt = mdt if flow.startswith(("genppo", "f16_pipeline")) else torch.float32
+    shape = (3, 5, 7) if "ragged" in flow else ((64, 16) if fm else (4, 16, 16))
+    B, n = 5, 9
+    fkw = dict(hidden_dim=32, num_actions=11)
+
+    def build():
+        if fm:
+            s = cb.FMPPOScheduler(shift=3.0, use_dynamic_shifting=True, order_dim=od, scaler_dim=2, mu_dim=0,
+                                  factor_net_kwargs=dict(fkw))
+        else:
+            s = cb.PPOScheduler(order_dim=od, scaler_dim=2, prediction_type="v_prediction", timestep_spacing="trailing",
+                                beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012,
+                                factor_net_kwargs=dict(embedding_dim=64, **fkw))
+        g = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for p in s.factor_net.parameters():
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * (0.02 if fm else 0.4))
+        s.factor_net.cuda()
+        if flow.startswith("genppo"):
+            s.factor_net.to("cuda", dtype=mdt)
+        return s
+
+    def run(s, pdl):
+        s.use_pdl = pdl
+        if fm:
+            s.set_timesteps(n, device="cuda", sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+            s.set_begin_index(0)
+        else:
+            s.set_timesteps(n, device="cuda")
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(B, *shape, generator=g).to(mdt if fm else xdt).cuda()
+        outs = []
+        ctx = torch.autocast("cuda", mdt) if flow.startswith("genppo") else __import__("contextlib").nullcontext()
+        with ctx, torch.no_grad():
+            for i in range(n):
+                e = torch.randn(B, *shape, generator=g).to(mdt).cuda()
+                torch.manual_seed(100 + i)
+                x = s.step(e, s.timesteps[i], x, return_dict=False)[0]
+                outs.append(x)
+        return outs
+
+    base = run(build(), False)
+    for rep in range(12):
+        got = run(build(), True)
+        for i, (a, b) in enumerate(zip(got, base)):
+            assert a.dtype == b.dtype and torch.equal(a, b), f"{flow}: repetition {rep}, step {i}"
