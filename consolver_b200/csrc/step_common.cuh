@@ -85,16 +85,18 @@ __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddep
 // kernel's lifetime, which (a) is not true of such data — the primary is still writing it when this grid starts — and
 // (b) lets nvcc treat the load as invariant and HOIST IT ABOVE THE WAIT: seen in SASS as LDG.E.CONSTANT of the
 // coefficient record before ACQBULK in 12 instantiations (16-bit depth-1 and the runtime-depth forms), where the live
-// differential fuzzing caught stale coefficients (profiles/live_fuzz_r02.md).  These are volatile asm statements, which
-// the compiler keeps in order with the wait, on the L2-coherent path (.cg): no L1 line of an earlier grid can serve them.
+// differential fuzzing caught stale coefficients (profiles/live_fuzz_r02.md).  These are ordinary (weak, coherent-path)
+// global loads — what the PDL contract covers: after the wait, the prerequisite grids' writes are visible to them —
+// written as volatile asm, which the compiler keeps in order with the wait.  (.cg / STRONG.GPU loads are also correct
+// but cost 1.8 us per launch at batch 64: every CTA's coefficient read then goes to the L2 point of coherence.)
 __device__ __forceinline__ float ld_produced_f32(const float* p) {
   float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ uint4 ld_produced16(const void* p) {
   uint4 r;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
   return r;
 }
@@ -126,11 +128,11 @@ template <typename T> struct Raw<T, 1> {
   __device__ __forceinline__ void load_produced(const T* p) {
     if constexpr (sizeof(T) == 4) {
       unsigned r;
-      asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+      asm volatile("ld.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
       v = *reinterpret_cast<const T*>(&r);
     } else {
       unsigned short r;
-      asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+      asm volatile("ld.global.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
       v = *reinterpret_cast<const T*>(&r);
     }
   }

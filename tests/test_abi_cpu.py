@@ -143,8 +143,9 @@ def test_no_load_of_pdl_produced_data_is_hoisted_above_the_wait(obj):
     """The step kernel starts while the policy kernel that writes its coefficient record is still running (programmatic
     dependent launch) and reads the record after griddepcontrol.wait (SASS: ACQBULK).  `__ldg` loads are invariant to
     nvcc, which hoisted two of them above the wait in 12 instantiations (stale coefficients, found by the live
-    differential fuzzing).  The loads are now volatile ld.global.cg: in every 128-bit instantiation, each load before the
-    wait must be one of the 128-bit streaming loads of the model outputs / latent, and each load after it L2-coherent."""
+    differential fuzzing).  The loads are now volatile asm (ordinary coherent-path ld.global): in every 128-bit
+    instantiation each load before the wait must be one of the 128-bit streaming loads of the model outputs / latent,
+    and no load after it may take the non-coherent (LDG.CONSTANT) path."""
     from consolver_b200 import build
 
     path = os.path.join(build.PKG, "build", obj)
