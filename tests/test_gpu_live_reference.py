@@ -417,3 +417,51 @@ def test_wide_random_fm_configurations_step_for_step(case):
         torch.testing.assert_close(po, pr, rtol=p_rtol, atol=1e-6)
         assert xo.dtype == xr.dtype and torch.equal(xo, xr), tag + ": latent"
         assert torch.equal(torch.cuda.get_rng_state(), rng_after_ref), tag + ": default generator consumed differently"
+
+
+@pytest.mark.parametrize("case", range(max(WIDE_CASES // 2, 1)))
+def test_wide_random_use_conv_configurations_step_for_step(case):
+    """use_conv=True over the wider space (fp32 model outputs; order 3-6, K to 161, batch to 16, fused CFG): the per-sample
+    policy kernel (cosine features -> MLP -> draw) feeds the step kernel through the same programmatic dependent launch."""
+    rng = random.Random(9000 + case)
+    kind = rng.choice(["sd", "sd", "fm"])
+    od = rng.choice([3, 4, 4, 5, 6])
+    K = rng.choice([11, 11, 161])
+    hidden = rng.choice([16, 64, 256])
+    n = rng.choice([2, 5, 8, 12])
+    B = rng.choice([1, 2, 5, 16])
+    fused_cfg = kind == "sd" and rng.choice([False, True])
+    if kind == "sd":
+        cfg = dict(order_dim=od, scaler_dim=rng.choice([0, 1, 2]), prediction_type=rng.choice(["epsilon", "v_prediction"]),
+                   **dict(SD_PROD, use_conv=True))
+        shape = rng.choice([(4, 16, 16), (4, 32, 32), (3, 5, 7)])
+    else:
+        cfg = dict(shift=3.0, use_dynamic_shifting=True, order_dim=od, scaler_dim=rng.choice([0, 2]), mu_dim=0, use_conv=True)
+        shape = rng.choice([(64, 16), (256, 64), (5, 7)])
+    last_std = 0.5 if kind == "sd" else 0.02
+    r, o = _wide_pair(kind, 300 + case, hidden, K, last_std, **cfg)
+    for s in (r, o):
+        if kind == "sd":
+            s.set_timesteps(n, device="cuda")
+        else:
+            s.set_timesteps(n, device="cuda", sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
+            s.set_begin_index(0)
+    g = torch.Generator().manual_seed(case)
+    xr = xo = torch.randn(B, *shape, generator=g).cuda()
+    for i in range(n):
+        pair = torch.randn(2 * B, *shape, generator=g).cuda()
+        u, c = pair.chunk(2)
+        e = u + 3.0 * (c - u)
+        torch.manual_seed(9 + i)
+        with ref_shim.quiet(), torch.no_grad():
+            xr, ar, pr, cr, mr = r.step(e, r.timesteps[i], xr, return_dict=False)
+        torch.manual_seed(9 + i)
+        with torch.no_grad():
+            if fused_cfg:
+                xo, ao, po, co, mo = o.step_cfg(pair, o.timesteps[i], xo, 3.0)
+            else:
+                xo, ao, po, co, mo = o.step(e, o.timesteps[i], xo, return_dict=False)
+        tag = f"wide use_conv case {case} ({kind}, K={K}, H={hidden}, n={n}, B={B}, {shape}, cfg={fused_cfg}, {cfg}) step {i}"
+        assert torch.equal(ao, ar), tag + ": actions"
+        torch.testing.assert_close(po, pr, rtol=2e-4, atol=4e-6)
+        assert torch.equal(xo, xr), tag + ": latent"
