@@ -328,6 +328,9 @@ def test_wide_random_sd_configurations_step_for_step(case):
     fused_cfg = rng.choice([False, True])
     guidance = rng.choice([3.0, 7.5, 1.0])
     last_std = rng.choice([0.5, 0.05, 2.0])
+    # which timesteps the caller walks: the grid; the grid from a later point (img2img-style `timesteps[t_start:]`); or
+    # integers of its own that are not grid points (the reference honours whatever it is handed, scheduler_ppo.py:203-207)
+    walk = rng.choice(["grid", "grid", "grid", "from_k", "off_grid"])
     r, o = _wide_pair("sd", case, hidden, K, last_std, **cfg)
     mdt = torch.float32 if flow == "f32" else (torch.float16 if "f16" in flow and "bf16" not in flow else torch.bfloat16)
     xdt = mdt if flow.endswith("_pipeline") or flow.startswith("genppo") else torch.float32
@@ -339,22 +342,26 @@ def test_wide_random_sd_configurations_step_for_step(case):
     xr = xo = torch.randn(B, *shape, generator=g).to(xdt).cuda()
     ctx = (lambda: torch.autocast("cuda", ac)) if ac is not None else __import__("contextlib").nullcontext
     tag0 = (f"wide case {case} ({flow}, K={K}, H={hidden}, std={last_std}, n={n}, B={B}, {shape}, t as {style}, "
-            f"cfg={fused_cfg}, {cfg})")
-    for i in range(n):
+            f"walk={walk}, cfg={fused_cfg}, {cfg})")
+    first = rng.randrange(n) if walk == "from_k" else 0
+    own = sorted(rng.sample(range(1000), n), reverse=True) if walk == "off_grid" else None
+    for i in range(first, n):
         pair = torch.randn(2 * B, *shape, generator=g).to(mdt).cuda()
         u, c = pair.chunk(2)
         e = u + guidance * (c - u)                       # the caller's combine, denoise_ppo.py:96-100
         torch.manual_seed(77 + i)
+        t_r = own[i] if own else _hand_over(style, r, i)
+        t_o = own[i] if own else _hand_over(style, o, i)
         with ref_shim.quiet(), ctx(), torch.no_grad():
-            xr, ar, pr, cr, mr = r.step(e, _hand_over(style, r, i), xr, return_dict=False)
+            xr, ar, pr, cr, mr = r.step(e, t_r, xr, return_dict=False)
         rng_after_ref = torch.cuda.get_rng_state()
         torch.manual_seed(77 + i)
         with ctx(), torch.no_grad():
             if fused_cfg:
-                xo, ao, po, co, mo = o.step_cfg(pair, _hand_over(style, o, i), xo, guidance)
+                xo, ao, po, co, mo = o.step_cfg(pair, t_o, xo, guidance)
                 assert torch.equal(o.ets[-1], e), tag0 + f" step {i}: ring slot != caller-side combine"
             else:
-                xo, ao, po, co, mo = o.step(e, _hand_over(style, o, i), xo, return_dict=False)
+                xo, ao, po, co, mo = o.step(e, t_o, xo, return_dict=False)
         tag = tag0 + f" step {i}"
         assert ao.dtype == ar.dtype and torch.equal(ao, ar), tag + ": actions"
         assert torch.equal(mo, mr) and torch.equal(co["x"], cr["x"]), tag
