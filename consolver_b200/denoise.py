@@ -146,7 +146,7 @@ class GraphedPreview:
         `set_timesteps_kwargs` (e.g. sigmas=..., mu=... for FM) are passed through."""
         self.scheduler = scheduler
         self.x_T, self.pairs, self.guidance, self.n = x_T, list(pairs), guidance, num_inference_steps
-        self.out = torch.empty_like(x_T) if guidance is not None else None
+        self.out = None
         dev = x_T.device
         scheduler.set_timesteps(num_inference_steps, device=dev, **(set_timesteps_kwargs or {}))
         if hasattr(scheduler, "set_begin_index"):
@@ -166,8 +166,13 @@ class GraphedPreview:
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
-            run()
+            warm = run()
         torch.cuda.current_stream(dev).wait_stream(s)
+        if guidance is not None:
+            # fixed result buffer, in the dtype the trajectory ends in (a 16-bit pipeline's latent is fp32 from its
+            # second step on — scheduler.next_latent_dtype — so it is not always x_T's)
+            self.out = torch.empty_like(warm)
+        del warm
         # graph-safe fused RNG: the sample kernels read {seed, offset} from a device buffer that replay() refreshes
         # from the default generator (and advances it), so every replay draws what eager execution would draw
         from . import _lib, rng as _rng
