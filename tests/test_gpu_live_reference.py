@@ -472,3 +472,42 @@ def test_wide_random_use_conv_configurations_step_for_step(case):
         assert torch.equal(ao, ar), tag + ": actions"
         torch.testing.assert_close(po, pr, rtol=2e-4, atol=4e-6)
         assert torch.equal(xo, xr), tag + ": latent"
+
+
+@pytest.mark.parametrize("case", range(max(WIDE_CASES // 2, 1)))
+def test_our_caller_loop_equals_the_references_caller_loop(case):
+    """BOTH sides of the boundary swapped: consolver_b200.denoise.denoise_loop (no torch.cat of the CFG-doubled input, the
+    step kernel writes the next latent into both halves; rollout record as views) driving the drop-in scheduler, against
+    the reference's denoise_ppo.denoise_diffusion driving the reference scheduler — random configurations, fp32 and 16-bit
+    denoiser outputs: final latents and the whole rollout record."""
+    from consolver_b200.denoise import denoise_loop
+
+    caller = _load_caller()
+    rng = random.Random(10000 + case)
+    od = rng.choice([2, 3, 4, 4, 6])
+    cfg = dict(order_dim=od, scaler_dim=rng.choice([0, 0, 1, 2]), prediction_type=rng.choice(["epsilon", "v_prediction"]),
+               **SD_PROD)
+    n, B = rng.choice([2, 3, 8, 15]), rng.choice([1, 2, 5, 16])
+    shape = rng.choice([(4, 16, 16), (4, 8, 8), (4, 32, 32)])
+    odt = rng.choice([torch.float32, torch.float32, torch.bfloat16, torch.float16])   # the denoiser's output dtype
+    guidance = rng.choice([3.0, 7.5])
+    r, o = _wide_pair("sd", 700 + case, rng.choice([64, 256]), rng.choice([11, 161]), 0.5, **cfg)
+    noise = torch.randn(B, *shape, generator=torch.Generator().manual_seed(case)).cuda()
+    text = [f"prompt {i}" * (i + 1) for i in range(B)]
+    unet = lambda x, t, encoder_hidden_states=None, return_dict=False: (  # noqa: E731
+        _unet(x, t, encoder_hidden_states)[0].to(odt),)
+    tok = _Tok()
+    ids = lambda t_: tok(t_).input_ids.cuda()  # noqa: E731
+    embeds = torch.cat([_text_encoder(ids([""] * B))[0], _text_encoder(ids(text))[0]])
+    torch.manual_seed(4321)
+    with ref_shim.quiet(), torch.no_grad():
+        lat_r, conds_r, probs_r, act_r, masks_r, _ = caller.denoise_diffusion(
+            _text_encoder, r, unet, noise, text, tok, cfg=guidance, num_inference_steps=n)
+    torch.manual_seed(4321)
+    with torch.no_grad():
+        lat_o, rec = denoise_loop(o, lambda x, t, i: unet(x, t, embeds)[0], noise, cfg=guidance, num_inference_steps=n)
+    tag = f"caller case {case} (n={n}, B={B}, {shape}, out {odt}, g={guidance}, {cfg})"
+    assert torch.equal(rec["actions"], act_r), tag + ": actions"
+    assert torch.equal(rec["masks"], masks_r) and torch.equal(rec["x"].to(conds_r["x"].dtype), conds_r["x"]), tag
+    torch.testing.assert_close(rec["probs"], probs_r, rtol=0, atol=2.2e-6)
+    assert lat_o.dtype == lat_r.dtype and torch.equal(lat_o, lat_r), tag + ": final latents"
