@@ -396,6 +396,16 @@ def test_wide_random_fm_configurations_step_for_step(case):
     dt = rng.choice([torch.bfloat16, torch.bfloat16, torch.float32, torch.float16])
     style = rng.choice(["view", "view", "clone", "float"])
     last_std = rng.choice([0.02, 0.002, 0.1])
+    # sigma-grid options (edit_ppo/scheduler_fmppo.py:218-236) and how the step index is found (:249-268)
+    opt = rng.choice([None, None, None, "use_karras_sigmas", "use_exponential_sigmas", "use_beta_sigmas"])
+    if opt:
+        cfg[opt] = True
+    cfg["shift_terminal"] = rng.choice([None, None, 0.02])
+    if n == 1:
+        cfg["shift_terminal"] = None      # a one-point grid stretched to a terminal value is 0/0 in the reference (and here)
+    cfg["invert_sigmas"] = rng.choice([False, False, False, True])
+    cfg["time_shift_type"] = rng.choice(["exponential", "exponential", "linear"])
+    begin = rng.choice([0, 0, None, "mid"])
     r, o = _wide_pair("fm", 50 + case, hidden, K, last_std, **cfg)
     # softmax(logits / 0.01): a rounding difference of the logits is multiplied by 100, and the logits grow with the last
     # layer's scale — the measured 8e-6 belongs to last_std 0.02
@@ -405,11 +415,17 @@ def test_wide_random_fm_configurations_step_for_step(case):
             s.set_timesteps(n, device="cuda", sigmas=np.linspace(1.0, 1 / n, n), mu=1.15)
         else:
             s.set_timesteps(n, device="cuda")
-        s.set_begin_index(0)
+    assert torch.equal(r.timesteps, o.timesteps) and torch.equal(r.sigmas, o.sigmas), f"wide fm case {case}: grid {cfg}"
+    # the step index: set by the pipeline (0, or mid-grid for image-to-image), or looked up from the first timestep
+    unique = len(set(r.timesteps.tolist())) == n
+    first = rng.randrange(n) if begin == "mid" else 0
+    for s in (r, o):
+        if begin is not None or not unique:
+            s.set_begin_index(first)
     g = torch.Generator().manual_seed(case)
     xr = xo = torch.randn(B, *shape, generator=g).to(dt).cuda()
     hand = lambda s, i: float(s.timesteps[i]) if style == "float" else _hand_over(style, s, i)  # noqa: E731
-    for i in range(n):
+    for i in range(first, n):
         v = torch.randn(B, *shape, generator=g).to(dt).cuda()
         torch.manual_seed(5 + i)
         with ref_shim.quiet(), torch.no_grad():
@@ -418,7 +434,8 @@ def test_wide_random_fm_configurations_step_for_step(case):
         torch.manual_seed(5 + i)
         with torch.no_grad():
             xo, ao, po, co, mo = o.step(v, hand(o, i), xo, return_dict=False)
-        tag = f"wide fm case {case} (K={K}, H={hidden}, n={n}, B={B}, {shape}, {dt}, t as {style}, {cfg}) step {i}"
+        tag = (f"wide fm case {case} (K={K}, H={hidden}, n={n}, B={B}, {shape}, {dt}, t as {style}, begin={begin}, {cfg}) "
+               f"step {i}")
         assert torch.equal(ao, ar), tag + ": actions"
         assert torch.equal(mo, mr) and torch.equal(co["x"], cr["x"]), tag
         torch.testing.assert_close(po, pr, rtol=p_rtol, atol=1e-6)
