@@ -425,7 +425,7 @@ CONSOLVER_API int consolver_ppo_loss_grad_allreduce_f32(const float* w1, const f
 
 /* Tuning knobs for benchmarking (process-global; not part of the numerical contract).
  *   threads: CTA size of the step kernels (32..512, multiple of 32; 0 = default)
- *   unroll : 16-byte vectors per thread per stream (1, 2 or 4; 0 = default)                          */
+ *   unroll : 16-byte vectors per thread per stream (1 or 2; 0 = default = 1)                          */
 CONSOLVER_API int consolver_set_step_launch(int threads, int unroll);
 
 #ifdef __cplusplus

@@ -167,8 +167,11 @@ def _oracle(eps, hist, x, c, od, scalars, vpred, sdim):
 @pytest.mark.parametrize("n_hist", [1, 2, 4, 6])
 @pytest.mark.parametrize("vpred,sdim", [(False, 0), (True, 2), (False, 1)])
 def test_step_sd_f32_bit_exact_with_cuda_rules(B, shape, n_hist, vpred, sdim):
-    """fp32: `(x - sb*e) / sa` is `(x - sb*e) * (1/sa)` on CUDA tensors.  B=160 takes the two-vectors-per-thread
-    instantiation (grid >= 8 CTAs per SM), the others the one-vector form; (3,5,7) the scalar path."""
+    """fp32: `(x - sb*e) / sa` is `(x - sb*e) * (1/sa)` on CUDA tensors.  B=160 is run through the two-vectors-per-thread
+    instantiation (consolver_set_step_launch), the others through the default one-vector form; (3,5,7) the scalar path."""
+    from consolver_b200 import _lib
+
+    lib = _lib.load()
     od = max(n_hist, 4)
     g = torch.Generator().manual_seed(n_hist * 10 + B)
     rn = lambda: torch.randn(B, *shape, generator=g)  # noqa: E731
@@ -179,8 +182,12 @@ def test_step_sd_f32_bit_exact_with_cuda_rules(B, shape, n_hist, vpred, sdim):
     flags = (1 if vpred else 0) | (2 if sdim >= 1 else 0) | (4 if sdim >= 2 else 0)
     eps = orc.cfg_combine(e0, cond, 3.0)
     ref = _oracle(eps, hist, x, c, od, scalars, vpred, sdim)
-    out, slot = ah.step_sd(e0.cuda(), cond.cuda(), 3.0, [h.cuda() for h in hist], x.cuda(), c.cuda(), od, scalars,
-                           flags, slot=True, host=False)
+    assert lib.consolver_set_step_launch(0, 2 if B == 160 else 0) == 0
+    try:
+        out, slot = ah.step_sd(e0.cuda(), cond.cuda(), 3.0, [h.cuda() for h in hist], x.cuda(), c.cuda(), od, scalars,
+                               flags, slot=True, host=False)
+    finally:
+        lib.consolver_set_step_launch(0, 0)
     assert torch.equal(slot.cpu(), eps)
     assert torch.equal(out.cpu(), ref)
     host_out, _ = ah.step_sd(e0.cuda(), cond.cuda(), 3.0, [h.cuda() for h in hist], x.cuda(), c.cuda(), od, scalars,
