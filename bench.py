@@ -712,6 +712,16 @@ def run_ours(args, rank, world, device):
         out["roofline_sweep"] = sweep
         out["roofline_sweep_traffic_source"] = traffic_src
         out["solver_loop"]["frac_of_peak"] = round(out["solver_loop"]["achieved_gbs_per_gpu"] / peak, 4)
+        # the same kernel INSIDE the timed region of `value`: the region's device time divided by the step launches it
+        # contains (8 per preview; the policy kernels run on a parallel graph branch) against the mean algorithmic bytes
+        # of those launches (58 tensors per 8 launches: history depths 1,2,3,4,4,4,4,4)
+        per_launch_bytes = TENSORS_PER_PREVIEW * B * SHAPE[0] * SHAPE[1] * SHAPE[2] * 4 / N_STEPS
+        us_in = out["ms_per_step"] * 1e3 / N_STEPS
+        out["roofline"]["in_timed_region"] = {
+            "us_per_launch": round(us_in, 3), "algorithmic_bytes": int(per_launch_bytes),
+            "achieved": round(per_launch_bytes / us_in / 1e3, 1), "frac": round(per_launch_bytes / us_in / 1e3 / peak, 4),
+            "note": "timed region of `value` / step launches in it (several previews in flight, so one launch's ramp and "
+                    "tail overlap other launches' streaming phases); `frac` above is ONE launch alone on an idle GPU"}
         fm = []
         for Bs in (1, 8, 64, 512):
             us, nbytes = time_fm_kernel(Bs, device)

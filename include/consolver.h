@@ -49,7 +49,10 @@ extern "C" {
 #define CONSOLVER_FLAG_EFF_SCALE    2   /* scaler_dim >= 1: eff *= coef[order_dim]     (scheduler_ppo.py:274-277)  */
 #define CONSOLVER_FLAG_X_SCALE      4   /* scaler_dim == 2: sample *= coef[order_dim+1] (scheduler_ppo.py:278)     */
 #define CONSOLVER_FLAG_PDL          8   /* launch with programmatic dependent launch: the bulk loads are issued
-                                           before waiting on the preceding (policy) kernel's coefficients        */
+                                           before waiting on the preceding (policy) kernel's coefficients.  Only
+                                           valid when the kernel launched right before on this stream is the one that
+                                           writes `coef` (or writes nothing this step reads): e0 / cond / hist / x are
+                                           loaded BEFORE the wait, `coef` after it                                  */
 
 #define CONSOLVER_FLAG_CHAIN       16   /* back-to-back solver steps on one stream: this step is a programmatic
                                            dependent launch of the PREVIOUS STEP; loads of e0/cond and of history
