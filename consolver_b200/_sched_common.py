@@ -199,8 +199,9 @@ class SolverOptions:
         #: True (default): a CUDA `timestep` tensor is NOT read back; the value is taken from the host copy of the grid
         #: at the current step count (pipelines step in grid order).  False: `.item()` it (one sync per step).
         self.sync_free = True
-        #: link the policy and step kernels with programmatic dependent launch
-        self.use_pdl = True
+        #: link the policy and step kernels with programmatic dependent launch (CONSOLVER_NO_PDL=1 turns it off for a
+        #: whole process: the first thing to try when a result looks order-dependent — profiles/live_fuzz_r02.md)
+        self.use_pdl = os.environ.get("CONSOLVER_NO_PDL") != "1"
         #: generate the Exp(1) draw inside the sample kernel (bit-identical to torch's exponential_, see rng.py)
         self.use_fused_rng = True
         #: optional side stream for the policy kernels (set by GraphedPreview): the sample kernel needs nothing from the
