@@ -1075,12 +1075,16 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
         if ok.item() == 0:
             exchange = None
 
-    def one(it, ex=None):
+    # one CUDA graph of the whole sampling loop per step count (2..15), built before anything is timed
+    rolls = ppo.GraphedRollouts(s, den, noise, batch, GUIDANCE, step_counts=range(2, 16))
+    target_b = target.unsqueeze(0).expand(batch, *target.shape)
+
+    def one(it, ex=None, read_back=False):
         n = ppo.shared_step_count(it, seed=0)
-        lat, rec = ppo.rollout_sd(s, den, noise, batch, GUIDANCE, n)
-        r = ppo.latent_mse_reward(lat, target.unsqueeze(0).expand_as(lat))
+        lat, rec = rolls.rollout(n)
+        r = ppo.latent_mse_reward(lat, target_b)
         return ppo.ppo_update(s.factor_net, flat, opt, rec, r, ppo_epochs=ppo_epochs, entropy_coef=0.01,
-                              exchange=ex), n
+                              exchange=ex, read_back=read_back), n
 
     for it in range(3):
         one(it, exchange)
@@ -1166,7 +1170,9 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
     t0 = time.perf_counter()
     steps = 0
     for it in range(8, 8 + iters):
-        st, n = one(it, exchange)
+        # the loss is read back every 10th iteration (the reference logs it every iteration, train_ppo.py:458; nothing
+        # in the update depends on the read-back)
+        st, n = one(it, exchange, read_back=(it % 10 == 9) or it == 8 + iters - 1)
         steps += n
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
@@ -1190,8 +1196,10 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
             "grad_buffer_floats": flat.numel, "grad_buffer_bytes": flat.numel * 4,
             "param_checksum_identical_across_ranks": abs(stats["checksum"] / world - flat.checksum()) < 1e-6,
             "last_loss": st["loss"],
-            "what": "BASELINE configs[4]: rollouts with random step counts 2-15 + native PPO loss/grad kernel + flat "
-                    "gradient all-reduce + AdamW; stand-in denoiser = 4x4 channel mix, reward = latent MSE"}
+            "what": "BASELINE configs[4]: rollouts with random step counts 2-15 (one CUDA graph of the whole sampling "
+                    "loop per step count, ppo.GraphedRollouts) + native PPO loss/grad kernel + flat gradient all-reduce "
+                    "+ torch AdamW; loss read back every 10th iteration; stand-in denoiser = 4x4 channel mix, reward = "
+                    "latent MSE"}
 
 
 def main():

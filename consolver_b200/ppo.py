@@ -218,12 +218,15 @@ def ppo_loss_grad_cuda(factor_net, flat: FlatParams, x_rows: torch.Tensor, idx_r
 def ppo_update(factor_net, flat: FlatParams, optimizer, record: Dict[str, torch.Tensor], rewards: torch.Tensor,
                ppo_epochs: int = 1, clip_range: float = 0.2, entropy_coef: float = 0.0,
                max_grad_norm: Optional[float] = 1.0, native: Optional[bool] = None,
-               exchange: Optional["PeerGradExchange"] = None) -> Dict[str, float]:
+               exchange: Optional["PeerGradExchange"] = None, read_back: bool = True) -> Dict[str, float]:
     """ppo_epochs x (loss, backward, flat all-reduce, clip, optimizer step) — train_ppo.py:406-437.
     `record` is `scheduler.trajectory()` (views); it is detached/cloned here because the next rollout reuses the
     buffers.  `native` (default: on for CUDA tensors with the shared-row policy) runs forward + loss + backward as the
     hand-written kernels of csrc/ppo.cu; otherwise torch autograd on the distinct rows.  `exchange` (PeerGradExchange, native
-    path only): the gradient all-reduce is fused into the reduction kernel over NVLink peer memory instead of a NCCL call."""
+    path only): the gradient all-reduce is fused into the reduction kernel over NVLink peer memory instead of a NCCL call.
+    `read_back=False` (native path): no host synchronisation at all — the statistics come back as DEVICE tensors
+    (`stats` [4] = loss, policy loss, entropy, mean ratio; `grad_norm` 0-d), for loops that log every k-th iteration (the
+    reference reads the loss back every iteration, train_ppo.py:458)."""
     fn0 = factor_net.module if hasattr(factor_net, "module") else factor_net
     if getattr(fn0, "use_conv", False):
         # use_conv makes the policy input per-sample (cosine features of the model-output history), which the rollout
@@ -257,6 +260,11 @@ def ppo_update(factor_net, flat: FlatParams, optimizer, record: Dict[str, torch.
                 norm = flat.grad.norm()
                 flat.grad.mul_(torch.clamp(max_grad_norm / (norm + 1e-6), max=1.0))
             optimizer.step()
+        if not read_back:
+            stats.update(stats=st)
+            if max_grad_norm is not None:
+                stats["grad_norm"] = norm
+            return stats
         vals = st.tolist()      # one read-back per update, after the last epoch
         stats.update(loss=vals[0], policy_loss=vals[1], entropy=vals[2], ratio_mean=vals[3])
         if max_grad_norm is not None:
@@ -287,6 +295,48 @@ def rollout_sd(scheduler, denoiser, noise_one: torch.Tensor, batch: int, cfg: fl
     noise = noise_one.unsqueeze(0).expand(batch, *noise_one.shape).contiguous()
     with torch.no_grad():
         return denoise_loop(scheduler, denoiser, noise, cfg=cfg, num_inference_steps=num_inference_steps)
+
+
+class GraphedRollouts:
+    """Rollouts as CUDA graphs, one per step count.  train_ppo.py:345 draws the number of inference steps of every rollout
+    from 2..15, so the whole CFG sampling loop (denoiser included) is captured once per count (`GraphedDenoiseLoop`) and a
+    rollout is ONE graph launch instead of ~10 eager launches per step — eager stepping costs ~175 us of host time per
+    solver step against ~15 us of GPU time at batch 80.  Every count has its own scheduler object (its own trajectory
+    buffers and history ring) sharing ONE `factor_net`: the graphs re-evaluate the probability tables from the live
+    weights at every replay, so optimizer steps between rollouts are seen.  The default generator is consumed exactly as
+    by eager rollouts (same draws, same order).
+
+    `denoiser(model_in [2B,...], t, i)` must be capturable.  Build it AFTER `FlatParams(factor_net)` (the graphs hold the
+    parameter addresses)."""
+
+    def __init__(self, scheduler, denoiser, noise_one: torch.Tensor, batch: int, cfg: float,
+                 step_counts=range(2, 16), prebuild: bool = True):
+        self.proto, self.denoiser, self.cfg, self.batch = scheduler, denoiser, float(cfg), int(batch)
+        self.noise = noise_one.unsqueeze(0).expand(batch, *noise_one.shape).contiguous()
+        self.loops: Dict[int, object] = {}
+        if prebuild:
+            for n in step_counts:
+                self._loop(int(n))
+
+    def _loop(self, n: int):
+        from .denoise import GraphedDenoiseLoop
+
+        if n not in self.loops:
+            s = type(self.proto)(**dict(self.proto.config))
+            s.factor_net = self.proto.factor_net                     # shared, live weights
+            for k in ("reference_device", "use_pdl", "use_fused_rng"):
+                setattr(s, k, getattr(self.proto, k))
+            self.loops[n] = GraphedDenoiseLoop(s, self.denoiser, self.noise, self.cfg, n)
+        return self.loops[n]
+
+    def rollout(self, num_inference_steps: int, noise_one: Optional[torch.Tensor] = None):
+        """-> (final latents [B,...], rollout record as views — valid until the next rollout with the same step count)"""
+        loop = self._loop(int(num_inference_steps))
+        noise = None
+        if noise_one is not None:
+            noise = noise_one.unsqueeze(0).expand(self.batch, *noise_one.shape)
+        lat = loop.replay(noise)
+        return lat, loop.record()
 
 
 def latent_mse_reward(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

@@ -412,3 +412,48 @@ def test_graphed_denoise_loop_with_a_denoiser_matches_eager():
     assert torch.equal(rec1["idx"], idx1) and torch.equal(ref1, out1)
     ref2, _ = denoise_loop(e, den, noise2, cfg=3.0, num_inference_steps=6)
     assert torch.equal(ref2, out2)
+
+
+def test_graphed_rollouts_equal_eager_rollouts_and_see_weight_updates():
+    """GraphedRollouts (one CUDA graph of the whole sampling loop per step count, schedulers sharing one factor_net) vs
+    eager ppo.rollout_sd: same latents, same record, same generator consumption — also after optimizer steps between
+    the rollouts (the graphs re-evaluate the probability tables from the live weights) and with the sync-free update."""
+    import consolver_b200 as cb
+    from consolver_b200 import ppo
+
+    def make():
+        torch.manual_seed(0)
+        s = cb.PPOScheduler(**PROD)
+        with torch.no_grad():
+            s.factor_net.mlp[4].weight.normal_(0, 0.05)
+        s.factor_net.cuda()
+        flat = ppo.FlatParams(s.factor_net)
+        return s, flat, torch.optim.AdamW(s.factor_net.parameters(), lr=1e-2)
+
+    w = torch.randn(4, 4, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 0.3
+    den = lambda x, t, i: torch.einsum("oc,bchw->bohw", w, x)  # noqa: E731
+    g = torch.Generator(device="cuda").manual_seed(4)
+    noise, target = (torch.randn(4, 16, 16, device="cuda", generator=g) for _ in range(2))
+    B, counts = 12, [5, 2, 9, 5, 3, 9]
+    (s_g, flat_g, opt_g), (s_e, flat_e, opt_e) = make(), make()
+    assert torch.equal(flat_g.flat, flat_e.flat)
+    rolls = ppo.GraphedRollouts(s_g, den, noise, B, 3.0, step_counts=sorted(set(counts)))
+    outs = {}
+    for mode, s, flat, opt in (("graph", s_g, flat_g, opt_g), ("eager", s_e, flat_e, opt_e)):
+        torch.manual_seed(99)
+        res = []
+        for n in counts:
+            lat, rec = rolls.rollout(n) if mode == "graph" else ppo.rollout_sd(s, den, noise, B, 3.0, n)
+            res.append((lat.clone(), {k: v.clone() for k, v in rec.items()}))
+            r = ppo.latent_mse_reward(lat, target.unsqueeze(0).expand_as(lat))
+            st = ppo.ppo_update(s.factor_net, flat, opt, rec, r, ppo_epochs=2, entropy_coef=0.01,
+                                read_back=mode == "eager")
+            if mode == "graph":
+                assert isinstance(st["stats"], torch.Tensor) and st["stats"].is_cuda and st["grad_norm"].is_cuda
+        outs[mode] = (res, flat.flat.clone(), torch.cuda.get_rng_state())
+    for k, ((lat_g, rec_g), (lat_e, rec_e)) in enumerate(zip(outs["graph"][0], outs["eager"][0])):
+        assert torch.equal(lat_g, lat_e), f"rollout {k} (n={counts[k]}): latents"
+        for key in ("idx", "actions", "probs", "masks", "x"):
+            assert torch.equal(rec_g[key], rec_e[key]), f"rollout {k} (n={counts[k]}): {key}"
+    assert torch.equal(outs["graph"][1], outs["eager"][1]), "weights after the updates"
+    assert torch.equal(outs["graph"][2], outs["eager"][2]), "default generator consumed differently"
