@@ -1057,7 +1057,9 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
     s.factor_net.to(device)
     flat = ppo.FlatParams(s.factor_net)
     ppo.broadcast_parameters(flat, 0)
-    opt = torch.optim.AdamW(s.factor_net.parameters(), lr=1e-4)
+    # the reference's optimizer (AdamW, train_ppo.py:223-229) at a tenth of its default rate: the synthetic reward below
+    # carries no signal, and at 1e-4 several hundred updates of pure noise collapse the policy (ratios of 1e5 in the loss)
+    opt = torch.optim.AdamW(s.factor_net.parameters(), lr=1e-5)
     g = torch.Generator(device=device).manual_seed(rank)
     w = torch.randn(4, 4, device=device, generator=g) * 0.3
     den = lambda x, t, i: torch.einsum("oc,bchw->bohw", w, x)  # noqa: E731  stand-in denoiser (not the product)
@@ -1195,7 +1197,7 @@ def ppo_rollout_leg(rank, world, device, batch=80, ppo_epochs=2, target_s=0.4):
                 "fused_exchange_error": exchange_err},
             "grad_buffer_floats": flat.numel, "grad_buffer_bytes": flat.numel * 4,
             "param_checksum_identical_across_ranks": abs(stats["checksum"] / world - flat.checksum()) < 1e-6,
-            "last_loss": st["loss"],
+            "last_loss": st["loss"], "parameters_finite": bool(torch.isfinite(flat.flat).all()),
             "what": "BASELINE configs[4]: rollouts with random step counts 2-15 (one CUDA graph of the whole sampling "
                     "loop per step count, ppo.GraphedRollouts) + native PPO loss/grad kernel + flat gradient all-reduce "
                     "+ torch AdamW; loss read back every 10th iteration; stand-in denoiser = 4x4 channel mix, reward = "
