@@ -133,3 +133,50 @@ def test_two_rank_gloo_training_keeps_replicas_identical():
         assert p.exitcode == 0
     assert res[0][1] == pytest.approx(res[1][1], rel=0, abs=0)      # the reference's per-rank checksum check
     assert res[0][2] == res[1][2]
+
+
+def test_graphed_rollouts_build_one_loop_per_step_count_sharing_the_live_policy(monkeypatch):
+    """Host logic of ppo.GraphedRollouts without a GPU: the capture itself (denoise.GraphedDenoiseLoop) is replaced by a
+    recorder.  One loop per step count, each on its OWN scheduler (own trajectory buffers) built from the prototype's
+    config, all of them holding the prototype's factor_net object (the graphs must see optimizer steps) and its
+    semantics switches; a rollout replays the loop of its count and hands back that loop's record."""
+    from consolver_b200 import denoise
+
+    made = []
+
+    class FakeLoop:
+        def __init__(self, scheduler, denoiser, noise, cfg, n):
+            self.scheduler, self.denoiser, self.noise, self.cfg, self.n = scheduler, denoiser, noise, cfg, n
+            self.replays = []
+            made.append(self)
+
+        def replay(self, noise=None):
+            self.replays.append(noise)
+            return ("latents", self.n)
+
+        def record(self):
+            return {"n": self.n}
+
+    monkeypatch.setattr(denoise, "GraphedDenoiseLoop", FakeLoop)
+    proto = cb.PPOScheduler(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, steps_offset=1,
+                            timestep_spacing="trailing", order_dim=3, scaler_dim=1, prediction_type="v_prediction",
+                            factor_net_kwargs=dict(embedding_dim=64, hidden_dim=16, num_actions=5))
+    proto.reference_device, proto.use_pdl = "cpu", False
+    den = object()
+    noise = torch.randn(4, 8, 8)
+    rolls = ppo.GraphedRollouts(proto, den, noise, batch=6, cfg=3.0, step_counts=[2, 5])
+    assert sorted(rolls.loops) == [2, 5] and len(made) == 2
+    for loop in made:
+        s = loop.scheduler
+        assert s is not proto and s.factor_net is proto.factor_net
+        assert dict(s.config) == dict(proto.config)
+        assert (s.reference_device, s.use_pdl, s.use_fused_rng) == ("cpu", False, proto.use_fused_rng)
+        assert loop.noise.shape == (6, 4, 8, 8) and torch.equal(loop.noise[3], noise) and loop.cfg == 3.0
+        assert loop.denoiser is den
+    lat, rec = rolls.rollout(5)
+    assert lat == ("latents", 5) and rec == {"n": 5} and made[1].replays == [None]
+    other = torch.randn(4, 8, 8)
+    rolls.rollout(2, noise_one=other)
+    assert made[0].replays[0].shape == (6, 4, 8, 8) and torch.equal(made[0].replays[0][5], other)
+    rolls.rollout(9)                                   # a count that was not prebuilt is captured on first use
+    assert sorted(rolls.loops) == [2, 5, 9] and made[2].n == 9
