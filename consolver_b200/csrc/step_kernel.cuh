@@ -235,12 +235,11 @@ static int launch_nh(StepParams& p, cudaStream_t stream) {
   if constexpr (MODE == kModeSD) {
     if (p.flags & CONSOLVER_FLAG_HOST_SCALARS) return launch_one<T, TX, NH, MODE, E, 1, true>(p, threads, stream);
   }
-  // default: one 16-byte vector per thread and stream at every size.  Round 1 switched to two vectors per thread once the
-  // grid reached ~8 CTAs per SM; re-measured on the final kernel (profiles/launch_shape_sweep_r02.jsonl, batch 32..4096,
-  // SD fp32 and FM bf16) the one-vector form is never behind and 1.5-2 % ahead at batch 256 (0.98 vs 0.967 of the copy
-  // peak).  The two-vector form stays reachable through consolver_set_step_launch.
-  const int unroll = lc.unroll > 0 ? lc.unroll : 1;
-  if (unroll >= 2) return launch_one<T, TX, NH, MODE, E, 2>(p, threads, stream);
+  // One 16-byte vector per thread and stream at every size.  Round 1 switched to two vectors per thread once the grid
+  // reached ~8 CTAs per SM; re-measured on the final kernel (profiles/launch_shape_sweep_r02.jsonl, batch 32..4096, SD
+  // fp32 and FM bf16) the one-vector form is never behind and 1.5-2 % ahead at batch 256 (0.98 vs 0.967 of the copy peak),
+  // so the two-vector instantiations are no longer compiled (consolver_set_step_launch still accepts unroll = 2 and runs
+  // this form): 165 -> 105 step kernels in the library.
   return launch_one<T, TX, NH, MODE, E, 1>(p, threads, stream);
 }
 

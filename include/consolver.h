@@ -428,7 +428,8 @@ CONSOLVER_API int consolver_ppo_loss_grad_allreduce_f32(const float* w1, const f
 
 /* Tuning knobs for benchmarking (process-global; not part of the numerical contract).
  *   threads: CTA size of the step kernels (32..512, multiple of 32; 0 = default)
- *   unroll : 16-byte vectors per thread per stream (1 or 2; 0 = default = 1)                          */
+ *   unroll : 16-byte vectors per thread per stream; only the one-vector form is compiled in (round 2: the
+ *            two-vector form was never ahead), so 0, 1 and 2 all run it — kept so that callers need not change */
 CONSOLVER_API int consolver_set_step_launch(int threads, int unroll);
 
 #ifdef __cplusplus

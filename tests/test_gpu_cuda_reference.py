@@ -167,8 +167,8 @@ def _oracle(eps, hist, x, c, od, scalars, vpred, sdim):
 @pytest.mark.parametrize("n_hist", [1, 2, 4, 6])
 @pytest.mark.parametrize("vpred,sdim", [(False, 0), (True, 2), (False, 1)])
 def test_step_sd_f32_bit_exact_with_cuda_rules(B, shape, n_hist, vpred, sdim):
-    """fp32: `(x - sb*e) / sa` is `(x - sb*e) * (1/sa)` on CUDA tensors.  B=160 is run through the two-vectors-per-thread
-    instantiation (consolver_set_step_launch), the others through the default one-vector form; (3,5,7) the scalar path."""
+    """fp32: `(x - sb*e) / sa` is `(x - sb*e) * (1/sa)` on CUDA tensors.  B=160 is a multi-wave grid and is launched with
+    the legacy `unroll = 2` knob (accepted, runs the one-vector form — the only one compiled); (3,5,7) the scalar path."""
     from consolver_b200 import _lib
 
     lib = _lib.load()
