@@ -116,3 +116,68 @@ def test_fm_oracle_next_to_the_reference_on_cpu(case):
         assert torch.equal(mo, mr) and torch.equal(co["x"], cr["x"]), tag
         torch.testing.assert_close(po, pr, rtol=2e-5, atol=1e-6)
         assert xo.dtype == xr.dtype and torch.equal(xo, xr), tag + ": latent"
+
+
+@pytest.mark.parametrize("case", range(max(CASES // 2, 1)))
+def test_update_side_loss_and_gradients_next_to_the_reference_modules(case):
+    """PPO update side on CPU: the REFERENCE's FactorNetPPO modules evaluate `curr_probs, entropy =
+    factor_net(conds, actions)` on the B*(n-1) replicated rows (factor_net_ppo.py:170-184) and the loss lines of
+    train_ppo.py:376-427 are written out on top; consolver_b200.ppo.ppo_loss evaluates the n-1 DISTINCT rows and gathers.
+    Loss and every parameter gradient must agree, and so must the oracle's restatement, over random widths, bin counts,
+    action dims, rollout lengths, masks, clip ranges and entropy weights (SD and FM policies)."""
+    import consolver_b200 as cb
+    from consolver_b200 import ppo
+
+    ref = ref_shim.load_reference()
+    rng = random.Random(23000 + case)
+    variant = rng.choice(["sd", "sd", "fm"])
+    od, sc = rng.choice([2, 3, 4, 6]), rng.choice([0, 1, 2])
+    H, K = rng.choice([16, 64]), rng.choice([3, 11, 161])
+    B, n1 = rng.choice([2, 5, 12]), rng.choice([1, 2, 7, 14])
+    clip, ent_coef = rng.choice([0.2, 0.05, 0.5]), rng.choice([0.0, 0.01, 0.1])
+    with ref_shim.quiet():
+        if variant == "sd":
+            rfn = ref.FactorNetPPO_SD(hidden_dim=H, num_actions=K, order_dim=od, scaler_dim=sc)
+            ofn = cb.FactorNetPPO(hidden_dim=H, num_actions=K, order_dim=od, scaler_dim=sc)
+        else:
+            mu = rng.choice([0, 1])
+            rfn = ref.FactorNetPPO_FM(hidden_dim=H, num_actions=K, order_dim=od, scaler_dim=sc, mu_dim=mu)
+            ofn = cb.FactorNetPPOFM(hidden_dim=H, num_actions=K, order_dim=od, scaler_dim=sc, mu_dim=mu)
+    _seed_policy(rfn, case, 0.3 if variant == "sd" else 0.004)
+    ofn.load_state_dict(rfn.state_dict())
+    g = torch.Generator().manual_seed(case)
+    A = ofn.action_dims
+    if variant == "sd":
+        t = torch.tensor(sorted(rng.sample(range(70, 1000), n1), reverse=True), dtype=torch.float32)
+        rows = torch.stack([t, t - 66], 1)
+    else:
+        rows = torch.rand(n1, 2, generator=g)
+    idx = torch.randint(0, K, (B, n1, A), generator=g)
+    actions = ofn.action_values[torch.arange(A).view(1, 1, A).expand(B, n1, A), idx]
+    old = torch.rand(B, n1, A, generator=g) * 0.5 + 0.01
+    masks = (torch.rand(B, n1, A, generator=g) > 0.25).float()
+    rewards = torch.randn(B, 1, generator=g)
+    x = rows.unsqueeze(0).expand(B, n1, 2)
+    # the reference, literally (train_ppo.py:376-390 advantages, :406-427 loss) on its own module
+    adv = (rewards - rewards.mean()) / (rewards.std() + 1e-8) * 10
+    adv = adv.repeat(1, n1).reshape(B * n1, -1) * masks.reshape(B * n1, A)
+    cur, entropy = rfn({"x": x.reshape(B * n1, 2)}, actions.reshape(B * n1, A))
+    logp = (cur + 1e-9).log().sum(dim=1).unsqueeze(1)
+    old_logp = (old.reshape(B * n1, A) + 1e-9).log().sum(dim=1).unsqueeze(1)
+    ratio = (logp - old_logp).exp()
+    loss_ref = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - clip, 1 + clip)).mean() - ent_coef * entropy.mean()
+    g_ref = torch.autograd.grad(loss_ref, list(rfn.parameters()))
+    # the drop-in: distinct rows, recorded indices
+    loss, _ = ppo.ppo_loss(ofn, rows, idx, old, ppo.advantages_from_rewards(rewards, masks), clip, ent_coef)
+    g_own = torch.autograd.grad(loss, list(ofn.parameters()))
+    tag = f"update case {case} ({variant}, od={od}, sc={sc}, H={H}, K={K}, B={B}, n'={n1}, clip={clip}, ent={ent_coef})"
+    torch.testing.assert_close(loss, loss_ref.detach(), rtol=2e-5, atol=2e-6, msg=lambda m: tag + "\n" + m)
+    for (name, _), a, b in zip(ofn.named_parameters(), g_own, g_ref):
+        scale = float(b.abs().max())
+        # fp32 summation order differs (B-fold replicated rows summed by autograd vs distinct rows then a gather), and the
+        # FM policy's temperature 0.01 multiplies it by 100: the bar is relative to the gradient's own scale
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=max(scale, 1e-12) * 2e-4, msg=lambda m: f"{tag}: d/d{name}\n{m}")
+    # and the oracle's restatement of the same lines
+    sd = {k: v.detach().clone() for k, v in rfn.state_dict().items()}
+    loss_orc = orc.ppo_loss_replicated(sd, x, actions, old, masks, rewards, variant, clip, ent_coef)
+    torch.testing.assert_close(loss_orc, loss_ref.detach(), rtol=2e-5, atol=2e-6, msg=lambda m: tag + " (oracle)\n" + m)
